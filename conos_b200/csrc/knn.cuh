@@ -1,0 +1,74 @@
+// Exact k-nearest-neighbour search between projected cell matrices
+// (replaces N2R::crossKnn / N2R::Knn, reference call sites R/conos.R:595,851-855).
+//
+// Canonical float32 arithmetic (identical in oracle/conos_oracle.c, bit for bit):
+//   angular: ss = fma-chain_i(x_i*x_i), i ascending; inv = 1/sqrtf(ss) (0 if ss==0); xh_i = x_i*inv;
+//            four interleaved fma chains a_j = sum_{i = j mod 4} qh_i*rh_i (i ascending, from 0) -- the
+//            4-lane SIMD accumulation a CPU dot product uses -- dot = (a_0 + a_1) + (a_2 + a_3);
+//            dist = 1.0f - dot
+//   L2     : same four chains over (q_i - r_i)^2; dist = (a_0 + a_1) + (a_2 + a_3)  (squared Euclidean)
+//   order  : (dist ascending, reference index ascending); the first k are returned.
+//
+// Operand panels live in HBM in "core-matrix tiled" fp32 layout
+//   tiled[(row/8)][chunk = col/4][row%8][col%4],   KC = d_pad/4 chunks, d_pad in {32, 64}
+// i.e. exactly the shared-memory image a K-major, no-swizzle tcgen05 (kind::tf32) operand needs, so a
+// tile of R rows (R % 8 == 0) is one contiguous byte range that a single 1-D bulk copy moves.
+// Rows are zero-padded up to a multiple of 256.
+#pragma once
+#include "common.cuh"
+
+namespace cg {
+
+constexpr int KNN_ROW_PAD = 256;  // panel rows are padded to a multiple of this
+constexpr int KNN_TC_MAXK = 32;   // largest k served by the tensor-core kernel
+
+enum Metric : int { METRIC_ANGULAR = 0, METRIC_L2 = 1 };
+
+struct KnnPanel {
+  int n = 0;      // valid rows
+  int d = 0;      // valid columns
+  int d_pad = 0;  // 32 or 64
+  int n_pad = 0;  // multiple of KNN_ROW_PAD
+  float* tiled = nullptr;  // n_pad * d_pad floats (not owned)
+  static size_t elems(int n, int d) { return round_up(n, KNN_ROW_PAD) * (size_t)(d <= 32 ? 32 : 64); }
+};
+
+__host__ __device__ inline size_t knn_tiled_offset(int row, int col, int d_pad) {
+  return (size_t)(row >> 3) * (size_t)(8 * d_pad) + (size_t)(col >> 2) * 32 + (size_t)(row & 7) * 4 + (col & 3);
+}
+
+struct KnnProblem {
+  const float* q_tiled;
+  const float* r_tiled;
+  int nq;
+  int nr;
+  int* out_idx;     // [nq][k], -1 where fewer than k references exist
+  float* out_dist;  // [nq][k], +inf where idx == -1
+};
+
+struct KnnItem {
+  int prob;
+  int qblock;  // block of 256 query rows
+};
+
+// Fill a tiled panel from a column-major double matrix (R layout) -- angular panels are L2-normalised.
+void knn_prep_from_f64_colmajor(Context& ctx, const double* d_src, int n, int d, int ld, Metric metric,
+                                KnnPanel& out);
+// Same from a row-major fp32 device matrix [n][ld] (output of the projection kernels).
+void knn_prep_from_f32_rowmajor(Context& ctx, const float* d_src, int n, int d, int ld, Metric metric,
+                                KnnPanel& out);
+
+// Exact SIMT kernel: any k, both metrics. One warp per query row.
+void knn_simt_launch(Context& ctx, const KnnProblem* d_probs, const KnnProblem* h_probs, int n_probs, int k,
+                     int d_pad, Metric metric);
+
+// Tensor-core kernel (angular, k <= KNN_TC_MAXK): TF32 tcgen05 distance tiles in TMEM as a filter,
+// canonical fp32 re-rank of the survivors, per-row sorted top-k lists in shared memory.
+void knn_tc_launch(Context& ctx, const KnnProblem* d_probs, const KnnProblem* h_probs, int n_probs, int k,
+                   int d_pad);
+
+// Dispatch by (k, metric): the tensor-core kernel whenever it applies.
+void knn_launch(Context& ctx, const KnnProblem* d_probs, const KnnProblem* h_probs, int n_probs, int k, int d_pad,
+                Metric metric);
+
+}  // namespace cg

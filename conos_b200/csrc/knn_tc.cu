@@ -1,0 +1,439 @@
+// K2 fused exact cross-kNN on the sm_100a tensor cores (angular metric, k <= 32).
+//
+// One persistent CTA per SM walks work items (problem, block of 256 query rows):
+//   warp 0   producer : 1-D bulk async copies (TMA engine) of the query block (A, 256 rows) and of
+//                       reference tiles (B, 128 rows) from the pre-tiled fp32 panels into shared memory
+//   warp 1   MMA      : tcgen05.mma kind::tf32, 2 x (M=128, N=128) accumulators per reference tile,
+//                       fp32 accumulate in TMEM, double-buffered (4 x 128 = 512 TMEM columns)
+//   warps 2-9 select  : one query row per thread. tcgen05.ld the row's 128 approximate dot products,
+//                       branch-free compare against (1 - kth_dist) - margin into bit masks, release
+//                       TMEM; then, per warp: compact the (row, column) survivors into a shared-memory
+//                       queue, re-score them lane-parallel with the canonical fp32 fma chains from the
+//                       SAME fp32 tiles (A and B) in shared memory, and let each row's owner thread
+//                       insert its survivors into the row's sorted top-k list.
+// The TF32 product is only a filter: |tf32 dot - fp32 chain| < margin is a rigorous bound for unit
+// vectors, so the returned (dist, index) lists are bit-identical to the exact fp32 search
+// (oracle/conos_oracle.c) including tie order (dist, then lower reference index).
+//
+// Algorithmic work per launch: 2*nq*nr*d flops; HBM bytes 4*d*(nq+nr) read + 8*k*nq written.
+#include "knn.cuh"
+#include "ptx.cuh"
+
+namespace cg {
+namespace {
+
+constexpr int TC_THREADS = 320;
+constexpr int TILE_N = 128;
+constexpr int QBLOCK = 256;
+constexpr int LIST_STRIDE = KNN_TC_MAXK + 1;  // odd stride: thread-private rows hit distinct banks
+constexpr int QCAP = 512;                     // survivor queue entries per select warp (32 rows x 16 columns)
+// TF32 keeps 10 mantissa bits of each operand (worst case truncation): relative product error
+// < 2*2^-10 + 2^-20, sum |q_i r_i| <= 1 for unit vectors, plus fp32 accumulation and the rounding of
+// dist = 1 - dot. 2.2e-3 leaves > 10 % slack over the 1.96e-3 bound.
+constexpr float TF32_MARGIN = 2.2e-3f;
+
+template <int D_PAD>
+struct TcCfg {
+  static constexpr int KC = D_PAD / 4;             // 16-byte chunks per row
+  static constexpr int ROW_BYTES = D_PAD * 4;
+  static constexpr int A_BYTES = QBLOCK * ROW_BYTES;
+  static constexpr int B_BYTES = TILE_N * ROW_BYTES;
+  static constexpr int NSTAGE = D_PAD == 32 ? 4 : 2;
+  static constexpr int KSTEPS = D_PAD / 8;          // tf32 MMA K = 8
+  static constexpr int PEND = D_PAD == 32 ? 8 : 6;  // re-scored survivors a row buffers before it merges them
+  static constexpr int PEND_STRIDE = PEND + 1;      // odd: thread-private rows hit distinct banks
+  static constexpr int OFF_A = 0;
+  static constexpr int OFF_B = OFF_A + A_BYTES;
+  static constexpr int OFF_LD = OFF_B + NSTAGE * B_BYTES;
+  static constexpr int OFF_LI = OFF_LD + QBLOCK * LIST_STRIDE * 4;
+  static constexpr int OFF_Q = OFF_LI + QBLOCK * LIST_STRIDE * 4;   // per-warp survivor queues
+  static constexpr int OFF_PD = OFF_Q + 8 * QCAP * 4;                // per-row pending survivors (dist)
+  static constexpr int OFF_PI = OFF_PD + QBLOCK * PEND_STRIDE * 4;    // per-row pending survivors (index)
+  static constexpr int OFF_BAR = OFF_PI + QBLOCK * PEND_STRIDE * 4;
+  static constexpr int N_BAR = 2 + 2 * NSTAGE + 4;
+  static constexpr int OFF_TMEM = OFF_BAR + N_BAR * 8;
+  static constexpr int SMEM_BYTES = OFF_TMEM + 16;
+};
+
+template <int D_PAD, int KT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+knn_tc_kernel(const KnnProblem* __restrict__ probs, const KnnItem* __restrict__ items, int n_items, int k) {
+  using C = TcCfg<D_PAD>;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  float* smA = reinterpret_cast<float*>(smem + C::OFF_A);
+  float* smB = reinterpret_cast<float*>(smem + C::OFF_B);
+  float* list_d = reinterpret_cast<float*>(smem + C::OFF_LD);
+  int* list_i = reinterpret_cast<int*>(smem + C::OFF_LI);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* a_full = bars + 0;
+  uint64_t* a_empty = bars + 1;
+  uint64_t* b_full = bars + 2;
+  uint64_t* b_empty = bars + 2 + C::NSTAGE;
+  uint64_t* acc_full = bars + 2 + 2 * C::NSTAGE;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_TMEM);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(a_full, 1);
+    ptx::mbar_init(a_empty, 1 + 8);  // MMA commit + 8 select warps (they re-rank from the A tile)
+    for (int s = 0; s < C::NSTAGE; ++s) {
+      ptx::mbar_init(b_full + s, 1);
+      ptx::mbar_init(b_empty + s, 1 + 8);  // MMA commit + 8 select warps (they re-rank from the tile)
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(acc_full + s, 1);
+      ptx::mbar_init(acc_empty + s, 8);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ producer
+    if (lane == 0) {
+      uint32_t g = 0, it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const KnnItem wi = items[item];
+        const KnnProblem pb = probs[wi.prob];
+        ptx::mbar_wait(a_empty, (it & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(a_full, C::A_BYTES);
+        ptx::bulk_g2s(smA, pb.q_tiled + (size_t)wi.qblock * QBLOCK * D_PAD, C::A_BYTES, a_full);
+        const int n_tiles = (pb.nr + TILE_N - 1) / TILE_N;
+        for (int t = 0; t < n_tiles; ++t, ++g) {
+          const uint32_t slot = g % C::NSTAGE, ph = (g / C::NSTAGE) & 1;
+          while (!ptx::mbar_try_wait(b_empty + slot, ph ^ 1)) __nanosleep(64);  // not latency critical
+          ptx::mbar_arrive_expect_tx(b_full + slot, C::B_BYTES);
+          ptx::bulk_g2s(smB + (size_t)slot * (C::B_BYTES / 4), pb.r_tiled + (size_t)t * TILE_N * D_PAD, C::B_BYTES,
+                        b_full + slot);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ---------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc(2u, 128u, (uint32_t)TILE_N);
+      const uint32_t a_addr = ptx::smem_u32(smA), b_addr0 = ptx::smem_u32(smB);
+      uint32_t g = 0, it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const KnnItem wi = items[item];
+        const int nr = probs[wi.prob].nr;
+        const int n_tiles = (nr + TILE_N - 1) / TILE_N;
+        ptx::mbar_wait(a_full, it & 1);
+        for (int t = 0; t < n_tiles; ++t, ++g) {
+          const uint32_t slot = g % C::NSTAGE, ph = (g / C::NSTAGE) & 1;
+          const uint32_t stage = g & 1, aph = (g >> 1) & 1;
+          ptx::mbar_wait(b_full + slot, ph);
+          ptx::mbar_wait(acc_empty + stage, aph ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t b_addr = b_addr0 + slot * C::B_BYTES;
+#pragma unroll
+          for (int mb = 0; mb < 2; ++mb) {
+            const uint32_t d_tmem = tmem_base + (stage * 2 + mb) * TILE_N;
+#pragma unroll
+            for (int ks = 0; ks < C::KSTEPS; ++ks) {
+              const uint64_t ad = ptx::umma_desc_kmajor_noswz(a_addr + mb * 128 * C::ROW_BYTES + ks * 256, 128,
+                                                               C::KC * 128);
+              const uint64_t bd = ptx::umma_desc_kmajor_noswz(b_addr + ks * 256, 128, C::KC * 128);
+              ptx::mma_tf32_ss(d_tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
+            }
+          }
+          ptx::mma_commit(b_empty + slot);
+          ptx::mma_commit(acc_full + stage);
+        }
+        ptx::mma_commit(a_empty);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------ select / re-rank warps
+    const int e = warp - 2;
+    const int mb = e >> 2;
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    const int warp_row0 = mb * 128 + quarter * 32;
+    const int row_local = warp_row0 + lane;
+    float* my_d = list_d + row_local * LIST_STRIDE;
+    int* my_i = list_i + row_local * LIST_STRIDE;
+    uint32_t* qbuf = reinterpret_cast<uint32_t*>(smem + C::OFF_Q) + e * QCAP;
+    float* pend_d = reinterpret_cast<float*>(smem + C::OFF_PD) + row_local * C::PEND_STRIDE;
+    int* pend_i = reinterpret_cast<int*>(smem + C::OFF_PI) + row_local * C::PEND_STRIDE;
+    // survivors accepted per row between two scheduled merges ~ k*ln(t1/t0): keep it near PEND/2
+    const float flush_growth = expf((float)(C::PEND / 2) / (float)k) - 1.0f;
+    uint32_t g = 0, it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const KnnItem wi = items[item];
+      const KnnProblem pb = probs[wi.prob];
+      const int qrow = wi.qblock * QBLOCK + row_local;
+      const bool valid_row = qrow < pb.nq;  // zero padding rows would tie with every reference
+      const int n_tiles = (pb.nr + TILE_N - 1) / TILE_N;
+      for (int p = 0; p < KT; ++p) { my_d[p] = INFINITY; my_i[p] = -1; }
+      float kth = INFINITY;
+      int npend = 0;
+      int next_flush = 0;
+      // Merge the buffered survivors of all 32 rows into their sorted lists, in lock step: the list
+      // goes to registers, every survivor runs through a branch-free insertion network
+      //   new[p] = old[p-1] > x ? old[p-1] : (old[p] > x ? x : old[p])
+      // (arrival = ascending reference index order, strict compares: equal distances keep the lower
+      // index, survivors not below the k-th distance fall off the end), and the list goes back.
+      auto flush = [&]() {
+        const int maxp = __reduce_max_sync(0xffffffffu, npend);
+        if (maxp == 0) return;
+        float ld[KT];
+        int li[KT];
+#pragma unroll
+        for (int p = 0; p < KT; ++p) { ld[p] = my_d[p]; li[p] = my_i[p]; }
+        for (int u = 0; u < maxp; ++u) {
+          const bool has = u < npend;
+          const float x = has ? pend_d[u] : INFINITY;
+          const int j = has ? pend_i[u] : -1;
+          bool c_hi = ld[KT - 1] > x;
+#pragma unroll
+          for (int p = KT - 1; p >= 1; --p) {
+            const bool c_lo = ld[p - 1] > x;
+            ld[p] = c_lo ? ld[p - 1] : (c_hi ? x : ld[p]);
+            li[p] = c_lo ? li[p - 1] : (c_hi ? j : li[p]);
+            c_hi = c_lo;
+          }
+          ld[0] = c_hi ? x : ld[0];
+          li[0] = c_hi ? j : li[0];
+        }
+#pragma unroll
+        for (int p = 0; p < KT; ++p) {
+          my_d[p] = ld[p];
+          my_i[p] = li[p];
+          if (p == k - 1) kth = ld[p];
+        }
+        npend = 0;
+      };
+      ptx::mbar_wait(a_full, it & 1);  // the fp32 query block (re-rank operand)
+      for (int t = 0; t < n_tiles; ++t, ++g) {
+        const uint32_t slot = g % C::NSTAGE, ph = (g / C::NSTAGE) & 1;
+        const uint32_t stage = g & 1, aph = (g >> 1) & 1;
+        // survivors satisfy tf32_dot > (1 - kth) - margin; -inf while the list is not full
+        const float thr = valid_row ? (1.0f - kth) - TF32_MARGIN : INFINITY;
+        ptx::mbar_wait(acc_full + stage, aph);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (stage * 2 + mb) * TILE_N;
+        uint32_t mask[4];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v0[32], v1[32];
+          ptx::tmem_ld_32x32b_x32(taddr + (2 * half) * 32, v0);
+          ptx::tmem_ld_32x32b_x32(taddr + (2 * half + 1) * 32, v1);
+          ptx::tmem_wait_ld();
+          uint32_t m0 = 0, m1 = 0;
+          // sign bit of (thr - v) is set iff v > thr; the funnel shift appends it (column 31 first)
+#pragma unroll
+          for (int c = 31; c >= 0; --c) {
+            m0 = __funnelshift_l(__float_as_uint(thr - __uint_as_float(v0[c])), m0, 1);
+            m1 = __funnelshift_l(__float_as_uint(thr - __uint_as_float(v1[c])), m1, 1);
+          }
+          mask[2 * half] = m0;
+          mask[2 * half + 1] = m1;
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(acc_empty + stage);
+
+        const int jbase = t * TILE_N;
+        if (jbase + TILE_N > pb.nr) {  // zero padding rows of the last reference tile
+          const int nv = pb.nr - jbase;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const int lo = nv - w * 32;
+            mask[w] &= lo >= 32 ? 0xffffffffu : (lo <= 0 ? 0u : ((1u << lo) - 1u));
+          }
+        }
+        const int cnt_all = __popc(mask[0]) + __popc(mask[1]) + __popc(mask[2]) + __popc(mask[3]);
+        const int total = __reduce_add_sync(0xffffffffu, cnt_all);
+        if (total > 0) {
+          // the fp32 tile itself (async-proxy write, observed complete through its own barrier)
+          ptx::mbar_wait(b_full + slot, ph);
+          const float* tile = smB + (size_t)slot * (C::B_BYTES / 4);
+          // one round over all 128 columns when the survivors fit the queue, else 8 rounds of 16 columns
+          const int n_rounds = total <= QCAP ? 1 : 8;
+#pragma unroll 1
+          for (int r = 0; r < n_rounds; ++r) {
+            uint32_t sm[4];
+#pragma unroll
+            for (int w = 0; w < 4; ++w)
+              sm[w] = n_rounds == 1 ? mask[w]
+                                    : ((r >> 1) == w ? (mask[w] & ((r & 1) ? 0xffff0000u : 0x0000ffffu)) : 0u);
+            const int cnt = __popc(sm[0]) + __popc(sm[1]) + __popc(sm[2]) + __popc(sm[3]);
+            int incl = cnt;
+#pragma unroll
+            for (int dlt = 1; dlt < 32; dlt <<= 1) {
+              int tt = __shfl_up_sync(0xffffffffu, incl, dlt);
+              if (lane >= dlt) incl += tt;
+            }
+            const int E = __shfl_sync(0xffffffffu, incl, 31);
+            if (E == 0) continue;
+            const int off = incl - cnt;
+            const int maxc = __reduce_max_sync(0xffffffffu, cnt);
+            // A: compaction -- each row appends its (row, column) survivors, ascending column
+            {
+              uint32_t s0 = sm[0], s1 = sm[1], s2 = sm[2], s3 = sm[3];
+              for (int u = 0; u < maxc; ++u) {
+                if (u < cnt) {
+                  int col;
+                  if (s0) { col = __ffs(s0) - 1; s0 &= s0 - 1; }
+                  else if (s1) { col = 32 + __ffs(s1) - 1; s1 &= s1 - 1; }
+                  else if (s2) { col = 64 + __ffs(s2) - 1; s2 &= s2 - 1; }
+                  else { col = 96 + __ffs(s3) - 1; s3 &= s3 - 1; }
+                  qbuf[off + u] = ((uint32_t)lane << 7) | (uint32_t)col;
+                }
+              }
+            }
+            __syncwarp();
+            // B: canonical fp32 re-score, one survivor per lane
+            for (int q0 = 0; q0 < E; q0 += 32) {
+              const int qi = q0 + lane;
+              if (qi < E) {
+                const uint32_t ent = qbuf[qi];
+                const int rl = warp_row0 + (int)(ent >> 7);
+                const int col = (int)(ent & 127u);
+                const float* qp = smA + (size_t)(rl >> 3) * (8 * D_PAD) + (size_t)(rl & 7) * 4;
+                const float* rp = tile + (size_t)(col >> 3) * (8 * D_PAD) + (size_t)(col & 7) * 4;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                for (int cc = 0; cc < C::KC; ++cc) {
+                  const float4 qv = *reinterpret_cast<const float4*>(qp + cc * 32);
+                  const float4 rv = *reinterpret_cast<const float4*>(rp + cc * 32);
+                  a0 = fmaf(qv.x, rv.x, a0);
+                  a1 = fmaf(qv.y, rv.y, a1);
+                  a2 = fmaf(qv.z, rv.z, a2);
+                  a3 = fmaf(qv.w, rv.w, a3);
+                }
+                const float dist = 1.0f - ((a0 + a1) + (a2 + a3));
+                qbuf[qi] = __float_as_uint(dist);
+              }
+            }
+            __syncwarp();
+            // C: each row's owner buffers its survivors that beat the (possibly stale) k-th distance
+            {
+              uint32_t s0 = sm[0], s1 = sm[1], s2 = sm[2], s3 = sm[3];
+              for (int u = 0; u < maxc; ++u) {
+                const bool has = u < cnt;
+                float dist = INFINITY;
+                int col = 0;
+                if (has) {
+                  dist = __uint_as_float(qbuf[off + u]);
+                  if (s0) { col = __ffs(s0) - 1; s0 &= s0 - 1; }
+                  else if (s1) { col = 32 + __ffs(s1) - 1; s1 &= s1 - 1; }
+                  else if (s2) { col = 64 + __ffs(s2) - 1; s2 &= s2 - 1; }
+                  else { col = 96 + __ffs(s3) - 1; s3 &= s3 - 1; }
+                }
+                const bool take = has && dist < kth;
+                if (__any_sync(0xffffffffu, take && npend == C::PEND)) flush();
+                if (take && dist < kth) {
+                  pend_d[npend] = dist;
+                  pend_i[npend] = jbase + col;
+                  ++npend;
+                }
+              }
+            }
+            __syncwarp();
+          }
+        }
+        // scheduled merge: the same tiles for every warp of the CTA, geometrically spaced
+        if (t >= next_flush) {
+          flush();
+          const int step = (int)((float)(t + 1) * flush_growth);
+          next_flush = t + (step > 1 ? step : 1);
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(b_empty + slot);
+      }
+      flush();
+      if (valid_row) {
+        for (int p = 0; p < k; ++p) {
+          pb.out_idx[(size_t)qrow * k + p] = my_i[p];
+          pb.out_dist[(size_t)qrow * k + p] = my_d[p];
+        }
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(a_empty);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+template <int D_PAD, int KT>
+void launch_tc(Context& ctx, const KnnProblem* d_probs, const KnnItem* d_items, int n_items, int k) {
+  using C = TcCfg<D_PAD>;
+  static_assert(C::SMEM_BYTES <= 227 * 1024, "shared memory budget");
+  CG_CUDA(cudaFuncSetAttribute(knn_tc_kernel<D_PAD, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               C::SMEM_BYTES));
+  int grid = n_items < ctx.sm_count ? n_items : ctx.sm_count;
+  knn_tc_kernel<D_PAD, KT><<<grid, TC_THREADS, C::SMEM_BYTES, ctx.stream>>>(d_probs, d_items, n_items, k);
+  ctx.stats.kernels++;
+  CG_CUDA(cudaGetLastError());
+}
+
+}  // namespace
+
+void knn_tc_launch(Context& ctx, const KnnProblem* d_probs, const KnnProblem* h_probs, int n_probs, int k,
+                   int d_pad) {
+  CG_CHECK(k >= 1 && k <= KNN_TC_MAXK, "tensor-core kNN serves 1 <= k <= 32");
+  std::vector<KnnItem> items;
+  double cand = 0.0, bytes = 0.0;
+  for (int p = 0; p < n_probs; ++p) {
+    if (h_probs[p].nq <= 0) continue;
+    int nb = (h_probs[p].nq + QBLOCK - 1) / QBLOCK;
+    for (int b = 0; b < nb; ++b) items.push_back(KnnItem{p, b});
+    cand += (double)h_probs[p].nq * (double)h_probs[p].nr;
+    bytes += 4.0 * d_pad * ((double)h_probs[p].nq + h_probs[p].nr) + 8.0 * k * (double)h_probs[p].nq;
+  }
+  if (items.empty()) return;
+  DevBuf<KnnItem> d_items;
+  d_items.upload(items.data(), items.size(), ctx.stream);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (ctx.time_knn) {
+    CG_CUDA(cudaEventCreate(&e0));
+    CG_CUDA(cudaEventCreate(&e1));
+    CG_CUDA(cudaEventRecord(e0, ctx.stream));
+  }
+  CG_CHECK(d_pad == 32 || d_pad == 64, "d_pad must be 32 or 64");
+  const int ni = (int)items.size();
+  if (d_pad == 32) {
+    if (k <= 16) launch_tc<32, 16>(ctx, d_probs, d_items.p, ni, k);
+    else launch_tc<32, 32>(ctx, d_probs, d_items.p, ni, k);
+  } else {
+    if (k <= 16) launch_tc<64, 16>(ctx, d_probs, d_items.p, ni, k);
+    else launch_tc<64, 32>(ctx, d_probs, d_items.p, ni, k);
+  }
+  if (ctx.time_knn) {
+    CG_CUDA(cudaEventRecord(e1, ctx.stream));
+    CG_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    ctx.knn_ms_accum += ms;
+    ctx.knn_launches++;
+    ctx.knn_candidates += cand;
+    ctx.knn_bytes += bytes;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
+  // d_items is freed by cudaFree, which synchronises with the kernel that reads it
+  CG_CUDA(cudaStreamSynchronize(ctx.stream));
+}
+
+void knn_launch(Context& ctx, const KnnProblem* d_probs, const KnnProblem* h_probs, int n_probs, int k, int d_pad,
+                Metric metric) {
+  if (metric == METRIC_ANGULAR && k <= KNN_TC_MAXK) knn_tc_launch(ctx, d_probs, h_probs, n_probs, k, d_pad);
+  else knn_simt_launch(ctx, d_probs, h_probs, n_probs, k, d_pad, metric);
+}
+
+}  // namespace cg
