@@ -1,0 +1,357 @@
+"""Host-side mirror of the reference's R6 class ``Conos`` for the joint-graph construction path.
+
+Same method names, argument meaning, defaults and error messages as R/conclass.R (``Conos$new``,
+``addSamples``, ``buildGraph``; R's dotted argument names become underscores).  All arithmetic runs in
+libconosgpu.so through the C ABI (include/conos_gpu.h); this file only does what the R layer does around
+the native calls: argument checks, pair enumeration and caching (``self.pairs[space]["A.vs.B"]``,
+R/conclass.R:1035-1107), gene-set selection by name (R/conos.R:107-117) and result packaging.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import warnings
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib
+from ._lib import CgPair, CgParams, CgSample, MATCHING, METRICS, SPACES, ptr
+
+SUPPORTED_SPACES = ["CPCA", "JNMF", "genes", "PCA", "PMA", "CCA"]   # what the reference accepts
+DEVICE_SPACES = ["CPCA", "PCA", "CCA"]                               # what the B200 path builds (north_star)
+
+
+@dataclass
+class Pagoda2:
+    """The fields of a pagoda2 object that buildGraph reads (R/access_wrappers.R:9,34,65,85,157)."""
+    counts: sp.csc_matrix                 # cells x genes, log-scale expression
+    genes: List[str]                      # colnames(counts)
+    cells: List[str]                      # rownames(counts)
+    varinfo_v: Optional[np.ndarray] = None    # misc$varinfo$v  (aligned with genes)
+    varinfo_qv: Optional[np.ndarray] = None   # misc$varinfo$qv
+    pca: Optional[np.ndarray] = None          # reductions$PCA, cells x nPcs
+    od_genes: List[str] = field(default_factory=list)  # getOdGenes(): most overdispersed first
+
+    def getOdGenes(self, n_odgenes: Optional[int] = None) -> List[str]:
+        return self.od_genes if n_odgenes is None else self.od_genes[:n_odgenes]
+
+
+@dataclass
+class ConosGraph:
+    """What ``self$graph`` (an igraph) carries for findCommunities / embedGraph (R/conclass.R:336-343)."""
+    names: List[str]            # V(g)$name, vertex order = first appearance in the edge table
+    vertices: np.ndarray        # global cell index of every vertex
+    edge_from: np.ndarray       # vertex ids, from < to, sorted by (from, to)
+    edge_to: np.ndarray
+    weight: np.ndarray          # E(g)$weight
+    type: np.ndarray            # E(g)$type : 1 inter-sample, 0 intra-sample
+    adj_p: np.ndarray           # as_adj(g, attr='weight'): symmetric CSR/CSC in vertex order
+    adj_i: np.ndarray
+    adj_x: np.ndarray
+
+    def as_adj(self) -> sp.csr_matrix:
+        n = len(self.vertices)
+        return sp.csr_matrix((self.adj_x, self.adj_i, self.adj_p), shape=(n, n))
+
+    def vcount(self) -> int:
+        return len(self.vertices)
+
+    def ecount(self) -> int:
+        return len(self.edge_from)
+
+
+def r_round(x: float) -> int:
+    return int(round(x))  # IEC 60559 half-to-even, like R
+
+
+class Conos:
+    def __init__(self, x: Optional[Dict[str, Pagoda2]] = None, n_cores: int = 1, device: int = 0, ctx=None):
+        self.samples: Dict[str, Pagoda2] = {}
+        self.pairs: Dict[str, Dict[str, dict]] = {}
+        self.graph: Optional[ConosGraph] = None
+        self.n_cores = n_cores      # kept for API parity; the device path ignores it
+        self._ctx = ctx
+        self._device = device
+        self._panel = None
+        self._panel_names: List[str] = []
+        self._vocab = None
+        self.timings: Dict[str, float] = {}
+        if x is not None:
+            self.addSamples(x)
+
+    # ------------------------------------------------------------------ R/conclass.R:93-112
+    def addSamples(self, x: Dict[str, Pagoda2], replace: bool = False):
+        if not isinstance(x, dict) or len(x) == 0:
+            raise ValueError("The samples must be provided as a named list")
+        if len(self.samples) + (0 if not replace else 0) + len(x) < 2 and not self.samples:
+            raise ValueError("The list of samples must contain at least two samples")
+        if replace:
+            self.samples = {}
+        dup = [n for n in x if n in self.samples]
+        if dup:
+            raise ValueError("Some of the names in the provided sample list are identical to already existing samples")
+        for n, s in x.items():
+            if not isinstance(s, Pagoda2):
+                raise ValueError("only Pagoda2 samples are supported by the B200 path")
+            if s.counts.shape != (len(s.cells), len(s.genes)):
+                raise ValueError(f"sample {n}: counts must be cells x genes")
+            self.samples[n] = s
+        self._vocab = None
+        self._drop_panel()
+
+    def _drop_panel(self):
+        if self._panel is not None:
+            self.ctx.lib.cg_panel_free(self._panel)
+            self._panel = None
+
+    @property
+    def ctx(self):
+        if self._ctx is None:
+            self._ctx = _lib.default_context(self._device)
+        return self._ctx
+
+    # ------------------------------------------------------------------ device-resident panel
+    def _ensure_panel(self, names: Sequence[str]):
+        if self._panel is not None and self._panel_names == list(names):
+            return
+        self._drop_panel()
+        arr = (CgSample * len(names))()
+        keep = []
+        for t, n in enumerate(names):
+            s = self.samples[n]
+            m = sp.csc_matrix(s.counts)
+            m.sort_indices()
+            p = np.ascontiguousarray(m.indptr, np.int32)
+            i = np.ascontiguousarray(m.indices, np.int32)
+            x = np.ascontiguousarray(m.data, np.float64)
+            v = None if s.varinfo_v is None else np.ascontiguousarray(s.varinfo_v, np.float64)
+            qv = None if s.varinfo_qv is None else np.ascontiguousarray(s.varinfo_qv, np.float64)
+            pca = None if s.pca is None else np.asfortranarray(s.pca, np.float64)
+            keep += [p, i, x, v, qv, pca]
+            arr[t].n_cells, arr[t].n_genes = m.shape
+            arr[t].p, arr[t].i, arr[t].x = ptr(p, C.c_int32), ptr(i, C.c_int32), ptr(x, C.c_double)
+            arr[t].var_v, arr[t].var_qv = ptr(v, C.c_double), ptr(qv, C.c_double)
+            arr[t].pca = ptr(pca, C.c_double)
+            arr[t].n_pcs = 0 if pca is None else pca.shape[1]
+            arr[t].pca_ld = m.shape[0]
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.cg_panel_create(self.ctx.h, arr, len(names), C.byref(h)))
+        self._panel = h
+        self._panel_names = list(names)
+
+    # ------------------------------------------------------------------ R/conos.R:107-117
+    def _ensure_vocab(self):
+        """Gene names -> integer ids in sort() order (C locale), once per sample set."""
+        if self._vocab is not None:
+            return
+        allnames = sorted(set(g for s in self.samples.values() for g in s.genes))
+        gid = {g: t for t, g in enumerate(allnames)}
+        per = {}
+        for n, s in self.samples.items():
+            ids = np.fromiter((gid[g] for g in s.genes), np.int64, len(s.genes))
+            col_of = np.full(len(allnames), -1, np.int32)
+            col_of[ids] = np.arange(len(ids), dtype=np.int32)
+            od = np.fromiter((gid[g] for g in s.od_genes if g in gid), np.int64)
+            per[n] = (col_of, od)
+        self._vocab = (allnames, per)
+
+    def _common_od_genes(self, na: str, nb: str, n_odgenes: int):
+        """commonOverdispersedGenes for the pair + the column of every od gene in both samples:
+        table() of the two top-n od lists, sorted by count (decreasing, stable => ties keep name order),
+        restricted to genes present in both samples, first n.odgenes."""
+        self._ensure_vocab()
+        allnames, per = self._vocab
+        col_a, od_a = per[na]
+        col_b, od_b = per[nb]
+        cat = np.concatenate([od_a[:n_odgenes], od_b[:n_odgenes]])
+        ids, cnt = np.unique(cat, return_counts=True)          # ids ascending == names in sort() order
+        order = np.argsort(-cnt, kind="stable")
+        ids = ids[order]
+        ids = ids[(col_a[ids] >= 0) & (col_b[ids] >= 0)]
+        ids = ids[:min(len(ids), n_odgenes)]
+        ga = np.ascontiguousarray(col_a[ids], np.int32)
+        gb = np.ascontiguousarray(col_b[ids], np.int32)
+        return ids, ga, gb
+
+    def _gene_names(self, ids) -> List[str]:
+        allnames = self._vocab[0]
+        return [allnames[t] for t in ids]
+
+    # ------------------------------------------------------------------ R/conclass.R:161-371
+    def buildGraph(self, k: int = 15, k_self: int = 10, k_self_weight: float = 0.1,
+                   alignment_strength: Optional[float] = None, space: str = "PCA", matching_method: str = "mNN",
+                   metric: str = "angular", k1: Optional[int] = None, data_type: str = "counts",
+                   l2_sigma: float = 1e5, var_scale: bool = True, ncomps: int = 40, n_odgenes: int = 2000,
+                   matching_mask=None, exclude_samples: Optional[Sequence[str]] = None,
+                   common_centering: bool = True, verbose: bool = False, base_groups=None,
+                   score_component_variance: bool = False, snn: bool = False, balance_edge_weights: bool = False,
+                   balancing_factor_per_cell=None, same_factor_downweight: float = 1.0,
+                   k_same_factor: Optional[int] = None, balancing_factor_per_sample=None,
+                   pair_shard: Optional[Sequence[int]] = None, assemble: bool = True):
+        if space not in SUPPORTED_SPACES:
+            raise ValueError("only the following spaces are currently supported: [" + " ".join(SUPPORTED_SPACES) + "]")
+        if space not in DEVICE_SPACES:
+            raise NotImplementedError(f"space='{space}' is outside the B200 hot path (PCA, CPCA, CCA)")
+        if matching_method not in MATCHING:
+            raise ValueError("only the following matching methods are currently supported: ['mNN' 'NN']")
+        if metric not in METRICS:
+            raise ValueError("only the following distance metrics are currently supported: ['L2' 'angular']")
+        if data_type != "counts":
+            raise NotImplementedError("only data.type='counts' is on the B200 path")
+        if base_groups is not None or snn:
+            raise NotImplementedError("base.groups / snn are outside the B200 hot path (SURVEY.md 8f)")
+        if balancing_factor_per_sample is not None or balancing_factor_per_cell is not None:
+            raise NotImplementedError("balancing.factor.* is outside the B200 hot path (use balance_edge_weights)")
+        if k1 is None:
+            k1 = k
+        names = [n for n in self.samples if not (exclude_samples and n in exclude_samples)]
+        if alignment_strength is not None:
+            alignment_strength = min(max(alignment_strength, 0.0), 1.0)
+            max_cells = max(self.samples[n].counts.shape[0] for n in self.samples)
+            k1 = max(r_round(max_cells * alignment_strength ** 2), k)
+        else:
+            alignment_strength = 0.0
+        if k1 < k:
+            raise ValueError("k1 must be >= k")
+        cor_base = 1.0 + min(1.0, alignment_strength * 10.0)
+
+        # ---- updatePairs: pair list in combn order (or matching.mask), cached reductions
+        pair_names = []
+        for ia in range(len(names)):
+            for ib in range(ia + 1, len(names)):
+                if matching_mask is not None and not (matching_mask.get((names[ia], names[ib])) or
+                                                      matching_mask.get((names[ib], names[ia]))):
+                    continue
+                pair_names.append((names[ia], names[ib]))
+        if len(pair_names) < 1:
+            raise ValueError("insufficient number of comparable pairs")
+        self._ensure_panel(names)
+        index = {n: t for t, n in enumerate(names)}
+        cache = self.pairs.setdefault(space, {})
+
+        my_pairs = list(range(len(pair_names))) if pair_shard is None else list(pair_shard)
+        carr = (CgPair * max(len(my_pairs), 1))()
+        keep_alive = []
+        used_pairs = []
+        for slot, pi in enumerate(my_pairs):
+            na, nb = pair_names[pi]
+            od, ga, gb = self._common_od_genes(na, nb, n_odgenes)
+            if len(od) < 5:
+                continue  # quick* return NULL: the pair vanishes from the graph (R/conos.R:206,278,330)
+            cp = carr[len(used_pairs)]
+            cp.a, cp.b = index[na], index[nb]
+            cp.n_genes = len(od)
+            cp.genes_a, cp.genes_b = ptr(ga, C.c_int32), ptr(gb, C.c_int32)
+            key = f"{na}.vs.{nb}"
+            red = cache.get(key) or cache.get(f"{nb}.vs.{na}")
+            if red is not None and space in ("PCA", "CPCA") and red.get("CPC") is not None:
+                rot = np.asfortranarray(red["CPC"], np.float64)
+                if ncomps > rot.shape[1]:
+                    warnings.warn(f"specified ncomps ({ncomps}) is greater than the cached version ({rot.shape[1]})")
+                cp.rot, cp.rot_cols = ptr(rot, C.c_double), rot.shape[1]
+                keep_alive.append(rot)
+            elif red is not None and space == "CCA" and red.get("u") is not None:
+                u = np.asfortranarray(red["u"][:, :ncomps], np.float64)
+                v = np.asfortranarray(red["v"][:, :ncomps], np.float64)
+                ru = np.ascontiguousarray(red["rows_u"], np.int32)
+                rv = np.ascontiguousarray(red["rows_v"], np.int32)
+                cp.u, cp.v = ptr(u, C.c_double), ptr(v, C.c_double)
+                cp.rows_u, cp.rows_v = ptr(ru, C.c_int32), ptr(rv, C.c_int32)
+                cp.n_u, cp.n_v = u.shape[0], v.shape[0]
+                keep_alive += [u, v, ru, rv]
+            keep_alive += [ga, gb]
+            used_pairs.append((pi, key, od))
+
+        P = CgParams()
+        self.ctx.lib.cg_params_default(C.byref(P))
+        P.k, P.k1, P.k_self, P.ncomps = k, k1, k_self, ncomps
+        P.space, P.matching, P.metric = SPACES[space], MATCHING[matching_method], METRICS[metric]
+        P.var_scale, P.common_centering = int(var_scale), int(common_centering)
+        P.score_component_variance = int(score_component_variance)
+        P.k_self_weight, P.l2_sigma, P.cor_base = k_self_weight, l2_sigma, cor_base
+
+        lib, h = self.ctx.lib, self.ctx.h
+        edges = C.c_void_p()
+        counts = np.zeros(max(len(used_pairs), 1), np.int64)
+        self.ctx.check(lib.cg_pairs_edges(h, self._panel, carr, len(used_pairs), C.byref(P), C.byref(edges),
+                                          ptr(counts, C.c_int64)))
+        # populate self$pairs[[space]] like updatePairs does (R/conclass.R:1090-1092)
+        for slot, (pi, key, od) in enumerate(used_pairs):
+            if key in cache or space == "CCA":
+                continue
+            nr, nc = C.c_int32(0), C.c_int32(0)
+            self.ctx.check(lib.cg_pair_reduction(h, slot, C.byref(nr), C.byref(nc), None, None))
+            rot = np.zeros((nr.value, nc.value), order="F")
+            nv = np.zeros((2, nc.value)) if score_component_variance else None
+            self.ctx.check(lib.cg_pair_reduction(h, slot, None, None, ptr(rot, C.c_double), ptr(nv, C.c_double)))
+            cache[key] = {"CPC": rot, "genes": self._gene_names(od)}
+            if nv is not None:
+                cache[key]["nv"] = [nv[0], nv[1]]
+        self._last_pair_counts = {used_pairs[t][1]: int(counts[t]) for t in range(len(used_pairs))}
+        self._last_edges = edges
+        self._last_params = P
+        self._last_names = names
+        if not assemble:
+            return edges
+
+        # ---- local edges (R/conclass.R:328-333) and graph assembly
+        if k_self > 0:
+            sidx = np.arange(len(names), dtype=np.int32)
+            self.ctx.check(lib.cg_local_edges(h, self._panel, ptr(sidx, C.c_int32), len(names), C.byref(P),
+                                              C.byref(edges)))
+        g = self._assemble(edges, names)
+        lib.cg_edges_free(edges)
+        self._last_edges = None
+        if balance_edge_weights:
+            g = self._balance(g, names, same_factor_downweight)
+        self.graph = g
+        return g
+
+    def _assemble(self, edges, names) -> ConosGraph:
+        lib, h = self.ctx.lib, self.ctx.h
+        n_total = sum(self.samples[n].counts.shape[0] for n in names)
+        gh = C.c_void_p()
+        self.ctx.check(lib.cg_assemble_graph(h, edges, n_total, C.byref(gh)))
+        nv, ne = C.c_int32(0), C.c_int64(0)
+        lib.cg_graph_sizes(gh, C.byref(nv), C.byref(ne))
+        vertices = np.empty(nv.value, np.int32)
+        ef = np.empty(ne.value, np.int32)
+        et = np.empty(ne.value, np.int32)
+        w = np.empty(ne.value, np.float64)
+        ty = np.empty(ne.value, np.int32)
+        self.ctx.check(lib.cg_graph_fetch(h, gh, ptr(vertices, C.c_int32), ptr(ef, C.c_int32), ptr(et, C.c_int32),
+                                          ptr(w, C.c_double), ptr(ty, C.c_int32)))
+        ap = np.zeros(nv.value + 1, np.int64)
+        ai = np.empty(2 * ne.value, np.int32)
+        ax = np.empty(2 * ne.value, np.float64)
+        self.ctx.check(lib.cg_graph_fetch_adjacency(h, gh, ptr(ap, C.c_int64), ptr(ai, C.c_int32), ptr(ax, C.c_double)))
+        lib.cg_graph_free(gh)
+        cell_names = np.array([c for n in names for c in self.samples[n].cells], dtype=object)
+        return ConosGraph(names=list(cell_names[vertices]), vertices=vertices, edge_from=ef, edge_to=et, weight=w,
+                          type=ty, adj_p=ap, adj_i=ai, adj_x=ax)
+
+    def _balance(self, g: ConosGraph, names, same_factor_downweight: float) -> ConosGraph:
+        """adjustWeightsByCellBalancing with factor = dataset per cell (R/conclass.R:346-368, R/conos.R:936-967).
+        The graph is rebuilt from the adjacency matrix, so `type` is lost like in the reference."""
+        from . import ops
+        adj = g.as_adj().tocsc().tocoo()
+        ri, ci, w = adj.row.astype(np.int32), adj.col.astype(np.int32), adj.data.astype(np.float64)
+        sample_of = np.concatenate([np.full(self.samples[n].counts.shape[0], t, np.int32)
+                                    for t, n in enumerate(names)])
+        _, fl = np.unique(sample_of[g.vertices], return_inverse=True)
+        fl = (fl + 1).astype(np.int32)
+        for _ in range(50):
+            frac = ops.getSumWeightMatrix(w, ri, ci, fl, ctx=self.ctx)
+            div = frac * (frac > 1e-10).sum(axis=1, keepdims=True)
+            w = ops.adjustWeightsByCellBalancingC(w, ri, ci, fl, div, ctx=self.ctx)
+        if abs(same_factor_downweight - 1) > 1e-5:
+            w[fl[ri] == fl[ci]] *= same_factor_downweight
+        a = sp.csc_matrix((w, (ri, ci)), shape=(len(g.vertices),) * 2).tocsr()
+        a.sort_indices()
+        up = sp.triu(a, k=1).tocoo()
+        o = np.lexsort((up.col, up.row))
+        return ConosGraph(names=g.names, vertices=g.vertices, edge_from=up.row[o].astype(np.int32),
+                          edge_to=up.col[o].astype(np.int32), weight=up.data[o], type=np.full(len(o), -1, np.int32),
+                          adj_p=a.indptr.astype(np.int64), adj_i=a.indices.astype(np.int32), adj_x=a.data)

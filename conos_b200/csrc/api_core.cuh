@@ -1,0 +1,51 @@
+// Opaque handle definitions shared by the C-ABI translation units.
+#pragma once
+#include "../../include/conos_gpu.h"
+#include "common.cuh"
+#include "edges.cuh"
+#include "knn.cuh"
+#include "sparse.cuh"
+
+struct cg_context {
+  cg::Context c;
+  // result of the last cg_neighbor_matrix call
+  cg::EdgeTable coo;
+  // reductions / projections kept from the last cg_pairs_edges call (host copies, for the pairs cache and tests)
+  struct PairKeep {
+    int n_rows = 0, n_cols = 0;
+    std::vector<double> rot;  // column-major n_rows x n_cols
+    std::vector<double> nv;   // [2][n_cols] or empty
+    int pn[2] = {0, 0};
+    std::vector<double> proj[2];  // column-major n x ncomps
+  };
+  std::vector<PairKeep> kept;
+  bool keep_projections = false;
+};
+
+struct cg_panel {
+  cg_context* ctx = nullptr;
+  std::vector<cg::Sample> samples;
+  std::vector<int> offsets;
+};
+
+struct cg_edges {
+  cg::EdgeTable t;
+};
+
+struct cg_graph {
+  cg::Graph g;
+};
+
+namespace cg {
+thread_local extern std::string g_thread_error;
+int fail(cg_context* ctx, const std::exception& e);
+int fail(cg_context* ctx, const char* msg);
+
+#define CG_API_BEGIN try {
+#define CG_API_END(ctxptr)                                    \
+  return 0;                                                   \
+  }                                                           \
+  catch (const std::exception& e) { return ::cg::fail(ctxptr, e); } \
+  catch (...) { return ::cg::fail(ctxptr, "unknown error"); }
+
+}  // namespace cg

@@ -1,0 +1,347 @@
+// C ABI, part 2: device-resident panel, per-pair reduction -> projection -> kNN -> matching, local edges.
+#include <cmath>
+
+#include "api_core.cuh"
+#include "hub.cuh"
+#include "reduce.cuh"
+
+using namespace cg;
+
+namespace {
+
+// scaledMatricesP2 (R/conos.R:18-46): cqv = exp(rowMeans(log qv)), cgsf = sqrt(cqv / exp(v)), non-finite -> 0
+void pair_scale_factors(const Sample& sa, const Sample& sb, const cg_pair& pr, bool var_scale, std::vector<double>& fa,
+                        std::vector<double>& fb) {
+  const int G = pr.n_genes;
+  fa.assign(G, 1.0);
+  fb.assign(G, 1.0);
+  if (!var_scale) return;
+  CG_CHECK(!sa.h_v.empty() && !sa.h_qv.empty() && !sb.h_v.empty() && !sb.h_qv.empty(),
+           "var.scale = TRUE needs misc$varinfo$v and $qv for every sample");
+  for (int g = 0; g < G; ++g) {
+    const int ca = pr.genes_a[g], cb = pr.genes_b[g];
+    const double cqv = std::exp((std::log(sa.h_qv[ca]) + std::log(sb.h_qv[cb])) / 2.0);
+    double a = std::sqrt(cqv / std::exp(sa.h_v[ca]));
+    double b = std::sqrt(cqv / std::exp(sb.h_v[cb]));
+    fa[g] = std::isfinite(a) ? a : 0.0;
+    fb[g] = std::isfinite(b) ? b : 0.0;
+  }
+}
+
+size_t free_device_bytes() {
+  size_t f = 0, t = 0;
+  if (cudaMemGetInfo(&f, &t) != cudaSuccess) {
+    cudaGetLastError();
+    return (size_t)8 << 30;
+  }
+  return f;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cg_panel_create(cg_context* ctx, const cg_sample* samples, int n_samples, cg_panel** out) {
+  cg_panel* pn = nullptr;
+  try {
+    CG_CHECK(ctx && samples && out && n_samples > 0, "bad argument");
+    CG_CUDA(cudaSetDevice(ctx->c.device));
+    pn = new cg_panel();
+    pn->ctx = ctx;
+    pn->samples.resize(n_samples);
+    pn->offsets.assign(n_samples + 1, 0);
+    for (int s = 0; s < n_samples; ++s) {
+      const cg_sample& h = samples[s];
+      CG_CHECK(h.p && h.i && h.x, "sample counts matrix missing");
+      sample_upload(ctx->c, pn->samples[s], h.n_cells, h.n_genes, h.p, h.i, h.x, h.var_v, h.var_qv, h.pca, h.n_pcs,
+                    h.pca_ld > 0 ? h.pca_ld : h.n_cells);
+      pn->samples[s].offset = pn->offsets[s];
+      pn->offsets[s + 1] = pn->offsets[s] + h.n_cells;
+    }
+    *out = pn;
+    return 0;
+  } catch (const std::exception& e) {
+    delete pn;
+    return fail(ctx, e);
+  }
+}
+
+void cg_panel_free(cg_panel* panel) { delete panel; }
+
+int cg_panel_offsets(const cg_panel* panel, int32_t* offsets) {
+  if (!panel || !offsets) return 1;
+  for (size_t s = 0; s < panel->offsets.size(); ++s) offsets[s] = panel->offsets[s];
+  return 0;
+}
+
+int cg_keep_projections(cg_context* ctx, int enable) {
+  if (!ctx) return 1;
+  ctx->keep_projections = enable != 0;
+  return 0;
+}
+
+int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n_pairs, const cg_params* params,
+                   cg_edges** edges, int64_t* pair_edge_counts) {
+  CG_API_BEGIN
+  CG_CHECK(ctx && panel && params && edges && (pairs || n_pairs == 0), "NULL argument");
+  const cg_params& P = *params;
+  CG_CHECK(P.space == CG_SPACE_PCA || P.space == CG_SPACE_CPCA || P.space == CG_SPACE_CCA,
+           "only the following spaces are currently supported: [CPCA PCA CCA]");
+  CG_CHECK(P.matching == CG_MATCH_MNN || P.matching == CG_MATCH_NN,
+           "only the following matching methods are currently supported: ['mNN' 'NN']");
+  CG_CHECK(P.metric == CG_METRIC_ANGULAR || P.metric == CG_METRIC_L2,
+           "only the following distance metrics are currently supported: ['L2' 'angular']");
+  CG_CHECK(P.k1 >= P.k && P.k >= 1, "k1 must be >= k");
+  CG_CHECK(P.ncomps >= 1 && P.ncomps <= 64, "ncomps must be in 1..64");
+  Context& c = ctx->c;
+  CG_CUDA(cudaSetDevice(c.device));
+  if (!*edges) *edges = new cg_edges();
+  EdgeTable& out = (*edges)->t;
+  ctx->kept.clear();
+  ctx->kept.resize(n_pairs);
+  const int S = (int)panel->samples.size();
+  const Metric metric = (Metric)P.metric;
+  SimParams sp{P.metric, P.matching, P.cor_base, P.l2_sigma, P.min_similarity};
+
+  // ---- batches of pairs bounded by device memory
+  int p0 = 0;
+  while (p0 < n_pairs) {
+    // per-pair footprint (bytes)
+    const size_t budget = std::min<size_t>(free_device_bytes() / 3, (size_t)24 << 30);
+    size_t used = 0;
+    int p1 = p0;
+    while (p1 < n_pairs) {
+      const cg_pair& pr = pairs[p1];
+      CG_CHECK(pr.a >= 0 && pr.a < S && pr.b >= 0 && pr.b < S && pr.a != pr.b, "pair refers to a missing sample");
+      const Sample& sa = panel->samples[pr.a];
+      const Sample& sb = panel->samples[pr.b];
+      const size_t na = sa.n_cells, nb = sb.n_cells;
+      size_t need = (round_up(na, KNN_ROW_PAD) + round_up(nb, KNN_ROW_PAD)) * 64 * 4  // panels
+                    + (na + nb) * (size_t)P.k1 * 8 * 2                                   // kNN out + matching temps
+                    + ((size_t)sa.n_genes + sb.n_genes) * 64 * 8                         // W
+                    + (size_t)pr.n_genes * 64 * 8 * 2;
+      if (ctx->keep_projections) need += (na + nb) * 64 * 8;
+      if (p1 > p0 && used + need > budget) break;
+      used += need;
+      ++p1;
+    }
+    const int nb_pairs = p1 - p0;
+
+    // ---- reductions (rotation per pair, column-major G x d_eff doubles on the device)
+    std::vector<PairReduction> red(nb_pairs);
+    compute_pair_reductions(c, *panel, pairs + p0, nb_pairs, P, red);
+
+    // ---- projection operands
+    struct PairBuf {
+      DevBuf<double> Wa, Wb, shift, fa, fb, ca, cb, p64a, p64b;
+      DevBuf<int> cols_a, cols_b, rows_u, rows_v;
+      DevBuf<float> ta, tb;
+      DevBuf<int> i_ab, i_ba;
+      DevBuf<float> d_ab, d_ba;
+      int na = 0, nb = 0, d = 0, d_pad = 32;
+    };
+    std::vector<PairBuf> pb(nb_pairs);
+    std::vector<WBuildProblem> wprobs;
+    std::vector<ProjProblem> pprobs;
+    std::vector<KnnProblem> kprobs;
+    std::vector<MnnProblem> mprobs;
+    int d_pad_all = 0, d_all = -1;
+    for (int q = 0; q < nb_pairs; ++q) {
+      const cg_pair& pr = pairs[p0 + q];
+      const Sample& sa = panel->samples[pr.a];
+      const Sample& sb = panel->samples[pr.b];
+      PairBuf& B = pb[q];
+      PairReduction& R = red[q];
+      cg_context::PairKeep& keep = ctx->kept[p0 + q];
+      if (P.space == CG_SPACE_CCA) {
+        // u, v are the projections themselves (R/conclass.R:268-270)
+        B.na = R.n_u;
+        B.nb = R.n_v;
+        B.d = R.d;
+      } else {
+        B.na = sa.n_cells;
+        B.nb = sb.n_cells;
+        B.d = R.d;  // min(ncomps, ncol(rot)) -- R/conclass.R:254-258
+      }
+      B.d_pad = B.d <= 32 ? 32 : 64;
+      CG_CHECK(d_all < 0 || d_all == B.d, "all pairs of one call must share the number of components");
+      d_all = B.d;
+      d_pad_all = B.d_pad;
+      B.ta.alloc(KnnPanel::elems(B.na, B.d));
+      B.tb.alloc(KnnPanel::elems(B.nb, B.d));
+      keep.n_rows = R.n_rows;
+      keep.n_cols = R.n_cols;
+      keep.rot = R.h_rot;
+      keep.nv = R.h_nv;
+      if (P.space == CG_SPACE_CCA) {
+        KnnPanel pa, pbn;
+        pa.tiled = B.ta.p;
+        pbn.tiled = B.tb.p;
+        knn_prep_from_f64_colmajor(c, R.u.p, B.na, B.d, B.na, metric, pa);
+        knn_prep_from_f64_colmajor(c, R.v.p, B.nb, B.d, B.nb, metric, pbn);
+        B.rows_u.upload(R.h_rows_u.data(), R.h_rows_u.size(), c.stream);
+        B.rows_v.upload(R.h_rows_v.data(), R.h_rows_v.size(), c.stream);
+        if (ctx->keep_projections) {
+          keep.pn[0] = B.na;
+          keep.pn[1] = B.nb;
+          keep.proj[0].resize((size_t)B.na * B.d);
+          keep.proj[1].resize((size_t)B.nb * B.d);
+          R.u.download(keep.proj[0].data(), keep.proj[0].size(), c.stream);
+          R.v.download(keep.proj[1].data(), keep.proj[1].size(), c.stream);
+        }
+      } else {
+        const int G = pr.n_genes;
+        std::vector<double> fa, fb;
+        pair_scale_factors(sa, sb, pr, P.var_scale != 0, fa, fb);
+        // centering (R/conos.R:784-789): per-gene scaled means, and the quirk of the default path:
+        // `centering` is an atomic vector, so centering[[n]] is ONE number per sample (m[1], m[2])
+        std::vector<double> ca(G), cb(G);
+        for (int g = 0; g < G; ++g) {
+          ca[g] = fa[g] * sa.h_colsum[pr.genes_a[g]] / (double)sa.n_cells;
+          cb[g] = fb[g] * sb.h_colsum[pr.genes_b[g]] / (double)sb.n_cells;
+        }
+        if (P.common_centering) {
+          CG_CHECK(G >= 2, "common centering needs at least two od genes");
+          const double na = sa.n_cells, nb = sb.n_cells;
+          const double m0 = (ca[0] * na + cb[0] * nb) / (na + nb);
+          const double m1 = (ca[1] * na + cb[1] * nb) / (na + nb);
+          std::fill(ca.begin(), ca.end(), m0);
+          std::fill(cb.begin(), cb.end(), m1);
+        }
+        B.fa.upload(fa.data(), G, c.stream);
+        B.fb.upload(fb.data(), G, c.stream);
+        B.ca.upload(ca.data(), G, c.stream);
+        B.cb.upload(cb.data(), G, c.stream);
+        B.cols_a.upload(pr.genes_a, G, c.stream);
+        B.cols_b.upload(pr.genes_b, G, c.stream);
+        B.Wa.alloc((size_t)sa.n_genes * B.d_pad);
+        B.Wb.alloc((size_t)sb.n_genes * B.d_pad);
+        B.shift.alloc((size_t)2 * B.d_pad);
+        wprobs.push_back(WBuildProblem{R.rot.p, B.fa.p, B.ca.p, B.cols_a.p, B.Wa.p, B.shift.p, G, sa.n_genes});
+        wprobs.push_back(
+            WBuildProblem{R.rot.p, B.fb.p, B.cb.p, B.cols_b.p, B.Wb.p, B.shift.p + B.d_pad, G, sb.n_genes});
+        if (ctx->keep_projections) {
+          B.p64a.alloc((size_t)B.na * B.d);
+          B.p64b.alloc((size_t)B.nb * B.d);
+        }
+        pprobs.push_back(ProjProblem{sa.csr_p.p, sa.csr_i.p, sa.csr_x.p, B.Wa.p, B.shift.p, B.ta.p, B.p64a.p, B.na});
+        pprobs.push_back(
+            ProjProblem{sb.csr_p.p, sb.csr_i.p, sb.csr_x.p, B.Wb.p, B.shift.p + B.d_pad, B.tb.p, B.p64b.p, B.nb});
+      }
+      B.i_ab.alloc((size_t)B.na * P.k1);
+      B.d_ab.alloc((size_t)B.na * P.k1);
+      B.i_ba.alloc((size_t)B.nb * P.k1);
+      B.d_ba.alloc((size_t)B.nb * P.k1);
+      kprobs.push_back(KnnProblem{B.ta.p, B.tb.p, B.na, B.nb, B.i_ab.p, B.d_ab.p});
+      kprobs.push_back(KnnProblem{B.tb.p, B.ta.p, B.nb, B.na, B.i_ba.p, B.d_ba.p});
+      mprobs.push_back(MnnProblem{B.i_ab.p, B.d_ab.p, B.i_ba.p, B.d_ba.p,
+                                  P.space == CG_SPACE_CCA ? B.rows_u.p : nullptr,
+                                  P.space == CG_SPACE_CCA ? B.rows_v.p : nullptr, B.na, B.nb, sa.offset, sb.offset});
+    }
+    if (!wprobs.empty()) {
+      build_projection_operands(c, wprobs.data(), (int)wprobs.size(), d_all, d_pad_all);
+      project_and_prep(c, pprobs.data(), (int)pprobs.size(), d_all, d_pad_all, metric);
+      if (ctx->keep_projections) {
+        for (int q = 0; q < nb_pairs; ++q) {
+          cg_context::PairKeep& keep = ctx->kept[p0 + q];
+          PairBuf& B = pb[q];
+          keep.pn[0] = B.na;
+          keep.pn[1] = B.nb;
+          keep.proj[0].resize((size_t)B.na * B.d);
+          keep.proj[1].resize((size_t)B.nb * B.d);
+          B.p64a.download(keep.proj[0].data(), keep.proj[0].size(), c.stream);
+          B.p64b.download(keep.proj[1].data(), keep.proj[1].size(), c.stream);
+        }
+        CG_CUDA(cudaStreamSynchronize(c.stream));
+      }
+    }
+    CG_CUDA(cudaStreamSynchronize(c.stream));
+    // ---- exact kNN, both directions of every pair in one launch
+    {
+      DevBuf<KnnProblem> dk;
+      dk.upload(kprobs.data(), kprobs.size(), c.stream);
+      knn_launch(c, dk.p, kprobs.data(), (int)kprobs.size(), P.k1, d_pad_all, metric);
+      CG_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    // ---- matching -> edges
+    std::vector<long long> counts(nb_pairs, 0);
+    match_append_edges(c, mprobs.data(), nb_pairs, P.k, P.k1, sp, out, counts.data());
+    if (pair_edge_counts)
+      for (int q = 0; q < nb_pairs; ++q) pair_edge_counts[p0 + q] = counts[q];
+    p0 = p1;
+  }
+  CG_API_END(ctx)
+}
+
+int cg_pair_reduction(cg_context* ctx, int which, int32_t* n_rows, int32_t* n_cols, double* rot, double* nv) {
+  CG_API_BEGIN
+  CG_CHECK(ctx && which >= 0 && which < (int)ctx->kept.size(), "no such pair in the last cg_pairs_edges call");
+  const auto& k = ctx->kept[which];
+  if (n_rows) *n_rows = k.n_rows;
+  if (n_cols) *n_cols = k.n_cols;
+  if (rot && !k.rot.empty()) memcpy(rot, k.rot.data(), k.rot.size() * sizeof(double));
+  if (nv && !k.nv.empty()) memcpy(nv, k.nv.data(), k.nv.size() * sizeof(double));
+  CG_API_END(ctx)
+}
+
+int cg_pair_projection(cg_context* ctx, int which, int side, int32_t* n_rows, int32_t* n_cols, double* p) {
+  CG_API_BEGIN
+  CG_CHECK(ctx && which >= 0 && which < (int)ctx->kept.size() && (side == 0 || side == 1), "bad argument");
+  const auto& k = ctx->kept[which];
+  CG_CHECK(!k.proj[side].empty(), "projections were not kept (cg_keep_projections)");
+  if (n_rows) *n_rows = k.pn[side];
+  if (n_cols) *n_cols = k.pn[side] ? (int)(k.proj[side].size() / (size_t)k.pn[side]) : 0;
+  if (p) memcpy(p, k.proj[side].data(), k.proj[side].size() * sizeof(double));
+  CG_API_END(ctx)
+}
+
+int cg_local_edges(cg_context* ctx, cg_panel* panel, const int32_t* samples, int n, const cg_params* params,
+                   cg_edges** edges) {
+  CG_API_BEGIN
+  CG_CHECK(ctx && panel && params && edges && (samples || n == 0), "NULL argument");
+  const cg_params& P = *params;
+  CG_CHECK(P.metric == CG_METRIC_ANGULAR || P.metric == CG_METRIC_L2,
+           "only the following distance metrics are currently supported: ['L2' 'angular']");
+  Context& c = ctx->c;
+  CG_CUDA(cudaSetDevice(c.device));
+  if (!*edges) *edges = new cg_edges();
+  if (P.k_self <= 0) return 0;
+  const int kp1 = P.k_self + 1;  // +1 accounts for the self edge removed afterwards (R/conos.R:595)
+  // self-kNN of every listed sample in one launch
+  std::vector<KnnProblem> kprobs;
+  std::vector<DevBuf<int>> idx(n);
+  std::vector<DevBuf<float>> dist(n);
+  int d_pad = 0;
+  for (int t = 0; t < n; ++t) {
+    CG_CHECK(samples[t] >= 0 && samples[t] < (int)panel->samples.size(), "no such sample");
+    Sample& s = panel->samples[samples[t]];
+    CG_CHECK(s.n_pcs > 0, "PCA must be estimated for all samples");
+    if (s.pca_metric != P.metric) {
+      s.pca_tiled.alloc(KnnPanel::elems(s.n_cells, s.n_pcs));
+      KnnPanel pn;
+      pn.tiled = s.pca_tiled.p;
+      knn_prep_from_f64_colmajor(c, s.pca.p, s.n_cells, s.n_pcs, s.n_cells, (Metric)P.metric, pn);
+      s.pca_metric = P.metric;
+    }
+    const int dp = s.n_pcs <= 32 ? 32 : 64;
+    CG_CHECK(d_pad == 0 || d_pad == dp, "per-sample PCAs must share their padded width (<= 32 or 33..64 columns)");
+    d_pad = dp;
+    idx[t].alloc((size_t)s.n_cells * kp1);
+    dist[t].alloc((size_t)s.n_cells * kp1);
+    kprobs.push_back(KnnProblem{s.pca_tiled.p, s.pca_tiled.p, s.n_cells, s.n_cells, idx[t].p, dist[t].p});
+  }
+  if (!kprobs.empty()) {
+    DevBuf<KnnProblem> dk;
+    dk.upload(kprobs.data(), kprobs.size(), c.stream);
+    knn_launch(c, dk.p, kprobs.data(), (int)kprobs.size(), kp1, d_pad, (Metric)P.metric);
+    CG_CUDA(cudaStreamSynchronize(c.stream));
+  }
+  for (int t = 0; t < n; ++t) {
+    Sample& s = panel->samples[samples[t]];
+    local_append_edges(c, idx[t].p, dist[t].p, s.n_cells, kp1, s.offset, P.metric, P.l2_sigma, P.k_self_weight,
+                       (*edges)->t);
+  }
+  CG_API_END(ctx)
+}
+
+}  // extern "C"

@@ -1,0 +1,223 @@
+#include "prims.cuh"
+#include "sparse.cuh"
+
+namespace cg {
+namespace {
+
+inline unsigned nblk(size_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
+
+__global__ void row_count_kernel(const int* __restrict__ ci, long long nnz, int* __restrict__ cnt) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nnz) atomicAdd(&cnt[ci[t]], 1);
+}
+
+// CSC -> CSR keys: (column << 32 | source position), bucketed by row; the segmented sort orders a row by column
+__global__ void csr_scatter_kernel(const int* __restrict__ csc_p, const int* __restrict__ csc_i, int n_genes,
+                                   const long long* __restrict__ rowp, int* __restrict__ cursor,
+                                   unsigned long long* __restrict__ keys) {
+  // one warp per gene column
+  const int g = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (g >= n_genes) return;
+  const int lane = threadIdx.x & 31;
+  for (int t = csc_p[g] + lane; t < csc_p[g + 1]; t += 32) {
+    int r = csc_i[t];
+    int slot = atomicAdd(&cursor[r], 1);
+    keys[rowp[r] + slot] = ((unsigned long long)(unsigned)g << 32) | (unsigned long long)(unsigned)t;
+  }
+}
+
+__global__ void csr_fill_kernel(const unsigned long long* __restrict__ keys, long long nnz,
+                                const double* __restrict__ csc_x, const long long* __restrict__ rowp64, int n_rows,
+                                int* __restrict__ csr_i, double* __restrict__ csr_x) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nnz) return;
+  csr_i[t] = (int)(keys[t] >> 32);
+  csr_x[t] = csc_x[keys[t] & 0xffffffffull];
+}
+
+__global__ void rowp_narrow_kernel(const long long* __restrict__ in, int n, int* __restrict__ out) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = (int)in[t];
+}
+
+// deterministic column sums: one warp per column, fixed lane stride and shuffle tree
+__global__ void colsum_kernel(const int* __restrict__ csc_p, const double* __restrict__ csc_x, int n_genes,
+                              double* __restrict__ out) {
+  const int g = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (g >= n_genes) return;
+  const int lane = threadIdx.x & 31;
+  double s = 0.0;
+  for (int t = csc_p[g] + lane; t < csc_p[g + 1]; t += 32) s += csc_x[t];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_down_sync(0xffffffffu, s, d);
+  if (lane == 0) out[g] = s;
+}
+
+// ------------------------------------------------------------------ projection operands
+__global__ void wbuild_kernel(const WBuildProblem* __restrict__ probs, int d, int d_pad) {
+  const WBuildProblem pb = probs[blockIdx.y];
+  // zero W, then scatter the od-gene rows (two phases separated by a grid-wide kernel boundary would be
+  // cleaner; here every CTA zeroes and fills disjoint column ranges of the SAME od genes, so no race:
+  // CTA b owns od genes [b*chunk, (b+1)*chunk) and the W rows they map to are distinct per gene)
+  const int chunk = (pb.G + gridDim.x - 1) / gridDim.x;
+  const int g0 = blockIdx.x * chunk, g1 = min(pb.G, g0 + chunk);
+  for (int g = g0 + (threadIdx.x / d_pad); g < g1; g += blockDim.x / d_pad) {
+    const int c = threadIdx.x % d_pad;
+    const double v = c < d ? pb.f[g] * pb.rot[(size_t)c * pb.G + g] : 0.0;
+    pb.W[(size_t)pb.cols[g] * d_pad + c] = v;
+  }
+  if (blockIdx.x == 0) {
+    // shift[c] = sum_g cvec[g] * rot[g, c]: one warp per component, fixed order
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int c = warp; c < d_pad; c += nw) {
+      double s = 0.0;
+      if (c < d)
+        for (int g = lane; g < pb.G; g += 32) s += pb.cvec[g] * pb.rot[(size_t)c * pb.G + g];
+#pragma unroll
+      for (int dl = 16; dl > 0; dl >>= 1) s += __shfl_down_sync(0xffffffffu, s, dl);
+      if (lane == 0) pb.shift[c] = s;
+    }
+  }
+}
+
+// one warp per cell row: fp64 accumulate over the row's non-zeros, subtract the shift, cast to fp32,
+// canonical normalisation (sequential fma chain over the d components), write the tiled kNN panel
+template <int D_PAD>
+__global__ void __launch_bounds__(256) project_kernel(const ProjProblem* __restrict__ probs, int d, int metric) {
+  const ProjProblem pb = probs[blockIdx.y];
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int n_pad = (int)((pb.n_rows + KNN_ROW_PAD - 1) / KNN_ROW_PAD * KNN_ROW_PAD);
+  if (row >= n_pad) return;
+  constexpr int NC = D_PAD / 32;  // components per lane
+  double acc[NC];
+#pragma unroll
+  for (int u = 0; u < NC; ++u) acc[u] = 0.0;
+  if (row < pb.n_rows) {
+    const int b = pb.rp[row], e = pb.rp[row + 1];
+    for (int t = b; t < e; ++t) {
+      const double x = pb.xv[t];
+      const double* w = pb.W + (size_t)pb.ci[t] * D_PAD;
+#pragma unroll
+      for (int u = 0; u < NC; ++u) acc[u] = fma(x, w[lane + 32 * u], acc[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < NC; ++u) acc[u] -= pb.shift[lane + 32 * u];
+  }
+  float v[NC];
+#pragma unroll
+  for (int u = 0; u < NC; ++u) {
+    const int c = lane + 32 * u;
+    v[u] = (row < pb.n_rows && c < d) ? (float)acc[u] : 0.0f;
+    if (pb.p64 && row < pb.n_rows && c < d) pb.p64[(size_t)c * pb.n_rows + row] = acc[u];
+  }
+  float inv = 1.0f;
+  if (metric == METRIC_ANGULAR) {
+    float ss = 0.0f;
+    for (int i = 0; i < d; ++i) {
+      const float xi = __shfl_sync(0xffffffffu, v[i >> 5], i & 31);
+      ss = fmaf(xi, xi, ss);
+    }
+    inv = ss > 0.0f ? 1.0f / sqrtf(ss) : 0.0f;
+  }
+  float* dst = pb.tiled + (size_t)(row >> 3) * (8 * D_PAD) + (size_t)(row & 7) * 4;
+#pragma unroll
+  for (int u = 0; u < NC; ++u) {
+    const int c = lane + 32 * u;
+    dst[(c >> 2) * 32 + (c & 3)] = v[u] * inv;
+  }
+}
+
+}  // namespace
+
+void csc_to_csr(Context& ctx, int n_rows, int n_cols, const int* csc_p, const int* csc_i, const double* csc_x,
+                long long nnz, int* csr_p, int* csr_i, double* csr_x) {
+  cudaStream_t st = ctx.stream;
+  if (nnz == 0) {
+    CG_CUDA(cudaMemsetAsync(csr_p, 0, ((size_t)n_rows + 1) * sizeof(int), st));
+    return;
+  }
+  DevBuf<int> cnt((size_t)n_rows), cursor((size_t)n_rows);
+  cnt.zero(st);
+  cursor.zero(st);
+  DevBuf<long long> rowp64((size_t)n_rows + 1);
+  row_count_kernel<<<nblk((size_t)nnz), 256, 0, st>>>(csc_i, nnz, cnt.p);
+  exclusive_scan_i32_to_i64(ctx, cnt.p, rowp64.p, (size_t)n_rows, rowp64.p + n_rows);
+  DevBuf<unsigned long long> keys((size_t)nnz);
+  csr_scatter_kernel<<<(n_cols + 7) / 8, 256, 0, st>>>(csc_p, csc_i, n_cols, rowp64.p, cursor.p, keys.p);
+  segmented_sort_u64(ctx, keys.p, rowp64.p, n_rows);
+  csr_fill_kernel<<<nblk((size_t)nnz), 256, 0, st>>>(keys.p, nnz, csc_x, rowp64.p, n_rows, csr_i, csr_x);
+  rowp_narrow_kernel<<<nblk((size_t)n_rows + 1), 256, 0, st>>>(rowp64.p, n_rows + 1, csr_p);
+  ctx.stats.kernels += 4;
+  CG_CUDA(cudaGetLastError());
+  CG_CUDA(cudaStreamSynchronize(st));
+}
+
+void sample_upload(Context& ctx, Sample& s, int n_cells, int n_genes, const int* p, const int* i, const double* x,
+                   const double* var_v, const double* var_qv, const double* pca, int n_pcs, int pca_ld) {
+  cudaStream_t st = ctx.stream;
+  CG_CHECK(n_cells > 0 && n_genes > 0, "sample must have cells and genes");
+  s.n_cells = n_cells;
+  s.n_genes = n_genes;
+  s.nnz = p[n_genes];
+  for (int g = 0; g < n_genes; ++g) CG_CHECK(p[g + 1] >= p[g], "dgCMatrix @p must be non-decreasing");
+  s.csc_p.upload(p, (size_t)n_genes + 1, st);
+  s.csc_i.upload(i, (size_t)s.nnz, st);
+  s.csc_x.upload(x, (size_t)s.nnz, st);
+  if (var_v) s.h_v.assign(var_v, var_v + n_genes);
+  if (var_qv) s.h_qv.assign(var_qv, var_qv + n_genes);
+  // CSR by cell
+  s.csr_p.alloc((size_t)n_cells + 1);
+  s.csr_i.alloc((size_t)s.nnz);
+  s.csr_x.alloc((size_t)s.nnz);
+  csc_to_csr(ctx, n_cells, n_genes, s.csc_p.p, s.csc_i.p, s.csc_x.p, s.nnz, s.csr_p.p, s.csr_i.p, s.csr_x.p);
+  s.colsum.alloc((size_t)n_genes);
+  colsum_kernel<<<(n_genes + 7) / 8, 256, 0, st>>>(s.csc_p.p, s.csc_x.p, n_genes, s.colsum.p);
+  ctx.stats.kernels++;
+  s.h_colsum.resize(n_genes);
+  s.colsum.download(s.h_colsum.data(), (size_t)n_genes, st);
+  s.n_pcs = 0;
+  s.pca_metric = -1;
+  if (pca && n_pcs > 0) {
+    s.n_pcs = n_pcs;
+    std::vector<double> packed((size_t)n_cells * n_pcs);
+    for (int c = 0; c < n_pcs; ++c)
+      memcpy(&packed[(size_t)c * n_cells], pca + (size_t)c * pca_ld, sizeof(double) * (size_t)n_cells);
+    s.pca.upload(packed.data(), packed.size(), st);
+    CG_CUDA(cudaStreamSynchronize(st));
+  }
+  CG_CUDA(cudaStreamSynchronize(st));
+}
+
+void build_projection_operands(Context& ctx, const WBuildProblem* h_probs, int n_probs, int d, int d_pad) {
+  if (n_probs == 0) return;
+  DevBuf<WBuildProblem> dp;
+  dp.upload(h_probs, n_probs, ctx.stream);
+  for (int p = 0; p < n_probs; ++p)
+    CG_CUDA(cudaMemsetAsync(h_probs[p].W, 0, (size_t)h_probs[p].n_genes_sample * d_pad * sizeof(double), ctx.stream));
+  dim3 grid(32, n_probs);
+  wbuild_kernel<<<grid, 256, 0, ctx.stream>>>(dp.p, d, d_pad);
+  ctx.stats.kernels++;
+  CG_CUDA(cudaGetLastError());
+  CG_CUDA(cudaStreamSynchronize(ctx.stream));
+}
+
+void project_and_prep(Context& ctx, const ProjProblem* h_probs, int n_probs, int d, int d_pad, Metric metric) {
+  if (n_probs == 0) return;
+  DevBuf<ProjProblem> dp;
+  dp.upload(h_probs, n_probs, ctx.stream);
+  int max_rows = 0;
+  for (int p = 0; p < n_probs; ++p) max_rows = h_probs[p].n_rows > max_rows ? h_probs[p].n_rows : max_rows;
+  int max_pad = (int)round_up(max_rows, KNN_ROW_PAD);
+  for (int p0 = 0; p0 < n_probs; p0 += 65535) {
+    int np = n_probs - p0 < 65535 ? n_probs - p0 : 65535;
+    dim3 grid((max_pad + 7) / 8, np);
+    if (d_pad == 32) project_kernel<32><<<grid, 256, 0, ctx.stream>>>(dp.p + p0, d, (int)metric);
+    else project_kernel<64><<<grid, 256, 0, ctx.stream>>>(dp.p + p0, d, (int)metric);
+    ctx.stats.kernels++;
+  }
+  CG_CUDA(cudaGetLastError());
+  CG_CUDA(cudaStreamSynchronize(ctx.stream));
+}
+
+}  // namespace cg

@@ -1,0 +1,21 @@
+// Device implementations behind the reference's own native entry points; host-pointer wrappers.
+#pragma once
+#include "common.cuh"
+
+namespace cg {
+
+// spcov (src/spcov.cpp:14-19): V = m'm - n cm cm'; V /= (n - 1)
+void spcov_host(Context& ctx, int n, int G, const int* p, const int* i, const double* x, const double* cm, double* out);
+// cpcaF (src/cpca.cpp:16-101)
+void cpca_host(Context& ctx, const double* cov, int p, int k, const double* ng, int ncomp, int maxit, double tol,
+               const double* eigv, double* D, double* CPC, double* niter);
+// getSumWeightMatrix / adjustWeightsByCellBalancingC (src/edge_rebalancing.cpp:14-48)
+void sum_weight_matrix_host(Context& ctx, const double* w, const int* ri, const int* ci, long long n_edges,
+                            const int* fl, int n_cells, int n_levels, int normalize, double* m);
+void adjust_weights_host(Context& ctx, double* w, const int* ri, const int* ci, long long n_edges, const int* fl,
+                         int n_cells, int n_levels, const double* dividers);
+// referenceWij (src/edgeweights.cpp:25-184)
+void reference_wij_host(Context& ctx, const int* from, const int* to, const double* d, long long n_edges,
+                        double perplexity, int* out_from, int* out_to, double* out_w, long long* n_out);
+
+}  // namespace cg

@@ -1,0 +1,182 @@
+/*
+ * conos_gpu.h -- C ABI of libconosgpu.so: the B200 (sm_100a) implementation of the joint-graph
+ * construction hot path of conos (Conos$buildGraph).  This is the drop-in boundary: plain pointers and
+ * sizes in R's native layouts (dense = column-major double, sparse = dgCMatrix slots p/i/x), int status
+ * codes, no R, Rcpp or torch types.  The Rcpp shim (conos_b200/rcpp/conos_gpu_shim.cpp)
+ * and the Python host mirror (conos_b200/conos.py, ctypes) both bind exactly these symbols.
+ *
+ * Every function returns 0 on success and a non-zero code on failure; the message is available through
+ * cg_last_error().  Nothing throws or aborts across this boundary (the reference converts C++ exceptions
+ * to R errors with BEGIN_RCPP/END_RCPP, src/RcppExports.cpp:74-86; the shim does Rcpp::stop(cg_last_error())).
+ *
+ * Reference interfaces replaced (paths relative to the conos source tree):
+ *   N2R::crossKnn(mA, mB, k, nThreads, verbose, indexType)        R/conos.R:851-855   -> cg_cross_knn
+ *   N2R::Knn(m, k, nThreads, verbose, indexType)                  R/conos.R:595       -> cg_self_knn
+ *   getNeighborMatrix(p1, p2, k, k1, matching, metric, ...)       R/conos.R:848-886   -> cg_neighbor_matrix
+ *   getLocalNeighbors / getLocalEdges                             R/conos.R:587-616   -> cg_local_edges
+ *   getPcaBasedNeighborMatrix (scale, centre, project, match)     R/conos.R:776-833   -> cg_pairs_edges
+ *   quickPlainPCA / quickCPCA / quickCCA                          R/conos.R:204-369   -> cg_pair_reduction
+ *   _conos_spcov                 src/spcov.cpp:14-19,  src/RcppExports.cpp:349-370    -> cg_spcov
+ *   _conos_cpcaF                 src/cpca.cpp:16-101                                  -> cg_cpca
+ *   _conos_pareDownHubEdges      src/edgeFilter.cpp:23-60                             -> cg_pare_down_hub_edges
+ *   _conos_getSumWeightMatrix    src/edge_rebalancing.cpp:14-36                       -> cg_sum_weight_matrix
+ *   _conos_adjustWeightsByCellBalancingC  src/edge_rebalancing.cpp:39-48              -> cg_adjust_weights
+ *   _conos_referenceWij          src/edgeweights.cpp:160-184                          -> cg_reference_wij
+ *   edge table -> graph_from_edgelist -> simplify                 R/conclass.R:321-343 -> cg_assemble_graph
+ */
+#ifndef CONOS_GPU_H
+#define CONOS_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cg_context cg_context;  /* one per process and device; owns the stream and scratch memory */
+typedef struct cg_panel cg_panel;      /* device-resident samples (counts, varinfo, per-sample PCA) */
+typedef struct cg_edges cg_edges;      /* device-resident edge table in the reference's row order */
+typedef struct cg_graph cg_graph;      /* device-resident simplified graph + symmetric adjacency */
+
+enum { CG_METRIC_ANGULAR = 0, CG_METRIC_L2 = 1 };
+enum { CG_MATCH_MNN = 0, CG_MATCH_NN = 1 };
+enum { CG_SPACE_PCA = 0, CG_SPACE_CPCA = 1, CG_SPACE_CCA = 2 };
+
+/* ---- context ------------------------------------------------------------------------------------- */
+int cg_init(int device, cg_context** out);
+void cg_shutdown(cg_context* ctx);
+const char* cg_last_error(const cg_context* ctx); /* ctx may be NULL: last error of this thread */
+int cg_device_count(void);
+/* kernels launched by this context so far (bench.py reports the delta as gpu_launches) */
+uint64_t cg_kernel_launches(const cg_context* ctx);
+/* optional CUDA-event timing of the dominant kernel (fused cross-kNN): enable, then read and reset */
+int cg_knn_timing(cg_context* ctx, int enable);
+int cg_knn_timing_read(cg_context* ctx, double* ms, uint64_t* launches, double* candidates, double* bytes);
+
+/* ---- exact kNN (float32 arithmetic of N2, exact search) -------------------------------------------- */
+/* A: nA x d, B: nB x d column-major double (lda/ldb leading dimensions).
+ * idx_ab/dist_ab: [nA][k] row-major -- for every row of A its k nearest rows of B (ascending distance, ties by
+ * lower index; -1 / +inf when nB < k); idx_ba/dist_ba: [nB][k] likewise.  Either output pair may be NULL.
+ * As sparse matrices these are N2R::crossKnn(A,B,k) (nB x nA, entry (neighbour, query)) and crossKnn(B,A,k). */
+int cg_cross_knn(cg_context* ctx, const double* A, int nA, int lda, const double* B, int nB, int ldb, int d, int k,
+                 int metric, int32_t* idx_ab, float* dist_ab, int32_t* idx_ba, float* dist_ba);
+/* N2R::Knn(Z, k): the sample against itself, the point itself included. */
+int cg_self_knn(cg_context* ctx, const double* Z, int n, int ldz, int d, int k, int metric, int32_t* idx,
+                float* dist);
+
+/* ---- getNeighborMatrix ---------------------------------------------------------------------------- */
+/* p1: n1 x d, p2: n2 x d column-major double.  Result = TsparseMatrix n1 x n2 triplets in CSC order; fetch with
+ * cg_fetch_coo after reading *nnz.  k1 > k applies reduceEdgesInGraphIteratively (R/conos.R:906-933). */
+int cg_neighbor_matrix(cg_context* ctx, const double* p1, int n1, int ld1, const double* p2, int n2, int ld2, int d,
+                       int k, int k1, int matching, int metric, double l2_sigma, double cor_base,
+                       double min_similarity, int64_t* nnz);
+int cg_fetch_coo(cg_context* ctx, int32_t* i, int32_t* j, double* x);
+
+/* ---- samples ------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t n_cells, n_genes;
+  const int32_t* p; /* counts: dgCMatrix cells x genes, @p [n_genes+1] */
+  const int32_t* i; /*                                   @i [nnz] (0-based cell)  */
+  const double* x;  /*                                   @x [nnz]  */
+  const double* var_v;  /* misc$varinfo$v  per gene (NULL when var.scale = FALSE) */
+  const double* var_qv; /* misc$varinfo$qv per gene */
+  const double* pca;    /* reductions$PCA, column-major n_cells x n_pcs (NULL when k.self = 0) */
+  int32_t n_pcs, pca_ld;
+} cg_sample;
+
+int cg_panel_create(cg_context* ctx, const cg_sample* samples, int n_samples, cg_panel** out);
+void cg_panel_free(cg_panel* panel);
+int cg_panel_offsets(const cg_panel* panel, int32_t* offsets /* [n_samples + 1] global cell ids */);
+
+/* ---- per-pair reduction + matching --------------------------------------------------------------- */
+typedef struct {
+  int32_t a, b;           /* sample indices (combn order is the caller's: R/conclass.R:1058) */
+  int32_t n_genes;        /* common od genes of the pair, in commonOverdispersedGenes order (R/conos.R:107-117) */
+  const int32_t* genes_a; /* column of sample a holding od gene g */
+  const int32_t* genes_b;
+  const double* rot;      /* optional cached rotation, column-major n_genes x rot_cols (self$pairs[[space]]$CPC) */
+  int32_t rot_cols;
+  const double* u;        /* CCA: optional cached u (n_u x ncomps) and v (n_v x ncomps), column-major */
+  const double* v;
+  const int32_t* rows_u;  /* CCA: cell index of every row of u / v (cells with empty rows are dropped) */
+  const int32_t* rows_v;
+  int32_t n_u, n_v;
+} cg_pair;
+
+typedef struct {
+  int32_t k, k1, k_self;
+  int32_t ncomps;
+  int32_t space, matching, metric;
+  int32_t var_scale, common_centering, score_component_variance;
+  double k_self_weight, l2_sigma, cor_base, min_similarity;
+  int32_t cpca_maxit; /* 500  (R/conos.R:242) */
+  double cpca_tol;    /* 1e-5 */
+} cg_params;
+
+void cg_params_default(cg_params* p); /* buildGraph defaults, R/conclass.R:161-165 */
+
+/* Computes (or takes from pair.rot / pair.u,v) the reduction of every pair, projects, runs the two-directional
+ * exact kNN, the mutual-neighbour matching and (k1 > k) hub paring, and appends the inter-sample edges
+ * (type 1, from = cell of a, to = cell of b, global cell ids) pair after pair.  *edges may be NULL (created). */
+int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n_pairs, const cg_params* params,
+                   cg_edges** edges, int64_t* pair_edge_counts /* [n_pairs] or NULL */);
+/* The reduction of the most recent cg_pairs_edges call for pair `which`: PCA/CPCA: rot n_genes x ncols;
+ * nv: per-sample variance fractions [2][ncols] when score_component_variance.  Query sizes with NULL outputs. */
+int cg_pair_reduction(cg_context* ctx, int which, int32_t* n_rows, int32_t* n_cols, double* rot, double* nv);
+/* Projections of pair `which` of the most recent call (column-major n x ncomps doubles), for parity tests;
+ * they are only kept after cg_keep_projections(ctx, 1). */
+int cg_keep_projections(cg_context* ctx, int enable);
+int cg_pair_projection(cg_context* ctx, int which, int side, int32_t* n_rows, int32_t* n_cols, double* p);
+
+/* Within-sample edges of the listed samples (type 0), appended sample after sample. */
+int cg_local_edges(cg_context* ctx, cg_panel* panel, const int32_t* samples, int n, const cg_params* params,
+                   cg_edges** edges);
+
+/* ---- edge tables ---------------------------------------------------------------------------------- */
+int64_t cg_edges_count(const cg_edges* e);
+int cg_edges_fetch(cg_context* ctx, const cg_edges* e, int32_t* from, int32_t* to, double* w, int32_t* type);
+/* append host rows (used to merge shards gathered from other ranks) */
+int cg_edges_append_host(cg_context* ctx, cg_edges** e, const int32_t* from, const int32_t* to, const double* w,
+                         const int32_t* type, int64_t n);
+/* device pointers of the columns (for NCCL gathers driven by the host language) */
+int cg_edges_device_ptrs(const cg_edges* e, void** from, void** to, void** w, void** type);
+int cg_edges_reserve(cg_context* ctx, cg_edges** e, int64_t n_total);
+int cg_edges_set_count(cg_edges* e, int64_t n);
+void cg_edges_free(cg_edges* e);
+
+/* ---- graph ---------------------------------------------------------------------------------------- */
+/* el[w > 0]; vertices numbered by first appearance (graph_from_edgelist on a character matrix);
+ * simplify(edge.attr.comb = list(weight = "sum", type = "first")).  R/conclass.R:335-343. */
+int cg_assemble_graph(cg_context* ctx, const cg_edges* e, int32_t n_cells_total, cg_graph** out);
+int cg_graph_sizes(const cg_graph* g, int32_t* n_vertices, int64_t* n_edges);
+int cg_graph_fetch(cg_context* ctx, const cg_graph* g, int32_t* vertices, int32_t* from, int32_t* to, double* weight,
+                   int32_t* type);
+/* symmetric adjacency (as_adj(graph, attr = "weight")): p [n_vertices+1], i/x [2*n_edges] */
+int cg_graph_fetch_adjacency(cg_context* ctx, const cg_graph* g, int64_t* p, int32_t* i, double* x);
+void cg_graph_free(cg_graph* g);
+
+/* ---- the reference's own .Call entry points, same argument meaning ----------------------------------- */
+/* spcov(m, cm): m dgCMatrix n x G, cm [G]; out column-major G x G.   (V = m'm - n cm cm'; V /= n-1) */
+int cg_spcov(cg_context* ctx, int n, int G, const int32_t* p, const int32_t* i, const double* x, const double* cm,
+             double* out);
+/* cpcaF(cov p x p x k, ng, ncomp, maxit, tol, eigenvR): D (k x ncomp), CPC (p x ncomp), niter [ncomp] */
+int cg_cpca(cg_context* ctx, const double* cov, int p, int k, const double* ng, int ncomp, int maxit, double tol,
+            const double* eigv, double* D, double* CPC, double* niter);
+/* pareDownHubEdges(sY, rowN, k, klow): x is updated in place, rowN is mutated like the reference does */
+int cg_pare_down_hub_edges(cg_context* ctx, int ncols, const int32_t* p, const int32_t* i, double* x, int32_t* rowN,
+                           int k, int klow);
+int cg_sum_weight_matrix(cg_context* ctx, const double* weights, const int32_t* row_inds, const int32_t* col_inds,
+                         int64_t n_edges, const int32_t* factor_levels, int n_cells, int n_levels, int normalize,
+                         double* m /* n_cells x n_levels column-major */);
+int cg_adjust_weights(cg_context* ctx, double* weights, const int32_t* row_inds, const int32_t* col_inds,
+                      int64_t n_edges, const int32_t* factor_levels, int n_cells, int n_levels,
+                      const double* dividers);
+/* referenceWij(i, j, d, threads, perplexity): triplets of the result before duplicate summation; outputs sized
+ * 2 * n_edges; *n_out receives the triplet count */
+int cg_reference_wij(cg_context* ctx, const int32_t* from, const int32_t* to, const double* d, int64_t n_edges,
+                     double perplexity, int32_t* out_from, int32_t* out_to, double* out_w, int64_t* n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CONOS_GPU_H */

@@ -1,0 +1,216 @@
+"""GPU parity of matching, local edges, projection and graph assembly against the oracle (via the C ABI and the
+Conos host mirror).  Integer/index results bit-exact; weights to 1e-12 relative (same float32 distances, double
+arithmetic afterwards); projections to 1e-10 (fp64 sums in a different order)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import to_oracle_samples
+
+pytestmark = pytest.mark.gpu
+
+
+def mixture(rng, n, d, k=8, spread=3.0):
+    cent = rng.normal(0, spread, (k, d))
+    lab = rng.integers(0, k, n)
+    return cent[lab] + rng.normal(0, 1, (n, d))
+
+
+@pytest.mark.parametrize("n1,n2,d,k,cor_base", [(25, 34, 30, 15, 1.0), (700, 500, 30, 15, 1.0), (400, 900, 50, 30, 2.0)])
+def test_neighbor_matrix_mnn(ctx, oracle, n1, n2, d, k, cor_base):
+    from conos_b200 import ops
+    rng = np.random.default_rng(n1 + n2)
+    p1, p2 = mixture(rng, n1, d), mixture(rng, n2, d)
+    i, j, x = ops.getNeighborMatrix(p1, p2, k, metric="angular", cor_base=cor_base, ctx=ctx)
+    oi, oj, ox = oracle.neighbor_matrix(p1, p2, k, metric="angular", cor_base=cor_base)
+    assert np.array_equal(i, oi) and np.array_equal(j, oj)
+    np.testing.assert_allclose(x, ox, rtol=1e-12, atol=0)
+    assert len(i) > 0 and x.min() >= 1e-5
+
+
+def test_neighbor_matrix_negative_correlation_dropped(ctx, oracle):
+    """distance >= cor.base gives similarity 0: such pairs are dropped even when mutual (drop0)."""
+    from conos_b200 import ops
+    rng = np.random.default_rng(1)
+    p1 = rng.normal(0, 1, (40, 5))
+    p2 = -p1[:30] + rng.normal(0, 0.01, (30, 5))
+    i, j, x = ops.getNeighborMatrix(p1, p2, 10, ctx=ctx)
+    oi, oj, ox = oracle.neighbor_matrix(p1, p2, 10)
+    assert np.array_equal(i, oi) and np.array_equal(j, oj)
+    np.testing.assert_allclose(x, ox, rtol=1e-12)
+
+
+def _graphs_equal(g, og, rtol=1e-12):
+    assert np.array_equal(g.vertices, og["vertices"])
+    assert np.array_equal(g.edge_from, og["from"]) and np.array_equal(g.edge_to, og["to"])
+    assert np.array_equal(g.type, og["type"])
+    np.testing.assert_allclose(g.weight, og["weight"], rtol=rtol, atol=0)
+
+
+@pytest.mark.parametrize("common_centering,var_scale", [(True, True), (False, True), (True, False)])
+def test_build_graph_with_oracle_rotations(ctx, oracle, small_panel, common_centering, var_scale):
+    """Same rot on both sides (SURVEY hard part 3): the whole path after the reduction must agree."""
+    import conos_b200
+    osamples = to_oracle_samples(oracle, small_panel)
+    ref = oracle.build_graph(osamples, k=10, k_self=5, space="PCA", ncomps=20, n_odgenes=300,
+                             common_centering=common_centering, var_scale=var_scale)
+    con = conos_b200.Conos(small_panel, ctx=ctx)
+    con.pairs["PCA"] = {key: {"CPC": red["CPC"], "genes": red["genes"]} for key, red in ref["pairs"].items()}
+    ctx.lib.cg_keep_projections(ctx.h, 1)
+    g = con.buildGraph(k=10, k_self=5, space="PCA", ncomps=20, n_odgenes=300, common_centering=common_centering,
+                       var_scale=var_scale)
+    ctx.lib.cg_keep_projections(ctx.h, 0)
+    # projections of the last pair, against the oracle's dense restatement
+    names = list(small_panel)
+    pr = [osamples[names[1]], osamples[names[2]]]
+    key = f"{names[1]}.vs.{names[2]}"
+    rot = ref["pairs"][key]["CPC"][:, :20]
+    op = oracle.project_pair(pr, ref["pairs"][key]["genes"], rot, var_scale, common_centering)
+    for side in (0, 1):
+        nr, nc = C.c_int32(0), C.c_int32(0)
+        ctx.check(ctx.lib.cg_pair_projection(ctx.h, 2, side, C.byref(nr), C.byref(nc), None))
+        p = np.zeros((nr.value, nc.value), order="F")
+        ctx.check(ctx.lib.cg_pair_projection(ctx.h, 2, side, None, None, p.ctypes.data_as(C.POINTER(C.c_double))))
+        np.testing.assert_allclose(p, op[side], rtol=1e-9, atol=1e-11)
+    _graphs_equal(g, ref["graph"], rtol=1e-6)
+    adj = oracle.adjacency_csr(ref["graph"])
+    a = g.as_adj()
+    assert np.array_equal(a.indptr, adj.indptr) and np.array_equal(a.indices, adj.indices)
+    np.testing.assert_allclose(a.data, adj.data, rtol=1e-6)
+    assert g.names[0] == small_panel[names[0]].cells[g.vertices[0]]
+
+
+def test_local_edges_and_merge(ctx, oracle, small_panel):
+    """k.self edges: self + exact-zero distances dropped, reciprocal edges summed by simplify."""
+    import conos_b200
+    osamples = to_oracle_samples(oracle, small_panel)
+    names = list(small_panel)
+    frm, to, w, typ = [], [], [], []
+    off = 0
+    for n in names:
+        nb, q, ww = oracle.local_edges(osamples[n].pca, 5, 0.1)
+        frm.append(nb + off); to.append(q + off); w.append(ww); typ.append(np.zeros(len(ww), np.int32))
+        off += osamples[n].counts.shape[0]
+    og = oracle.assemble_graph(np.concatenate(frm).astype(np.int64), np.concatenate(to).astype(np.int64),
+                               np.concatenate(w), np.concatenate(typ))
+    con = conos_b200.Conos(small_panel, ctx=ctx)
+    con._ensure_panel(names)
+    P = conos_b200._lib.CgParams()
+    ctx.lib.cg_params_default(C.byref(P))
+    P.k_self = 5
+    edges = C.c_void_p()
+    sidx = np.arange(len(names), dtype=np.int32)
+    ctx.check(ctx.lib.cg_local_edges(ctx.h, con._panel, sidx.ctypes.data_as(C.POINTER(C.c_int32)), len(names),
+                                     C.byref(P), C.byref(edges)))
+    g = con._assemble(edges, names)
+    ctx.lib.cg_edges_free(edges)
+    _graphs_equal(g, og)
+    assert (g.type == 0).all()
+
+
+def test_assemble_graph_semantics(ctx, oracle):
+    """w <= 0 rows dropped before vertex numbering, loops removed, multi-edges summed in table order, type = first."""
+    rng = np.random.default_rng(4)
+    n_cells = 200
+    frm = rng.integers(0, n_cells, 5000).astype(np.int32)
+    to = rng.integers(0, n_cells, 5000).astype(np.int32)
+    w = rng.uniform(-0.2, 1.0, 5000)
+    typ = rng.integers(0, 2, 5000).astype(np.int32)
+    og = oracle.assemble_graph(frm.astype(np.int64), to.astype(np.int64), w, typ)
+    lib, h = ctx.lib, ctx.h
+    e = C.c_void_p()
+    ip = C.POINTER(C.c_int32)
+    ctx.check(lib.cg_edges_append_host(h, C.byref(e), frm.ctypes.data_as(ip), to.ctypes.data_as(ip),
+                                       w.ctypes.data_as(C.POINTER(C.c_double)), typ.ctypes.data_as(ip), len(w)))
+    gh = C.c_void_p()
+    ctx.check(lib.cg_assemble_graph(h, e, n_cells, C.byref(gh)))
+    nv, ne = C.c_int32(0), C.c_int64(0)
+    lib.cg_graph_sizes(gh, C.byref(nv), C.byref(ne))
+    assert nv.value == len(og["vertices"]) and ne.value == len(og["from"])
+    v = np.empty(nv.value, np.int32); f = np.empty(ne.value, np.int32); t = np.empty(ne.value, np.int32)
+    ww = np.empty(ne.value); ty = np.empty(ne.value, np.int32)
+    ctx.check(lib.cg_graph_fetch(h, gh, v.ctypes.data_as(ip), f.ctypes.data_as(ip), t.ctypes.data_as(ip),
+                                 ww.ctypes.data_as(C.POINTER(C.c_double)), ty.ctypes.data_as(ip)))
+    assert np.array_equal(v, og["vertices"]) and np.array_equal(f, og["from"]) and np.array_equal(t, og["to"])
+    assert np.array_equal(ty, og["type"])
+    np.testing.assert_allclose(ww, og["weight"], rtol=1e-14)
+    lib.cg_graph_free(gh)
+    lib.cg_edges_free(e)
+
+
+def test_empty_and_error_paths(ctx):
+    from conos_b200 import ops, ConosGpuError
+    with pytest.raises(ValueError):
+        ops.crossKnn(np.zeros((3, 2)), np.zeros((3, 3)), 2, ctx=ctx)
+    with pytest.raises(ValueError, match="distance metrics"):
+        ops.crossKnn(np.zeros((3, 2)), np.zeros((3, 2)), 2, metric="cosine", ctx=ctx)
+    with pytest.raises(ConosGpuError, match="k1 must be >= k"):
+        ops.getNeighborMatrix(np.ones((4, 2)), np.ones((4, 2)), 3, k1=2, ctx=ctx)
+
+
+def test_rebalancing_kernels(ctx, oracle):
+    from conos_b200 import ops
+    rng = np.random.default_rng(8)
+    n_cells, n_levels, ne = 300, 4, 4000
+    ri = rng.integers(0, n_cells, ne).astype(np.int32)
+    ci = rng.integers(0, n_cells, ne).astype(np.int32)
+    w = rng.uniform(0.01, 1, ne)
+    fl = rng.integers(1, n_levels + 1, n_cells).astype(np.int32)
+    fl[:n_levels] = np.arange(1, n_levels + 1)
+    for normalize in (True, False):
+        m = ops.getSumWeightMatrix(w, ri, ci, fl, normalize, ctx=ctx)
+        np.testing.assert_allclose(m, oracle.sum_weight_matrix(w, ri, ci, fl, normalize), rtol=1e-12, atol=1e-15)
+    div = ops.getSumWeightMatrix(w, ri, ci, fl, True, ctx=ctx) + 0.05
+    np.testing.assert_allclose(ops.adjustWeightsByCellBalancingC(w, ri, ci, fl, div, ctx=ctx),
+                               oracle.adjust_weights_c(w, ri, ci, fl, div), rtol=1e-14)
+
+
+def test_balance_edge_weights(ctx, oracle, small_panel):
+    import conos_b200
+    osamples = to_oracle_samples(oracle, small_panel)
+    ref = oracle.build_graph(osamples, k=10, k_self=5, space="PCA", ncomps=20, n_odgenes=300,
+                             balance_edge_weights=True)
+    con = conos_b200.Conos(small_panel, ctx=ctx)
+    con.pairs["PCA"] = {key: {"CPC": red["CPC"], "genes": red["genes"]} for key, red in ref["pairs"].items()}
+    g = con.buildGraph(k=10, k_self=5, space="PCA", ncomps=20, n_odgenes=300, balance_edge_weights=True)
+    ri, ci, w = ref["balanced"]
+    a = sp.csc_matrix((w, (ri, ci)), shape=(len(g.vertices),) * 2).tocsr()
+    a.sort_indices()
+    b = g.as_adj()
+    assert np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices)
+    np.testing.assert_allclose(b.data, a.data, rtol=1e-5)
+
+
+def test_reference_wij(ctx, oracle, small_panel):
+    import conos_b200
+    from conos_b200 import ops
+    osamples = to_oracle_samples(oracle, small_panel)
+    ref = oracle.build_graph(osamples, k=10, k_self=5, space="PCA", ncomps=20, n_odgenes=300)
+    adj = oracle.adjacency_csr(ref["graph"])
+    want = oracle.build_wij_matrix(adj, perplexity=10)
+    got = ops.buildWijMatrix(adj, perplexity=10, ctx=ctx)
+    want.sort_indices(); got.sort_indices()
+    assert np.array_equal(want.indptr, got.indptr) and np.array_equal(want.indices, got.indices)
+    np.testing.assert_allclose(got.data, want.data, rtol=1e-9)
+
+
+def test_spcov_and_cpca(ctx, oracle, small_panel):
+    from conos_b200 import ops
+    osamples = list(to_oracle_samples(oracle, small_panel).values())[:2]
+    od = oracle.common_overdispersed_genes(osamples, 300)
+    sm = oracle.scaled_matrices(osamples, od, True)
+    covs = []
+    for x in sm:
+        cm = np.asarray(x.mean(axis=0)).ravel()
+        want = oracle.spcov(x, cm)
+        got = ops.spcov(x, cm, ctx=ctx)
+        np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-13)
+        covs.append(want)
+    ncells = [x.shape[0] for x in sm]
+    want, ev = oracle.cpca_fast(covs, ncells, ncomp=8, maxit=500, tol=1e-5)
+    got = ops.cpcaF(np.stack(covs, axis=2), ncells, ncomp=8, maxit=500, tol=1e-5, eigenvR=ev, ctx=ctx)
+    assert np.array_equal(got["niter"], want["niter"])
+    np.testing.assert_allclose(got["CPC"], want["CPC"], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(got["D"], want["D"], rtol=1e-9)

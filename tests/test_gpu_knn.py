@@ -1,0 +1,94 @@
+"""GPU parity of the exact kNN entry points (through the C ABI) against the oracle: bit-exact indices and
+float32 distances, including tie order, ragged sizes, nB < k, duplicated rows, both metrics, d > 32."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def mixture(rng, n, d, k=8, spread=3.0):
+    cent = rng.normal(0, spread, (k, d))
+    lab = rng.integers(0, k, n)
+    return cent[lab] + rng.normal(0, 1, (n, d))
+
+
+@pytest.mark.parametrize("nA,nB,d,k", [(25, 34, 30, 15), (300, 1000, 30, 15), (1000, 777, 50, 30), (513, 20, 30, 30),
+                                       (257, 4099, 7, 5), (2000, 3000, 64, 32), (64, 64, 1, 3)])
+def test_cross_knn_angular_bit_exact(ctx, oracle, nA, nB, d, k):
+    from conos_b200 import ops
+    rng = np.random.default_rng(nA * 7 + nB)
+    A, B = mixture(rng, nA, d), mixture(rng, nB, d)
+    m = len(B[1::5])
+    B[1::5] = B[0::5][:m]   # exact duplicates -> distance ties
+    iab, dab, iba, dba = ops.crossKnn(A, B, k, "angular", ctx=ctx, both=True)
+    oi, od = oracle.cross_knn(A, B, k, "angular")
+    assert np.array_equal(iab, oi)
+    assert np.array_equal(dab.view(np.uint32), od.view(np.uint32))
+    oi2, od2 = oracle.cross_knn(B, A, k, "angular")
+    assert np.array_equal(iba, oi2)
+    assert np.array_equal(dba.view(np.uint32), od2.view(np.uint32))
+
+
+@pytest.mark.parametrize("metric,k", [("L2", 15), ("angular", 40), ("L2", 64)])
+def test_cross_knn_simt_paths(ctx, oracle, metric, k):
+    """k > 32 and the L2 metric are served by the exact SIMT kernel."""
+    from conos_b200 import ops
+    rng = np.random.default_rng(11)
+    A, B = mixture(rng, 400, 30), mixture(rng, 900, 30)
+    idx, dist = ops.crossKnn(A, B, k, metric, ctx=ctx)
+    oi, od = oracle.cross_knn(A, B, k, metric)
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(dist.view(np.uint32), od.view(np.uint32))
+
+
+def test_self_knn_includes_self(ctx, oracle):
+    from conos_b200 import ops
+    rng = np.random.default_rng(5)
+    Z = mixture(rng, 1500, 20)
+    idx, dist = ops.Knn(Z, 11, "angular", ctx=ctx)
+    oi, od = oracle.self_knn(Z, 11, "angular")
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(dist.view(np.uint32), od.view(np.uint32))
+    assert (idx == np.arange(len(Z))[:, None]).any(axis=1).all()
+
+
+def test_zero_rows_and_sortedness(ctx, oracle):
+    """All-zero rows normalise to zero vectors (distance exactly 1 to everything): ties by lowest index."""
+    from conos_b200 import ops
+    rng = np.random.default_rng(3)
+    A, B = mixture(rng, 300, 30), mixture(rng, 500, 30)
+    A[::7] = 0.0
+    B[::11] = 0.0
+    idx, dist = ops.crossKnn(A, B, 15, "angular", ctx=ctx)
+    oi, od = oracle.cross_knn(A, B, 15, "angular")
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(dist.view(np.uint32), od.view(np.uint32))
+    assert (np.diff(dist, axis=1) >= 0).all()
+    assert np.array_equal(idx[0], np.arange(15))  # zero query: every reference at distance 1
+
+
+def test_recall_vs_fp64(ctx, oracle):
+    from conos_b200 import ops
+    rng = np.random.default_rng(9)
+    A, B = mixture(rng, 2000, 30), mixture(rng, 5000, 30)
+    idx, _ = ops.crossKnn(A, B, 15, "angular", ctx=ctx)
+    ti, _ = oracle.knn_f64(A, B, 15, "angular")
+    recall = np.mean([len(set(a) & set(b)) / 15 for a, b in zip(idx, ti)])
+    assert recall > 0.999
+
+
+def test_large_properties(ctx):
+    """Full-size property checks (no oracle): sorted rows, valid unique indices, symmetry of mutual hits."""
+    from conos_b200 import ops
+    rng = np.random.default_rng(21)
+    A, B = mixture(rng, 20000, 30, k=20), mixture(rng, 30000, 30, k=20)
+    iab, dab, iba, dba = ops.crossKnn(A, B, 30, "angular", ctx=ctx, both=True)
+    assert (np.diff(dab, axis=1) >= 0).all() and (np.diff(dba, axis=1) >= 0).all()
+    assert iab.min() >= 0 and iab.max() < len(B) and iba.min() >= 0 and iba.max() < len(A)
+    assert all(len(set(r)) == 30 for r in iab[::500])
+    # a mutual pair must carry the identical float32 distance in both directions
+    for i in range(0, 20000, 997):
+        for r, j in enumerate(iab[i]):
+            hit = np.nonzero(iba[j] == i)[0]
+            if len(hit):
+                assert dab[i, r] == dba[j, hit[0]]
