@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py -- buildGraph sample-pairs/s on synthetic panels (BASELINE.json metric), one process per GPU.
+
+  python bench.py --gpus N --steps K --warmup W            # this repository's B200 path
+  python bench.py --impl reference --steps K --warmup W    # the reference's CPU algorithm (oracle), host cores
+
+A step is one full Conos.buildGraph over the panel (per-pair reduction, projection, exact two-directional kNN,
+mutual-neighbour matching, local k.self edges, graph assembly).  `value` is measured with the panel resident
+in HBM and the graph left on the device; `e2e` goes through the public host API with the panel in host memory
+(uploaded inside the timed region) and the graph copied back.  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+CONFIGS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on at N = 1
+    2: dict(workload="synthetic 8 samples x 50k cells x 2000 od-genes, space=PCA ncomps=30 k=30 (configs[1])",
+            n_samples=8, n_cells=50000, n_genes=2000, space="PCA", ncomps=30, k=30, k_self=10),
+    # configs[3]: the atlas, pair-sharded
+    4: dict(workload="synthetic atlas 100 samples x 10k cells (4950 pairs), space=PCA k=15 k.self=5 (configs[3])",
+            n_samples=100, n_cells=10000, n_genes=2000, space="PCA", ncomps=30, k=15, k_self=5),
+}
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d.get("hbm_gbs", 6650.0), bf16_tflops=d.get("bf16_tflops_sustained", 1400.0),
+                    source="measured (MEASURED_PEAKS.json, sustained bf16)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def panel_bytes(panel):
+    b = 0
+    for s in panel.values():
+        b += s.counts.indptr.size * 4 + s.counts.indices.size * 4 + s.counts.data.size * 8
+        b += s.varinfo_v.size * 8 + s.varinfo_qv.size * 8 + s.pca.size * 8
+    return b
+
+
+def graph_bytes(g):
+    return (g.vertices.nbytes + g.edge_from.nbytes + g.edge_to.nbytes + g.weight.nbytes + g.type.nbytes +
+            g.adj_p.nbytes + g.adj_i.nbytes + g.adj_x.nbytes)
+
+
+def cpu_reference_step(oracle, osamples, names, cfg, pair=(0, 1)):
+    """The reference algorithm (oracle restatement) for ONE sample pair at full size: reduction, projection,
+    exact kNN both ways, matching.  Returns seconds."""
+    pr = {names[pair[0]]: osamples[names[pair[0]]], names[pair[1]]: osamples[names[pair[1]]]}
+    t0 = time.perf_counter()
+    oracle.build_graph(pr, k=cfg["k"], k_self=0, space=cfg["space"], ncomps=cfg["ncomps"], n_odgenes=cfg["n_genes"])
+    return time.perf_counter() - t0
+
+
+def to_oracle(oracle, panel):
+    return {n: oracle.Sample(counts=s.counts, genes=s.genes, cells=s.cells, varinfo_v=s.varinfo_v,
+                             varinfo_qv=s.varinfo_qv, pca=s.pca, od_genes=s.od_genes) for n, s in panel.items()}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--n-samples", type=int, default=None, help="override (debug runs only)")
+    ap.add_argument("--n-cells", type=int, default=None, help="override (debug runs only)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    reduced = False
+    if args.n_samples:
+        cfg["n_samples"], reduced = args.n_samples, True
+    if args.n_cells:
+        cfg["n_cells"], reduced = args.n_cells, True
+    if reduced:
+        cfg["workload"] += f" [REDUCED to {cfg['n_samples']} x {cfg['n_cells']}: not a valid bench line]"
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_pairs = cfg["n_samples"] * (cfg["n_samples"] - 1) // 2
+    W = max(args.warmup, 0)
+    K = max(args.steps, 1)
+
+    # ------------------------------------------------------------------ reference arm: CPU, rank 0 only
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        import conos_oracle as oracle
+        oracle.build()
+        from conos_b200.panel import make_panel
+        cores = os.cpu_count() or 1
+        # two samples of the workload are enough for a one-pair step
+        panel = make_panel(args.config, 2, cfg["n_cells"], cfg["n_genes"], use_torch=None)
+        osamples = to_oracle(oracle, panel)
+        names = list(panel)
+        times = []
+        W = min(W, 1)  # a CPU run needs no clock warm-up; one untimed step pages the libraries in
+        for it in range(W + K):
+            dt = cpu_reference_step(oracle, osamples, names, cfg)
+            if it >= W:
+                times.append(dt)
+            if sum(times) > 150 and len(times) >= 1 and it >= W:  # keep the whole run within a few minutes
+                break
+        steps_done = len(times)
+        tot = sum(times)
+        val = steps_done / tot
+        sample = (f"1 of {n_pairs} sample pairs per step at full size (2 x {cfg['n_cells']} cells, {cfg['n_genes']} "
+                  f"genes): reduction + projection + exact kNN both ways + matching; oracle port (exact float32 "
+                  f"brute force, OpenMP), {steps_done} timed steps")
+        line = {"impl": "reference", "metric": "buildGraph sample-pairs/s", "value": val, "unit": "pairs/s",
+                "n_gpus": args.gpus, "steps": steps_done, "warmup": W, "ms_per_step": 1e3 * tot / steps_done,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": {"workload": cfg["workload"]},
+                "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ this repository's arm
+    import torch
+    import conos_b200
+    from conos_b200.panel import make_panel
+    torch.cuda.set_device(local_rank)
+    dist_group = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = conos_b200.Context(local_rank)
+    lib = ctx.lib
+    t_gen = time.perf_counter()
+    panel = make_panel(args.config, cfg["n_samples"], cfg["n_cells"], cfg["n_genes"])
+    t_gen = time.perf_counter() - t_gen
+    con = conos_b200.Conos(panel, ctx=ctx)
+    wtuple = (rank, world, dist_group) if world > 1 else None
+    kw = dict(k=cfg["k"], k_self=cfg["k_self"], space=cfg["space"], ncomps=cfg["ncomps"], n_odgenes=cfg["n_genes"])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step():
+        con.pairs = {}
+        return con.buildGraph(fetch=False, world=wtuple, **kw)
+
+    def e2e_step():
+        con.pairs = {}
+        con._drop_panel()       # the panel is re-uploaded from host memory inside the timed region
+        return con.buildGraph(fetch=True, world=wtuple, **kw)
+
+    import ctypes as C
+    # ---- device-resident throughput
+    for _ in range(W):
+        device_step()
+    barrier()
+    lib.cg_knn_timing(ctx.h, 1)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    n_launch0 = ctx.kernel_launches()
+    lib.cg_timer_start(ctx.h)
+    t0 = time.perf_counter()
+    for _ in range(K):
+        g = device_step()
+    ms = C.c_double(0)
+    lib.cg_timer_stop(ctx.h, C.byref(ms))
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.kernel_launches() - n_launch0
+    kms, kl, kc, kb = C.c_double(0), C.c_uint64(0), C.c_double(0), C.c_double(0)
+    lib.cg_knn_timing_read(ctx.h, C.byref(kms), C.byref(kl), C.byref(kc), C.byref(kb))
+    lib.cg_knn_timing(ctx.h, 0)
+    dev_ms = max(ms.value, 1e3 * wall)  # the host gaps between kernels belong to the step
+    if world > 1:
+        import torch.distributed as dist
+        tmax = torch.tensor([dev_ms], device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dev_ms = float(tmax.item())
+        lsum = torch.tensor([float(launches)], device="cuda")
+        dist.all_reduce(lsum)
+        launches = int(lsum.item())
+    n_inter = con._n_inter_edges
+    # ---- end to end through the host API
+    for _ in range(min(W, 1)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    K2 = max(1, min(K, 3))
+    for _ in range(K2):
+        g_host = e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        import torch.distributed as dist
+        tmax = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e_s = float(tmax.item())
+    if rank != 0:
+        return 0
+
+    peaks = read_peaks()
+    d = cfg["ncomps"]
+    knn_s = kms.value * 1e-3
+    flops = 2.0 * kc.value * d
+    achieved = flops / knn_s / 1e12 if knn_s > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "knn_tc_kernel (fused cross-kNN: tf32 tcgen05 filter + fp32 re-rank)",
+                "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
+                "launches": int(kl.value), "avg_launch_ms": kms.value / max(int(kl.value), 1),
+                "candidates_per_s": kc.value / knn_s if knn_s > 0 else 0.0,
+                "algorithmic_bytes_per_launch": kb.value / max(int(kl.value), 1),
+                "share_of_step": knn_s / (dev_ms * 1e-3) if dev_ms > 0 else None,
+                "note": "achieved = 2*n_query*n_ref*ncomps per launch / CUDA-event time on the launching stream; "
+                        "the kernel runs kind::tf32 (half the bf16 rate) and is selection-bound, see DESIGN.md"}
+    line = {"metric": "buildGraph sample-pairs/s", "value": n_pairs * K / (dev_ms * 1e-3), "unit": "pairs/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["workload"], "k": cfg["k"], "k_self": cfg["k_self"], "space": cfg["space"],
+                       "ncomps": cfg["ncomps"], "pairs": n_pairs,
+                       "l2": "inputs larger than L2 (panel and per-pair operands exceed 126 MB per step)",
+                       "panel_generation_s": t_gen},
+            "mnn_edges_per_s": n_inter * K / (dev_ms * 1e-3), "mnn_edges": n_inter,
+            "graph": {"vertices": getattr(g, "n_vertices_device", None), "edges": getattr(g, "n_edges_device", None)},
+            "e2e": {"value": n_pairs * K2 / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": panel_bytes(panel),
+                    "d2h_bytes_per_step": graph_bytes(g_host), "steps": K2},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
+    if not args.no_cpu_baseline:
+        import conos_oracle as oracle
+        oracle.build()
+        names = list(panel)
+        osamples = to_oracle(oracle, {n: panel[n] for n in names[:2]})
+        dt = cpu_reference_step(oracle, osamples, names, cfg)
+        line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "pairs/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                "sample": f"1 of {n_pairs} pairs at full size (2 x {cfg['n_cells']} cells): reduction "
+                                          f"+ projection + exact kNN both ways + matching, {dt:.1f} s"}
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -189,7 +189,11 @@ class Conos:
                    score_component_variance: bool = False, snn: bool = False, balance_edge_weights: bool = False,
                    balancing_factor_per_cell=None, same_factor_downweight: float = 1.0,
                    k_same_factor: Optional[int] = None, balancing_factor_per_sample=None,
-                   pair_shard: Optional[Sequence[int]] = None, assemble: bool = True):
+                   pair_shard: Optional[Sequence[int]] = None, assemble: bool = True, fetch: bool = True,
+                   world=None):
+        """`world` = (rank, world_size, process group or None) shards the sample pairs (and the per-sample
+        local-neighbour searches) over one process per GPU; every rank ends with the full graph.
+        `fetch=False` keeps the assembled graph on the device (self.graph is a size-only stub)."""
         if space not in SUPPORTED_SPACES:
             raise ValueError("only the following spaces are currently supported: [" + " ".join(SUPPORTED_SPACES) + "]")
         if space not in DEVICE_SPACES:
@@ -231,6 +235,12 @@ class Conos:
         index = {n: t for t, n in enumerate(names)}
         cache = self.pairs.setdefault(space, {})
 
+        rank, world_size, group = world if world is not None else (0, 1, None)
+        if world_size > 1:
+            from .dist import partition_contiguous
+            costs = [float(self.samples[a].counts.shape[0]) * self.samples[b].counts.shape[0] for a, b in pair_names]
+            lo, hi = partition_contiguous(costs, world_size)[rank]
+            pair_shard = range(lo, hi)
         my_pairs = list(range(len(pair_names))) if pair_shard is None else list(pair_shard)
         carr = (CgPair * max(len(my_pairs), 1))()
         keep_alive = []
@@ -288,7 +298,8 @@ class Conos:
             self.ctx.check(lib.cg_pair_reduction(h, slot, None, None, ptr(rot, C.c_double), ptr(nv, C.c_double)))
             cache[key] = {"CPC": rot, "genes": self._gene_names(od)}
             if nv is not None:
-                cache[key]["nv"] = [nv[0], nv[1]]
+                rr = nc.value // 2 if space == "PCA" else nc.value
+                cache[key]["nv"] = [nv[0, :rr], nv[1, :rr]]
         self._last_pair_counts = {used_pairs[t][1]: int(counts[t]) for t in range(len(used_pairs))}
         self._last_edges = edges
         self._last_params = P
@@ -297,11 +308,28 @@ class Conos:
             return edges
 
         # ---- local edges (R/conclass.R:328-333) and graph assembly
-        if k_self > 0:
+        if world_size > 1:
+            from .dist import gather_edges, partition_contiguous, device_columns
+            edges, _ = gather_edges(self.ctx, edges, group)          # allgatherv, rank order == combn order
+            if k_self > 0:
+                scost = [float(self.samples[n].counts.shape[0]) ** 2 for n in names]
+                lo, hi = partition_contiguous(scost, world_size)[rank]
+                sidx = np.arange(lo, hi, dtype=np.int32)
+                ledges = C.c_void_p()
+                self.ctx.check(lib.cg_local_edges(h, self._panel, ptr(sidx, C.c_int32), len(sidx), C.byref(P),
+                                                  C.byref(ledges)))
+                ledges, _ = gather_edges(self.ctx, ledges, group)
+                cols = device_columns(self.ctx, ledges)
+                self.ctx.check(lib.cg_edges_append_device(
+                    h, C.byref(edges), C.c_void_p(cols[0].data_ptr()), C.c_void_p(cols[1].data_ptr()),
+                    C.c_void_p(cols[2].data_ptr()), C.c_void_p(cols[3].data_ptr()), int(cols[0].numel())))
+                lib.cg_edges_free(ledges)
+        elif k_self > 0:
             sidx = np.arange(len(names), dtype=np.int32)
             self.ctx.check(lib.cg_local_edges(h, self._panel, ptr(sidx, C.c_int32), len(names), C.byref(P),
                                               C.byref(edges)))
-        g = self._assemble(edges, names)
+        self._n_inter_edges = int(sum(self._last_pair_counts.values()))
+        g = self._assemble(edges, names, fetch=fetch)
         lib.cg_edges_free(edges)
         self._last_edges = None
         if balance_edge_weights:
@@ -309,13 +337,20 @@ class Conos:
         self.graph = g
         return g
 
-    def _assemble(self, edges, names) -> ConosGraph:
+    def _assemble(self, edges, names, fetch: bool = True) -> ConosGraph:
         lib, h = self.ctx.lib, self.ctx.h
         n_total = sum(self.samples[n].counts.shape[0] for n in names)
         gh = C.c_void_p()
         self.ctx.check(lib.cg_assemble_graph(h, edges, n_total, C.byref(gh)))
         nv, ne = C.c_int32(0), C.c_int64(0)
         lib.cg_graph_sizes(gh, C.byref(nv), C.byref(ne))
+        if not fetch:
+            lib.cg_graph_free(gh)
+            z = np.zeros(0, np.int32)
+            g = ConosGraph(names=[], vertices=z, edge_from=z, edge_to=z, weight=np.zeros(0), type=z,
+                           adj_p=np.zeros(1, np.int64), adj_i=z, adj_x=np.zeros(0))
+            g.n_vertices_device, g.n_edges_device = nv.value, ne.value
+            return g
         vertices = np.empty(nv.value, np.int32)
         ef = np.empty(ne.value, np.int32)
         et = np.empty(ne.value, np.int32)

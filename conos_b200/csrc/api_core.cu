@@ -69,6 +69,27 @@ const char* cg_last_error(const cg_context* ctx) {
 
 uint64_t cg_kernel_launches(const cg_context* ctx) { return ctx ? ctx->c.stats.kernels : 0; }
 
+int cg_timer_start(cg_context* ctx) {
+  CG_API_BEGIN
+  CG_CHECK(ctx, "NULL context");
+  if (!ctx->ev0) {
+    CG_CUDA(cudaEventCreate(&ctx->ev0));
+    CG_CUDA(cudaEventCreate(&ctx->ev1));
+  }
+  CG_CUDA(cudaEventRecord(ctx->ev0, ctx->c.stream));
+  CG_API_END(ctx)
+}
+int cg_timer_stop(cg_context* ctx, double* ms) {
+  CG_API_BEGIN
+  CG_CHECK(ctx && ctx->ev0 && ms, "timer not started");
+  CG_CUDA(cudaEventRecord(ctx->ev1, ctx->c.stream));
+  CG_CUDA(cudaEventSynchronize(ctx->ev1));
+  float f = 0.f;
+  CG_CUDA(cudaEventElapsedTime(&f, ctx->ev0, ctx->ev1));
+  *ms = f;
+  CG_API_END(ctx)
+}
+
 int cg_knn_timing(cg_context* ctx, int enable) {
   CG_API_BEGIN
   CG_CHECK(ctx, "NULL context");
@@ -293,6 +314,25 @@ int cg_edges_append_host(cg_context* ctx, cg_edges** e, const int32_t* from, con
     CG_CUDA(cudaMemcpyAsync(t.to.p + t.n, to, (size_t)n * 4, cudaMemcpyHostToDevice, s));
     CG_CUDA(cudaMemcpyAsync(t.w.p + t.n, w, (size_t)n * 8, cudaMemcpyHostToDevice, s));
     CG_CUDA(cudaMemcpyAsync(t.type.p + t.n, type, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    CG_CUDA(cudaStreamSynchronize(s));
+    t.n += (size_t)n;
+  }
+  CG_API_END(ctx)
+}
+
+int cg_edges_append_device(cg_context* ctx, cg_edges** e, const void* from, const void* to, const void* w,
+                           const void* type, int64_t n) {
+  CG_API_BEGIN
+  CG_CHECK(ctx && e && n >= 0, "bad argument");
+  if (!*e) *e = new cg_edges();
+  EdgeTable& t = (*e)->t;
+  t.reserve(t.n + (size_t)n, ctx->c.stream);
+  if (n) {
+    cudaStream_t s = ctx->c.stream;
+    CG_CUDA(cudaMemcpyAsync(t.from.p + t.n, from, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+    CG_CUDA(cudaMemcpyAsync(t.to.p + t.n, to, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+    CG_CUDA(cudaMemcpyAsync(t.w.p + t.n, w, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+    CG_CUDA(cudaMemcpyAsync(t.type.p + t.n, type, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
     CG_CUDA(cudaStreamSynchronize(s));
     t.n += (size_t)n;
   }

@@ -20,6 +20,7 @@ struct cg_context {
   };
   std::vector<PairKeep> kept;
   bool keep_projections = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
 struct cg_panel {

@@ -1,33 +1,230 @@
+#include <cmath>
+
+#include "eig.cuh"
 #include "reduce.cuh"
+#include "stage.cuh"
 
 namespace cg {
+namespace {
+
+inline unsigned nblk(size_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
+
+// scaled covariance of one sample on the pair's od genes (spcov of the column-scaled matrix, without ever
+// forming it):  C[i][j] = f_i f_j (M[c_i][c_j] - n m_i m_j) / (n - 1),  m = colSums / n of the unscaled counts,
+// M = X'X of the whole sample (cached per sample).  Zero padded to Gp x Gp.
+__global__ void scaled_cov_kernel(const double* __restrict__ M, int Gs, const double* __restrict__ colsum,
+                                  const int* __restrict__ cols, const double* __restrict__ f, int G, int Gp, double n,
+                                  double* __restrict__ C) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)Gp * Gp) return;
+  const int i = (int)(t % Gp), j = (int)(t / Gp);
+  double v = 0.0;
+  if (i < G && j < G) {
+    const int ci = cols[i], cj = cols[j];
+    const double mi = colsum[ci] / n, mj = colsum[cj] / n;
+    v = f[i] * f[j] * (M[(size_t)cj * Gs + ci] - n * mi * mj) / (n - 1.0);
+  }
+  C[t] = v;
+}
+
+__global__ void mirror_upper_kernel(double* __restrict__ M, int G) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)G * G) return;
+  const int r = (int)(t % G), c = (int)(t / G);
+  if (r > c) M[t] = M[(size_t)r * G + c];
+}
+
+// rot[:, 2j] = Va[:, j], rot[:, 2j+1] = Vb[:, j]   (interleave <- order(c((1:n1)-0.5, 1:n2)), R/conos.R:300-304)
+__global__ void interleave_kernel(const double* __restrict__ Va, const double* __restrict__ Vb, int G, int Gp, int r,
+                                  double* __restrict__ rot) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)G * 2 * r) return;
+  const int g = (int)(t % G), c = (int)(t / G);
+  const double* src = (c & 1) ? Vb : Va;
+  rot[t] = src[(size_t)(c >> 1) * Gp + g];
+}
+
+__global__ void trace_kernel(const double* __restrict__ C, int Gp, double* __restrict__ out) {
+  // single block
+  double s = 0.0;
+  for (int i = threadIdx.x; i < Gp; i += blockDim.x) s += C[(size_t)i * Gp + i];
+  __shared__ double red[32];
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+    *out = tot;
+  }
+}
+
+int r_round_half_even(double x) { return (int)std::nearbyint(x); }  // default rounding mode = to nearest even
+
+}  // namespace
+
+// X'X of the whole sample in FP64 (upper triangle accumulated, then mirrored); cached on the sample.
+void ensure_gram(Context& ctx, Sample& s);
 
 void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs, int n_pairs, const cg_params& P,
                              std::vector<PairReduction>& out) {
+  cudaStream_t st = ctx.stream;
+  // ---- supplied reductions (the cache-hit path of updatePairs, R/conclass.R:1062-1071)
+  std::vector<int> todo;
   for (int q = 0; q < n_pairs; ++q) {
     const cg_pair& pr = pairs[q];
     PairReduction& R = out[q];
     if (P.space == CG_SPACE_CCA) {
-      CG_CHECK(pr.u && pr.v, "device CCA is not built yet: supply u and v");
-      CG_CHECK(pr.n_u > 0 && pr.n_v > 0 && pr.rows_u && pr.rows_v, "CCA needs the row maps of u and v");
-      R.n_u = pr.n_u;
-      R.n_v = pr.n_v;
-      R.d = P.ncomps;
-      R.u.upload(pr.u, (size_t)pr.n_u * P.ncomps, ctx.stream);
-      R.v.upload(pr.v, (size_t)pr.n_v * P.ncomps, ctx.stream);
-      R.h_rows_u.assign(pr.rows_u, pr.rows_u + pr.n_u);
-      R.h_rows_v.assign(pr.rows_v, pr.rows_v + pr.n_v);
+      if (pr.u && pr.v) {
+        CG_CHECK(pr.n_u > 0 && pr.n_v > 0 && pr.rows_u && pr.rows_v, "CCA needs the row maps of u and v");
+        R.n_u = pr.n_u;
+        R.n_v = pr.n_v;
+        R.d = P.ncomps;
+        R.u.upload(pr.u, (size_t)pr.n_u * P.ncomps, st);
+        R.v.upload(pr.v, (size_t)pr.n_v * P.ncomps, st);
+        R.h_rows_u.assign(pr.rows_u, pr.rows_u + pr.n_u);
+        R.h_rows_v.assign(pr.rows_v, pr.rows_v + pr.n_v);
+      } else {
+        todo.push_back(q);
+      }
     } else {
       CG_CHECK(pr.n_genes >= 5, "fewer than 5 common od genes: the reference drops such pairs (R/conos.R:206,278)");
-      CG_CHECK(pr.rot && pr.rot_cols > 0, "device PCA / CPCA is not built yet: supply rot");
-      R.n_rows = pr.n_genes;
-      R.n_cols = pr.rot_cols;
-      R.d = P.ncomps < pr.rot_cols ? P.ncomps : pr.rot_cols;
-      R.rot.upload(pr.rot, (size_t)pr.n_genes * pr.rot_cols, ctx.stream);
-      R.h_rot.assign(pr.rot, pr.rot + (size_t)pr.n_genes * pr.rot_cols);
+      if (pr.rot && pr.rot_cols > 0) {
+        R.n_rows = pr.n_genes;
+        R.n_cols = pr.rot_cols;
+        R.d = P.ncomps < pr.rot_cols ? P.ncomps : pr.rot_cols;
+        R.rot.upload(pr.rot, (size_t)pr.n_genes * pr.rot_cols, st);
+        R.h_rot.assign(pr.rot, pr.rot + (size_t)pr.n_genes * pr.rot_cols);
+      } else {
+        todo.push_back(q);
+      }
     }
   }
-  CG_CUDA(cudaStreamSynchronize(ctx.stream));
+  CG_CUDA(cudaStreamSynchronize(st));
+  if (todo.empty()) return;
+  CG_CHECK(P.space != CG_SPACE_CCA, "device CCA is not built yet: supply u and v");
+
+  // ---- per-sample Gram matrices
+  for (int q : todo) {
+    ensure_gram(ctx, panel.samples[pairs[q].a]);
+    ensure_gram(ctx, panel.samples[pairs[q].b]);
+  }
+
+  if (P.space == CG_SPACE_PCA) {
+    // quickPlainPCA (R/conos.R:273-315): r = round(ncomps / 2) leading right singular vectors of each
+    // centred, scaled sample == leading eigenvectors of its scaled covariance; columns interleaved.
+    const int r = r_round_half_even(P.ncomps / 2.0);
+    CG_CHECK(r >= 1 && r <= 56, "ncomps out of range for the device PCA");
+    const int B = r <= 24 ? 32 : 64;
+    // chunks of pairs bounded by memory (2 covariance matrices per pair)
+    size_t i0 = 0;
+    while (i0 < todo.size()) {
+      size_t freeb = 0, totb = 0;
+      cudaMemGetInfo(&freeb, &totb);
+      size_t per = 0;
+      size_t i1 = i0;
+      size_t used = 0;
+      while (i1 < todo.size()) {
+        const int G = pairs[todo[i1]].n_genes;
+        const int Gp = G > B ? G : B;
+        per = 2 * ((size_t)Gp * Gp * 8 + (size_t)Gp * (2 * B + r) * 8);
+        if (i1 > i0 && used + per > freeb / 3) break;
+        used += per;
+        ++i1;
+      }
+      const int nq = (int)(i1 - i0);
+      struct Buf {
+        DevBuf<double> C[2], V[2], theta[2], f[2], tr;
+        DevBuf<int> cols[2];
+        int G, Gp;
+      };
+      std::vector<Buf> bufs(nq);
+      std::vector<EigProblem> eprobs;
+      for (int t = 0; t < nq; ++t) {
+        const cg_pair& pr = pairs[todo[i0 + t]];
+        Buf& b = bufs[t];
+        b.G = pr.n_genes;
+        b.Gp = b.G > B ? b.G : B;
+        Sample* sm[2] = {&panel.samples[pr.a], &panel.samples[pr.b]};
+        const int* gcols[2] = {pr.genes_a, pr.genes_b};
+        // scale factors (same arithmetic as api_pairs.cu: scaledMatricesP2)
+        std::vector<double> f[2];
+        f[0].assign(b.G, 1.0);
+        f[1].assign(b.G, 1.0);
+        if (P.var_scale) {
+          CG_CHECK(!sm[0]->h_qv.empty() && !sm[1]->h_qv.empty() && !sm[0]->h_v.empty() && !sm[1]->h_v.empty(),
+                   "var.scale = TRUE needs misc$varinfo$v and $qv for every sample");
+          for (int g = 0; g < b.G; ++g) {
+            const int ca = pr.genes_a[g], cb = pr.genes_b[g];
+            const double cqv = std::exp((std::log(sm[0]->h_qv[ca]) + std::log(sm[1]->h_qv[cb])) / 2.0);
+            const double fa = std::sqrt(cqv / std::exp(sm[0]->h_v[ca]));
+            const double fb = std::sqrt(cqv / std::exp(sm[1]->h_v[cb]));
+            f[0][g] = std::isfinite(fa) ? fa : 0.0;
+            f[1][g] = std::isfinite(fb) ? fb : 0.0;
+          }
+        }
+        b.tr.alloc(2);
+        for (int side = 0; side < 2; ++side) {
+          b.C[side].alloc((size_t)b.Gp * b.Gp);
+          b.V[side].alloc((size_t)b.Gp * r);
+          b.theta[side].alloc((size_t)r);
+          b.f[side].upload(f[side].data(), (size_t)b.G, st);
+          b.cols[side].upload(gcols[side], (size_t)b.G, st);
+          scaled_cov_kernel<<<nblk((size_t)b.Gp * b.Gp), 256, 0, st>>>(sm[side]->gram.p, sm[side]->n_genes,
+                                                                        sm[side]->colsum.p, b.cols[side].p,
+                                                                        b.f[side].p, b.G, b.Gp,
+                                                                        (double)sm[side]->n_cells, b.C[side].p);
+          ctx.stats.kernels++;
+          if (P.score_component_variance) {
+            trace_kernel<<<1, 256, 0, st>>>(b.C[side].p, b.Gp, b.tr.p + side);
+            ctx.stats.kernels++;
+          }
+          eprobs.push_back(EigProblem{b.C[side].p, b.Gp, b.V[side].p, b.theta[side].p});
+        }
+      }
+      CG_CUDA(cudaGetLastError());
+      top_eigenvectors_batched(ctx, eprobs.data(), (int)eprobs.size(), r, 1e-10, 400);
+      for (int t = 0; t < nq; ++t) {
+        Buf& b = bufs[t];
+        PairReduction& R = out[todo[i0 + t]];
+        R.n_rows = b.G;
+        R.n_cols = 2 * r;
+        R.d = P.ncomps < R.n_cols ? P.ncomps : R.n_cols;
+        R.rot.alloc((size_t)b.G * R.n_cols);
+        interleave_kernel<<<nblk((size_t)b.G * R.n_cols), 256, 0, st>>>(b.V[0].p, b.V[1].p, b.G, b.Gp, r, R.rot.p);
+        ctx.stats.kernels++;
+        R.h_rot.resize((size_t)b.G * R.n_cols);
+        R.rot.download(R.h_rot.data(), R.h_rot.size(), st);
+        if (P.score_component_variance) {
+          // nv_j = var(projection on v_j) / sum of column variances = theta_j / trace(C)   (R/conos.R:289-296)
+          std::vector<double> th(2 * (size_t)r), tr(2);
+          b.theta[0].download(th.data(), (size_t)r, st);
+          b.theta[1].download(th.data() + r, (size_t)r, st);
+          b.tr.download(tr.data(), 2, st);
+          CG_CUDA(cudaStreamSynchronize(st));
+          R.h_nv.assign(2 * (size_t)R.n_cols, 0.0);
+          for (int side = 0; side < 2; ++side)
+            for (int j = 0; j < r; ++j) R.h_nv[(size_t)side * R.n_cols + j] = th[(size_t)side * r + j] / tr[side];
+        }
+      }
+      CG_CUDA(cudaStreamSynchronize(st));
+      i0 = i1;
+    }
+    return;
+  }
+  CG_CHECK(false, "device CPCA is not built yet: supply rot");
+}
+
+void ensure_gram(Context& ctx, Sample& s) {
+  if (s.gram.n) return;
+  CG_CHECK(s.n_genes <= 16384, "subset the counts matrix to the od-gene universe before upload (Gram matrix too big)");
+  const size_t G = (size_t)s.n_genes;
+  s.gram.alloc(G * G);
+  s.gram.zero(ctx.stream);
+  gram_upper_from_csr(ctx, s.csr_p.p, s.csr_i.p, s.csr_x.p, s.n_cells, s.n_genes, s.gram.p);
+  mirror_upper_kernel<<<nblk(G * G), 256, 0, ctx.stream>>>(s.gram.p, s.n_genes);
+  ctx.stats.kernels++;
+  CG_CUDA(cudaGetLastError());
 }
 
 }  // namespace cg

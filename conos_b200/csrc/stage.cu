@@ -239,6 +239,12 @@ __global__ void wij_emit_kernel(const int* __restrict__ from, const int* __restr
 
 }  // namespace
 
+void gram_upper_from_csr(Context& ctx, const int* rp, const int* ci, const double* xv, int n_rows, int G, double* M) {
+  gram_rows_kernel<<<(n_rows + 7) / 8, 256, 0, ctx.stream>>>(rp, ci, xv, n_rows, G, M);
+  ctx.stats.kernels++;
+  CG_CUDA(cudaGetLastError());
+}
+
 void spcov_host(Context& ctx, int n, int G, const int* p, const int* i, const double* x, const double* cm, double* out) {
   cudaStream_t s = ctx.stream;
   const long long nnz = p[G];

@@ -6,6 +6,11 @@ namespace cg {
 
 // spcov (src/spcov.cpp:14-19): V = m'm - n cm cm'; V /= (n - 1)
 void spcov_host(Context& ctx, int n, int G, const int* p, const int* i, const double* x, const double* cm, double* out);
+// upper triangle of X'X (column-major, M pre-zeroed) from CSR rows, FP64 atomics
+void gram_upper_from_csr(Context& ctx, const int* rp, const int* ci, const double* xv, int n_rows, int G, double* M);
+// cpcaF on device-resident operands
+void cpca_device(Context& ctx, const double* d_cov, int p, int k, const double* d_ng, int ncomp, int maxit, double tol,
+                 const double* d_eigv, double* d_D, double* d_CPC, double* d_niter);
 // cpcaF (src/cpca.cpp:16-101)
 void cpca_host(Context& ctx, const double* cov, int p, int k, const double* ng, int ncomp, int maxit, double tol,
                const double* eigv, double* D, double* CPC, double* niter);

@@ -49,6 +49,9 @@ const char* cg_last_error(const cg_context* ctx); /* ctx may be NULL: last error
 int cg_device_count(void);
 /* kernels launched by this context so far (bench.py reports the delta as gpu_launches) */
 uint64_t cg_kernel_launches(const cg_context* ctx);
+/* CUDA events on the context's stream: start, then stop returns the elapsed device time in ms */
+int cg_timer_start(cg_context* ctx);
+int cg_timer_stop(cg_context* ctx, double* ms);
 /* optional CUDA-event timing of the dominant kernel (fused cross-kNN): enable, then read and reset */
 int cg_knn_timing(cg_context* ctx, int enable);
 int cg_knn_timing_read(cg_context* ctx, double* ms, uint64_t* launches, double* candidates, double* bytes);
@@ -138,6 +141,9 @@ int cg_edges_fetch(cg_context* ctx, const cg_edges* e, int32_t* from, int32_t* t
 /* append host rows (used to merge shards gathered from other ranks) */
 int cg_edges_append_host(cg_context* ctx, cg_edges** e, const int32_t* from, const int32_t* to, const double* w,
                          const int32_t* type, int64_t n);
+/* append rows that already live on this device (the shards gathered over NCCL) */
+int cg_edges_append_device(cg_context* ctx, cg_edges** e, const void* from, const void* to, const void* w,
+                           const void* type, int64_t n);
 /* device pointers of the columns (for NCCL gathers driven by the host language) */
 int cg_edges_device_ptrs(const cg_edges* e, void** from, void** to, void** w, void** type);
 int cg_edges_reserve(cg_context* ctx, cg_edges** e, int64_t n_total);

@@ -1,0 +1,115 @@
+"""Host-side logic of the Conos mirror (no GPU): argument checks with the reference's messages, gene-set
+selection, pair partitioning, and the world_size-2 gloo allgatherv plumbing."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_argument_validation(small_panel):
+    import conos_b200
+    con = conos_b200.Conos(small_panel)
+    with pytest.raises(ValueError, match="only the following spaces are currently supported"):
+        con.buildGraph(space="UMAP")
+    with pytest.raises(ValueError, match="matching methods"):
+        con.buildGraph(matching_method="xNN")
+    with pytest.raises(ValueError, match="distance metrics"):
+        con.buildGraph(metric="cosine")
+    with pytest.raises(ValueError, match="k1 must be >= k"):
+        con.buildGraph(k=15, k1=10)
+    with pytest.raises(NotImplementedError):
+        con.buildGraph(space="JNMF")
+    with pytest.raises(ValueError, match="named list"):
+        conos_b200.Conos([1, 2])
+    with pytest.raises(ValueError, match="identical to already existing"):
+        con.addSamples({list(small_panel)[0]: list(small_panel.values())[0]})
+
+
+def test_common_od_genes_matches_oracle(oracle, small_panel):
+    import conos_b200
+    from conftest import to_oracle_samples
+    con = conos_b200.Conos(small_panel)
+    S = to_oracle_samples(oracle, small_panel)
+    names = list(small_panel)
+    for n_od in (300, 50, 7):
+        for a in range(3):
+            for b in range(a + 1, 3):
+                ids, ga, gb = con._common_od_genes(names[a], names[b], n_od)
+                want = oracle.common_overdispersed_genes([S[names[a]], S[names[b]]], n_od)
+                assert con._gene_names(ids) == want
+                assert [small_panel[names[a]].genes[t] for t in ga] == want
+                assert [small_panel[names[b]].genes[t] for t in gb] == want
+
+
+def test_common_od_genes_partial_overlap(oracle):
+    import scipy.sparse as sp
+    import conos_b200
+    rng = np.random.default_rng(0)
+
+    def mk(genes, od):
+        n = 6
+        return conos_b200.Pagoda2(counts=sp.csc_matrix(rng.random((n, len(genes)))), genes=genes,
+                                  cells=[f"c{t}" for t in range(n)], varinfo_v=np.zeros(len(genes)),
+                                  varinfo_qv=np.ones(len(genes)), pca=rng.random((n, 3)), od_genes=od)
+    a = mk(["B", "a", "C", "d", "E"], ["E", "a", "C", "B"])
+    b = mk(["d", "C", "E", "Z", "a"], ["Z", "C", "d", "E"])
+    con = conos_b200.Conos({"x": a, "y": b})
+    ids, ga, gb = con._common_od_genes("x", "y", 3)
+    S = {"x": oracle.Sample(a.counts, a.genes, a.cells, a.varinfo_v, a.varinfo_qv, a.pca, a.od_genes),
+         "y": oracle.Sample(b.counts, b.genes, b.cells, b.varinfo_v, b.varinfo_qv, b.pca, b.od_genes)}
+    want = oracle.common_overdispersed_genes([S["x"], S["y"]], 3)
+    assert con._gene_names(ids) == want == ["C", "E", "a"]   # count 2 first (name order), 'Z'/'B' absent in one sample
+
+
+def test_partition_contiguous():
+    from conos_b200.dist import partition_contiguous
+    for n, parts in [(28, 8), (4950, 8), (3, 8), (1, 2), (0, 4)]:
+        pr = partition_contiguous([1.0] * n, parts)
+        assert len(pr) == parts and pr[0][0] == 0 and pr[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(pr, pr[1:]))
+        sizes = [b - a for a, b in pr]
+        assert max(sizes) - min(sizes) <= 1
+    costs = np.random.default_rng(0).integers(1, 100, 500).astype(float)
+    pr = partition_contiguous(costs, 8)
+    loads = [costs[a:b].sum() for a, b in pr]
+    assert max(loads) <= costs.sum() / 8 + costs.max()
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from conos_b200.dist import allgather_columns, partition_contiguous
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    pairs = list(range(11))
+    lo, hi = partition_contiguous([1.0] * len(pairs), world)[rank]
+    # every "pair" p contributes p+1 rows (from=p, to=row, w=p+row/10)
+    frm = torch.tensor([p for p in pairs[lo:hi] for _ in range(p + 1)], dtype=torch.int32)
+    to = torch.tensor([r for p in pairs[lo:hi] for r in range(p + 1)], dtype=torch.int32)
+    w = frm.double() + to.double() / 10
+    ty = torch.ones_like(frm)
+    (gf, gt, gw, gty), counts = allgather_columns([frm, to, w, ty])
+    q.put((rank, gf.tolist(), gt.tolist(), gw.tolist(), counts))
+    dist.destroy_process_group()
+
+
+def test_allgatherv_two_ranks_gloo():
+    import torch.multiprocessing as mp
+    ctxmp = mp.get_context("spawn")
+    q = ctxmp.Queue()
+    port = 29500 + os.getpid() % 1000
+    procs = [ctxmp.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    want_f = [p for p in range(11) for _ in range(p + 1)]
+    want_t = [r for p in range(11) for r in range(p + 1)]
+    for rank, gf, gt, gw, counts in res:
+        assert gf == want_f and gt == want_t           # rank order == pair order, no interleaving needed
+        assert sum(counts) == len(want_f)
+        assert np.allclose(gw, np.array(want_f) + np.array(want_t) / 10)

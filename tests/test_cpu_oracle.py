@@ -1,0 +1,200 @@
+"""The oracle against independent restatements and its own invariants (CPU only).  The reference ships no
+golden vectors for this path (parity unpinned); these tests pin the oracle's pieces against
+slow, obviously-correct NumPy / pure-Python versions and against the committed regression fixtures."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def fma32(a, b, c):
+    """float32 fma through float64 (exact product; the one float64 rounding of the sum is a double rounding
+    only in ~2^-29 of the cases)."""
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+
+
+def slow_knn(q, r, k, metric):
+    nq, d = q.shape
+    acc = [np.zeros((nq, r.shape[0]), np.float32) for _ in range(4)]
+    for c in range(d):
+        if metric == "angular":
+            acc[c & 3] = fma32(np.broadcast_to(q[:, c:c + 1], acc[0].shape), np.broadcast_to(r[None, :, c], acc[0].shape),
+                               acc[c & 3])
+        else:
+            df = (q[:, c:c + 1] - r[None, :, c]).astype(np.float32)
+            acc[c & 3] = fma32(df, df, acc[c & 3])
+    tot = (acc[0] + acc[1]) + (acc[2] + acc[3])
+    dist = (np.float32(1.0) - tot) if metric == "angular" else tot
+    idx = np.argsort(dist, axis=1, kind="stable")[:, :k]
+    return idx.astype(np.int32), np.take_along_axis(dist, idx, axis=1)
+
+
+@pytest.mark.parametrize("metric", ["angular", "L2"])
+@pytest.mark.parametrize("nq,nr,d,k", [(40, 60, 30, 15), (33, 17, 7, 5), (50, 200, 50, 30)])
+def test_knn_f32_canonical_arithmetic(oracle, metric, nq, nr, d, k):
+    rng = np.random.default_rng(nq + nr)
+    A, B = rng.normal(size=(nq, d)), rng.normal(size=(nr, d))
+    B[3] = B[1]
+    q, r = oracle.prepare_f32(A, metric), oracle.prepare_f32(B, metric)
+    idx, dist = oracle.knn_f32(q, r, k, metric)
+    si, sd = slow_knn(q, r, min(k, nr), metric)
+    assert np.array_equal(idx[:, :si.shape[1]], si)
+    assert np.array_equal(dist[:, :si.shape[1]].view(np.uint32), sd.view(np.uint32))
+    if metric == "angular":
+        nrm = np.sqrt((q.astype(np.float64) ** 2).sum(axis=1))
+        assert np.allclose(nrm, 1.0, atol=1e-6)
+
+
+def test_knn_fewer_refs_than_k(oracle):
+    rng = np.random.default_rng(0)
+    idx, dist = oracle.cross_knn(rng.normal(size=(5, 4)), rng.normal(size=(3, 4)), 6)
+    assert (idx[:, 3:] == -1).all() and np.isinf(dist[:, 3:]).all() and (idx[:, :3] >= 0).all()
+
+
+def test_knn_f32_close_to_f64(oracle):
+    rng = np.random.default_rng(1)
+    A, B = rng.normal(size=(300, 30)), rng.normal(size=(500, 30))
+    i32, d32 = oracle.cross_knn(A, B, 10)
+    i64, d64 = oracle.knn_f64(A, B, 10)
+    assert np.mean(i32 == i64) > 0.995
+    assert np.abs(d32 - d64).max() < 1e-6
+
+
+def test_pare_down_hub_edges_against_python(oracle):
+    rng = np.random.default_rng(2)
+    m = sp.random(60, 40, density=0.3, random_state=3, format="csc")
+    m.sort_indices()
+    k, klow = 5, 3
+    rowN = np.bincount(m.indices, minlength=60).astype(np.int32)
+    want_x = m.data.copy()
+    want_rowN = rowN.copy()
+    for g in range(m.shape[1]):                       # src/edgeFilter.cpp:33-55, stable descending sort
+        p0, p1 = m.indptr[g], m.indptr[g + 1]
+        ne = p1 - p0
+        if ne <= k:
+            continue
+        cid = want_rowN[m.indices[p0:p1]].copy()
+        order = np.argsort(-cid, kind="stable")
+        j = 0
+        while ne > k and j < len(order) and cid[order[j]] > klow:
+            want_x[order[j] + p0] = 0
+            want_rowN[m.indices[order[j] + p0]] -= 1
+            ne -= 1
+            j += 1
+    got = oracle.pare_down_hub_edges(m, rowN, k, klow)
+    assert np.array_equal(got, want_x) and np.array_equal(rowN, want_rowN)
+
+
+def test_reduce_edges_degree_bounds(oracle):
+    adj = sp.random(200, 180, density=0.2, random_state=5, format="csc")
+    out = oracle.reduce_edges_in_graph_iteratively(adj, 10)
+    cc = np.diff(out.indptr)
+    rc = np.bincount(out.indices, minlength=200)
+    assert max(cc.max(), rc.max()) <= 10 + 5          # max.kdiff tolerance of the reference
+    assert out.nnz < adj.nnz
+    # surviving entries are a subset with unchanged values
+    d = (adj - out).tocsr()
+    assert (abs(out.multiply(out != 0) - adj.multiply(out != 0))).max() == 0 and d.min() >= 0
+
+
+def test_cpca_against_numpy(oracle):
+    rng = np.random.default_rng(4)
+    p, k, ncomp = 12, 2, 4
+    covs = []
+    for _ in range(k):
+        a = rng.normal(size=(40, p))
+        covs.append(np.cov(a, rowvar=False))
+    ng = [40.0, 55.0]
+    S = sum(n / sum(ng) * c for n, c in zip(ng, covs))
+    w, v = np.linalg.eigh(S)
+    ev = v[:, ::-1][:, :ncomp]
+    got = oracle.cpca_f(covs, ng, ncomp, 500, 1e-5, ev)
+    # plain NumPy restatement of src/cpca.cpp:44-91
+    Qw = np.eye(p)
+    CPC = np.zeros((p, ncomp))
+    D = np.zeros((ncomp, k))
+    nit = np.zeros(ncomp)
+    for comp in range(ncomp):
+        q = ev[:, comp].copy()
+        d = np.array([q @ (c @ q) for c in covs])
+        cost0 = 0.0
+        it = 0
+        for it in range(500):
+            Sm = sum(c * (n / di) for c, n, di in zip(covs, ng, d))
+            wv = Sm @ q
+            if comp != 0:
+                wv = Qw @ wv
+            q = wv / np.sqrt(np.sum(wv * wv))
+            d = np.array([q @ (c @ q) for c in covs])
+            cost = float(np.sum(np.log(d) * np.array(ng)))
+            if abs((cost - cost0) / cost) < 1e-5:
+                break
+            cost0 = cost
+        else:
+            it = 500
+        nit[comp] = it
+        D[comp] = d
+        CPC[:, comp] = q
+        Qw -= np.outer(q, q)
+    assert np.array_equal(got["niter"], nit)
+    np.testing.assert_allclose(got["CPC"], CPC, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(got["D"], D, rtol=1e-10)
+
+
+def test_assemble_graph_small_example(oracle):
+    # rows: (5,3,w) (3,5,w) duplicate undirected; (2,2) loop; (7,1,0) dropped before numbering
+    frm = np.array([5, 3, 2, 7, 5, 9])
+    to = np.array([3, 5, 2, 1, 9, 3])
+    w = np.array([0.5, 0.25, 1.0, 0.0, 0.125, 2.0])
+    typ = np.array([1, 0, 0, 1, 1, 0])
+    g = oracle.assemble_graph(frm, to, w, typ)
+    assert g["vertices"].tolist() == [5, 3, 2, 9]          # first appearance; 7 and 1 never appear
+    assert list(zip(g["from"], g["to"])) == [(0, 1), (0, 3), (1, 3)]
+    assert g["weight"].tolist() == [0.75, 0.125, 2.0] and g["type"].tolist() == [1, 1, 0]
+
+
+def test_scalars(oracle):
+    assert oracle.r_round(0.5) == 0 and oracle.r_round(1.5) == 2 and oracle.r_round(2.5) == 2
+    assert oracle.resolve_k1(15, None, None, 1000) == (15, 0.0)
+    assert oracle.resolve_k1(15, None, 0.3, 25000) == (2250, 0.3)
+    assert oracle.resolve_k1(15, None, 5.0, 100)[0] == 100
+    assert oracle.cor_base_of(0.0) == 1.0 and oracle.cor_base_of(0.05) == 1.5 and oracle.cor_base_of(0.3) == 2.0
+    with pytest.raises(ValueError):
+        oracle.resolve_k1(15, 10, None, 100)
+
+
+def test_centering_quirk(oracle, small_panel):
+    """common.centering=TRUE subtracts ONE NUMBER per sample (m[1], m[2]) -- bug-compatible default."""
+    from conftest import to_oracle_samples
+    s = list(to_oracle_samples(oracle, small_panel).values())[:2]
+    od = oracle.common_overdispersed_genes(s, 300)
+    rot = np.linalg.qr(np.random.default_rng(0).normal(size=(len(od), 6)))[0]
+    p = oracle.project_pair(s, od, rot, True, True)
+    sm = oracle.scaled_matrices(s, od, True)
+    n = np.array([x.shape[0] for x in sm], float)
+    means = np.stack([np.asarray(x.mean(axis=0)).ravel() for x in sm])
+    m = (means * n[:, None]).sum(0) / n.sum()
+    for side in (0, 1):
+        want = sm[side] @ rot - m[side] * rot.sum(axis=0)[None, :]
+        np.testing.assert_allclose(p[side], want, rtol=1e-10, atol=1e-12)
+
+
+def test_build_graph_invariants(oracle, small_panel):
+    from conftest import to_oracle_samples
+    S = to_oracle_samples(oracle, small_panel)
+    r = oracle.build_graph(S, k=10, k_self=5, space="PCA", ncomps=20, n_odgenes=300)
+    g = r["graph"]
+    assert (g["from"] < g["to"]).all()
+    key = g["from"].astype(np.int64) * len(g["vertices"]) + g["to"]
+    assert (np.diff(key) > 0).all()                       # sorted, unique
+    assert (g["weight"] > 0).all()
+    offs = np.cumsum([0] + [s.counts.shape[0] for s in S.values()])
+    sample_of = np.searchsorted(offs, g["vertices"], side="right") - 1
+    inter = sample_of[g["from"]] != sample_of[g["to"]]
+    assert np.array_equal(inter, g["type"] == 1)
+    assert g["weight"][inter].max() <= 1.0 + 1e-12 and g["weight"][~inter].max() <= 0.2 + 1e-12
+    a = oracle.adjacency_csr(g)
+    assert abs(a - a.T).max() == 0

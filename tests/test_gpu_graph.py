@@ -214,3 +214,43 @@ def test_spcov_and_cpca(ctx, oracle, small_panel):
     assert np.array_equal(got["niter"], want["niter"])
     np.testing.assert_allclose(got["CPC"], want["CPC"], rtol=1e-7, atol=1e-9)
     np.testing.assert_allclose(got["D"], want["D"], rtol=1e-9)
+
+
+def _principal_cosines(a, b):
+    qa, _ = np.linalg.qr(a)
+    qb, _ = np.linalg.qr(b)
+    return np.linalg.svd(qa.T @ qb, compute_uv=False)
+
+
+@pytest.mark.parametrize("ncomps,score", [(20, True), (30, False)])
+def test_device_pca_rotation(ctx, oracle, small_panel, ncomps, score):
+    """quickPlainPCA on the device: per-sample subspaces equal the exact ones (irlba itself is only 1e-5 accurate),
+    columns interleaved A1,B1,A2,..., nv = variance fractions; the downstream graph matches the oracle's."""
+    import conos_b200
+    osamples = to_oracle_samples(oracle, small_panel)
+    ref = oracle.build_graph(osamples, k=10, k_self=5, space="PCA", ncomps=ncomps, n_odgenes=300,
+                             score_component_variance=score)
+    con = conos_b200.Conos(small_panel, ctx=ctx)
+    g = con.buildGraph(k=10, k_self=5, space="PCA", ncomps=ncomps, n_odgenes=300, score_component_variance=score)
+    r = ncomps // 2
+    for key, red in ref["pairs"].items():
+        mine = con.pairs["PCA"][key]
+        assert mine["genes"] == red["genes"]
+        assert mine["CPC"].shape == red["CPC"].shape
+        for side in (0, 1):
+            cs = _principal_cosines(mine["CPC"][:, side::2], red["CPC"][:, side::2])
+            assert cs.min() > 1 - 1e-10, (key, side, cs.min())
+            # individual eigenvectors (up to sign): well separated spectrum in this panel
+            dots = np.abs(np.sum(mine["CPC"][:, side::2] * red["CPC"][:, side::2], axis=0))
+            assert dots.min() > 1 - 1e-8
+        if score:
+            for side in (0, 1):
+                np.testing.assert_allclose(mine["nv"][side], red["nv"][side], rtol=1e-8)
+    og = ref["graph"]
+    # the rotations agree to ~1e-9, so at most a handful of near-tied neighbours may differ
+    mine_e = set(zip(g.vertices[g.edge_from].tolist(), g.vertices[g.edge_to].tolist()))
+    ref_e = set(zip(og["vertices"][og["from"]].tolist(), og["vertices"][og["to"]].tolist()))
+    mine_e = {(min(a, b), max(a, b)) for a, b in mine_e}
+    ref_e = {(min(a, b), max(a, b)) for a, b in ref_e}
+    jacc = len(mine_e & ref_e) / len(mine_e | ref_e)
+    assert jacc > 0.999, jacc
