@@ -74,6 +74,8 @@ SIGNATURES = {
     "cg_edges_fetch": (C.c_int, [_VP, _VP, c_int_p, c_int_p, c_dbl_p, c_int_p]),
     "cg_edges_append_host": (C.c_int, [_VP, C.POINTER(_VP), c_int_p, c_int_p, c_dbl_p, c_int_p, C.c_int64]),
     "cg_edges_append_device": (C.c_int, [_VP, C.POINTER(_VP), _VP, _VP, _VP, _VP, C.c_int64]),
+    "cg_profile": (C.c_int, [_VP, C.c_int]),
+    "cg_profile_dump": (C.c_int, [_VP, C.c_char_p, C.c_int]),
     "cg_timer_start": (C.c_int, [_VP]),
     "cg_timer_stop": (C.c_int, [_VP, c_dbl_p]),
     "cg_edges_device_ptrs": (C.c_int, [_VP, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP)]),

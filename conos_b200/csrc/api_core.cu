@@ -49,6 +49,13 @@ int cg_init(int device, cg_context** out) {
   ctx->c.device = device;
   ctx->c.sm_count = prop.multiProcessorCount;
   CG_CUDA(cudaStreamCreateWithFlags(&ctx->c.stream, cudaStreamNonBlocking));
+  {
+    // keep freed blocks cached in the device's default pool (stream-ordered DevBuf allocations)
+    cudaMemPool_t pool;
+    CG_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = UINT64_MAX;
+    CG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  }
   *out = ctx;
   CG_API_END(ctx)
 }
@@ -88,6 +95,24 @@ int cg_timer_stop(cg_context* ctx, double* ms) {
   CG_CUDA(cudaEventElapsedTime(&f, ctx->ev0, ctx->ev1));
   *ms = f;
   CG_API_END(ctx)
+}
+
+int cg_profile(cg_context* ctx, int enable) {
+  if (!ctx) return 1;
+  ctx->c.profile = enable != 0;
+  ctx->c.stage_ms.clear();
+  return 0;
+}
+int cg_profile_dump(cg_context* ctx, char* buf, int buf_len) {
+  if (!ctx || !buf || buf_len <= 0) return 1;
+  std::string s;
+  for (auto& kv : ctx->c.stage_ms) {
+    char t[128];
+    snprintf(t, sizeof(t), "%s=%.3f;", kv.first.c_str(), kv.second);
+    s += t;
+  }
+  snprintf(buf, (size_t)buf_len, "%s", s.c_str());
+  return 0;
 }
 
 int cg_knn_timing(cg_context* ctx, int enable) {
@@ -174,6 +199,7 @@ int cg_cross_knn(cg_context* ctx, const double* A, int nA, int lda, const double
   CG_CHECK(nA > 0 && nB > 0, "empty matrix");
   Context& c = ctx->c;
   CG_CUDA(cudaSetDevice(c.device));
+  CG_BIND(ctx);
   HostPanel pa, pb;
   upload_panel(c, A, nA, lda, d, (Metric)metric, pa);
   upload_panel(c, B, nB, ldb, d, (Metric)metric, pb);
@@ -212,6 +238,7 @@ int cg_self_knn(cg_context* ctx, const double* Z, int n, int ldz, int d, int k, 
   CG_CHECK(k >= 1 && n > 0, "bad arguments");
   Context& c = ctx->c;
   CG_CUDA(cudaSetDevice(c.device));
+  CG_BIND(ctx);
   HostPanel pz;
   upload_panel(c, Z, n, ldz, d, (Metric)metric, pz);
   DevBuf<int> di((size_t)n * k);
@@ -238,6 +265,7 @@ int cg_neighbor_matrix(cg_context* ctx, const double* p1, int n1, int ld1, const
   CG_CHECK(n1 > 0 && n2 > 0, "empty matrix");
   Context& c = ctx->c;
   CG_CUDA(cudaSetDevice(c.device));
+  CG_BIND(ctx);
   HostPanel pa, pb;
   upload_panel(c, p1, n1, ld1, d, (Metric)metric, pa);
   upload_panel(c, p2, n2, ld2, d, (Metric)metric, pb);
@@ -258,6 +286,7 @@ int cg_neighbor_matrix(cg_context* ctx, const double* p1, int n1, int ld1, const
 
 int cg_fetch_coo(cg_context* ctx, int32_t* i, int32_t* j, double* x) {
   CG_API_BEGIN
+  CG_BIND(ctx);
   CG_CHECK(ctx, "NULL context");
   Context& c = ctx->c;
   const size_t n = ctx->coo.n;
@@ -275,6 +304,7 @@ int64_t cg_edges_count(const cg_edges* e) { return e ? (int64_t)e->t.n : 0; }
 
 int cg_edges_fetch(cg_context* ctx, const cg_edges* e, int32_t* from, int32_t* to, double* w, int32_t* type) {
   CG_API_BEGIN
+  CG_BIND(ctx);
   CG_CHECK(ctx && e, "NULL argument");
   const size_t n = e->t.n;
   if (n) {
@@ -289,6 +319,7 @@ int cg_edges_fetch(cg_context* ctx, const cg_edges* e, int32_t* from, int32_t* t
 
 int cg_edges_reserve(cg_context* ctx, cg_edges** e, int64_t n_total) {
   CG_API_BEGIN
+  CG_BIND(ctx);
   CG_CHECK(ctx && e && n_total >= 0, "bad argument");
   if (!*e) *e = new cg_edges();
   (*e)->t.reserve((size_t)n_total, ctx->c.stream);
@@ -304,6 +335,7 @@ int cg_edges_set_count(cg_edges* e, int64_t n) {
 int cg_edges_append_host(cg_context* ctx, cg_edges** e, const int32_t* from, const int32_t* to, const double* w,
                          const int32_t* type, int64_t n) {
   CG_API_BEGIN
+  CG_BIND(ctx);
   CG_CHECK(ctx && e && n >= 0, "bad argument");
   if (!*e) *e = new cg_edges();
   EdgeTable& t = (*e)->t;
@@ -323,6 +355,7 @@ int cg_edges_append_host(cg_context* ctx, cg_edges** e, const int32_t* from, con
 int cg_edges_append_device(cg_context* ctx, cg_edges** e, const void* from, const void* to, const void* w,
                            const void* type, int64_t n) {
   CG_API_BEGIN
+  CG_BIND(ctx);
   CG_CHECK(ctx && e && n >= 0, "bad argument");
   if (!*e) *e = new cg_edges();
   EdgeTable& t = (*e)->t;
@@ -356,8 +389,12 @@ int cg_assemble_graph(cg_context* ctx, const cg_edges* e, int32_t n_cells_total,
   try {
     CG_CHECK(ctx && e && out, "NULL argument");
     CG_CUDA(cudaSetDevice(ctx->c.device));
+  CG_BIND(ctx);
     g = new cg_graph();
-    assemble_graph(ctx->c, e->t, n_cells_total, g->g);
+    {
+      StageScope sc(ctx->c, "assemble_graph");
+      assemble_graph(ctx->c, e->t, n_cells_total, g->g);
+    }
     *out = g;
     return 0;
   } catch (const std::exception& ex) {
@@ -376,6 +413,7 @@ int cg_graph_sizes(const cg_graph* g, int32_t* n_vertices, int64_t* n_edges) {
 int cg_graph_fetch(cg_context* ctx, const cg_graph* g, int32_t* vertices, int32_t* from, int32_t* to, double* weight,
                    int32_t* type) {
   CG_API_BEGIN
+  CG_BIND(ctx);
   CG_CHECK(ctx && g, "NULL argument");
   cudaStream_t s = ctx->c.stream;
   const size_t nv = (size_t)g->g.n_vertices, ne = (size_t)g->g.n_edges;
@@ -392,6 +430,7 @@ int cg_graph_fetch(cg_context* ctx, const cg_graph* g, int32_t* vertices, int32_
 
 int cg_graph_fetch_adjacency(cg_context* ctx, const cg_graph* g, int64_t* p, int32_t* i, double* x) {
   CG_API_BEGIN
+  CG_BIND(ctx);
   CG_CHECK(ctx && g, "NULL argument");
   cudaStream_t s = ctx->c.stream;
   const size_t nv = (size_t)g->g.n_vertices, ne2 = (size_t)(2 * g->g.n_edges);

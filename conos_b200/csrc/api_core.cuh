@@ -43,6 +43,7 @@ int fail(cg_context* ctx, const std::exception& e);
 int fail(cg_context* ctx, const char* msg);
 
 #define CG_API_BEGIN try {
+#define CG_BIND(ctxptr) ::cg::StreamBinding _cg_binding((ctxptr) ? (ctxptr)->c.stream : nullptr)
 #define CG_API_END(ctxptr)                                    \
   return 0;                                                   \
   }                                                           \

@@ -46,10 +46,12 @@ int cg_panel_create(cg_context* ctx, const cg_sample* samples, int n_samples, cg
   try {
     CG_CHECK(ctx && samples && out && n_samples > 0, "bad argument");
     CG_CUDA(cudaSetDevice(ctx->c.device));
+  CG_BIND(ctx);
     pn = new cg_panel();
     pn->ctx = ctx;
     pn->samples.resize(n_samples);
     pn->offsets.assign(n_samples + 1, 0);
+    StageScope sc(ctx->c, "panel_upload");
     for (int s = 0; s < n_samples; ++s) {
       const cg_sample& h = samples[s];
       CG_CHECK(h.p && h.i && h.x, "sample counts matrix missing");
@@ -95,6 +97,7 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
   CG_CHECK(P.ncomps >= 1 && P.ncomps <= 64, "ncomps must be in 1..64");
   Context& c = ctx->c;
   CG_CUDA(cudaSetDevice(c.device));
+  CG_BIND(ctx);
   if (!*edges) *edges = new cg_edges();
   EdgeTable& out = (*edges)->t;
   ctx->kept.clear();
@@ -129,7 +132,11 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
 
     // ---- reductions (rotation per pair, column-major G x d_eff doubles on the device)
     std::vector<PairReduction> red(nb_pairs);
-    compute_pair_reductions(c, *panel, pairs + p0, nb_pairs, P, red);
+    {
+      StageScope sc(c, "reduction");
+      compute_pair_reductions(c, *panel, pairs + p0, nb_pairs, P, red);
+    }
+    StageScope* sc_setup = new StageScope(c, "pair_setup");
 
     // ---- projection operands
     struct PairBuf {
@@ -238,7 +245,9 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
                                   P.space == CG_SPACE_CCA ? B.rows_u.p : nullptr,
                                   P.space == CG_SPACE_CCA ? B.rows_v.p : nullptr, B.na, B.nb, sa.offset, sb.offset});
     }
+    delete sc_setup;
     if (!wprobs.empty()) {
+      StageScope sc(c, "projection");
       build_projection_operands(c, wprobs.data(), (int)wprobs.size(), d_all, d_pad_all);
       project_and_prep(c, pprobs.data(), (int)pprobs.size(), d_all, d_pad_all, metric);
       if (ctx->keep_projections) {
@@ -258,6 +267,7 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
     CG_CUDA(cudaStreamSynchronize(c.stream));
     // ---- exact kNN, both directions of every pair in one launch
     {
+      StageScope sc(c, "cross_knn");
       DevBuf<KnnProblem> dk;
       dk.upload(kprobs.data(), kprobs.size(), c.stream);
       knn_launch(c, dk.p, kprobs.data(), (int)kprobs.size(), P.k1, d_pad_all, metric);
@@ -265,7 +275,11 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
     }
     // ---- matching -> edges
     std::vector<long long> counts(nb_pairs, 0);
-    match_append_edges(c, mprobs.data(), nb_pairs, P.k, P.k1, sp, out, counts.data());
+    {
+      StageScope sc(c, "matching");
+      match_append_edges(c, mprobs.data(), nb_pairs, P.k, P.k1, sp, out, counts.data());
+    }
+    StageScope sc_free(c, "pair_free");
     if (pair_edge_counts)
       for (int q = 0; q < nb_pairs; ++q) pair_edge_counts[p0 + q] = counts[q];
     p0 = p1;
@@ -304,6 +318,7 @@ int cg_local_edges(cg_context* ctx, cg_panel* panel, const int32_t* samples, int
            "only the following distance metrics are currently supported: ['L2' 'angular']");
   Context& c = ctx->c;
   CG_CUDA(cudaSetDevice(c.device));
+  CG_BIND(ctx);
   if (!*edges) *edges = new cg_edges();
   if (P.k_self <= 0) return 0;
   const int kp1 = P.k_self + 1;  // +1 accounts for the self edge removed afterwards (R/conos.R:595)
@@ -331,11 +346,13 @@ int cg_local_edges(cg_context* ctx, cg_panel* panel, const int32_t* samples, int
     kprobs.push_back(KnnProblem{s.pca_tiled.p, s.pca_tiled.p, s.n_cells, s.n_cells, idx[t].p, dist[t].p});
   }
   if (!kprobs.empty()) {
+    StageScope sc(c, "self_knn");
     DevBuf<KnnProblem> dk;
     dk.upload(kprobs.data(), kprobs.size(), c.stream);
     knn_launch(c, dk.p, kprobs.data(), (int)kprobs.size(), kp1, d_pad, (Metric)P.metric);
     CG_CUDA(cudaStreamSynchronize(c.stream));
   }
+  StageScope sc_le(c, "local_edges");
   for (int t = 0; t < n; ++t) {
     Sample& s = panel->samples[samples[t]];
     local_append_edges(c, idx[t].p, dist[t].p, s.n_cells, kp1, s.offset, P.metric, P.l2_sigma, P.k_self_weight,

@@ -12,6 +12,7 @@ int cg_spcov(cg_context* ctx, int n, int G, const int32_t* p, const int32_t* i, 
   CG_API_BEGIN
   CG_CHECK(ctx && p && i && x && cm && out && n > 1 && G > 0, "bad argument");
   CG_CUDA(cudaSetDevice(ctx->c.device));
+  CG_BIND(ctx);
   spcov_host(ctx->c, n, G, p, i, x, cm, out);
   CG_API_END(ctx)
 }
@@ -21,6 +22,7 @@ int cg_cpca(cg_context* ctx, const double* cov, int p, int k, const double* ng, 
   CG_API_BEGIN
   CG_CHECK(ctx && cov && ng && eigv && D && CPC && niter && p > 0 && k > 0 && ncomp > 0 && ncomp <= p, "bad argument");
   CG_CUDA(cudaSetDevice(ctx->c.device));
+  CG_BIND(ctx);
   cpca_host(ctx->c, cov, p, k, ng, ncomp, maxit, tol, eigv, D, CPC, niter);
   CG_API_END(ctx)
 }
@@ -30,6 +32,7 @@ int cg_pare_down_hub_edges(cg_context* ctx, int ncols, const int32_t* p, const i
   CG_API_BEGIN
   CG_CHECK(ctx && p && i && x && rowN && ncols >= 0, "bad argument");
   CG_CUDA(cudaSetDevice(ctx->c.device));
+  CG_BIND(ctx);
   Context& c = ctx->c;
   const size_t nnz = (size_t)p[ncols];
   int nrow = 0;
@@ -53,6 +56,7 @@ int cg_sum_weight_matrix(cg_context* ctx, const double* weights, const int32_t* 
   CG_API_BEGIN
   CG_CHECK(ctx && weights && row_inds && col_inds && factor_levels && m && n_cells > 0 && n_levels > 0, "bad argument");
   CG_CUDA(cudaSetDevice(ctx->c.device));
+  CG_BIND(ctx);
   sum_weight_matrix_host(ctx->c, weights, row_inds, col_inds, n_edges, factor_levels, n_cells, n_levels, normalize, m);
   CG_API_END(ctx)
 }
@@ -64,6 +68,7 @@ int cg_adjust_weights(cg_context* ctx, double* weights, const int32_t* row_inds,
   CG_CHECK(ctx && weights && row_inds && col_inds && factor_levels && dividers && n_cells > 0 && n_levels > 0,
            "bad argument");
   CG_CUDA(cudaSetDevice(ctx->c.device));
+  CG_BIND(ctx);
   adjust_weights_host(ctx->c, weights, row_inds, col_inds, n_edges, factor_levels, n_cells, n_levels, dividers);
   CG_API_END(ctx)
 }
@@ -73,6 +78,7 @@ int cg_reference_wij(cg_context* ctx, const int32_t* from, const int32_t* to, co
   CG_API_BEGIN
   CG_CHECK(ctx && from && to && d && out_from && out_to && out_w && n_out && n_edges >= 0, "bad argument");
   CG_CUDA(cudaSetDevice(ctx->c.device));
+  CG_BIND(ctx);
   long long no = 0;
   reference_wij_host(ctx->c, from, to, d, n_edges, perplexity, out_from, out_to, out_w, &no);
   *n_out = (int64_t)no;

@@ -8,6 +8,8 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <chrono>
+#include <map>
 #include <vector>
 
 namespace cg {
@@ -32,28 +34,47 @@ struct Error : std::runtime_error {
     if (!(cond)) throw ::cg::Error(std::string("conosgpu: ") + (msg)); \
   } while (0)
 
+// Stream-ordered allocation: every C-ABI entry point binds the context's stream for the calling thread, and
+// DevBuf then allocates from / frees to the device's caching memory pool in stream order (no device-wide
+// synchronisation, no cudaMalloc/cudaFree latency inside buildGraph).  Without a bound stream (the stand-alone
+// probes) it falls back to cudaMalloc / cudaFree.
+inline cudaStream_t& bound_stream() {
+  static thread_local cudaStream_t s = nullptr;
+  return s;
+}
+struct StreamBinding {
+  cudaStream_t prev;
+  explicit StreamBinding(cudaStream_t s) : prev(bound_stream()) { bound_stream() = s; }
+  ~StreamBinding() { bound_stream() = prev; }
+};
+
 template <class T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
+  cudaStream_t owner = nullptr;  // stream the block was allocated on (nullptr: cudaMalloc)
   DevBuf() = default;
   explicit DevBuf(size_t count) { alloc(count); }
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
-  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), owner(o.owner) { o.p = nullptr; o.n = 0; }
   DevBuf& operator=(DevBuf&& o) noexcept {
-    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    if (this != &o) { release(); p = o.p; n = o.n; owner = o.owner; o.p = nullptr; o.n = 0; }
     return *this;
   }
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+      if (owner) cudaFreeAsync(p, owner); else cudaFree(p);
+    }
     p = nullptr; n = 0;
   }
   void alloc(size_t count) {
     release();
     if (count == 0) return;
-    CG_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    owner = bound_stream();
+    if (owner) CG_CUDA(cudaMallocAsync(&p, count * sizeof(T), owner));
+    else CG_CUDA(cudaMalloc(&p, count * sizeof(T)));
     n = count;
   }
   // grow-only (keeps capacity between calls; contents are NOT preserved)
@@ -89,6 +110,27 @@ struct Context {
   uint64_t knn_launches = 0;
   double knn_candidates = 0.0;  // sum over launches of n_query * n_ref
   double knn_bytes = 0.0;       // algorithmic HBM bytes
+  // optional per-stage wall-clock profile (stream synchronised at both ends of a stage)
+  bool profile = false;
+  std::map<std::string, double> stage_ms;
+};
+
+struct StageScope {
+  Context& c;
+  const char* name;
+  std::chrono::steady_clock::time_point t0;
+  StageScope(Context& ctx, const char* n) : c(ctx), name(n) {
+    if (c.profile) {
+      cudaStreamSynchronize(c.stream);
+      t0 = std::chrono::steady_clock::now();
+    }
+  }
+  ~StageScope() {
+    if (c.profile) {
+      cudaStreamSynchronize(c.stream);
+      c.stage_ms[name] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+  }
 };
 
 inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }

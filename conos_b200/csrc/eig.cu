@@ -380,11 +380,19 @@ void run_eig(Context& ctx, const EigProblem* h_probs, int n_probs, int r, double
   ctx.stats.kernels += 2;
   std::vector<int> hc(n_probs);
   const int rr_every = 4;
+  int it_done = 0;
   for (int it = 1; it <= max_iter; ++it) {
-    eig_matmul_kernel<B><<<gm, 256, 0, s>>>(dw.p);
+    it_done = it;
+    {
+      StageScope sc(ctx, "reduction.eig.matmul");
+      eig_matmul_kernel<B><<<gm, 256, 0, s>>>(dw.p);
+    }
     ctx.stats.kernels++;
     if (it % rr_every == 0) {
-      eig_rr_kernel<B><<<n_probs, EIG_THREADS, smem, s>>>(dw.p, r, tol, 0);
+      {
+        StageScope sc(ctx, "reduction.eig.rr");
+        eig_rr_kernel<B><<<n_probs, EIG_THREADS, smem, s>>>(dw.p, r, tol, 0);
+      }
       ctx.stats.kernels++;
       conv.download(hc.data(), (size_t)n_probs, s);
       CG_CUDA(cudaStreamSynchronize(s));
@@ -392,8 +400,18 @@ void run_eig(Context& ctx, const EigProblem* h_probs, int n_probs, int r, double
       for (int p = 0; p < n_probs; ++p) all = all && hc[p] != 0;
       if (all) break;
     }
-    eig_orth_kernel<B><<<n_probs, EIG_THREADS, smem, s>>>(dw.p);
+    {
+      StageScope sc(ctx, "reduction.eig.orth");
+      eig_orth_kernel<B><<<n_probs, EIG_THREADS, smem, s>>>(dw.p);
+    }
     ctx.stats.kernels++;
+  }
+  if (ctx.profile) {
+    ctx.stage_ms["reduction.eig.iterations"] += it_done;
+    int nconv = 0;
+    for (int p = 0; p < n_probs; ++p) nconv += hc[p] != 0;
+    ctx.stage_ms["reduction.eig.converged_problems"] += nconv;
+    ctx.stage_ms["reduction.eig.problems"] += n_probs;
   }
   // final Rayleigh-Ritz from an orthonormal basis
   eig_orth_kernel<B><<<n_probs, EIG_THREADS, smem, s>>>(dw.p);

@@ -105,9 +105,12 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
   CG_CHECK(P.space != CG_SPACE_CCA, "device CCA is not built yet: supply u and v");
 
   // ---- per-sample Gram matrices
-  for (int q : todo) {
-    ensure_gram(ctx, panel.samples[pairs[q].a]);
-    ensure_gram(ctx, panel.samples[pairs[q].b]);
+  {
+    StageScope sc(ctx, "reduction.gram");
+    for (int q : todo) {
+      ensure_gram(ctx, panel.samples[pairs[q].a]);
+      ensure_gram(ctx, panel.samples[pairs[q].b]);
+    }
   }
 
   if (P.space == CG_SPACE_PCA) {
@@ -183,7 +186,10 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
         }
       }
       CG_CUDA(cudaGetLastError());
-      top_eigenvectors_batched(ctx, eprobs.data(), (int)eprobs.size(), r, 1e-10, 400);
+      {
+        StageScope sc(ctx, "reduction.eig");
+        top_eigenvectors_batched(ctx, eprobs.data(), (int)eprobs.size(), r, 1e-10, 400);
+      }
       for (int t = 0; t < nq; ++t) {
         Buf& b = bufs[t];
         PairReduction& R = out[todo[i0 + t]];

@@ -52,6 +52,9 @@ uint64_t cg_kernel_launches(const cg_context* ctx);
 /* CUDA events on the context's stream: start, then stop returns the elapsed device time in ms */
 int cg_timer_start(cg_context* ctx);
 int cg_timer_stop(cg_context* ctx, double* ms);
+/* optional per-stage wall-clock profile: enable (resets), then dump "name=ms;name=ms;..." into buf */
+int cg_profile(cg_context* ctx, int enable);
+int cg_profile_dump(cg_context* ctx, char* buf, int buf_len);
 /* optional CUDA-event timing of the dominant kernel (fused cross-kNN): enable, then read and reset */
 int cg_knn_timing(cg_context* ctx, int enable);
 int cg_knn_timing_read(cg_context* ctx, double* ms, uint64_t* launches, double* candidates, double* bytes);

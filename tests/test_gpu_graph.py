@@ -254,3 +254,42 @@ def test_device_pca_rotation(ctx, oracle, small_panel, ncomps, score):
     ref_e = {(min(a, b), max(a, b)) for a, b in ref_e}
     jacc = len(mine_e & ref_e) / len(mine_e | ref_e)
     assert jacc > 0.999, jacc
+
+
+@pytest.mark.parametrize("matching,k,k1", [("NN", 10, 10), ("mNN", 40, 40), ("mNN", 8, 60), ("NN", 6, 25), ("mNN", 15, 200)])
+def test_neighbor_matrix_general_paths(ctx, oracle, matching, k, k1):
+    """matching='NN', k > 32, and k1 > k (reduceEdgesInGraphIteratively + pareDownHubEdges) against the oracle."""
+    from conos_b200 import ops
+    rng = np.random.default_rng(k * 100 + k1)
+    p1, p2 = mixture(rng, 500, 20, k=5), mixture(rng, 380, 20, k=5)
+    i, j, x = ops.getNeighborMatrix(p1, p2, k, k1=k1, matching=matching, ctx=ctx)
+    oi, oj, ox = oracle.neighbor_matrix(p1, p2, k, k1=k1, matching=matching)
+    assert np.array_equal(i, oi) and np.array_equal(j, oj)
+    np.testing.assert_allclose(x, ox, rtol=1e-12)
+    if k1 > k:
+        # the greedy reduction is a heuristic: degrees end near k, well below the k1 it started from
+        assert max(np.bincount(i).max(), np.bincount(j).max()) <= 2 * k + 5
+
+
+def test_pare_down_hub_edges_entry_point(ctx, oracle):
+    from conos_b200 import ops
+    m = sp.random(300, 220, density=0.15, random_state=7, format="csc")
+    m.sort_indices()
+    for k, klow in [(5, -1), (8, 3), (40, 2)]:
+        rn_o = np.bincount(m.indices, minlength=300).astype(np.int32)
+        rn_g = rn_o.copy()
+        want = oracle.pare_down_hub_edges(m, rn_o, k, klow)
+        got = ops.pareDownHubEdges(m, rn_g, k, klow, ctx=ctx)
+        assert np.array_equal(got, want) and np.array_equal(rn_g, rn_o)
+
+
+def test_build_graph_alignment_strength(ctx, oracle, small_panel):
+    """alignment.strength > 0: k1 = max(k, round(max_cells * a^2)), cor.base = 1 + min(1, 10a), hub paring."""
+    import conos_b200
+    osamples = to_oracle_samples(oracle, small_panel)
+    ref = oracle.build_graph(osamples, k=10, k_self=5, space="PCA", ncomps=20, n_odgenes=300, alignment_strength=0.3)
+    assert ref["k1"] == 38 and ref["cor_base"] == 2.0
+    con = conos_b200.Conos(small_panel, ctx=ctx)
+    con.pairs["PCA"] = {key: {"CPC": red["CPC"], "genes": red["genes"]} for key, red in ref["pairs"].items()}
+    g = con.buildGraph(k=10, k_self=5, space="PCA", ncomps=20, n_odgenes=300, alignment_strength=0.3)
+    _graphs_equal(g, ref["graph"], rtol=1e-6)
