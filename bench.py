@@ -205,7 +205,9 @@ def main():
         torch.cuda.synchronize()
 
     def device_step():
-        con.pairs = {}
+        con.pairs = {}                                   # no cached reductions (updatePairs recomputes every pair)
+        if con._panel is not None:
+            lib.cg_panel_drop_cache(con._panel)          # nor cached Gram matrices / PCA panels: inputs only
         return con.buildGraph(fetch=False, world=wtuple, **kw)
 
     def e2e_step():

@@ -64,6 +64,7 @@ SIGNATURES = {
     "cg_panel_create": (C.c_int, [_VP, C.POINTER(CgSample), C.c_int, C.POINTER(_VP)]),
     "cg_panel_free": (None, [_VP]),
     "cg_panel_offsets": (C.c_int, [_VP, c_int_p]),
+    "cg_panel_drop_cache": (C.c_int, [_VP]),
     "cg_params_default": (None, [C.POINTER(CgParams)]),
     "cg_pairs_edges": (C.c_int, [_VP, _VP, C.POINTER(CgPair), C.c_int, C.POINTER(CgParams), C.POINTER(_VP), c_i64_p]),
     "cg_pair_reduction": (C.c_int, [_VP, C.c_int, c_int_p, c_int_p, c_dbl_p, c_dbl_p]),
@@ -74,6 +75,7 @@ SIGNATURES = {
     "cg_edges_fetch": (C.c_int, [_VP, _VP, c_int_p, c_int_p, c_dbl_p, c_int_p]),
     "cg_edges_append_host": (C.c_int, [_VP, C.POINTER(_VP), c_int_p, c_int_p, c_dbl_p, c_int_p, C.c_int64]),
     "cg_edges_append_device": (C.c_int, [_VP, C.POINTER(_VP), _VP, _VP, _VP, _VP, C.c_int64]),
+    "cg_set_option": (C.c_int, [_VP, C.c_char_p, C.c_double]),
     "cg_profile": (C.c_int, [_VP, C.c_int]),
     "cg_profile_dump": (C.c_int, [_VP, C.c_char_p, C.c_int]),
     "cg_timer_start": (C.c_int, [_VP]),

@@ -97,6 +97,15 @@ int cg_timer_stop(cg_context* ctx, double* ms) {
   CG_API_END(ctx)
 }
 
+int cg_set_option(cg_context* ctx, const char* name, double value) {
+  if (!ctx || !name) return 1;
+  if (strcmp(name, "exact_reduction") == 0) {
+    ctx->c.exact_reduction = value != 0.0;
+    return 0;
+  }
+  return ::cg::fail(ctx, "unknown option");
+}
+
 int cg_profile(cg_context* ctx, int enable) {
   if (!ctx) return 1;
   ctx->c.profile = enable != 0;

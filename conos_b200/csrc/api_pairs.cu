@@ -76,6 +76,18 @@ int cg_panel_offsets(const cg_panel* panel, int32_t* offsets) {
   return 0;
 }
 
+int cg_panel_drop_cache(cg_panel* panel) {
+  if (!panel) return 1;
+  ::cg::StreamBinding bind(panel->ctx ? panel->ctx->c.stream : nullptr);
+  for (auto& s : panel->samples) {
+    s.gram.release();
+    s.h_gram_diag.clear();
+    s.pca_tiled.release();
+    s.pca_metric = -1;
+  }
+  return 0;
+}
+
 int cg_keep_projections(cg_context* ctx, int enable) {
   if (!ctx) return 1;
   ctx->keep_projections = enable != 0;

@@ -110,6 +110,8 @@ struct Context {
   uint64_t knn_launches = 0;
   double knn_candidates = 0.0;  // sum over launches of n_query * n_ref
   double knn_bytes = 0.0;       // algorithmic HBM bytes
+  // 1: FP64 reductions (atomics Gram, explicit covariance, plain subspace iteration) instead of the tensor-core path
+  bool exact_reduction = false;
   // optional per-stage wall-clock profile (stream synchronised at both ends of a stage)
   bool profile = false;
   std::map<std::string, double> stage_ms;

@@ -1,4 +1,5 @@
 #include "eig.cuh"
+#include "gemm_tc.cuh"
 
 namespace cg {
 namespace {
@@ -13,7 +14,8 @@ struct EigWork {
   double* theta;   // [B] current Ritz values
   double* V;       // out
   double* theta_out;
-  int* converged;  // 1 when the top-r Ritz values stagnated
+  int* converged;  // 1 when the leading r residuals are below tol * theta_1
+  double* resid;   // optional: worst relative residual of the leading r pairs
 };
 
 __device__ __forceinline__ double hash_unit(unsigned a, unsigned b) {
@@ -337,6 +339,7 @@ __global__ void __launch_bounds__(EIG_THREADS) eig_rr_kernel(const EigWork* __re
     for (int j = 0; j < r; ++j) worst = fmax(worst, sqrt(sm.cs[j]));
     const double scale = fmax(fabs(sm.ev[0]), 1e-300);
     *w.converged = finalize ? 2 : ((worst <= tol * scale) ? 1 : 0);
+    if (w.resid && !finalize) *w.resid = worst / scale;
   }
   if (finalize) {
     for (size_t t = tid; t < (size_t)w.G * r; t += EIG_THREADS) {
@@ -365,7 +368,7 @@ void run_eig(Context& ctx, const EigProblem* h_probs, int n_probs, int r, double
   size_t o = 0;
   for (int p = 0; p < n_probs; ++p) {
     works[p] = EigWork{h_probs[p].C, h_probs[p].G, Q.p + o, Z.p + o, theta.p + (size_t)p * B, h_probs[p].V,
-                       h_probs[p].theta, conv.p + p};
+                       h_probs[p].theta, conv.p + p, nullptr};
     o += (size_t)h_probs[p].G * B;
   }
   DevBuf<EigWork> dw;
@@ -422,6 +425,154 @@ void run_eig(Context& ctx, const EigProblem* h_probs, int n_probs, int r, double
   CG_CUDA(cudaStreamSynchronize(s));
 }
 
+
+// =================================================================== tensor-core path (shared Gram operator)
+constexpr int TB = 32;  // block width of the tensor-core path
+
+struct TcSampleDev {
+  const double* colsum;
+  int G, n_cells;
+  int n_cols;          // 32 * problems of this sample
+  float* X;            // column-major G x n_cols panels
+  float* Y;
+  float* V;
+  __nv_bfloat16* Uh;   // B operand (rows = columns of the panel, k = genes), pre-zeroed padding
+  __nv_bfloat16* Ul;
+  int u_rows_pad;
+  double* t;           // [n_cols]  m' D y per column
+  int first_prob;
+};
+struct TcProbDev {
+  int sample, col0;
+  const double* f;
+  double* Q;  // [G][32] row-major
+  double* Z;
+  double* theta;
+  int* converged;
+};
+
+// Mc = M - n m m'  (FP64; the centring is done before the bf16 split so that no cancellation happens in low precision)
+__global__ void tc_center_gram_kernel(const double* __restrict__ M, const double* __restrict__ colsum, int G, double n,
+                                      double* __restrict__ Mc) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)G * G) return;
+  const int i = (int)(t % G), j = (int)(t / G);
+  Mc[t] = M[t] - (colsum[i] / n) * (colsum[j] / n) * n;
+}
+
+__global__ void tc_init_kernel(const TcSampleDev* __restrict__ S) {
+  const TcSampleDev sd = S[blockIdx.y];
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < (size_t)sd.G * sd.n_cols) sd.Y[t] = (float)hash_unit((unsigned)(t % sd.G), (unsigned)(t / sd.G) + 977u * blockIdx.y);
+}
+
+__global__ void tc_to64_kernel(const TcSampleDev* __restrict__ S, const TcProbDev* __restrict__ P) {
+  const TcProbDev pd = P[blockIdx.y];
+  const TcSampleDev sd = S[pd.sample];
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)sd.G * TB) return;
+  const int g = (int)(t / TB), j = (int)(t % TB);
+  pd.Z[t] = (double)sd.Y[(size_t)(pd.col0 + j) * sd.G + g];
+}
+
+__device__ __forceinline__ void store_u(const TcSampleDev& sd, int col, int g, float u) {
+  const size_t o = tiled_operand_offset(col, g, sd.u_rows_pad);
+  const __nv_bfloat16 h = __float2bfloat16_rn(u);
+  sd.Uh[o] = h;
+  sd.Ul[o] = __float2bfloat16_rn(u - __bfloat162float(h));
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+// mode 0: U = D Q (operand of the Rayleigh-Ritz product), t = m' U
+// mode 1: first Chebyshev step from the Ritz pairs  X = Q, Y = a1 (Z - c Q), then U, t from Y
+// mode 2: generic Chebyshev step  z = D (V - n m t) / (n-1); Ynew = al (z - c Y) - be X; X = Y; Y = Ynew; U, t
+// mode 3: Z (FP64 row-major) = D (V - n m t) / (n-1)                    (the Rayleigh-Ritz product itself)
+__global__ void __launch_bounds__(256) tc_column_kernel(const TcSampleDev* __restrict__ S, const TcProbDev* __restrict__ P,
+                                                        const int* __restrict__ col_sample,
+                                                        const int* __restrict__ col_local, int n_cols_total, int mode,
+                                                        const float* __restrict__ al, const float* __restrict__ be,
+                                                        const float* __restrict__ cc) {
+  const int lane = threadIdx.x & 31;
+  const int gc = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (gc >= n_cols_total) return;
+  const TcSampleDev sd = S[col_sample[gc]];
+  const int col = col_local[gc];
+  const int pidx = sd.first_prob + col / TB, j = col % TB;
+  const TcProbDev pd = P[pidx];
+  const int G = sd.G;
+  const double n = (double)sd.n_cells;
+  const double t_old = sd.t[col];
+  const float a = al ? al[pidx] : 0.f, b = be ? be[pidx] : 0.f, c = cc ? cc[pidx] : 0.f;
+  double tacc = 0.0;
+  for (int g = lane; g < G; g += 32) {
+    const double f = pd.f[g];
+    const double m = sd.colsum ? sd.colsum[g] / n : 0.0;
+    const size_t pc = (size_t)col * G + g;
+    if (mode == 0) {
+      const float u = (float)(f * pd.Q[(size_t)g * TB + j]);
+      store_u(sd, col, g, u);
+      tacc += m * (double)u;
+    } else if (mode == 1) {
+      const float q = (float)pd.Q[(size_t)g * TB + j];
+      const float z = (float)pd.Z[(size_t)g * TB + j];
+      const float y = a * (z - c * q);
+      sd.X[pc] = q;
+      sd.Y[pc] = y;
+      const float u = (float)(f * (double)y);
+      store_u(sd, col, g, u);
+      tacc += m * (double)u;
+    } else if (mode == 2) {
+      const float z = (float)(f * ((double)sd.V[pc] - n * m * t_old) / (n - 1.0));
+      const float x = sd.X[pc], y = sd.Y[pc];
+      const float yn = a * (z - c * y) - b * x;
+      sd.X[pc] = y;
+      sd.Y[pc] = yn;
+      const float u = (float)(f * (double)yn);
+      store_u(sd, col, g, u);
+      tacc += m * (double)u;
+    } else {
+      pd.Z[(size_t)g * TB + j] = f * ((double)sd.V[pc] - n * m * t_old) / (n - 1.0);
+    }
+  }
+  if (mode != 3) {
+    tacc = warp_sum_d(tacc);
+    if (lane == 0) sd.t[col] = tacc;
+  }
+}
+
+// Chebyshev coefficients of every step from the current Ritz values: unwanted interval [0, theta_{B-1}],
+// scaling at theta_0 (Zhou & Saad's scaled three-term recurrence)
+__global__ void tc_coeff_kernel(const TcProbDev* __restrict__ P, int n_probs, int degree, float* __restrict__ al,
+                                float* __restrict__ be, float* __restrict__ cc) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_probs) return;
+  const double a0 = P[p].theta[0];
+  double b = P[p].theta[TB - 1];
+  if (!(b > 1e-7 * a0)) b = 1e-7 * a0;
+  if (!(a0 > 0.0)) {  // degenerate (zero matrix): identity filter
+    for (int i = 1; i <= degree; ++i) { al[(size_t)i * n_probs + p] = 0.f; be[(size_t)i * n_probs + p] = 0.f; }
+    cc[p] = 0.f;
+    return;
+  }
+  const double e = b / 2.0, c = b / 2.0;
+  const double denom = a0 - c;
+  double sigma1 = e / denom, sigma = sigma1;
+  cc[p] = (float)c;
+  al[(size_t)1 * n_probs + p] = (float)(sigma1 / e);
+  be[(size_t)1 * n_probs + p] = 0.f;
+  for (int i = 2; i <= degree; ++i) {
+    const double s2 = 1.0 / (2.0 / sigma1 - sigma);
+    al[(size_t)i * n_probs + p] = (float)(2.0 * s2 / e);
+    be[(size_t)i * n_probs + p] = (float)(sigma * s2);
+    sigma = s2;
+  }
+}
+
 }  // namespace
 
 void top_eigenvectors_batched(Context& ctx, const EigProblem* h_probs, int n_probs, int r, double tol, int max_iter) {
@@ -429,6 +580,175 @@ void top_eigenvectors_batched(Context& ctx, const EigProblem* h_probs, int n_pro
   CG_CHECK(r >= 1 && r <= 56, "1..56 eigenvectors per problem");
   if (r <= 24) run_eig<32>(ctx, h_probs, n_probs, r, tol, max_iter);
   else run_eig<64>(ctx, h_probs, n_probs, r, tol, max_iter);
+}
+
+
+void top_eigenvectors_shared_gram(Context& ctx, const TcEigSample* samples, int n_samples,
+                                  const TcEigProblem* probs, int n_probs, int r, double tol, int max_outer,
+                                  int degree) {
+  if (n_probs == 0) return;
+  CG_CHECK(r >= 1 && r <= 24, "tensor-core eigen path: 1..24 eigenvectors per problem");
+  cudaStream_t s = ctx.stream;
+  constexpr int B = TB;
+  // problems grouped by sample (stable)
+  std::vector<std::vector<int>> by_sample(n_samples);
+  for (int p = 0; p < n_probs; ++p) {
+    CG_CHECK(probs[p].sample >= 0 && probs[p].sample < n_samples, "bad sample index");
+    by_sample[probs[p].sample].push_back(p);
+  }
+  std::vector<int> order;  // internal problem order
+  std::vector<TcSampleDev> hs(n_samples);
+  std::vector<TcProbDev> hp;
+  std::vector<int> col_sample, col_local;
+  size_t panel_elems = 0, u_elems = 0, qz_elems = 0, n_cols_total = 0;
+  for (int si = 0; si < n_samples; ++si) {
+    const int G = samples[si].G;
+    CG_CHECK(G >= B, "tensor-core eigen path needs at least 32 genes");
+    const int nc = B * (int)by_sample[si].size();
+    hs[si].colsum = nullptr;  // the operand is the centred Gram matrix: no rank-one correction left
+    hs[si].G = G;
+    hs[si].n_cells = samples[si].n_cells;
+    hs[si].n_cols = nc;
+    hs[si].u_rows_pad = (int)round_up(nc > 0 ? nc : 1, GEMM_ROW_PAD);
+    hs[si].first_prob = (int)order.size();
+    panel_elems += (size_t)G * nc;
+    u_elems += (size_t)hs[si].u_rows_pad * round_up(G, GEMM_K_PAD);
+    for (int t = 0; t < (int)by_sample[si].size(); ++t) {
+      order.push_back(by_sample[si][t]);
+      qz_elems += (size_t)G * B;
+    }
+    for (int c = 0; c < nc; ++c) { col_sample.push_back(si); col_local.push_back(c); }
+    n_cols_total += nc;
+  }
+  DevBuf<float> X(panel_elems), Y(panel_elems), V(panel_elems);
+  DevBuf<__nv_bfloat16> Uh(u_elems), Ul(u_elems);
+  DevBuf<double> tvec(n_cols_total), Q(qz_elems), Z(qz_elems), theta((size_t)n_probs * B);
+  DevBuf<int> conv((size_t)n_probs);
+  DevBuf<double> resid((size_t)n_probs);
+  resid.zero(s);
+  Uh.zero(s);
+  Ul.zero(s);
+  tvec.zero(s);
+  theta.zero(s);
+  conv.zero(s);
+  // per-sample Gram operands (bf16 hi / lo, tiled)
+  std::vector<DevBuf<__nv_bfloat16>> Mh(n_samples), Ml(n_samples);
+  std::vector<TiledOperand> Mop(n_samples);
+  {
+    size_t po = 0, uo = 0, qo = 0, co = 0;
+    int pi = 0;
+    for (int si = 0; si < n_samples; ++si) {
+      const int G = hs[si].G, nc = hs[si].n_cols;
+      hs[si].X = X.p + po; hs[si].Y = Y.p + po; hs[si].V = V.p + po;
+      hs[si].Uh = Uh.p + uo; hs[si].Ul = Ul.p + uo;
+      hs[si].t = tvec.p + co;
+      po += (size_t)G * nc;
+      uo += (size_t)hs[si].u_rows_pad * round_up(G, GEMM_K_PAD);
+      co += nc;
+      for (int t = 0; t < (int)by_sample[si].size(); ++t, ++pi) {
+        const TcEigProblem& ep = probs[order[pi]];
+        hp.push_back(TcProbDev{si, t * B, ep.f, Q.p + qo, Z.p + qo, theta.p + (size_t)pi * B, conv.p + pi});
+        qo += (size_t)G * B;
+      }
+      if (nc == 0) continue;
+      Mh[si].alloc(TiledOperand::elems(G, G));
+      Ml[si].alloc(TiledOperand::elems(G, G));
+      Mop[si].hi = Mh[si].p;
+      Mop[si].lo = Ml[si].p;
+      {
+        DevBuf<double> Mc((size_t)G * G);
+        tc_center_gram_kernel<<<(unsigned)(((size_t)G * G + 255) / 256), 256, 0, s>>>(
+            samples[si].gram, samples[si].colsum, G, (double)samples[si].n_cells, Mc.p);
+        tiled_from_colmajor_f64(ctx, Mc.p, G, G, G, Mop[si]);
+        ctx.stats.kernels++;
+      }
+    }
+  }
+  DevBuf<TcSampleDev> dS;
+  DevBuf<TcProbDev> dP;
+  DevBuf<int> dcs, dcl;
+  dS.upload(hs.data(), hs.size(), s);
+  dP.upload(hp.data(), hp.size(), s);
+  dcs.upload(col_sample.data(), col_sample.size(), s);
+  dcl.upload(col_local.data(), col_local.size(), s);
+  DevBuf<float> al((size_t)(degree + 1) * n_probs), be((size_t)(degree + 1) * n_probs), cc((size_t)n_probs);
+  // EigWork views for the FP64 orthonormalisation / Rayleigh-Ritz kernels
+  std::vector<EigWork> works(n_probs);
+  for (int pi = 0; pi < n_probs; ++pi)
+    works[pi] = EigWork{nullptr, hs[hp[pi].sample].G, hp[pi].Q, hp[pi].Z, hp[pi].theta, probs[order[pi]].V,
+                        probs[order[pi]].theta, hp[pi].converged, resid.p + pi};
+  DevBuf<EigWork> dw;
+  dw.upload(works.data(), works.size(), s);
+  std::vector<GemmProblem> gprobs;
+  int maxG = 0;
+  for (int si = 0; si < n_samples; ++si) {
+    if (hs[si].n_cols == 0) continue;
+    const int G = hs[si].G;
+    maxG = G > maxG ? G : maxG;
+    gprobs.push_back(GemmProblem{Mop[si].hi, Mop[si].lo, hs[si].Uh, hs[si].Ul, Mop[si].rows_pad, hs[si].u_rows_pad,
+                                 Mop[si].k_pad, G, hs[si].n_cols, hs[si].V, (long long)G, 0});
+  }
+  const size_t smem = sizeof(EigSmem<B>);
+  CG_CUDA(cudaFuncSetAttribute(eig_orth_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CG_CUDA(cudaFuncSetAttribute(eig_rr_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned colblocks = (unsigned)((n_cols_total + 7) / 8);
+  auto column = [&](int mode, const float* a, const float* b, const float* c) {
+    tc_column_kernel<<<colblocks, 256, 0, s>>>(dS.p, dP.p, dcs.p, dcl.p, (int)n_cols_total, mode, a, b, c);
+    ctx.stats.kernels++;
+  };
+  {
+    int maxcols = 0;
+    for (auto& h : hs) maxcols = h.n_cols > maxcols ? h.n_cols : maxcols;
+    dim3 gi((unsigned)(((size_t)maxG * maxcols + 255) / 256), n_samples);
+    tc_init_kernel<<<gi, 256, 0, s>>>(dS.p);
+    ctx.stats.kernels++;
+  }
+  std::vector<int> hc(n_probs);
+  int outer_done = 0;
+  for (int outer = 0; outer <= max_outer; ++outer) {
+    outer_done = outer;
+    // orthonormal basis of the filtered block
+    dim3 g64((unsigned)(((size_t)maxG * B + 255) / 256), n_probs);
+    tc_to64_kernel<<<g64, 256, 0, s>>>(dS.p, dP.p);
+    eig_orth_kernel<B><<<n_probs, EIG_THREADS, smem, s>>>(dw.p);
+    ctx.stats.kernels += 2;
+    // Rayleigh-Ritz: Z = C Q through the shared Gram GEMM
+    column(0, nullptr, nullptr, nullptr);
+    gemm_tn_bf16x3(ctx, gprobs.data(), (int)gprobs.size());
+    column(3, nullptr, nullptr, nullptr);
+    eig_rr_kernel<B><<<n_probs, EIG_THREADS, smem, s>>>(dw.p, r, tol, 0);
+    ctx.stats.kernels++;
+    conv.download(hc.data(), (size_t)n_probs, s);
+    CG_CUDA(cudaStreamSynchronize(s));
+    bool all = true;
+    for (int p = 0; p < n_probs; ++p) all = all && hc[p] != 0;
+    if (all || outer == max_outer) break;
+    // Chebyshev filter of the given degree
+    tc_coeff_kernel<<<(n_probs + 127) / 128, 128, 0, s>>>(dP.p, n_probs, degree, al.p, be.p, cc.p);
+    ctx.stats.kernels++;
+    column(1, al.p + (size_t)1 * n_probs, nullptr, cc.p);
+    for (int i = 2; i <= degree; ++i) {
+      gemm_tn_bf16x3(ctx, gprobs.data(), (int)gprobs.size());
+      column(2, al.p + (size_t)i * n_probs, be.p + (size_t)i * n_probs, cc.p);
+    }
+  }
+  if (ctx.profile) {
+    ctx.stage_ms["reduction.eig.outer_iterations"] += outer_done;
+    std::vector<double> hr(n_probs);
+    resid.download(hr.data(), (size_t)n_probs, s);
+    CG_CUDA(cudaStreamSynchronize(s));
+    double wr = 0.0;
+    for (double v : hr) wr = v > wr ? v : wr;
+    ctx.stage_ms["reduction.eig.worst_rel_residual_x1e9"] = wr * 1e9;
+    int nconv = 0;
+    for (int p = 0; p < n_probs; ++p) nconv += hc[p] != 0;
+    ctx.stage_ms["reduction.eig.converged_problems"] += nconv;
+    ctx.stage_ms["reduction.eig.problems"] += n_probs;
+  }
+  eig_rr_kernel<B><<<n_probs, EIG_THREADS, smem, s>>>(dw.p, r, tol, 1);
+  ctx.stats.kernels++;
+  CG_CUDA(cudaGetLastError());
+  CG_CUDA(cudaStreamSynchronize(s));
 }
 
 }  // namespace cg

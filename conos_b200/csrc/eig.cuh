@@ -17,4 +17,28 @@ struct EigProblem {
 // Block width is 32 for r <= 24 and 64 for r <= 56.
 void top_eigenvectors_batched(Context& ctx, const EigProblem* h_probs, int n_probs, int r, double tol, int max_iter);
 
+// ---------------------------------------------------------------------------------------------------------------
+// Tensor-core path for the common case "every pair uses all genes of its samples in storage order": the scaled
+// covariance of problem p (sample s, scale vector f_p) is applied as an operator on the SHARED per-sample Gram
+// matrix,   C_p Y = D_p (M_s (D_p Y) - n_s m_s (m_s' D_p Y)) / (n_s - 1),   D_p = diag(f_p),
+// so the block products of all problems of a sample are ONE bf16x3 tcgen05 GEMM against M_s (gemm_tc.cuh).
+// Chebyshev-filtered subspace iteration: degree-m filter damping [0, smallest Ritz value of the block], FP64
+// orthonormalisation and Rayleigh-Ritz between filters; stops when the residuals of the leading r Ritz pairs are
+// below tol * theta_1 (the stopping rule of irlba, whose default tol is 1e-5).
+struct TcEigSample {
+  const double* gram;    // G x G column-major FP64 (X'X)
+  const double* colsum;  // [G]
+  int n_cells;
+  int G;
+};
+struct TcEigProblem {
+  int sample;
+  const double* f;  // [G] scale factors (device)
+  double* V;        // out: G x r column-major
+  double* theta;    // out: [r]
+};
+void top_eigenvectors_shared_gram(Context& ctx, const TcEigSample* samples, int n_samples,
+                                  const TcEigProblem* probs, int n_probs, int r, double tol, int max_outer,
+                                  int degree);
+
 }  // namespace cg

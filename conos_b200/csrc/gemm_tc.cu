@@ -1,0 +1,225 @@
+#include "gemm_tc.cuh"
+#include "ptx.cuh"
+
+namespace cg {
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int G_THREADS = 192;  // warp 0 producer, warp 1 MMA, warps 2-5 epilogue
+constexpr int G_STAGES = 2;
+constexpr int A_BYTES = BM * BK * 2;  // 16 KB per hi / lo tile
+constexpr int B_BYTES = BN * BK * 2;  // 32 KB
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+constexpr int G_OFF_BAR = G_STAGES * STAGE_BYTES;
+constexpr int G_SMEM = G_OFF_BAR + 64;
+
+struct GemmTile {
+  int prob, mt, nt;
+};
+
+__global__ void __launch_bounds__(G_THREADS, 1)
+gemm_tn_bf16x3_kernel(const GemmProblem* __restrict__ probs, const GemmTile* __restrict__ tiles) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_OFF_BAR);
+  uint64_t* full = bars;                 // [2]
+  uint64_t* empty = bars + G_STAGES;     // [2]
+  uint64_t* acc_full = bars + 2 * G_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * G_STAGES + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const GemmTile tl = tiles[blockIdx.x];
+  const GemmProblem pb = probs[tl.prob];
+  const int n_slabs = pb.k_pad / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < G_STAGES; ++s) {
+      ptx::mbar_init(full + s, 1);
+      ptx::mbar_init(empty + s, 1);
+    }
+    ptx::mbar_init(acc_full, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 256);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int sl = 0; sl < n_slabs; ++sl) {
+        const int st = sl % G_STAGES, ph = (sl / G_STAGES) & 1;
+        ptx::mbar_wait(empty + st, ph ^ 1);
+        unsigned char* base = smem + st * STAGE_BYTES;
+        const size_t a_off = ((size_t)sl * (size_t)(pb.m_pad >> 3) + (size_t)tl.mt * (BM / 8)) * 512;
+        const size_t b_off = ((size_t)sl * (size_t)(pb.n_pad >> 3) + (size_t)tl.nt * (BN / 8)) * 512;
+        ptx::mbar_arrive_expect_tx(full + st, STAGE_BYTES);
+        ptx::bulk_g2s(base, pb.a_hi + a_off, A_BYTES, full + st);
+        ptx::bulk_g2s(base + A_BYTES, pb.a_lo + a_off, A_BYTES, full + st);
+        ptx::bulk_g2s(base + 2 * A_BYTES, pb.b_hi + b_off, B_BYTES, full + st);
+        ptx::bulk_g2s(base + 2 * A_BYTES + B_BYTES, pb.b_lo + b_off, B_BYTES, full + st);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc(1u, (uint32_t)BM, (uint32_t)BN);  // bf16 x bf16 -> fp32
+      const uint32_t s0 = ptx::smem_u32(smem);
+      for (int sl = 0; sl < n_slabs; ++sl) {
+        const int st = sl % G_STAGES, ph = (sl / G_STAGES) & 1;
+        ptx::mbar_wait(full + st, ph);
+        ptx::tc_fence_after();
+        const uint32_t a_hi = s0 + st * STAGE_BYTES, a_lo = a_hi + A_BYTES;
+        const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < BK / 16; ++ks) {
+          const uint64_t dah = ptx::umma_desc_kmajor_noswz(a_hi + ks * 256, 128, 1024);
+          const uint64_t dal = ptx::umma_desc_kmajor_noswz(a_lo + ks * 256, 128, 1024);
+          const uint64_t dbh = ptx::umma_desc_kmajor_noswz(b_hi + ks * 256, 128, 1024);
+          const uint64_t dbl = ptx::umma_desc_kmajor_noswz(b_lo + ks * 256, 128, 1024);
+          // small terms first
+          ptx::mma_f16_ss(tmem_base, dal, dbh, idesc, (sl > 0 || ks > 0) ? 1u : 0u);
+          ptx::mma_f16_ss(tmem_base, dah, dbl, idesc, 1u);
+          ptx::mma_f16_ss(tmem_base, dah, dbh, idesc, 1u);
+        }
+        ptx::mma_commit(empty + st);
+      }
+      ptx::mma_commit(acc_full);
+    }
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3;
+    ptx::mbar_wait(acc_full, 0);
+    ptx::tc_fence_after();
+    const int m = tl.mt * BM + quarter * 32 + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
+      ptx::tmem_wait_ld();
+      if (m < pb.M) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = tl.nt * BN + c * 32 + j;
+          if (n < pb.N) {
+            const float f = __uint_as_float(v[j]);
+            if (pb.out_fp64) reinterpret_cast<double*>(pb.C)[(size_t)n * pb.ldc + m] = (double)f;
+            else reinterpret_cast<float*>(pb.C)[(size_t)n * pb.ldc + m] = f;
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, 256);
+}
+
+// ------------------------------------------------------------------ operand builders
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+__global__ void tiled_from_csc_kernel(const int* __restrict__ csc_p, const int* __restrict__ csc_i,
+                                      const double* __restrict__ csc_x, int n_genes, int rows_pad,
+                                      __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  // one warp per gene column
+  const int g = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (g >= n_genes) return;
+  const int lane = threadIdx.x & 31;
+  for (int t = csc_p[g] + lane; t < csc_p[g + 1]; t += 32) {
+    const size_t o = tiled_operand_offset(g, csc_i[t], rows_pad);
+    __nv_bfloat16 h, l;
+    split_bf16((float)csc_x[t], h, l);
+    hi[o] = h;
+    lo[o] = l;
+  }
+}
+
+template <class T>
+__global__ void tiled_from_colmajor_kernel(const T* __restrict__ src, int k, int rows, long long ld, int rows_pad,
+                                           int k_pad, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  // one thread per padded element, k fastest (coalesced reads)
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)rows_pad * k_pad) return;
+  const int kk = (int)(t % k_pad), r = (int)(t / k_pad);
+  float x = 0.f;
+  if (kk < k && r < rows) x = (float)src[(size_t)r * ld + kk];
+  __nv_bfloat16 h, l;
+  split_bf16(x, h, l);
+  const size_t o = tiled_operand_offset(r, kk, rows_pad);
+  hi[o] = h;
+  lo[o] = l;
+}
+
+inline unsigned nblk(size_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace
+
+void gemm_tn_bf16x3(Context& ctx, const GemmProblem* h_probs, int n_probs) {
+  if (n_probs == 0) return;
+  std::vector<GemmTile> tiles;
+  for (int p = 0; p < n_probs; ++p) {
+    const GemmProblem& g = h_probs[p];
+    CG_CHECK(g.m_pad % GEMM_ROW_PAD == 0 && g.n_pad % GEMM_ROW_PAD == 0 && g.k_pad % GEMM_K_PAD == 0 && g.k_pad > 0,
+             "GEMM operands must be padded (rows to 256, k to 64)");
+    const int mts = (g.M + BM - 1) / BM, nts = (g.N + BN - 1) / BN;
+    for (int nt = 0; nt < nts; ++nt)
+      for (int mt = 0; mt < mts; ++mt) tiles.push_back(GemmTile{p, mt, nt});
+  }
+  if (tiles.empty()) return;
+  DevBuf<GemmProblem> dp;
+  DevBuf<GemmTile> dt;
+  dp.upload(h_probs, (size_t)n_probs, ctx.stream);
+  dt.upload(tiles.data(), tiles.size(), ctx.stream);
+  CG_CUDA(cudaFuncSetAttribute(gemm_tn_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
+  gemm_tn_bf16x3_kernel<<<(unsigned)tiles.size(), G_THREADS, G_SMEM, ctx.stream>>>(dp.p, dt.p);
+  ctx.stats.kernels++;
+  CG_CUDA(cudaGetLastError());
+  CG_CUDA(cudaStreamSynchronize(ctx.stream));
+}
+
+void tiled_from_csc(Context& ctx, const int* csc_p, const int* csc_i, const double* csc_x, int n_cells, int n_genes,
+                    TiledOperand& op) {
+  op.rows = n_genes;
+  op.k = n_cells;
+  op.rows_pad = (int)round_up(n_genes, GEMM_ROW_PAD);
+  op.k_pad = (int)round_up(n_cells, GEMM_K_PAD);
+  const size_t n = (size_t)op.rows_pad * op.k_pad;
+  CG_CUDA(cudaMemsetAsync(op.hi, 0, n * sizeof(__nv_bfloat16), ctx.stream));
+  CG_CUDA(cudaMemsetAsync(op.lo, 0, n * sizeof(__nv_bfloat16), ctx.stream));
+  tiled_from_csc_kernel<<<(n_genes + 7) / 8, 256, 0, ctx.stream>>>(csc_p, csc_i, csc_x, n_genes, op.rows_pad, op.hi,
+                                                                  op.lo);
+  ctx.stats.kernels++;
+  CG_CUDA(cudaGetLastError());
+}
+
+void tiled_from_colmajor_f64(Context& ctx, const double* src, int k, int rows, long long ld, TiledOperand& op) {
+  op.rows = rows;
+  op.k = k;
+  op.rows_pad = (int)round_up(rows, GEMM_ROW_PAD);
+  op.k_pad = (int)round_up(k, GEMM_K_PAD);
+  const size_t n = (size_t)op.rows_pad * op.k_pad;
+  tiled_from_colmajor_kernel<double><<<nblk(n), 256, 0, ctx.stream>>>(src, k, rows, ld, op.rows_pad, op.k_pad, op.hi,
+                                                                      op.lo);
+  ctx.stats.kernels++;
+  CG_CUDA(cudaGetLastError());
+}
+
+void tiled_from_colmajor_f32(Context& ctx, const float* src, int k, int rows, long long ld, TiledOperand& op) {
+  op.rows = rows;
+  op.k = k;
+  op.rows_pad = (int)round_up(rows, GEMM_ROW_PAD);
+  op.k_pad = (int)round_up(k, GEMM_K_PAD);
+  const size_t n = (size_t)op.rows_pad * op.k_pad;
+  tiled_from_colmajor_kernel<float><<<nblk(n), 256, 0, ctx.stream>>>(src, k, rows, ld, op.rows_pad, op.k_pad, op.hi,
+                                                                     op.lo);
+  ctx.stats.kernels++;
+  CG_CUDA(cudaGetLastError());
+}
+
+}  // namespace cg

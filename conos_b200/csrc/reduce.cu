@@ -1,6 +1,7 @@
 #include <cmath>
 
 #include "eig.cuh"
+#include "gemm_tc.cuh"
 #include "reduce.cuh"
 #include "stage.cuh"
 
@@ -118,6 +119,102 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
     // centred, scaled sample == leading eigenvectors of its scaled covariance; columns interleaved.
     const int r = r_round_half_even(P.ncomps / 2.0);
     CG_CHECK(r >= 1 && r <= 56, "ncomps out of range for the device PCA");
+    // tensor-core path: every pair uses all genes of both samples in storage order (shared gene universe)
+    bool shared = !ctx.exact_reduction && r <= 24;
+    for (int q : todo) {
+      const cg_pair& pr = pairs[q];
+      const Sample& sa = panel.samples[pr.a];
+      const Sample& sb = panel.samples[pr.b];
+      if (pr.n_genes != sa.n_genes || pr.n_genes != sb.n_genes || pr.n_genes < 32) shared = false;
+      for (int g = 0; g < pr.n_genes && shared; ++g)
+        if (pr.genes_a[g] != g || pr.genes_b[g] != g) shared = false;
+      if (!shared) break;
+    }
+    if (shared) {
+      const int S = (int)panel.samples.size();
+      std::vector<TcEigSample> ts(S);
+      for (int si = 0; si < S; ++si) {
+        Sample& sm = panel.samples[si];
+        ts[si] = TcEigSample{sm.gram.p, sm.colsum.p, sm.n_cells, sm.n_genes};
+      }
+      struct PB {
+        DevBuf<double> f[2], V[2], theta[2], tr;
+      };
+      std::vector<PB> pbs(todo.size());
+      std::vector<TcEigProblem> tp;
+      for (size_t t = 0; t < todo.size(); ++t) {
+        const cg_pair& pr = pairs[todo[t]];
+        const int G = pr.n_genes;
+        Sample* sm[2] = {&panel.samples[pr.a], &panel.samples[pr.b]};
+        std::vector<double> f[2];
+        f[0].assign(G, 1.0);
+        f[1].assign(G, 1.0);
+        if (P.var_scale) {
+          CG_CHECK(!sm[0]->h_qv.empty() && !sm[1]->h_qv.empty() && !sm[0]->h_v.empty() && !sm[1]->h_v.empty(),
+                   "var.scale = TRUE needs misc$varinfo$v and $qv for every sample");
+          for (int g = 0; g < G; ++g) {
+            const double cqv = std::exp((std::log(sm[0]->h_qv[g]) + std::log(sm[1]->h_qv[g])) / 2.0);
+            const double fa = std::sqrt(cqv / std::exp(sm[0]->h_v[g]));
+            const double fb = std::sqrt(cqv / std::exp(sm[1]->h_v[g]));
+            f[0][g] = std::isfinite(fa) ? fa : 0.0;
+            f[1][g] = std::isfinite(fb) ? fb : 0.0;
+          }
+        }
+        for (int side = 0; side < 2; ++side) {
+          pbs[t].f[side].upload(f[side].data(), (size_t)G, st);
+          pbs[t].V[side].alloc((size_t)G * r);
+          pbs[t].theta[side].alloc((size_t)r);
+          tp.push_back(TcEigProblem{side == 0 ? pr.a : pr.b, pbs[t].f[side].p, pbs[t].V[side].p, pbs[t].theta[side].p});
+        }
+      }
+      {
+        StageScope sc(ctx, "reduction.eig");
+        top_eigenvectors_shared_gram(ctx, ts.data(), S, tp.data(), (int)tp.size(), r, 1e-5, 12, 10);
+      }
+      for (size_t t = 0; t < todo.size(); ++t) {
+        const cg_pair& pr = pairs[todo[t]];
+        const int G = pr.n_genes;
+        PairReduction& R = out[todo[t]];
+        R.n_rows = G;
+        R.n_cols = 2 * r;
+        R.d = P.ncomps < R.n_cols ? P.ncomps : R.n_cols;
+        R.rot.alloc((size_t)G * R.n_cols);
+        interleave_kernel<<<nblk((size_t)G * R.n_cols), 256, 0, st>>>(pbs[t].V[0].p, pbs[t].V[1].p, G, G, r, R.rot.p);
+        ctx.stats.kernels++;
+        R.h_rot.resize((size_t)G * R.n_cols);
+        R.rot.download(R.h_rot.data(), R.h_rot.size(), st);
+        if (P.score_component_variance) {
+          // trace(C) = sum_g f_g^2 (M_gg - n m_g^2) / (n - 1): from the host copies
+          std::vector<double> th(2 * (size_t)r);
+          pbs[t].theta[0].download(th.data(), (size_t)r, st);
+          pbs[t].theta[1].download(th.data() + r, (size_t)r, st);
+          CG_CUDA(cudaStreamSynchronize(st));
+          R.h_nv.assign(2 * (size_t)R.n_cols, 0.0);
+          for (int side = 0; side < 2; ++side) {
+            Sample& sm = panel.samples[side == 0 ? pr.a : pr.b];
+            if (sm.h_gram_diag.empty()) {
+              sm.h_gram_diag.resize(sm.n_genes);
+              CG_CUDA(cudaMemcpy2DAsync(sm.h_gram_diag.data(), sizeof(double), sm.gram.p,
+                                        ((size_t)sm.n_genes + 1) * sizeof(double), sizeof(double), sm.n_genes,
+                                        cudaMemcpyDeviceToHost, st));
+              CG_CUDA(cudaStreamSynchronize(st));
+            }
+            std::vector<double> fh((size_t)G);
+            pbs[t].f[side].download(fh.data(), (size_t)G, st);
+            CG_CUDA(cudaStreamSynchronize(st));
+            const double n = sm.n_cells;
+            double tr = 0.0;
+            for (int g = 0; g < G; ++g) {
+              const double m = sm.h_colsum[g] / n;
+              tr += fh[g] * fh[g] * (sm.h_gram_diag[g] - n * m * m) / (n - 1.0);
+            }
+            for (int j = 0; j < r; ++j) R.h_nv[(size_t)side * R.n_cols + j] = th[(size_t)side * r + j] / tr;
+          }
+        }
+      }
+      CG_CUDA(cudaStreamSynchronize(st));
+      return;
+    }
     const int B = r <= 24 ? 32 : 64;
     // chunks of pairs bounded by memory (2 covariance matrices per pair)
     size_t i0 = 0;
@@ -226,11 +323,23 @@ void ensure_gram(Context& ctx, Sample& s) {
   CG_CHECK(s.n_genes <= 16384, "subset the counts matrix to the od-gene universe before upload (Gram matrix too big)");
   const size_t G = (size_t)s.n_genes;
   s.gram.alloc(G * G);
-  s.gram.zero(ctx.stream);
-  gram_upper_from_csr(ctx, s.csr_p.p, s.csr_i.p, s.csr_x.p, s.n_cells, s.n_genes, s.gram.p);
-  mirror_upper_kernel<<<nblk(G * G), 256, 0, ctx.stream>>>(s.gram.p, s.n_genes);
-  ctx.stats.kernels++;
-  CG_CUDA(cudaGetLastError());
+  if (ctx.exact_reduction) {
+    s.gram.zero(ctx.stream);
+    gram_upper_from_csr(ctx, s.csr_p.p, s.csr_i.p, s.csr_x.p, s.n_cells, s.n_genes, s.gram.p);
+    mirror_upper_kernel<<<nblk(G * G), 256, 0, ctx.stream>>>(s.gram.p, s.n_genes);
+    ctx.stats.kernels++;
+    CG_CUDA(cudaGetLastError());
+    return;
+  }
+  // X'X on the tensor cores: the sparse counts become a dense bf16 hi/lo operand (rows = genes, k = cells)
+  DevBuf<__nv_bfloat16> hi(TiledOperand::elems(s.n_genes, s.n_cells)), lo(TiledOperand::elems(s.n_genes, s.n_cells));
+  TiledOperand op;
+  op.hi = hi.p;
+  op.lo = lo.p;
+  tiled_from_csc(ctx, s.csc_p.p, s.csc_i.p, s.csc_x.p, s.n_cells, s.n_genes, op);
+  GemmProblem gp{op.hi, op.lo, op.hi, op.lo, op.rows_pad, op.rows_pad, op.k_pad, s.n_genes, s.n_genes, s.gram.p,
+                 (long long)s.n_genes, 1};
+  gemm_tn_bf16x3(ctx, &gp, 1);
 }
 
 }  // namespace cg

@@ -20,6 +20,7 @@ struct Sample {
   DevBuf<double> colsum;          // per gene, sum over cells (device)
   DevBuf<double> gram;            // X'X over all genes, FP64 column-major (built on first use by the reductions)
   std::vector<double> h_colsum;   // host copy
+  std::vector<double> h_gram_diag;  // host copy of diag(X'X), filled on demand
   std::vector<double> h_v, h_qv;  // misc$varinfo$v / $qv (empty when not supplied)
   DevBuf<float> pca_tiled;        // reductions$PCA as a normalised kNN panel (metric dependent, built lazily)
   DevBuf<double> pca;             // column-major n_cells x n_pcs

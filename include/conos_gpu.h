@@ -52,6 +52,10 @@ uint64_t cg_kernel_launches(const cg_context* ctx);
 /* CUDA events on the context's stream: start, then stop returns the elapsed device time in ms */
 int cg_timer_start(cg_context* ctx);
 int cg_timer_stop(cg_context* ctx, double* ms);
+/* options: "exact_reduction" = 1 runs the per-pair reductions in FP64 on the CUDA cores (Gram by FP64 atomics,
+ * explicit covariance, subspace iteration to 1e-10) instead of the default tensor-core path (bf16x3 GEMMs,
+ * Chebyshev-filtered iteration to irlba's own tolerance 1e-5) -- used by the parity tests */
+int cg_set_option(cg_context* ctx, const char* name, double value);
 /* optional per-stage wall-clock profile: enable (resets), then dump "name=ms;name=ms;..." into buf */
 int cg_profile(cg_context* ctx, int enable);
 int cg_profile_dump(cg_context* ctx, char* buf, int buf_len);
@@ -93,6 +97,8 @@ typedef struct {
 int cg_panel_create(cg_context* ctx, const cg_sample* samples, int n_samples, cg_panel** out);
 void cg_panel_free(cg_panel* panel);
 int cg_panel_offsets(const cg_panel* panel, int32_t* offsets /* [n_samples + 1] global cell ids */);
+/* drop derived per-sample data (Gram matrices, kNN panels of the PCA) so that the next call recomputes them */
+int cg_panel_drop_cache(cg_panel* panel);
 
 /* ---- per-pair reduction + matching --------------------------------------------------------------- */
 typedef struct {

@@ -222,8 +222,9 @@ def _principal_cosines(a, b):
     return np.linalg.svd(qa.T @ qb, compute_uv=False)
 
 
+@pytest.mark.parametrize("exact", [True, False])
 @pytest.mark.parametrize("ncomps,score", [(20, True), (30, False)])
-def test_device_pca_rotation(ctx, oracle, small_panel, ncomps, score):
+def test_device_pca_rotation(ctx, oracle, small_panel, ncomps, score, exact):
     """quickPlainPCA on the device: per-sample subspaces equal the exact ones (irlba itself is only 1e-5 accurate),
     columns interleaved A1,B1,A2,..., nv = variance fractions; the downstream graph matches the oracle's."""
     import conos_b200
@@ -231,7 +232,14 @@ def test_device_pca_rotation(ctx, oracle, small_panel, ncomps, score):
     ref = oracle.build_graph(osamples, k=10, k_self=5, space="PCA", ncomps=ncomps, n_odgenes=300,
                              score_component_variance=score)
     con = conos_b200.Conos(small_panel, ctx=ctx)
-    g = con.buildGraph(k=10, k_self=5, space="PCA", ncomps=ncomps, n_odgenes=300, score_component_variance=score)
+    # exact: FP64 CUDA-core reduction (tight parity); default: bf16x3 tensor-core Gram + Chebyshev iteration to
+    # irlba's own tolerance (1e-5 relative residual), so only irlba-level agreement can be asked for
+    ctx.lib.cg_set_option(ctx.h, b"exact_reduction", 1.0 if exact else 0.0)
+    try:
+        g = con.buildGraph(k=10, k_self=5, space="PCA", ncomps=ncomps, n_odgenes=300, score_component_variance=score)
+    finally:
+        ctx.lib.cg_set_option(ctx.h, b"exact_reduction", 0.0)
+    cos_tol, dot_tol, nv_tol, jac_tol = (1e-10, 1e-8, 1e-8, 0.999) if exact else (1e-6, None, 1e-4, 0.98)
     r = ncomps // 2
     for key, red in ref["pairs"].items():
         mine = con.pairs["PCA"][key]
@@ -239,13 +247,14 @@ def test_device_pca_rotation(ctx, oracle, small_panel, ncomps, score):
         assert mine["CPC"].shape == red["CPC"].shape
         for side in (0, 1):
             cs = _principal_cosines(mine["CPC"][:, side::2], red["CPC"][:, side::2])
-            assert cs.min() > 1 - 1e-10, (key, side, cs.min())
-            # individual eigenvectors (up to sign): well separated spectrum in this panel
-            dots = np.abs(np.sum(mine["CPC"][:, side::2] * red["CPC"][:, side::2], axis=0))
-            assert dots.min() > 1 - 1e-8
+            assert cs.min() > 1 - cos_tol, (key, side, cs.min())
+            if dot_tol is not None:
+                # individual eigenvectors (up to sign): well separated spectrum in this panel
+                dots = np.abs(np.sum(mine["CPC"][:, side::2] * red["CPC"][:, side::2], axis=0))
+                assert dots.min() > 1 - dot_tol
         if score:
             for side in (0, 1):
-                np.testing.assert_allclose(mine["nv"][side], red["nv"][side], rtol=1e-8)
+                np.testing.assert_allclose(mine["nv"][side], red["nv"][side], rtol=nv_tol)
     og = ref["graph"]
     # the rotations agree to ~1e-9, so at most a handful of near-tied neighbours may differ
     mine_e = set(zip(g.vertices[g.edge_from].tolist(), g.vertices[g.edge_to].tolist()))
@@ -253,7 +262,7 @@ def test_device_pca_rotation(ctx, oracle, small_panel, ncomps, score):
     mine_e = {(min(a, b), max(a, b)) for a, b in mine_e}
     ref_e = {(min(a, b), max(a, b)) for a, b in ref_e}
     jacc = len(mine_e & ref_e) / len(mine_e | ref_e)
-    assert jacc > 0.999, jacc
+    assert jacc > jac_tol, jacc
 
 
 @pytest.mark.parametrize("matching,k,k1", [("NN", 10, 10), ("mNN", 40, 40), ("mNN", 8, 60), ("NN", 6, 25), ("mNN", 15, 200)])

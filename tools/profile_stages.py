@@ -22,6 +22,7 @@ kw = dict(k=cfg["k"], k_self=cfg["k_self"], space=cfg["space"], ncomps=cfg["ncom
 con.buildGraph(fetch=False, **kw)  # warm
 for rep in range(a.reps):
     con.pairs = {}
+    ctx.lib.cg_panel_drop_cache(con._panel)
     ctx.lib.cg_profile(ctx.h, 1)
     t0 = time.perf_counter()
     g = con.buildGraph(fetch=False, **kw)
