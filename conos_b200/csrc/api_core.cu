@@ -228,7 +228,7 @@ int cg_cross_knn(cg_context* ctx, const double* A, int nA, int lda, const double
   if (!probs.empty()) {
     DevBuf<KnnProblem> dp;
     dp.upload(probs.data(), probs.size(), c.stream);
-    knn_launch(c, dp.p, probs.data(), (int)probs.size(), k, pa.panel.d_pad, (Metric)metric);
+    knn_launch(c, dp.p, probs.data(), (int)probs.size(), k, pa.panel.d_pad, d, (Metric)metric);
     if (idx_ab) i_ab.download(idx_ab, (size_t)nA * k, c.stream);
     if (dist_ab) d_ab.download(dist_ab, (size_t)nA * k, c.stream);
     if (idx_ba) i_ba.download(idx_ba, (size_t)nB * k, c.stream);
@@ -255,7 +255,7 @@ int cg_self_knn(cg_context* ctx, const double* Z, int n, int ldz, int d, int k, 
   KnnProblem pb{pz.panel.tiled, pz.panel.tiled, n, n, di.p, dd.p};
   DevBuf<KnnProblem> dp;
   dp.upload(&pb, 1, c.stream);
-  knn_launch(c, dp.p, &pb, 1, k, pz.panel.d_pad, (Metric)metric);
+  knn_launch(c, dp.p, &pb, 1, k, pz.panel.d_pad, d, (Metric)metric);
   if (idx) di.download(idx, (size_t)n * k, c.stream);
   if (dist) dd.download(dist, (size_t)n * k, c.stream);
   CG_CUDA(cudaStreamSynchronize(c.stream));
@@ -284,7 +284,7 @@ int cg_neighbor_matrix(cg_context* ctx, const double* p1, int n1, int ld1, const
                          {pb.panel.tiled, pa.panel.tiled, n2, n1, i_ba.p, d_ba.p}};
   DevBuf<KnnProblem> dp;
   dp.upload(probs, 2, c.stream);
-  knn_launch(c, dp.p, probs, 2, k1, pa.panel.d_pad, (Metric)metric);
+  knn_launch(c, dp.p, probs, 2, k1, pa.panel.d_pad, d, (Metric)metric);
   MnnProblem mp{i_ab.p, d_ab.p, i_ba.p, d_ba.p, nullptr, nullptr, n1, n2, 0, 0};
   SimParams sp{metric, matching, cor_base, l2_sigma, min_similarity};
   ctx->coo.n = 0;

@@ -282,7 +282,7 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
       StageScope sc(c, "cross_knn");
       DevBuf<KnnProblem> dk;
       dk.upload(kprobs.data(), kprobs.size(), c.stream);
-      knn_launch(c, dk.p, kprobs.data(), (int)kprobs.size(), P.k1, d_pad_all, metric);
+      knn_launch(c, dk.p, kprobs.data(), (int)kprobs.size(), P.k1, d_pad_all, d_all, metric);
       CG_CUDA(cudaStreamSynchronize(c.stream));
     }
     // ---- matching -> edges
@@ -338,7 +338,7 @@ int cg_local_edges(cg_context* ctx, cg_panel* panel, const int32_t* samples, int
   std::vector<KnnProblem> kprobs;
   std::vector<DevBuf<int>> idx(n);
   std::vector<DevBuf<float>> dist(n);
-  int d_pad = 0;
+  int d_pad = 0, d_pcs = 0;
   for (int t = 0; t < n; ++t) {
     CG_CHECK(samples[t] >= 0 && samples[t] < (int)panel->samples.size(), "no such sample");
     Sample& s = panel->samples[samples[t]];
@@ -351,8 +351,9 @@ int cg_local_edges(cg_context* ctx, cg_panel* panel, const int32_t* samples, int
       s.pca_metric = P.metric;
     }
     const int dp = s.n_pcs <= 32 ? 32 : 64;
-    CG_CHECK(d_pad == 0 || d_pad == dp, "per-sample PCAs must share their padded width (<= 32 or 33..64 columns)");
+    CG_CHECK(d_pad == 0 || (d_pad == dp && d_pcs == s.n_pcs), "per-sample PCAs must have the same number of columns");
     d_pad = dp;
+    d_pcs = s.n_pcs;
     idx[t].alloc((size_t)s.n_cells * kp1);
     dist[t].alloc((size_t)s.n_cells * kp1);
     kprobs.push_back(KnnProblem{s.pca_tiled.p, s.pca_tiled.p, s.n_cells, s.n_cells, idx[t].p, dist[t].p});
@@ -361,7 +362,7 @@ int cg_local_edges(cg_context* ctx, cg_panel* panel, const int32_t* samples, int
     StageScope sc(c, "self_knn");
     DevBuf<KnnProblem> dk;
     dk.upload(kprobs.data(), kprobs.size(), c.stream);
-    knn_launch(c, dk.p, kprobs.data(), (int)kprobs.size(), kp1, d_pad, (Metric)P.metric);
+    knn_launch(c, dk.p, kprobs.data(), (int)kprobs.size(), kp1, d_pad, d_pcs, (Metric)P.metric);
     CG_CUDA(cudaStreamSynchronize(c.stream));
   }
   StageScope sc_le(c, "local_edges");

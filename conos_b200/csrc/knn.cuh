@@ -13,7 +13,9 @@
 //   tiled[(row/8)][chunk = col/4][row%8][col%4],   KC = d_pad/4 chunks, d_pad in {32, 64}
 // i.e. exactly the shared-memory image a K-major, no-swizzle tcgen05 (kind::tf32) operand needs, so a
 // tile of R rows (R % 8 == 0) is one contiguous byte range that a single 1-D bulk copy moves.
-// Rows are zero-padded up to a multiple of 256.
+// Rows are zero-padded up to a multiple of 256.  When d < d_pad the LAST padded column of every row holds -1:
+// the tensor-core kernel uses it to subtract a per-query threshold inside the MMA; every exact computation
+// (re-rank, SIMT kernel) only touches the d real columns.
 #pragma once
 #include "common.cuh"
 
@@ -60,15 +62,15 @@ void knn_prep_from_f32_rowmajor(Context& ctx, const float* d_src, int n, int d, 
 
 // Exact SIMT kernel: any k, both metrics. One warp per query row.
 void knn_simt_launch(Context& ctx, const KnnProblem* d_probs, const KnnProblem* h_probs, int n_probs, int k,
-                     int d_pad, Metric metric);
+                     int d_pad, int d, Metric metric);
 
 // Tensor-core kernel (angular, k <= KNN_TC_MAXK): TF32 tcgen05 distance tiles in TMEM as a filter,
 // canonical fp32 re-rank of the survivors, per-row sorted top-k lists in shared memory.
 void knn_tc_launch(Context& ctx, const KnnProblem* d_probs, const KnnProblem* h_probs, int n_probs, int k,
-                   int d_pad);
+                   int d_pad, int d);
 
 // Dispatch by (k, metric): the tensor-core kernel whenever it applies.
 void knn_launch(Context& ctx, const KnnProblem* d_probs, const KnnProblem* h_probs, int n_probs, int k, int d_pad,
-                Metric metric);
+                int d, Metric metric);
 
 }  // namespace cg

@@ -12,8 +12,10 @@ __global__ void knn_prep_kernel(const SrcT* __restrict__ src, int n, int d, int 
   if (row >= n_pad) return;
   const int KC = d_pad >> 2;
   float* dst = tiled + (size_t)(row >> 3) * (size_t)(8 * d_pad) + (size_t)(row & 7) * 4;
+  const bool fold = d < d_pad;  // spare last column: -1 (threshold dimension of the tensor-core kernel)
   if (row >= n) {
-    for (int c = 0; c < KC; ++c) *reinterpret_cast<float4*>(dst + c * 32) = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < KC; ++c)
+      *reinterpret_cast<float4*>(dst + c * 32) = make_float4(0.f, 0.f, 0.f, (fold && c == KC - 1) ? -1.0f : 0.f);
     return;
   }
   float inv = 1.0f;
@@ -33,6 +35,7 @@ __global__ void knn_prep_kernel(const SrcT* __restrict__ src, int n, int d, int 
       float x = 0.0f;
       if (i < d) x = COLMAJOR ? (float)src[(size_t)i * ld + row] : (float)src[(size_t)row * ld + i];
       v[e] = x * inv;
+      if (fold && i == d_pad - 1) v[e] = -1.0f;
     }
     *reinterpret_cast<float4*>(dst + c * 32) = make_float4(v[0], v[1], v[2], v[3]);
   }

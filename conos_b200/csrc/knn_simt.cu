@@ -11,7 +11,7 @@ constexpr int SIMT_WARPS = 8;
 
 template <int D_PAD>
 __global__ void __launch_bounds__(SIMT_WARPS * 32) knn_simt_kernel(const KnnProblem* __restrict__ probs, int k,
-                                                                   int metric) {
+                                                                   int metric, int d) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const KnnProblem pb = probs[blockIdx.y];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -32,6 +32,10 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32) knn_simt_kernel(const KnnProb
       float4 v = *reinterpret_cast<const float4*>(qp + c * 32);
       q[4 * c + 0] = v.x; q[4 * c + 1] = v.y; q[4 * c + 2] = v.z; q[4 * c + 3] = v.w;
     }
+    // only the d real columns take part (the padding may carry the tensor-core threshold dimension)
+#pragma unroll
+    for (int i = 0; i < D_PAD; ++i)
+      if (i >= d) q[i] = 0.0f;
   }
   __syncwarp();
   for (int base = 0; base < pb.nr; base += 32) {
@@ -55,6 +59,10 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32) knn_simt_kernel(const KnnProb
         for (int c = 0; c < KC; ++c) {
           float4 v = __ldg(reinterpret_cast<const float4*>(rp + c * 32));
           float d0 = q[4 * c + 0] - v.x, d1 = q[4 * c + 1] - v.y, d2 = q[4 * c + 2] - v.z, d3 = q[4 * c + 3] - v.w;
+          if (4 * c + 0 >= d) d0 = 0.f;
+          if (4 * c + 1 >= d) d1 = 0.f;
+          if (4 * c + 2 >= d) d2 = 0.f;
+          if (4 * c + 3 >= d) d3 = 0.f;
           a0 = fmaf(d0, d0, a0);
           a1 = fmaf(d1, d1, a1);
           a2 = fmaf(d2, d2, a2);
@@ -102,7 +110,7 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32) knn_simt_kernel(const KnnProb
 }  // namespace
 
 void knn_simt_launch(Context& ctx, const KnnProblem* d_probs, const KnnProblem* h_probs, int n_probs, int k,
-                     int d_pad, Metric metric) {
+                     int d_pad, int d, Metric metric) {
   if (n_probs == 0) return;
   CG_CHECK(k >= 1, "k must be >= 1");
   int max_nq = 0;
@@ -115,11 +123,11 @@ void knn_simt_launch(Context& ctx, const KnnProblem* d_probs, const KnnProblem* 
     dim3 grid((max_nq + SIMT_WARPS - 1) / SIMT_WARPS, np);
     if (d_pad == 32) {
       CG_CUDA(cudaFuncSetAttribute(knn_simt_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      knn_simt_kernel<32><<<grid, SIMT_WARPS * 32, smem, ctx.stream>>>(d_probs + p0, k, (int)metric);
+      knn_simt_kernel<32><<<grid, SIMT_WARPS * 32, smem, ctx.stream>>>(d_probs + p0, k, (int)metric, d);
     } else {
       CG_CHECK(d_pad == 64, "d_pad must be 32 or 64");
       CG_CUDA(cudaFuncSetAttribute(knn_simt_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      knn_simt_kernel<64><<<grid, SIMT_WARPS * 32, smem, ctx.stream>>>(d_probs + p0, k, (int)metric);
+      knn_simt_kernel<64><<<grid, SIMT_WARPS * 32, smem, ctx.stream>>>(d_probs + p0, k, (int)metric, d);
     }
     ctx.stats.kernels++;
     CG_CUDA(cudaGetLastError());

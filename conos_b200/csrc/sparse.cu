@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(256) project_kernel(const ProjProblem* __restr
 #pragma unroll
   for (int u = 0; u < NC; ++u) {
     const int c = lane + 32 * u;
-    dst[(c >> 2) * 32 + (c & 3)] = v[u] * inv;
+    dst[(c >> 2) * 32 + (c & 3)] = (d < D_PAD && c == D_PAD - 1) ? -1.0f : v[u] * inv;
   }
 }
 

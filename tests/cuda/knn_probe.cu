@@ -86,14 +86,14 @@ static int run_case(Context& ctx, int nq, int nr, int d, int k, bool check_host,
   float ms_s = 0, ms_t = 0;
   for (int r = 0; r < reps; ++r) {
     cudaEventRecord(e0, ctx.stream);
-    knn_simt_launch(ctx, dps.p, &ps, 1, k, pq.d_pad, METRIC_ANGULAR);
+    knn_simt_launch(ctx, dps.p, &ps, 1, k, pq.d_pad, d, METRIC_ANGULAR);
     cudaEventRecord(e1, ctx.stream);
     CG_CUDA(cudaStreamSynchronize(ctx.stream));
     cudaEventElapsedTime(&ms_s, e0, e1);
   }
   for (int r = 0; r < reps; ++r) {
     cudaEventRecord(e0, ctx.stream);
-    knn_tc_launch(ctx, dpt.p, &pt, 1, k, pq.d_pad);
+    knn_tc_launch(ctx, dpt.p, &pt, 1, k, pq.d_pad, d);
     cudaEventRecord(e1, ctx.stream);
     CG_CUDA(cudaStreamSynchronize(ctx.stream));
     cudaEventElapsedTime(&ms_t, e0, e1);
@@ -158,6 +158,8 @@ int main(int argc, char** argv) {
       rc |= run_case(ctx, 10000, 10000, 30, 15, false, 3);
       rc |= run_case(ctx, 50000, 50000, 30, 30, false, 3);
       rc |= run_case(ctx, 20000, 20000, 50, 15, false, 3);
+      rc |= run_case(ctx, 3000, 5000, 32, 15, false, 1);   // d == d_pad: no spare dimension, compare path
+      rc |= run_case(ctx, 3000, 5000, 64, 30, false, 1);
     }
     printf(rc ? "KNN_PROBE FAIL\n" : "KNN_PROBE OK\n");
     return rc;

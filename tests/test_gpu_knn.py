@@ -92,3 +92,19 @@ def test_large_properties(ctx):
             hit = np.nonzero(iba[j] == i)[0]
             if len(hit):
                 assert dab[i, r] == dba[j, hit[0]]
+
+
+@pytest.mark.parametrize("d,k", [(30, 15), (32, 15), (64, 30), (50, 30)])
+def test_many_items_per_cta(ctx, oracle, d, k):
+    """More 256-row work items than SMs (persistent CTAs walk several items): d = 32 / 64 leave no spare
+    dimension for the folded threshold and take the compare path."""
+    from conos_b200 import ops
+    rng = np.random.default_rng(d * 31 + k)
+    A, B = mixture(rng, 40000, d), mixture(rng, 700, d)
+    iab, dab, iba, dba = ops.crossKnn(A, B, k, "angular", ctx=ctx, both=True)
+    oi, od = oracle.cross_knn(A, B, k, "angular")
+    assert np.array_equal(iab, oi)
+    assert np.array_equal(dab.view(np.uint32), od.view(np.uint32))
+    oi2, od2 = oracle.cross_knn(B, A, k, "angular")
+    assert np.array_equal(iba, oi2)
+    assert np.array_equal(dba.view(np.uint32), od2.view(np.uint32))
