@@ -248,6 +248,11 @@ def main():
         dist.all_reduce(lsum)
         launches = int(lsum.item())
     n_inter = con._n_inter_edges
+    if world > 1:
+        import torch.distributed as dist
+        ni = torch.tensor([float(n_inter)], device="cuda")
+        dist.all_reduce(ni)
+        n_inter = int(ni.item())
     # ---- end to end through the host API
     for _ in range(min(W, 1)):
         e2e_step()
@@ -263,6 +268,10 @@ def main():
         tmax = torch.tensor([e2e_s], device="cuda")
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         e2e_s = float(tmax.item())
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return 0
 

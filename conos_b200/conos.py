@@ -297,6 +297,8 @@ class Conos:
             nv = np.zeros((2, nc.value)) if score_component_variance else None
             self.ctx.check(lib.cg_pair_reduction(h, slot, None, None, ptr(rot, C.c_double), ptr(nv, C.c_double)))
             cache[key] = {"CPC": rot, "genes": self._gene_names(od)}
+            if space == "CPCA":
+                cache[key]["ncomp"] = nc.value
             if nv is not None:
                 rr = nc.value // 2 if space == "PCA" else nc.value
                 cache[key]["nv"] = [nv[0, :rr], nv[1, :rr]]

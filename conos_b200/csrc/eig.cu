@@ -1,3 +1,5 @@
+#include <functional>
+
 #include "eig.cuh"
 #include "gemm_tc.cuh"
 
@@ -350,16 +352,18 @@ __global__ void __launch_bounds__(EIG_THREADS) eig_rr_kernel(const EigWork* __re
   }
 }
 
-template <int B>
-void run_eig(Context& ctx, const EigProblem* h_probs, int n_probs, int r, double tol, int max_iter) {
+// Generic driver: `matmul(works)` must fill Z = Op(Q) for every problem (Q, Z row-major [G][B] on the device).
+template <int B, class MatMul>
+void run_eig_generic(Context& ctx, const int* rows, double* const* Vout, double* const* theta_out, const double* const* Cmat,
+                     int n_probs, int r, double tol, int max_iter, MatMul&& matmul) {
   cudaStream_t s = ctx.stream;
   std::vector<EigWork> works(n_probs);
   size_t tot = 0;
   int maxG = 0;
   for (int p = 0; p < n_probs; ++p) {
-    tot += (size_t)h_probs[p].G * B;
-    maxG = h_probs[p].G > maxG ? h_probs[p].G : maxG;
-    CG_CHECK(h_probs[p].G >= B, "eigen block wider than the matrix");
+    tot += (size_t)rows[p] * B;
+    maxG = rows[p] > maxG ? rows[p] : maxG;
+    CG_CHECK(rows[p] >= B, "eigen block wider than the matrix");
   }
   DevBuf<double> Q(tot), Z(tot), theta((size_t)n_probs * B);
   DevBuf<int> conv((size_t)n_probs);
@@ -367,9 +371,9 @@ void run_eig(Context& ctx, const EigProblem* h_probs, int n_probs, int r, double
   conv.zero(s);
   size_t o = 0;
   for (int p = 0; p < n_probs; ++p) {
-    works[p] = EigWork{h_probs[p].C, h_probs[p].G, Q.p + o, Z.p + o, theta.p + (size_t)p * B, h_probs[p].V,
-                       h_probs[p].theta, conv.p + p, nullptr};
-    o += (size_t)h_probs[p].G * B;
+    works[p] = EigWork{Cmat ? Cmat[p] : nullptr, rows[p], Q.p + o, Z.p + o, theta.p + (size_t)p * B, Vout[p],
+                       theta_out ? theta_out[p] : nullptr, conv.p + p, nullptr};
+    o += (size_t)rows[p] * B;
   }
   DevBuf<EigWork> dw;
   dw.upload(works.data(), works.size(), s);
@@ -377,20 +381,18 @@ void run_eig(Context& ctx, const EigProblem* h_probs, int n_probs, int r, double
   CG_CUDA(cudaFuncSetAttribute(eig_orth_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CG_CUDA(cudaFuncSetAttribute(eig_rr_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 gi((unsigned)(((size_t)maxG * B + 255) / 256), n_probs);
-  dim3 gm((maxG + 7) / 8, n_probs);
   eig_init_kernel<B><<<gi, 256, 0, s>>>(dw.p);
   eig_orth_kernel<B><<<n_probs, EIG_THREADS, smem, s>>>(dw.p);
   ctx.stats.kernels += 2;
-  std::vector<int> hc(n_probs);
+  std::vector<int> hc(n_probs, 0);
   const int rr_every = 4;
   int it_done = 0;
   for (int it = 1; it <= max_iter; ++it) {
     it_done = it;
     {
       StageScope sc(ctx, "reduction.eig.matmul");
-      eig_matmul_kernel<B><<<gm, 256, 0, s>>>(dw.p);
+      matmul(works, dw.p, maxG);
     }
-    ctx.stats.kernels++;
     if (it % rr_every == 0) {
       {
         StageScope sc(ctx, "reduction.eig.rr");
@@ -418,13 +420,32 @@ void run_eig(Context& ctx, const EigProblem* h_probs, int n_probs, int r, double
   }
   // final Rayleigh-Ritz from an orthonormal basis
   eig_orth_kernel<B><<<n_probs, EIG_THREADS, smem, s>>>(dw.p);
-  eig_matmul_kernel<B><<<gm, 256, 0, s>>>(dw.p);
+  matmul(works, dw.p, maxG);
   eig_rr_kernel<B><<<n_probs, EIG_THREADS, smem, s>>>(dw.p, r, tol, 1);
-  ctx.stats.kernels += 3;
+  ctx.stats.kernels += 2;
   CG_CUDA(cudaGetLastError());
   CG_CUDA(cudaStreamSynchronize(s));
 }
 
+template <int B>
+void run_eig(Context& ctx, const EigProblem* h_probs, int n_probs, int r, double tol, int max_iter) {
+  std::vector<int> rows(n_probs);
+  std::vector<double*> V(n_probs), th(n_probs);
+  std::vector<const double*> Cm(n_probs);
+  for (int p = 0; p < n_probs; ++p) {
+    rows[p] = h_probs[p].G;
+    V[p] = h_probs[p].V;
+    th[p] = h_probs[p].theta;
+    Cm[p] = h_probs[p].C;
+  }
+  cudaStream_t s = ctx.stream;
+  run_eig_generic<B>(ctx, rows.data(), V.data(), th.data(), Cm.data(), n_probs, r, tol, max_iter,
+                     [&](std::vector<EigWork>&, const EigWork* dw, int maxG) {
+                       dim3 gm((maxG + 7) / 8, n_probs);
+                       eig_matmul_kernel<B><<<gm, 256, 0, s>>>(dw);
+                       ctx.stats.kernels++;
+                     });
+}
 
 // =================================================================== tensor-core path (shared Gram operator)
 constexpr int TB = 32;  // block width of the tensor-core path
@@ -582,6 +603,17 @@ void top_eigenvectors_batched(Context& ctx, const EigProblem* h_probs, int n_pro
   else run_eig<64>(ctx, h_probs, n_probs, r, tol, max_iter);
 }
 
+
+void top_eigenvectors_operator(Context& ctx, int n_rows, int r, double tol, int max_iter,
+                               const std::function<void(const double* Q, double* Z, int B)>& apply, double* V,
+                               double* theta) {
+  CG_CHECK(r >= 1 && r <= 56, "1..56 eigenvectors per problem");
+  double* Vp[1] = {V};
+  double* tp[1] = {theta};
+  auto mm = [&](std::vector<EigWork>& works, const EigWork*, int) { apply(works[0].Q, works[0].Z, r <= 24 ? 32 : 64); };
+  if (r <= 24) run_eig_generic<32>(ctx, &n_rows, Vp, tp, nullptr, 1, r, tol, max_iter, mm);
+  else run_eig_generic<64>(ctx, &n_rows, Vp, tp, nullptr, 1, r, tol, max_iter, mm);
+}
 
 void top_eigenvectors_shared_gram(Context& ctx, const TcEigSample* samples, int n_samples,
                                   const TcEigProblem* probs, int n_probs, int r, double tol, int max_outer,

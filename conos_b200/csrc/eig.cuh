@@ -3,6 +3,8 @@
 //   Z = C Q  ->  orthonormalise (Cholesky-QR twice; Jacobi eigen-decomposition of Z'Z when rank deficient)
 //   Rayleigh-Ritz (Jacobi on Q'CQ) every few iterations and at the end; stop when the residuals ||C q - theta q|| of the leading r pairs fall below tol * theta_1.
 #pragma once
+#include <functional>
+
 #include "common.cuh"
 
 namespace cg {
@@ -16,6 +18,12 @@ struct EigProblem {
 
 // Block width is 32 for r <= 24 and 64 for r <= 56.
 void top_eigenvectors_batched(Context& ctx, const EigProblem* h_probs, int n_probs, int r, double tol, int max_iter);
+
+// One symmetric PSD operator given as a callback: apply(Q, Z, B) must set Z = Op(Q) for the row-major [n_rows][B]
+// device blocks (used for the implicit n1 x n1 operator of the CCA reduction).
+void top_eigenvectors_operator(Context& ctx, int n_rows, int r, double tol, int max_iter,
+                               const std::function<void(const double* Q, double* Z, int B)>& apply, double* V,
+                               double* theta);
 
 // ---------------------------------------------------------------------------------------------------------------
 // Tensor-core path for the common case "every pair uses all genes of its samples in storage order": the scaled

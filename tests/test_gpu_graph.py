@@ -302,3 +302,32 @@ def test_build_graph_alignment_strength(ctx, oracle, small_panel):
     con.pairs["PCA"] = {key: {"CPC": red["CPC"], "genes": red["genes"]} for key, red in ref["pairs"].items()}
     g = con.buildGraph(k=10, k_self=5, space="PCA", ncomps=20, n_odgenes=300, alignment_strength=0.3)
     _graphs_equal(g, ref["graph"], rtol=1e-6)
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_device_cpca_rotation(ctx, oracle, small_panel, exact):
+    """quickCPCA on the device: covariances, irlba-replacing initial vectors and the cpcaF iteration; the common
+    components match the oracle's (exact mode tightly; the tensor-core Gram only to its 1e-6 accuracy)."""
+    import conos_b200
+    osamples = to_oracle_samples(oracle, small_panel)
+    ref = oracle.build_graph(osamples, k=10, k_self=5, space="CPCA", ncomps=12, n_odgenes=300,
+                             score_component_variance=True)
+    con = conos_b200.Conos(small_panel, ctx=ctx)
+    ctx.lib.cg_set_option(ctx.h, b"exact_reduction", 1.0 if exact else 0.0)
+    try:
+        g = con.buildGraph(k=10, k_self=5, space="CPCA", ncomps=12, n_odgenes=300, score_component_variance=True)
+    finally:
+        ctx.lib.cg_set_option(ctx.h, b"exact_reduction", 0.0)
+    tol = 1e-6 if exact else 2e-3
+    for key, red in ref["pairs"].items():
+        mine = con.pairs["CPCA"][key]
+        assert mine["CPC"].shape == red["CPC"].shape and mine["CPC"].shape[1] == 12
+        dots = np.abs(np.sum(mine["CPC"] * red["CPC"], axis=0))
+        assert dots.min() > 1 - tol, (key, dots.min())
+        for side in (0, 1):
+            np.testing.assert_allclose(mine["nv"][side], red["nv"][side], rtol=100 * tol)
+    og = ref["graph"]
+    mine_e = {(min(a, b), max(a, b)) for a, b in zip(g.vertices[g.edge_from].tolist(), g.vertices[g.edge_to].tolist())}
+    ref_e = {(min(a, b), max(a, b))
+             for a, b in zip(og["vertices"][og["from"]].tolist(), og["vertices"][og["to"]].tolist())}
+    assert len(mine_e & ref_e) / len(mine_e | ref_e) > (0.995 if exact else 0.97)
