@@ -289,7 +289,22 @@ class Conos:
                                           ptr(counts, C.c_int64)))
         # populate self$pairs[[space]] like updatePairs does (R/conclass.R:1090-1092)
         for slot, (pi, key, od) in enumerate(used_pairs):
-            if key in cache or space == "CCA":
+            if key in cache:
+                continue
+            if space == "CCA":
+                nu, nvv, dd = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+                self.ctx.check(lib.cg_pair_cca(h, slot, C.byref(nu), C.byref(nvv), C.byref(dd), None, None, None, None,
+                                               None))
+                if nu.value == 0:
+                    continue
+                u = np.zeros((nu.value, dd.value), order="F")
+                v = np.zeros((nvv.value, dd.value), order="F")
+                ru = np.zeros(nu.value, np.int32)
+                rv = np.zeros(nvv.value, np.int32)
+                sg = np.zeros(dd.value)
+                self.ctx.check(lib.cg_pair_cca(h, slot, None, None, None, ptr(u, C.c_double), ptr(v, C.c_double),
+                                               ptr(ru, C.c_int32), ptr(rv, C.c_int32), ptr(sg, C.c_double)))
+                cache[key] = {"u": u, "v": v, "rows_u": ru, "rows_v": rv, "d": sg, "genes": self._gene_names(od)}
                 continue
             nr, nc = C.c_int32(0), C.c_int32(0)
             self.ctx.check(lib.cg_pair_reduction(h, slot, C.byref(nr), C.byref(nc), None, None))

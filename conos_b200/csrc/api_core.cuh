@@ -17,6 +17,10 @@ struct cg_context {
     std::vector<double> nv;   // [2][n_cols] or empty
     int pn[2] = {0, 0};
     std::vector<double> proj[2];  // column-major n x ncomps
+    // CCA: scaled canonical variates, kept-cell row maps, singular values
+    std::vector<double> u, v, sigma;
+    std::vector<int> rows_u, rows_v;
+    int cca_d = 0;
   };
   std::vector<PairKeep> kept;
   bool keep_projections = false;

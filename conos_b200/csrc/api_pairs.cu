@@ -200,6 +200,16 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
         knn_prep_from_f64_colmajor(c, R.v.p, B.nb, B.d, B.nb, metric, pbn);
         B.rows_u.upload(R.h_rows_u.data(), R.h_rows_u.size(), c.stream);
         B.rows_v.upload(R.h_rows_v.data(), R.h_rows_v.size(), c.stream);
+        if (!pr.u) {  // computed on the device: keep host copies for the self$pairs$CCA cache
+          keep.cca_d = B.d;
+          keep.u.resize((size_t)B.na * B.d);
+          keep.v.resize((size_t)B.nb * B.d);
+          R.u.download(keep.u.data(), keep.u.size(), c.stream);
+          R.v.download(keep.v.data(), keep.v.size(), c.stream);
+          keep.rows_u = R.h_rows_u;
+          keep.rows_v = R.h_rows_v;
+          keep.sigma = R.h_sigma;
+        }
         if (ctx->keep_projections) {
           keep.pn[0] = B.na;
           keep.pn[1] = B.nb;
@@ -307,6 +317,23 @@ int cg_pair_reduction(cg_context* ctx, int which, int32_t* n_rows, int32_t* n_co
   if (n_cols) *n_cols = k.n_cols;
   if (rot && !k.rot.empty()) memcpy(rot, k.rot.data(), k.rot.size() * sizeof(double));
   if (nv && !k.nv.empty()) memcpy(nv, k.nv.data(), k.nv.size() * sizeof(double));
+  CG_API_END(ctx)
+}
+
+int cg_pair_cca(cg_context* ctx, int which, int32_t* n_u, int32_t* n_v, int32_t* d, double* u, double* v,
+                int32_t* rows_u, int32_t* rows_v, double* sigma) {
+  CG_API_BEGIN
+  CG_CHECK(ctx && which >= 0 && which < (int)ctx->kept.size(), "no such pair in the last cg_pairs_edges call");
+  const auto& k = ctx->kept[which];
+  CG_CUDA(cudaStreamSynchronize(ctx->c.stream));
+  if (n_u) *n_u = (int32_t)k.rows_u.size();
+  if (n_v) *n_v = (int32_t)k.rows_v.size();
+  if (d) *d = k.cca_d;
+  if (u && !k.u.empty()) memcpy(u, k.u.data(), k.u.size() * sizeof(double));
+  if (v && !k.v.empty()) memcpy(v, k.v.data(), k.v.size() * sizeof(double));
+  if (rows_u && !k.rows_u.empty()) memcpy(rows_u, k.rows_u.data(), k.rows_u.size() * sizeof(int));
+  if (rows_v && !k.rows_v.empty()) memcpy(rows_v, k.rows_v.data(), k.rows_v.size() * sizeof(int));
+  if (sigma && !k.sigma.empty()) memcpy(sigma, k.sigma.data(), k.sigma.size() * sizeof(double));
   CG_API_END(ctx)
 }
 

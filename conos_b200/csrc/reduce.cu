@@ -110,7 +110,11 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
   }
   CG_CUDA(cudaStreamSynchronize(st));
   if (todo.empty()) return;
-  CG_CHECK(P.space != CG_SPACE_CCA, "device CCA is not built yet: supply u and v");
+  if (P.space == CG_SPACE_CCA) {
+    StageScope sc(ctx, "reduction.cca");
+    for (int q : todo) compute_cca_reduction(ctx, panel, pairs[q], P, out[q]);
+    return;
+  }
 
   // ---- per-sample Gram matrices
   {

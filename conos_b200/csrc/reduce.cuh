@@ -16,9 +16,13 @@ struct PairReduction {
   DevBuf<double> u, v;        // column-major n_u x d, n_v x d
   int n_u = 0, n_v = 0;
   std::vector<int> h_rows_u, h_rows_v;
+  std::vector<double> h_sigma;  // singular values (res$d)
 };
 
 void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs, int n_pairs, const cg_params& P,
                              std::vector<PairReduction>& out);
+
+// quickCCA for one pair on the device (cca.cu)
+void compute_cca_reduction(Context& ctx, cg_panel& panel, const cg_pair& pr, const cg_params& P, PairReduction& R);
 
 }  // namespace cg

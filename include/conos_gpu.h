@@ -135,6 +135,11 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
 /* The reduction of the most recent cg_pairs_edges call for pair `which`: PCA/CPCA: rot n_genes x ncols;
  * nv: per-sample variance fractions [2][ncols] when score_component_variance.  Query sizes with NULL outputs. */
 int cg_pair_reduction(cg_context* ctx, int which, int32_t* n_rows, int32_t* n_cols, double* rot, double* nv);
+/* CCA reduction of pair `which` computed by the most recent call: u (n_u x d), v (n_v x d) column-major, already
+ * scaled by sqrt(d)/max (R/conos.R:363-366); rows_u / rows_v = cell index of every row (cells with empty rows are
+ * dropped, :336); sigma = res$d.  Query the sizes with NULL outputs. */
+int cg_pair_cca(cg_context* ctx, int which, int32_t* n_u, int32_t* n_v, int32_t* d, double* u, double* v,
+                int32_t* rows_u, int32_t* rows_v, double* sigma);
 /* Projections of pair `which` of the most recent call (column-major n x ncomps doubles), for parity tests;
  * they are only kept after cg_keep_projections(ctx, 1). */
 int cg_keep_projections(cg_context* ctx, int enable);

@@ -331,3 +331,47 @@ def test_device_cpca_rotation(ctx, oracle, small_panel, exact):
     ref_e = {(min(a, b), max(a, b))
              for a, b in zip(og["vertices"][og["from"]].tolist(), og["vertices"][og["to"]].tolist())}
     assert len(mine_e & ref_e) / len(mine_e | ref_e) > (0.995 if exact else 0.97)
+
+
+def test_cca_with_oracle_variates(ctx, oracle, small_panel):
+    """space='CCA' with the oracle's u, v supplied (cache-hit path): everything after the reduction must agree,
+    including cells dropped for empty rows and alignment.strength > 0 (k1 > k, cor.base = 2)."""
+    import conos_b200
+    osamples = to_oracle_samples(oracle, small_panel)
+    ref = oracle.build_graph(osamples, k=10, k_self=5, space="CCA", ncomps=10, n_odgenes=300, alignment_strength=0.2)
+    con = conos_b200.Conos(small_panel, ctx=ctx)
+    con.pairs["CCA"] = {key: {"u": red["u"], "v": red["v"], "rows_u": np.nonzero(red["keep"][0])[0],
+                              "rows_v": np.nonzero(red["keep"][1])[0]} for key, red in ref["pairs"].items()}
+    g = con.buildGraph(k=10, k_self=5, space="CCA", ncomps=10, n_odgenes=300, alignment_strength=0.2)
+    _graphs_equal(g, ref["graph"], rtol=1e-6)
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_device_cca_reduction(ctx, oracle, small_panel, exact):
+    """quickCCA on the device (implicit n1 x n1 operator instead of the dense n1 x n2 cross product).  With the
+    FP64 Gram the variates match the dense SVD tightly; the tensor-core Gram (bf16x3) limits it to ~1e-5."""
+    import conos_b200
+    osamples = to_oracle_samples(oracle, small_panel)
+    ref = oracle.build_graph(osamples, k=10, k_self=5, space="CCA", ncomps=10, n_odgenes=300)
+    con = conos_b200.Conos(small_panel, ctx=ctx)
+    ctx.lib.cg_set_option(ctx.h, b"exact_reduction", 1.0 if exact else 0.0)
+    try:
+        g = con.buildGraph(k=10, k_self=5, space="CCA", ncomps=10, n_odgenes=300)
+    finally:
+        ctx.lib.cg_set_option(ctx.h, b"exact_reduction", 0.0)
+    rt, at, jt = (1e-8, 1e-7, 0.995) if exact else (2e-4, 5e-3, 0.97)
+    for key, red in ref["pairs"].items():
+        mine = con.pairs["CCA"][key]
+        assert np.array_equal(mine["rows_u"], np.nonzero(red["keep"][0])[0])
+        assert np.array_equal(mine["rows_v"], np.nonzero(red["keep"][1])[0])
+        np.testing.assert_allclose(mine["d"], red["d"], rtol=rt)
+        for a, b in ((mine["u"], red["u"]), (mine["v"], red["v"])):
+            sign = np.sign(np.sum(a * b, axis=0))
+            np.testing.assert_allclose(a * sign[None, :], b, rtol=0, atol=at * np.abs(b).max())
+        # u_j and v_j flip together
+        assert np.array_equal(np.sign(np.sum(mine["u"] * red["u"], axis=0)), np.sign(np.sum(mine["v"] * red["v"], axis=0)))
+    og = ref["graph"]
+    mine_e = {(min(a, b), max(a, b)) for a, b in zip(g.vertices[g.edge_from].tolist(), g.vertices[g.edge_to].tolist())}
+    ref_e = {(min(a, b), max(a, b))
+             for a, b in zip(og["vertices"][og["from"]].tolist(), og["vertices"][og["to"]].tolist())}
+    assert len(mine_e & ref_e) / len(mine_e | ref_e) > jt
