@@ -77,6 +77,7 @@ SIGNATURES = {
     "cg_edges_append_host": (C.c_int, [_VP, C.POINTER(_VP), c_int_p, c_int_p, c_dbl_p, c_int_p, C.c_int64]),
     "cg_edges_append_device": (C.c_int, [_VP, C.POINTER(_VP), _VP, _VP, _VP, _VP, C.c_int64]),
     "cg_set_option": (C.c_int, [_VP, C.c_char_p, C.c_double]),
+    "cg_get_stat": (C.c_int, [_VP, C.c_char_p, C.POINTER(C.c_double)]),
     "cg_profile": (C.c_int, [_VP, C.c_int]),
     "cg_profile_dump": (C.c_int, [_VP, C.c_char_p, C.c_int]),
     "cg_timer_start": (C.c_int, [_VP]),

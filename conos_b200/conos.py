@@ -9,6 +9,7 @@ R/conclass.R:1035-1107), gene-set selection by name (R/conos.R:107-117) and resu
 from __future__ import annotations
 
 import ctypes as C
+import time
 import warnings
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence
@@ -41,7 +42,7 @@ class Pagoda2:
 @dataclass
 class ConosGraph:
     """What ``self$graph`` (an igraph) carries for findCommunities / embedGraph (R/conclass.R:336-343)."""
-    names: List[str]            # V(g)$name, vertex order = first appearance in the edge table
+    names: object               # V(g)$name (array of str), vertex order = first appearance in the edge table
     vertices: np.ndarray        # global cell index of every vertex
     edge_from: np.ndarray       # vertex ids, from < to, sorted by (from, to)
     edge_to: np.ndarray
@@ -77,6 +78,8 @@ class Conos:
         self._panel = None
         self._panel_names: List[str] = []
         self._vocab = None
+        self._cell_names = None
+        self._pinned = {}
         self.timings: Dict[str, float] = {}
         if x is not None:
             self.addSamples(x)
@@ -99,6 +102,7 @@ class Conos:
                 raise ValueError(f"sample {n}: counts must be cells x genes")
             self.samples[n] = s
         self._vocab = None
+        self._cell_names = None
         self._drop_panel()
 
     def _drop_panel(self):
@@ -231,7 +235,10 @@ class Conos:
                 pair_names.append((names[ia], names[ib]))
         if len(pair_names) < 1:
             raise ValueError("insufficient number of comparable pairs")
+        t_0 = time.perf_counter()
         self._ensure_panel(names)
+        self.timings["panel_ms"] = 1e3 * (time.perf_counter() - t_0)
+        t_0 = time.perf_counter()
         index = {n: t for t, n in enumerate(names)}
         cache = self.pairs.setdefault(space, {})
 
@@ -285,8 +292,12 @@ class Conos:
         lib, h = self.ctx.lib, self.ctx.h
         edges = C.c_void_p()
         counts = np.zeros(max(len(used_pairs), 1), np.int64)
+        self.timings["host_pairs_ms"] = 1e3 * (time.perf_counter() - t_0)
+        t_0 = time.perf_counter()
         self.ctx.check(lib.cg_pairs_edges(h, self._panel, carr, len(used_pairs), C.byref(P), C.byref(edges),
                                           ptr(counts, C.c_int64)))
+        self.timings["pairs_edges_ms"] = 1e3 * (time.perf_counter() - t_0)
+        t_0 = time.perf_counter()
         # populate self$pairs[[space]] like updatePairs does (R/conclass.R:1090-1092)
         for slot, (pi, key, od) in enumerate(used_pairs):
             if key in cache:
@@ -321,6 +332,8 @@ class Conos:
         self._last_edges = edges
         self._last_params = P
         self._last_names = names
+        self.timings["cache_fill_ms"] = 1e3 * (time.perf_counter() - t_0)
+        t_0 = time.perf_counter()
         if not assemble:
             return edges
 
@@ -346,13 +359,32 @@ class Conos:
             self.ctx.check(lib.cg_local_edges(h, self._panel, ptr(sidx, C.c_int32), len(names), C.byref(P),
                                               C.byref(edges)))
         self._n_inter_edges = int(sum(self._last_pair_counts.values()))
+        self.timings["local_edges_ms"] = 1e3 * (time.perf_counter() - t_0)
+        t_0 = time.perf_counter()
         g = self._assemble(edges, names, fetch=fetch)
+        self.timings["assemble_fetch_ms"] = 1e3 * (time.perf_counter() - t_0)
         lib.cg_edges_free(edges)
         self._last_edges = None
         if balance_edge_weights:
             g = self._balance(g, names, same_factor_downweight)
         self.graph = g
         return g
+
+    def _out(self, key: str, n: int, dtype):
+        """Result buffer in pinned host memory when torch is importable (grow-only, reused across calls; the
+        returned array is a private copy-free view valid until the next buildGraph), plain NumPy otherwise."""
+        try:
+            import torch
+            if not torch.cuda.is_available():
+                raise RuntimeError
+            tdt = {np.int32: torch.int32, np.int64: torch.int64, np.float64: torch.float64}[dtype]
+            buf = self._pinned.get(key)
+            if buf is None or buf.numel() < n or buf.dtype != tdt:
+                buf = torch.empty(max(n, 1), dtype=tdt).pin_memory()
+                self._pinned[key] = buf
+            return buf.numpy()[:n]
+        except Exception:
+            return np.empty(n, dtype)
 
     def _assemble(self, edges, names, fetch: bool = True) -> ConosGraph:
         lib, h = self.ctx.lib, self.ctx.h
@@ -368,20 +400,21 @@ class Conos:
                            adj_p=np.zeros(1, np.int64), adj_i=z, adj_x=np.zeros(0))
             g.n_vertices_device, g.n_edges_device = nv.value, ne.value
             return g
-        vertices = np.empty(nv.value, np.int32)
-        ef = np.empty(ne.value, np.int32)
-        et = np.empty(ne.value, np.int32)
-        w = np.empty(ne.value, np.float64)
-        ty = np.empty(ne.value, np.int32)
+        vertices = self._out("v", nv.value, np.int32)
+        ef = self._out("ef", ne.value, np.int32)
+        et = self._out("et", ne.value, np.int32)
+        w = self._out("w", ne.value, np.float64)
+        ty = self._out("ty", ne.value, np.int32)
         self.ctx.check(lib.cg_graph_fetch(h, gh, ptr(vertices, C.c_int32), ptr(ef, C.c_int32), ptr(et, C.c_int32),
                                           ptr(w, C.c_double), ptr(ty, C.c_int32)))
-        ap = np.zeros(nv.value + 1, np.int64)
-        ai = np.empty(2 * ne.value, np.int32)
-        ax = np.empty(2 * ne.value, np.float64)
+        ap = self._out("ap", nv.value + 1, np.int64)
+        ai = self._out("ai", 2 * ne.value, np.int32)
+        ax = self._out("ax", 2 * ne.value, np.float64)
         self.ctx.check(lib.cg_graph_fetch_adjacency(h, gh, ptr(ap, C.c_int64), ptr(ai, C.c_int32), ptr(ax, C.c_double)))
         lib.cg_graph_free(gh)
-        cell_names = np.array([c for n in names for c in self.samples[n].cells], dtype=object)
-        return ConosGraph(names=list(cell_names[vertices]), vertices=vertices, edge_from=ef, edge_to=et, weight=w,
+        if self._cell_names is None or self._cell_names[0] != list(names):
+            self._cell_names = (list(names), np.array([c for n in names for c in self.samples[n].cells], dtype=object))
+        return ConosGraph(names=self._cell_names[1][vertices], vertices=vertices, edge_from=ef, edge_to=et, weight=w,
                           type=ty, adj_p=ap, adj_i=ai, adj_x=ax)
 
     def _balance(self, g: ConosGraph, names, same_factor_downweight: float) -> ConosGraph:

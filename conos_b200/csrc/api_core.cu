@@ -103,7 +103,28 @@ int cg_set_option(cg_context* ctx, const char* name, double value) {
     ctx->c.exact_reduction = value != 0.0;
     return 0;
   }
+  if (strcmp(name, "knn_engine") == 0) {
+    ctx->c.knn_engine = (int)value;
+    return 0;
+  }
+  if (strcmp(name, "knn_cand_cap") == 0) {
+    ctx->c.knn_cand_cap = (int)value;
+    return 0;
+  }
   return ::cg::fail(ctx, "unknown option");
+}
+
+int cg_get_stat(cg_context* ctx, const char* name, double* value) {
+  if (!ctx || !name || !value) return 1;
+  if (strcmp(name, "knn_redo_blocks") == 0) {
+    *value = (double)ctx->c.knn_redo_blocks;
+    return 0;
+  }
+  if (strcmp(name, "kernel_launches") == 0) {
+    *value = (double)ctx->c.stats.kernels;
+    return 0;
+  }
+  return ::cg::fail(ctx, "unknown statistic");
 }
 
 int cg_profile(cg_context* ctx, int enable) {

@@ -110,6 +110,11 @@ struct Context {
   uint64_t knn_launches = 0;
   double knn_candidates = 0.0;  // sum over launches of n_query * n_ref
   double knn_bytes = 0.0;       // algorithmic HBM bytes
+  // kNN engine: 0 = auto (two-phase tensor-core kernel, streaming kernel for small problems and redo blocks),
+  // 1 = streaming tensor-core kernel only, 2 = exact SIMT kernel only
+  int knn_engine = 0;
+  int knn_cand_cap = 64;          // candidate slots per (row, half) the two-phase kernel may use (tests shrink it)
+  uint64_t knn_redo_blocks = 0;   // 256-row blocks the streaming kernel had to recompute
   // 1: FP64 reductions (atomics Gram, explicit covariance, plain subspace iteration) instead of the tensor-core path
   bool exact_reduction = false;
   // optional per-stage wall-clock profile (stream synchronised at both ends of a stage)

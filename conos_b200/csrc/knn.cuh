@@ -17,6 +17,8 @@
 // the tensor-core kernel uses it to subtract a per-query threshold inside the MMA; every exact computation
 // (re-rank, SIMT kernel) only touches the d real columns.
 #pragma once
+#include <vector>
+
 #include "common.cuh"
 
 namespace cg {
@@ -53,6 +55,19 @@ struct KnnItem {
   int qblock;  // block of 256 query rows
 };
 
+// Two-phase tensor-core kernel (knn_tc2.cu): per-problem plan and scratch
+constexpr int KNN_TC2_CAND_STRIDE = 64;  // candidate slots per (query row, 64-column half)
+struct KnnTc2Aux {
+  int sg = 0;   // columns per group inside a tile half: 64 (whole half), 32 or 16
+  int tg = 0;   // tiles per group (sg == 64 only)
+  int ngt = 0;  // groups per (row, half)
+  int pad = 0;
+  long long row0 = 0;   // first row of this problem in the chunk's scratch arrays
+  int* cand = nullptr;  // [rows][2][KNN_TC2_CAND_STRIDE] reference indices that passed the filter
+  int* cnt = nullptr;   // [rows][2] survivors seen (may exceed the capacity: overflow)
+  float* thr = nullptr; // [rows] threshold the filter applied to the approximate dot product
+};
+
 // Fill a tiled panel from a column-major double matrix (R layout) -- angular panels are L2-normalised.
 void knn_prep_from_f64_colmajor(Context& ctx, const double* d_src, int n, int d, int ld, Metric metric,
                                 KnnPanel& out);
@@ -68,6 +83,12 @@ void knn_simt_launch(Context& ctx, const KnnProblem* d_probs, const KnnProblem* 
 // canonical fp32 re-rank of the survivors, per-row sorted top-k lists in shared memory.
 void knn_tc_launch(Context& ctx, const KnnProblem* d_probs, const KnnProblem* h_probs, int n_probs, int k,
                    int d_pad, int d);
+
+// Two-phase kernel: decides whether a problem with nr references qualifies and fills the plan.
+bool knn_tc2_plan(int nr, int k, KnnTc2Aux& ax);
+// Runs the problems in `plist`; 256-row blocks that need the exact streaming kernel are appended to `redo`.
+void knn_tc2_run(Context& ctx, const KnnProblem* d_probs, const KnnProblem* h_probs, const std::vector<int>& plist,
+                 std::vector<KnnTc2Aux>& aux, int n_probs, int k, int d_pad, int d, std::vector<KnnItem>& redo);
 
 // Dispatch by (k, metric): the tensor-core kernel whenever it applies.
 void knn_launch(Context& ctx, const KnnProblem* d_probs, const KnnProblem* h_probs, int n_probs, int k, int d_pad,

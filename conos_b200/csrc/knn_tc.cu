@@ -506,33 +506,44 @@ void launch_tc(Context& ctx, const KnnProblem* d_probs, const KnnItem* d_items, 
 void knn_tc_launch(Context& ctx, const KnnProblem* d_probs, const KnnProblem* h_probs, int n_probs, int k,
                    int d_pad, int d) {
   CG_CHECK(k >= 1 && k <= KNN_TC_MAXK, "tensor-core kNN serves 1 <= k <= 32");
+  CG_CHECK(d_pad == 32 || d_pad == 64, "d_pad must be 32 or 64");
+  // problems large enough for the two-phase kernel go there; the rest, and the 256-row blocks it hands back
+  // (candidate overflow from ties / duplicates), run through the streaming kernel
   std::vector<KnnItem> items;
+  std::vector<KnnTc2Aux> aux((size_t)n_probs);
+  std::vector<int> plist;
   double cand = 0.0, bytes = 0.0;
   for (int p = 0; p < n_probs; ++p) {
     if (h_probs[p].nq <= 0) continue;
-    int nb = (h_probs[p].nq + QBLOCK - 1) / QBLOCK;
-    for (int b = 0; b < nb; ++b) items.push_back(KnnItem{p, b});
     cand += (double)h_probs[p].nq * (double)h_probs[p].nr;
     bytes += 4.0 * d_pad * ((double)h_probs[p].nq + h_probs[p].nr) + 8.0 * k * (double)h_probs[p].nq;
+    if (ctx.knn_engine == 0 && knn_tc2_plan(h_probs[p].nr, k, aux[p])) {
+      plist.push_back(p);
+      continue;
+    }
+    int nb = (h_probs[p].nq + QBLOCK - 1) / QBLOCK;
+    for (int b = 0; b < nb; ++b) items.push_back(KnnItem{p, b});
   }
-  if (items.empty()) return;
-  DevBuf<KnnItem> d_items;
-  d_items.upload(items.data(), items.size(), ctx.stream);
+  if (items.empty() && plist.empty()) return;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ctx.time_knn) {
     CG_CUDA(cudaEventCreate(&e0));
     CG_CUDA(cudaEventCreate(&e1));
     CG_CUDA(cudaEventRecord(e0, ctx.stream));
   }
-  CG_CHECK(d_pad == 32 || d_pad == 64, "d_pad must be 32 or 64");
-  const int ni = (int)items.size();
-  const bool fold = d < d_pad;  // a spare K dimension exists: the threshold rides in the MMA
-  if (d_pad == 32) {
-    if (k <= 16) { if (fold) launch_tc<32, 16, true>(ctx, d_probs, d_items.p, ni, k, d); else launch_tc<32, 16, false>(ctx, d_probs, d_items.p, ni, k, d); }
-    else { if (fold) launch_tc<32, 32, true>(ctx, d_probs, d_items.p, ni, k, d); else launch_tc<32, 32, false>(ctx, d_probs, d_items.p, ni, k, d); }
-  } else {
-    if (k <= 16) { if (fold) launch_tc<64, 16, true>(ctx, d_probs, d_items.p, ni, k, d); else launch_tc<64, 16, false>(ctx, d_probs, d_items.p, ni, k, d); }
-    else { if (fold) launch_tc<64, 32, true>(ctx, d_probs, d_items.p, ni, k, d); else launch_tc<64, 32, false>(ctx, d_probs, d_items.p, ni, k, d); }
+  if (!plist.empty()) knn_tc2_run(ctx, d_probs, h_probs, plist, aux, n_probs, k, d_pad, d, items);
+  if (!items.empty()) {
+    DevBuf<KnnItem> d_items;
+    d_items.upload(items.data(), items.size(), ctx.stream);
+    const int ni = (int)items.size();
+    const bool fold = d < d_pad;  // a spare K dimension exists: the threshold rides in the MMA
+    if (d_pad == 32) {
+      if (k <= 16) { if (fold) launch_tc<32, 16, true>(ctx, d_probs, d_items.p, ni, k, d); else launch_tc<32, 16, false>(ctx, d_probs, d_items.p, ni, k, d); }
+      else { if (fold) launch_tc<32, 32, true>(ctx, d_probs, d_items.p, ni, k, d); else launch_tc<32, 32, false>(ctx, d_probs, d_items.p, ni, k, d); }
+    } else {
+      if (k <= 16) { if (fold) launch_tc<64, 16, true>(ctx, d_probs, d_items.p, ni, k, d); else launch_tc<64, 16, false>(ctx, d_probs, d_items.p, ni, k, d); }
+      else { if (fold) launch_tc<64, 32, true>(ctx, d_probs, d_items.p, ni, k, d); else launch_tc<64, 32, false>(ctx, d_probs, d_items.p, ni, k, d); }
+    }
   }
   if (ctx.time_knn) {
     CG_CUDA(cudaEventRecord(e1, ctx.stream));
@@ -546,13 +557,12 @@ void knn_tc_launch(Context& ctx, const KnnProblem* d_probs, const KnnProblem* h_
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
   }
-  // d_items is freed by cudaFree, which synchronises with the kernel that reads it
-  CG_CUDA(cudaStreamSynchronize(ctx.stream));
 }
 
 void knn_launch(Context& ctx, const KnnProblem* d_probs, const KnnProblem* h_probs, int n_probs, int k, int d_pad,
                 int d, Metric metric) {
-  if (metric == METRIC_ANGULAR && k <= KNN_TC_MAXK) knn_tc_launch(ctx, d_probs, h_probs, n_probs, k, d_pad, d);
+  if (metric == METRIC_ANGULAR && k <= KNN_TC_MAXK && ctx.knn_engine != 2)
+    knn_tc_launch(ctx, d_probs, h_probs, n_probs, k, d_pad, d);
   else knn_simt_launch(ctx, d_probs, h_probs, n_probs, k, d_pad, d, metric);
 }
 

@@ -55,7 +55,13 @@ int cg_timer_stop(cg_context* ctx, double* ms);
 /* options: "exact_reduction" = 1 runs the per-pair reductions in FP64 on the CUDA cores (Gram by FP64 atomics,
  * explicit covariance, subspace iteration to 1e-10) instead of the default tensor-core path (bf16x3 GEMMs,
  * Chebyshev-filtered iteration to irlba's own tolerance 1e-5) -- used by the parity tests */
+/* "knn_engine": 0 = automatic (two-phase tensor-core kernel; the streaming tensor-core kernel for small problems
+ * and for blocks whose candidate lists overflow), 1 = streaming tensor-core kernel only, 2 = exact SIMT kernel
+ * only.  "knn_cand_cap": candidate slots per (query row, half tile) of the two-phase kernel, 1..64 (tests
+ * shrink it to force the overflow path).  Results are identical for every setting. */
 int cg_set_option(cg_context* ctx, const char* name, double value);
+/* counters: "knn_redo_blocks" (256-row blocks recomputed by the streaming kernel), "kernel_launches" */
+int cg_get_stat(cg_context* ctx, const char* name, double* value);
 /* optional per-stage wall-clock profile: enable (resets), then dump "name=ms;name=ms;..." into buf */
 int cg_profile(cg_context* ctx, int enable);
 int cg_profile_dump(cg_context* ctx, char* buf, int buf_len);
