@@ -140,6 +140,6 @@ struct StageScope {
   }
 };
 
-inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
+__host__ __device__ inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
 
 }  // namespace cg

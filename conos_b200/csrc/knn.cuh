@@ -13,6 +13,9 @@
 //   tiled[(row/8)][chunk = col/4][row%8][col%4],   KC = d_pad/4 chunks, d_pad in {32, 64}
 // i.e. exactly the shared-memory image a K-major, no-swizzle tcgen05 (kind::tf32) operand needs, so a
 // tile of R rows (R % 8 == 0) is one contiguous byte range that a single 1-D bulk copy moves.
+// The panel is stored twice: the exact fp32 values (every exact computation reads these) followed, n_pad * d_pad
+// floats later, by the same values rounded to nearest fp16 in the 16-bit core-matrix layout
+// [row/8][col/8][row%8][col%8] (the kind::f16 tensor-core operand of knn_tc2.cu).
 // Rows are zero-padded up to a multiple of 256.  When d < d_pad the LAST padded column of every row holds -1:
 // the tensor-core kernel uses it to subtract a per-query threshold inside the MMA; every exact computation
 // (re-rank, SIMT kernel) only touches the d real columns.
@@ -33,12 +36,17 @@ struct KnnPanel {
   int d = 0;      // valid columns
   int d_pad = 0;  // 32 or 64
   int n_pad = 0;  // multiple of KNN_ROW_PAD
-  float* tiled = nullptr;  // n_pad * d_pad floats (not owned)
-  static size_t elems(int n, int d) { return round_up(n, KNN_ROW_PAD) * (size_t)(d <= 32 ? 32 : 64); }
+  float* tiled = nullptr;  // 1.5 * n_pad * d_pad floats (not owned): the exact fp32 panel, then its fp16 copy
+  static size_t elems(int n, int d) { return round_up(n, KNN_ROW_PAD) * (size_t)(d <= 32 ? 32 : 64) * 3 / 2; }
 };
 
 __host__ __device__ inline size_t knn_tiled_offset(int row, int col, int d_pad) {
   return (size_t)(row >> 3) * (size_t)(8 * d_pad) + (size_t)(col >> 2) * 32 + (size_t)(row & 7) * 4 + (col & 3);
+}
+
+// element (row, col) of the fp16 copy: 16-byte chunks of 8 halves, [row/8][col/8][row%8][col%8]
+__host__ __device__ inline size_t knn_tiled16_offset(int row, int col, int d_pad) {
+  return (size_t)(row >> 3) * (size_t)(8 * d_pad) + (size_t)(col >> 3) * 64 + (size_t)(row & 7) * 8 + (col & 7);
 }
 
 struct KnnProblem {

@@ -1,5 +1,8 @@
 // K1 prep_rows: cast to fp32, (angular) L2-normalise with the canonical fma chain, and write the
-// core-matrix tiled operand panel (see knn.cuh). HBM-bound: reads 8 or 4 B/element, writes 4 B/element.
+// core-matrix tiled operand panel and its fp16 copy (see knn.cuh). HBM-bound: reads 8 or 4 B/element,
+// writes 8 B/element.
+#include <cuda_fp16.h>
+
 #include "knn.cuh"
 
 namespace cg {
@@ -12,10 +15,17 @@ __global__ void knn_prep_kernel(const SrcT* __restrict__ src, int n, int d, int 
   if (row >= n_pad) return;
   const int KC = d_pad >> 2;
   float* dst = tiled + (size_t)(row >> 3) * (size_t)(8 * d_pad) + (size_t)(row & 7) * 4;
+  __half* dst16 = reinterpret_cast<__half*>(tiled + (size_t)n_pad * d_pad) + (size_t)(row >> 3) * (size_t)(8 * d_pad) +
+                  (size_t)(row & 7) * 8;  // fp16 copy: chunk c8 at + c8 * 64
   const bool fold = d < d_pad;  // spare last column: -1 (threshold dimension of the tensor-core kernel)
   if (row >= n) {
-    for (int c = 0; c < KC; ++c)
-      *reinterpret_cast<float4*>(dst + c * 32) = make_float4(0.f, 0.f, 0.f, (fold && c == KC - 1) ? -1.0f : 0.f);
+    for (int c = 0; c < KC; ++c) {
+      const float4 z = make_float4(0.f, 0.f, 0.f, (fold && c == KC - 1) ? -1.0f : 0.f);
+      *reinterpret_cast<float4*>(dst + c * 32) = z;
+      __half2* h = reinterpret_cast<__half2*>(dst16 + (c >> 1) * 64 + (c & 1) * 4);
+      h[0] = __floats2half2_rn(z.x, z.y);
+      h[1] = __floats2half2_rn(z.z, z.w);
+    }
     return;
   }
   float inv = 1.0f;
@@ -38,6 +48,9 @@ __global__ void knn_prep_kernel(const SrcT* __restrict__ src, int n, int d, int 
       if (fold && i == d_pad - 1) v[e] = -1.0f;
     }
     *reinterpret_cast<float4*>(dst + c * 32) = make_float4(v[0], v[1], v[2], v[3]);
+    __half2* h = reinterpret_cast<__half2*>(dst16 + (c >> 1) * 64 + (c & 1) * 4);
+    h[0] = __floats2half2_rn(v[0], v[1]);
+    h[1] = __floats2half2_rn(v[2], v[3]);
   }
 }
 

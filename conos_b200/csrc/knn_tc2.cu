@@ -21,6 +21,8 @@
 // block and of the reference tiles, streamed twice), warp 1 MMA issuer (tcgen05.mma kind::tf32, two
 // M=128 x N=128 accumulators per tile, double buffered = 512 TMEM columns), warps 2-17 epilogue: thread =
 // (query row, 64-column half), tcgen05.ld 32x32b.x16.
+#include <cuda_fp16.h>
+
 #include "knn.cuh"
 #include "ptx.cuh"
 
@@ -31,16 +33,21 @@ constexpr int T2_THREADS = 576;
 constexpr int TILE_N = 128;
 constexpr int QBLOCK = 256;
 constexpr int NGT_MAX = 48;           // groups per (row, half) kept in shared memory
-constexpr float TF32_MARGIN = 2.2e-3f;  // > 1.96e-3 = worst |tf32 dot - fp32 chain| for unit vectors (knn_tc.cu)
+// Both operands are rounded to nearest fp16 (11 significant bits, the precision of TF32 at twice the tensor rate and
+// half the bytes; components of unit vectors never overflow, and below 2^-14 the absolute error is < 2^-25): the
+// products are exact in the tensor core and the accumulation is fp32, so for unit vectors
+// |approximate dot - canonical fp32 dot| <= (2*2^-11 + 2^-22) * sum|q_i r_i| + d*2^-24 + accumulation < 9.9e-4.
+constexpr float MMA_MARGIN = 1.1e-3f;
 
 template <int D_PAD>
 struct T2Cfg {
-  static constexpr int KC = D_PAD / 4;
-  static constexpr int ROW_BYTES = D_PAD * 4;
+  // operands are the fp16 copies of the panels: [row/8][k/8][row%8][k%8] halves (16-byte chunks of 8)
+  static constexpr int KC = D_PAD / 8;              // 16-byte chunks per row
+  static constexpr int ROW_BYTES = D_PAD * 2;
   static constexpr int A_BYTES = QBLOCK * ROW_BYTES;
   static constexpr int B_BYTES = TILE_N * ROW_BYTES;
-  static constexpr int NSTAGE = D_PAD == 32 ? 4 : 2;
-  static constexpr int KSTEPS = D_PAD / 8;
+  static constexpr int NSTAGE = D_PAD == 32 ? 10 : 6;  // reference tiles in flight: covers the L2 -> shared latency
+  static constexpr int KSTEPS = D_PAD / 16;         // kind::f16 MMA K = 16
   static constexpr int OFF_A = 0;
   static constexpr int OFF_B = OFF_A + A_BYTES;
   static constexpr int OFF_G = OFF_B + NSTAGE * B_BYTES;       // group maxima [NGT_MAX][2 halves][256 rows]
@@ -63,15 +70,15 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
                const KnnItem* __restrict__ items, int n_items, int k, int cap) {
   using C = T2Cfg<D_PAD>;
   extern __shared__ __align__(1024) unsigned char smem[];
-  float* smA = reinterpret_cast<float*>(smem + C::OFF_A);
-  float* smB = reinterpret_cast<float*>(smem + C::OFF_B);
+  __half* smA = reinterpret_cast<__half*>(smem + C::OFF_A);
+  unsigned char* smB = smem + C::OFF_B;
   float* gmax_s = reinterpret_cast<float*>(smem + C::OFF_G);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
   uint64_t* a_full = bars + 0;
   uint64_t* a_empty = bars + 1;
   uint64_t* b_full = bars + 2;
-  uint64_t* b_empty = bars + 2 + C::NSTAGE;
-  uint64_t* acc_full = bars + 2 + 2 * C::NSTAGE;
+  uint64_t* b_empty = b_full + C::NSTAGE;
+  uint64_t* acc_full = b_empty + C::NSTAGE;
   uint64_t* acc_empty = acc_full + 2;
   uint64_t* thr_ready = acc_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_TMEM);
@@ -104,21 +111,24 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
   if (warp == 0) {
     // ------------------------------------------------------------ producer
     if (lane == 0) {
-      uint32_t g = 0, it = 0;
+      uint32_t slot = 0, ph = 0, it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const KnnItem wi = items[item];
         const KnnProblem pb = probs[wi.prob];
-        while (!ptx::mbar_try_wait(a_empty, (it & 1) ^ 1)) __nanosleep(64);
+        ptx::mbar_wait(a_empty, (it & 1) ^ 1);
         ptx::mbar_arrive_expect_tx(a_full, C::A_BYTES);
-        ptx::bulk_g2s(smA, pb.q_tiled + (size_t)wi.qblock * QBLOCK * D_PAD, C::A_BYTES, a_full);
+        // both operands come from the fp16 copies of the panels (stored right after the fp32 values)
+        const __half* q_mma = reinterpret_cast<const __half*>(pb.q_tiled + round_up((size_t)pb.nq, KNN_ROW_PAD) * D_PAD);
+        const __half* r_mma = reinterpret_cast<const __half*>(pb.r_tiled + round_up((size_t)pb.nr, KNN_ROW_PAD) * D_PAD);
+        ptx::bulk_g2s(smA, q_mma + (size_t)wi.qblock * QBLOCK * D_PAD, C::A_BYTES, a_full);
         const int n_tiles = (pb.nr + TILE_N - 1) / TILE_N;
         for (int ph2 = 0; ph2 < 2; ++ph2) {
-          for (int t = 0; t < n_tiles; ++t, ++g) {
-            const uint32_t slot = g % C::NSTAGE, ph = (g / C::NSTAGE) & 1;
-            while (!ptx::mbar_try_wait(b_empty + slot, ph ^ 1)) __nanosleep(32);
+          for (int t = 0; t < n_tiles; ++t) {
+            ptx::mbar_wait(b_empty + slot, ph ^ 1);
             ptx::mbar_arrive_expect_tx(b_full + slot, C::B_BYTES);
-            ptx::bulk_g2s(smB + (size_t)slot * (C::B_BYTES / 4), pb.r_tiled + (size_t)t * TILE_N * D_PAD,
-                          C::B_BYTES, b_full + slot);
+            ptx::bulk_g2s(smB + (size_t)slot * C::B_BYTES, r_mma + (size_t)t * TILE_N * D_PAD, C::B_BYTES,
+                          b_full + slot);
+            if (++slot == C::NSTAGE) { slot = 0; ph ^= 1; }
           }
         }
       }
@@ -127,39 +137,48 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
   } else if (warp == 1) {
     // ---------------------------------------------------------- MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc(2u, 128u, (uint32_t)TILE_N);
-      const uint32_t a_addr = ptx::smem_u32(smA), b_addr0 = ptx::smem_u32(smB);
-      uint32_t g = 0, it = 0;
+      constexpr uint32_t idesc = ptx::umma_idesc(0u, 128u, (uint32_t)TILE_N);  // fp16 x fp16 -> fp32
+      // descriptors are built once: the loop only adds the (16-byte granular) offset of the ring slot
+      uint64_t adesc[2][C::KSTEPS];
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int ks = 0; ks < C::KSTEPS; ++ks)
+          adesc[mb][ks] = ptx::umma_desc_kmajor_noswz(ptx::smem_u32(smA) + mb * 128 * C::ROW_BYTES + ks * 256, 128,
+                                                     C::KC * 128);
+      const uint64_t bdesc0 = ptx::umma_desc_kmajor_noswz(ptx::smem_u32(smB), 128, C::KC * 128);
+      uint32_t slot = 0, ph = 0, stage = 0, aph = 0, it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const KnnItem wi = items[item];
         const int nr = probs[wi.prob].nr;
         const int n_tiles = (nr + TILE_N - 1) / TILE_N;
         ptx::mbar_wait(a_full, it & 1);
         for (int ph2 = 0; ph2 < 2; ++ph2) {
-          if (ph2 == 1) {
-            // the rows' thresholds are in the A tile (FOLD) / in the epilogue threads' registers
-            while (!ptx::mbar_try_wait(thr_ready, it & 1)) __nanosleep(32);
-          }
-          for (int t = 0; t < n_tiles; ++t, ++g) {
-            const uint32_t slot = g % C::NSTAGE, ph = (g / C::NSTAGE) & 1;
-            const uint32_t stage = g & 1, aph = (g >> 1) & 1;
-            while (!ptx::mbar_try_wait(b_full + slot, ph)) __nanosleep(20);
-            while (!ptx::mbar_try_wait(acc_empty + stage, aph ^ 1)) __nanosleep(20);
+          if (ph2 == 1) ptx::mbar_wait(thr_ready, it & 1);  // the rows' thresholds are in the A tile (FOLD)
+          for (int t = 0; t < n_tiles; ++t) {
+            ptx::mbar_wait(b_full + slot, ph);
+#if !defined(TC2_VARIANT) || TC2_VARIANT != 2
+            ptx::mbar_wait(acc_empty + stage, aph ^ 1);
+#endif
             ptx::tc_fence_after();
-            const uint32_t b_addr = b_addr0 + slot * C::B_BYTES;
+            const uint64_t bd = bdesc0 + (uint64_t)((slot * (uint32_t)C::B_BYTES) >> 4);
 #pragma unroll
             for (int mb = 0; mb < 2; ++mb) {
               const uint32_t d_tmem = tmem_base + (stage * 2 + mb) * TILE_N;
 #pragma unroll
               for (int ks = 0; ks < C::KSTEPS; ++ks) {
-                const uint64_t ad = ptx::umma_desc_kmajor_noswz(a_addr + mb * 128 * C::ROW_BYTES + ks * 256, 128,
-                                                                 C::KC * 128);
-                const uint64_t bd = ptx::umma_desc_kmajor_noswz(b_addr + ks * 256, 128, C::KC * 128);
-                ptx::mma_tf32_ss(d_tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
+#if !defined(TC2_VARIANT) || TC2_VARIANT != 1
+                ptx::mma_f16_ss(d_tmem, adesc[mb][ks], bd + (uint64_t)(ks * 16), idesc, ks > 0 ? 1u : 0u);
+#else
+                (void)d_tmem;
+#endif
               }
             }
             ptx::mma_commit(b_empty + slot);
             ptx::mma_commit(acc_full + stage);
+            if (++slot == C::NSTAGE) { slot = 0; ph ^= 1; }
+            aph ^= stage;
+            stage ^= 1;
           }
         }
         ptx::mma_commit(a_empty);
@@ -169,13 +188,15 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
   } else {
     // ------------------------------------------------------------ epilogue warps
     const int e = warp - 2;
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int sub = e >> 2;
     const int mb = sub & 1, half = sub >> 1;
     const int row_local = mb * 128 + quarter * 32 + lane;
+    const uint32_t tm_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     float* gm = gmax_s + half * 256 + row_local;  // + g * 512
-    float* thr_slot = smA + (size_t)(row_local >> 3) * (8 * D_PAD) + (size_t)(row_local & 7) * 4 +
-                      (size_t)((D_PAD - 1) >> 2) * 32 + ((D_PAD - 1) & 3);
+    // this row's threshold slot in the A tile: last K dimension
+    __half* thr_slot = smA + (size_t)(row_local >> 3) * (8 * D_PAD) + (size_t)((D_PAD - 1) >> 3) * 64 +
+                       (size_t)(row_local & 7) * 8 + ((D_PAD - 1) & 7);
     uint32_t g = 0, it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const KnnItem wi = items[item];
@@ -192,7 +213,13 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
           const uint32_t stage = g & 1, aph = (g >> 1) & 1;
           ptx::mbar_wait(acc_full + stage, aph);
           ptx::tc_fence_after();
-          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (stage * 2 + mb) * TILE_N + half * 64;
+#ifdef TC2_MMA_ONLY  // measurement build: tensor pipe + pipeline only, accumulators are dropped
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(acc_empty + stage);
+          continue;
+#endif
+          const uint32_t taddr = tm_lane + (stage * 2 + mb) * TILE_N + half * 64;
           uint32_t v0[16], v1[16], v2[16], v3[16];
           ptx::tmem_ld_32x32b_x16(taddr, v0);
           ptx::tmem_ld_32x32b_x16(taddr + 16, v1);
@@ -256,13 +283,12 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
           if (cge >= k) lo = mid; else hi = mid;
         }
         // phase A scores carry +1 when the spare dimension is in use (query -1 times reference -1)
-        thr = (lo - (FOLD ? 1.0f : 0.0f)) - 2.0f * TF32_MARGIN;
-        uint32_t bits = __float_as_uint(thr);  // toward -inf to a TF32-exact value
-        if ((bits & 0x1fffu) != 0u) bits = (bits & 0xffffe000u) + ((bits >> 31) ? 0x2000u : 0u);
-        thr = __uint_as_float(bits);
-        if (!valid_row) thr = 1e30f;
+        thr = (lo - (FOLD ? 1.0f : 0.0f)) - 2.0f * MMA_MARGIN;
+        const __half thr_h = __float2half_rd(valid_row ? thr : 60000.0f);  // toward -inf to an fp16 value
+        thr = __half2float(thr_h);
         if (FOLD) {
-          *thr_slot = thr;  // both halves of a row write the same value
+          // the threshold rides in the spare K dimension of the A tile: acc = dot - thr from now on
+          *thr_slot = thr_h;  // both halves of a row write the same value
           ptx::fence_proxy_async();
         }
         if (half == 0 && valid_row) ax.thr[(size_t)ax.row0 + qrow] = thr;
@@ -278,7 +304,13 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
           const uint32_t stage = g & 1, aph = (g >> 1) & 1;
           ptx::mbar_wait(acc_full + stage, aph);
           ptx::tc_fence_after();
-          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (stage * 2 + mb) * TILE_N + half * 64;
+#ifdef TC2_MMA_ONLY
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(acc_empty + stage);
+          continue;
+#endif
+          const uint32_t taddr = tm_lane + (stage * 2 + mb) * TILE_N + half * 64;
           uint32_t v0[16], v1[16], v2[16], v3[16];
           ptx::tmem_ld_32x32b_x16(taddr, v0);
           ptx::tmem_ld_32x32b_x16(taddr + 16, v1);
@@ -430,7 +462,7 @@ __device__ __forceinline__ void finish_row(const KnnProblem& pb, const int* __re
   // than the k-th candidate whenever dist_k <= (1 - thr) - margin
   const unsigned long long kk = __shfl_sync(0xffffffffu, key[0], k - 1);
   const float dist_k = kk == ~0ull ? INFINITY : f32_from_orderable((uint32_t)(kk >> 32));
-  ok = c >= k && dist_k <= (1.0f - thr) - TF32_MARGIN;
+  ok = c >= k && dist_k <= (1.0f - thr) - MMA_MARGIN;
   if (lane < k) {
     const bool has = key[0] != ~0ull;
     pb.out_idx[(size_t)qrow * k + lane] = has ? (int)(key[0] & 0xffffffffull) : -1;

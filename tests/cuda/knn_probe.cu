@@ -83,7 +83,7 @@ static int run_case(Context& ctx, int nq, int nr, int d, int k, bool check_host,
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  float ms_s = 0, ms_t = 0;
+  float ms_s = 0, ms_t = 0, ms_v7 = 0;
   for (int r = 0; r < reps; ++r) {
     cudaEventRecord(e0, ctx.stream);
     knn_simt_launch(ctx, dps.p, &ps, 1, k, pq.d_pad, d, METRIC_ANGULAR);
@@ -91,6 +91,30 @@ static int run_case(Context& ctx, int nq, int nr, int d, int k, bool check_host,
     CG_CUDA(cudaStreamSynchronize(ctx.stream));
     cudaEventElapsedTime(&ms_s, e0, e1);
   }
+  // streaming tensor-core kernel alone (engine 1), then the automatic engine (two-phase kernel + redo blocks)
+  ctx.knn_engine = 1;
+  for (int r = 0; r < reps; ++r) {
+    cudaEventRecord(e0, ctx.stream);
+    knn_tc_launch(ctx, dpt.p, &pt, 1, k, pq.d_pad, d);
+    cudaEventRecord(e1, ctx.stream);
+    CG_CUDA(cudaStreamSynchronize(ctx.stream));
+    cudaEventElapsedTime(&ms_v7, e0, e1);
+  }
+  {
+    std::vector<int> h7((size_t)nq * k);
+    i_t.download(h7.data(), h7.size(), ctx.stream);
+    CG_CUDA(cudaStreamSynchronize(ctx.stream));
+    CG_CUDA(cudaMemsetAsync(i_t.p, 0xff, i_t.n * 4, ctx.stream));
+    CG_CUDA(cudaMemsetAsync(d_t.p, 0xff, d_t.n * 4, ctx.stream));
+    std::vector<int> hs0((size_t)nq * k);
+    i_s.download(hs0.data(), hs0.size(), ctx.stream);
+    CG_CUDA(cudaStreamSynchronize(ctx.stream));
+    size_t bad7 = 0;
+    for (size_t i = 0; i < hs0.size(); ++i) bad7 += hs0[i] != h7[i];
+    if (bad7) printf("  streaming kernel != simt: %zu\n", bad7);
+  }
+  ctx.knn_engine = 0;
+  const uint64_t redo0 = ctx.knn_redo_blocks;
   for (int r = 0; r < reps; ++r) {
     cudaEventRecord(e0, ctx.stream);
     knn_tc_launch(ctx, dpt.p, &pt, 1, k, pq.d_pad, d);
@@ -121,9 +145,10 @@ static int run_case(Context& ctx, int nq, int nr, int d, int k, bool check_host,
       if (hs[i] != hi[i] || memcmp(&hds[i], &hd[i], 4) != 0) bad_sh++;
   }
   double cand = (double)nq * nr;
-  printf("case nq=%d nr=%d d=%d k=%d | simt %.3f ms (%.2e cand/s) | tc %.3f ms (%.2e cand/s, %.1f TFLOP/s) | "
-         "tc!=simt idx %zu dist %zu | simt!=host %zu%s\n",
-         nq, nr, d, k, ms_s, cand / (ms_s * 1e-3), ms_t, cand / (ms_t * 1e-3), 2.0 * cand * d / (ms_t * 1e-3) / 1e12,
+  printf("case nq=%d nr=%d d=%d k=%d | simt %.3f ms (%.2e cand/s) | streaming tc %.3f ms | two-phase tc %.3f ms (%.2e "
+         "cand/s, %.1f TFLOP/s, redo blocks %llu) | tc!=simt idx %zu dist %zu | simt!=host %zu%s\n",
+         nq, nr, d, k, ms_s, cand / (ms_s * 1e-3), ms_v7, ms_t, cand / (ms_t * 1e-3),
+         2.0 * cand * d / (ms_t * 1e-3) / 1e12, (unsigned long long)((ctx.knn_redo_blocks - redo0) / (reps ? reps : 1)),
          bad_ts, bad_d, bad_sh, check_host ? "" : " (host check skipped)");
   if (bad_ts && nq * k < 2000000) {
     int shown = 0;
@@ -146,6 +171,13 @@ int main(int argc, char** argv) {
     CG_CUDA(cudaGetDeviceProperties(&prop, 0));
     ctx.sm_count = prop.multiProcessorCount;
     CG_CUDA(cudaStreamCreate(&ctx.stream));
+    {
+      cudaMemPool_t pool;
+      CG_CUDA(cudaDeviceGetDefaultMemPool(&pool, 0));
+      unsigned long long thr = ~0ull;
+      CG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    }
+    StreamBinding sb(ctx.stream);  // DevBuf allocations come from the stream-ordered pool
     printf("device %s, %d SMs\n", prop.name, ctx.sm_count);
     int rc = 0;
     if (argc == 5) {

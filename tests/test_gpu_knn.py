@@ -108,3 +108,73 @@ def test_many_items_per_cta(ctx, oracle, d, k):
     oi2, od2 = oracle.cross_knn(B, A, k, "angular")
     assert np.array_equal(iba, oi2)
     assert np.array_equal(dba.view(np.uint32), od2.view(np.uint32))
+
+
+def _stat(ctx, name):
+    import ctypes as C
+    v = C.c_double()
+    ctx.check(ctx.lib.cg_get_stat(ctx.h, name.encode(), C.byref(v)))
+    return v.value
+
+
+@pytest.mark.parametrize("nA,nB,d,k", [(3000, 5000, 30, 30), (700, 20000, 30, 15), (5000, 1600, 32, 10),
+                                       (2500, 3100, 50, 32), (1200, 2050, 64, 20), (400, 650, 12, 30)])
+def test_two_phase_kernel_equals_streaming_and_oracle(ctx, oracle, nA, nB, d, k):
+    """Every kNN engine (two-phase tensor-core, streaming tensor-core, SIMT) returns the oracle's lists bit for bit;
+    sizes cover all three group plans (16/32-column groups, whole half tiles, several tiles per group)."""
+    from conos_b200 import ops
+    rng = np.random.default_rng(nA + 3 * nB + d)
+    A, B = mixture(rng, nA, d), mixture(rng, nB, d)
+    B[3::17] = B[2::17][:len(B[3::17])]   # exact duplicates -> ties
+    oi, od = oracle.cross_knn(A, B, k, "angular")
+    try:
+        for engine in (0, 1, 2):
+            ctx.check(ctx.lib.cg_set_option(ctx.h, b"knn_engine", float(engine)))
+            idx, dist = ops.crossKnn(A, B, k, "angular", ctx=ctx)
+            assert np.array_equal(idx, oi), engine
+            assert np.array_equal(dist.view(np.uint32), od.view(np.uint32)), engine
+    finally:
+        ctx.lib.cg_set_option(ctx.h, b"knn_engine", 0.0)
+
+
+def test_two_phase_overflow_blocks_are_recomputed(ctx, oracle):
+    """Candidate lists that overflow (here: capacity shrunk to 4; in production: masses of tied duplicates) hand
+    their 256-row block to the streaming kernel; the result does not change."""
+    from conos_b200 import ops
+    rng = np.random.default_rng(77)
+    A, B = mixture(rng, 1500, 30), mixture(rng, 6000, 30)
+    oi, od = oracle.cross_knn(A, B, 30, "angular")
+    before = _stat(ctx, "knn_redo_blocks")
+    try:
+        ctx.check(ctx.lib.cg_set_option(ctx.h, b"knn_cand_cap", 4.0))
+        idx, dist = ops.crossKnn(A, B, 30, "angular", ctx=ctx)
+    finally:
+        ctx.lib.cg_set_option(ctx.h, b"knn_cand_cap", 64.0)
+    assert _stat(ctx, "knn_redo_blocks") > before
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(dist.view(np.uint32), od.view(np.uint32))
+
+
+def test_two_phase_mass_duplicates(ctx, oracle):
+    """2000 copies of one reference point tie at the k-th distance for nearby queries: the overflow path must
+    return the lowest indices among the ties."""
+    from conos_b200 import ops
+    rng = np.random.default_rng(78)
+    A, B = mixture(rng, 600, 30), mixture(rng, 5000, 30)
+    B[1000:3000] = B[999]
+    A[:50] = B[999] + rng.normal(0, 1e-3, (50, 30))
+    before = _stat(ctx, "knn_redo_blocks")
+    idx, dist = ops.crossKnn(A, B, 15, "angular", ctx=ctx)
+    oi, od = oracle.cross_knn(A, B, 15, "angular")
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(dist.view(np.uint32), od.view(np.uint32))
+    assert _stat(ctx, "knn_redo_blocks") > before
+
+
+def test_two_phase_no_redo_on_regular_data(ctx):
+    from conos_b200 import ops
+    rng = np.random.default_rng(79)
+    A, B = mixture(rng, 6000, 30, k=20), mixture(rng, 9000, 30, k=20)
+    before = _stat(ctx, "knn_redo_blocks")
+    ops.crossKnn(A, B, 30, "angular", ctx=ctx, both=True)
+    assert _stat(ctx, "knn_redo_blocks") == before
