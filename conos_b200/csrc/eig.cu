@@ -18,6 +18,7 @@ struct EigWork {
   double* theta_out;
   int* converged;  // 1 when the leading r residuals are below tol * theta_1
   double* resid;   // optional: worst relative residual of the leading r pairs
+  double* colres = nullptr;  // optional [B]: relative residual of every leading Ritz pair (the filter degree uses it)
 };
 
 __device__ __forceinline__ double hash_unit(unsigned a, unsigned b) {
@@ -340,8 +341,12 @@ __global__ void __launch_bounds__(EIG_THREADS) eig_rr_kernel(const EigWork* __re
     double worst = 0.0;
     for (int j = 0; j < r; ++j) worst = fmax(worst, sqrt(sm.cs[j]));
     const double scale = fmax(fabs(sm.ev[0]), 1e-300);
-    *w.converged = finalize ? 2 : ((worst <= tol * scale) ? 1 : 0);
+    // a block that lost rank shows up as zero / non-finite Ritz values with zero residuals: never "converged"
+    const bool sane = isfinite(worst) && isfinite(sm.ev[0]) && (sm.ev[r - 1] > 0.0 || sm.ev[0] <= 0.0);
+    *w.converged = finalize ? 2 : ((sane && worst <= tol * scale) ? 1 : 0);
     if (w.resid && !finalize) *w.resid = worst / scale;
+    if (w.colres && !finalize)
+      for (int j = 0; j < r; ++j) w.colres[j] = sqrt(sm.cs[j]) / scale;
   }
   if (finalize) {
     for (size_t t = tid; t < (size_t)w.G * r; t += EIG_THREADS) {
@@ -517,7 +522,8 @@ __global__ void __launch_bounds__(256) tc_column_kernel(const TcSampleDev* __res
                                                         const int* __restrict__ col_sample,
                                                         const int* __restrict__ col_local, int n_cols_total, int mode,
                                                         const float* __restrict__ al, const float* __restrict__ be,
-                                                        const float* __restrict__ cc) {
+                                                        const float* __restrict__ cc, const int* __restrict__ deg,
+                                                        int step) {
   const int lane = threadIdx.x & 31;
   const int gc = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (gc >= n_cols_total) return;
@@ -525,6 +531,7 @@ __global__ void __launch_bounds__(256) tc_column_kernel(const TcSampleDev* __res
   const int col = col_local[gc];
   const int pidx = sd.first_prob + col / TB, j = col % TB;
   const TcProbDev pd = P[pidx];
+  if (mode == 2 && step > deg[pidx]) return;  // this problem's sweep is shorter: keep its X, Y
   const int G = sd.G;
   const double n = (double)sd.n_cells;
   const double t_old = sd.t[col];
@@ -567,9 +574,16 @@ __global__ void __launch_bounds__(256) tc_column_kernel(const TcSampleDev* __res
 }
 
 // Chebyshev coefficients of every step from the current Ritz values: unwanted interval [0, theta_{B-1}],
-// scaling at theta_0 (Zhou & Saad's scaled three-term recurrence)
-__global__ void tc_coeff_kernel(const TcProbDev* __restrict__ P, int n_probs, int degree, float* __restrict__ al,
-                                float* __restrict__ be, float* __restrict__ cc) {
+// scaling at theta_0 (Zhou & Saad's scaled three-term recurrence).
+// The filter multiplies the component of a column along eigenvector i by T_m(x_i); the panels are fp32 and the
+// GEMM operands bf16 hi+lo (16 bits), so a wanted column j must never be swamped by what is left in it of a
+// better-conditioned direction i < j.  With eps_i = relative residual of Ritz pair i (how much of v_i still leaks
+// into the other columns) the degree of this sweep is the largest m with eps_i * T_m(x_i) / T_m(x_j) <= 8 for all
+// i < j < r: narrow wanted spectra run the full degree from the start, wide ones ramp up as the leading pairs
+// converge.
+__global__ void tc_coeff_kernel(const TcProbDev* __restrict__ P, int n_probs, int degree, int r,
+                                const double* __restrict__ colres, float* __restrict__ al, float* __restrict__ be,
+                                float* __restrict__ cc, int* __restrict__ deg) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_probs) return;
   const double a0 = P[p].theta[0];
@@ -578,6 +592,7 @@ __global__ void tc_coeff_kernel(const TcProbDev* __restrict__ P, int n_probs, in
   if (!(a0 > 0.0)) {  // degenerate (zero matrix): identity filter
     for (int i = 1; i <= degree; ++i) { al[(size_t)i * n_probs + p] = 0.f; be[(size_t)i * n_probs + p] = 0.f; }
     cc[p] = 0.f;
+    deg[p] = 1;
     return;
   }
   const double e = b / 2.0, c = b / 2.0;
@@ -592,6 +607,26 @@ __global__ void tc_coeff_kernel(const TcProbDev* __restrict__ P, int n_probs, in
     be[(size_t)i * n_probs + p] = (float)(sigma * s2);
     sigma = s2;
   }
+  // log growth per degree of direction j: T_m(x) ~ (x + sqrt(x^2 - 1))^m / 2 for x >= 1
+  double lg[TB];
+  for (int j = 0; j < r; ++j) {
+    double x = (P[p].theta[j] - c) / e;
+    if (!(x > 1.0)) x = 1.0;
+    lg[j] = log(x + sqrt(x * x - 1.0));
+  }
+  double m_safe = (double)degree;
+  for (int i = 0; i + 1 < r; ++i) {
+    double eps = colres[(size_t)p * TB + i];
+    if (!(eps > 1e-7)) eps = 1e-7;
+    if (!(eps < 1.0)) eps = 1.0;
+    const double room = log(8.0 / eps);
+    for (int j = i + 1; j < r; ++j) {
+      const double dl = lg[i] - lg[j];
+      if (dl > 1e-12) m_safe = fmin(m_safe, room / dl);
+    }
+  }
+  int m = (int)floor(m_safe);
+  deg[p] = m < 1 ? 1 : (m > degree ? degree : m);
 }
 
 }  // namespace
@@ -656,8 +691,12 @@ void top_eigenvectors_shared_gram(Context& ctx, const TcEigSample* samples, int 
   DevBuf<__nv_bfloat16> Uh(u_elems), Ul(u_elems);
   DevBuf<double> tvec(n_cols_total), Q(qz_elems), Z(qz_elems), theta((size_t)n_probs * B);
   DevBuf<int> conv((size_t)n_probs);
-  DevBuf<double> resid((size_t)n_probs);
+  DevBuf<double> resid((size_t)n_probs), colres((size_t)n_probs * B);
   resid.zero(s);
+  {
+    std::vector<double> ones((size_t)n_probs * B, 1.0);  // nothing is known about the random start
+    colres.upload(ones.data(), ones.size(), s);
+  }
   Uh.zero(s);
   Ul.zero(s);
   tvec.zero(s);
@@ -708,7 +747,7 @@ void top_eigenvectors_shared_gram(Context& ctx, const TcEigSample* samples, int 
   std::vector<EigWork> works(n_probs);
   for (int pi = 0; pi < n_probs; ++pi)
     works[pi] = EigWork{nullptr, hs[hp[pi].sample].G, hp[pi].Q, hp[pi].Z, hp[pi].theta, probs[order[pi]].V,
-                        probs[order[pi]].theta, hp[pi].converged, resid.p + pi};
+                        probs[order[pi]].theta, hp[pi].converged, resid.p + pi, colres.p + (size_t)pi * B};
   DevBuf<EigWork> dw;
   dw.upload(works.data(), works.size(), s);
   std::vector<GemmProblem> gprobs;
@@ -724,8 +763,10 @@ void top_eigenvectors_shared_gram(Context& ctx, const TcEigSample* samples, int 
   CG_CUDA(cudaFuncSetAttribute(eig_orth_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CG_CUDA(cudaFuncSetAttribute(eig_rr_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned colblocks = (unsigned)((n_cols_total + 7) / 8);
-  auto column = [&](int mode, const float* a, const float* b, const float* c) {
-    tc_column_kernel<<<colblocks, 256, 0, s>>>(dS.p, dP.p, dcs.p, dcl.p, (int)n_cols_total, mode, a, b, c);
+  DevBuf<int> deg((size_t)n_probs);
+  auto column = [&](int mode, const float* a, const float* b, const float* c, int step) {
+    tc_column_kernel<<<colblocks, 256, 0, s>>>(dS.p, dP.p, dcs.p, dcl.p, (int)n_cols_total, mode, a, b, c, deg.p,
+                                               step);
     ctx.stats.kernels++;
   };
   {
@@ -735,8 +776,8 @@ void top_eigenvectors_shared_gram(Context& ctx, const TcEigSample* samples, int 
     tc_init_kernel<<<gi, 256, 0, s>>>(dS.p);
     ctx.stats.kernels++;
   }
-  std::vector<int> hc(n_probs);
-  int outer_done = 0;
+  std::vector<int> hc(n_probs), hdeg(n_probs);
+  int outer_done = 0, gemm_steps = 0;
   for (int outer = 0; outer <= max_outer; ++outer) {
     outer_done = outer;
     // orthonormal basis of the filtered block
@@ -745,9 +786,9 @@ void top_eigenvectors_shared_gram(Context& ctx, const TcEigSample* samples, int 
     eig_orth_kernel<B><<<n_probs, EIG_THREADS, smem, s>>>(dw.p);
     ctx.stats.kernels += 2;
     // Rayleigh-Ritz: Z = C Q through the shared Gram GEMM
-    column(0, nullptr, nullptr, nullptr);
+    column(0, nullptr, nullptr, nullptr, 0);
     gemm_tn_bf16x3(ctx, gprobs.data(), (int)gprobs.size());
-    column(3, nullptr, nullptr, nullptr);
+    column(3, nullptr, nullptr, nullptr, 0);
     eig_rr_kernel<B><<<n_probs, EIG_THREADS, smem, s>>>(dw.p, r, tol, 0);
     ctx.stats.kernels++;
     conv.download(hc.data(), (size_t)n_probs, s);
@@ -755,17 +796,24 @@ void top_eigenvectors_shared_gram(Context& ctx, const TcEigSample* samples, int 
     bool all = true;
     for (int p = 0; p < n_probs; ++p) all = all && hc[p] != 0;
     if (all || outer == max_outer) break;
-    // Chebyshev filter of the given degree
-    tc_coeff_kernel<<<(n_probs + 127) / 128, 128, 0, s>>>(dP.p, n_probs, degree, al.p, be.p, cc.p);
+    // Chebyshev filter: per-problem degree (<= degree) from the current residuals, see tc_coeff_kernel
+    tc_coeff_kernel<<<(n_probs + 127) / 128, 128, 0, s>>>(dP.p, n_probs, degree, r, colres.p, al.p, be.p, cc.p, deg.p);
     ctx.stats.kernels++;
-    column(1, al.p + (size_t)1 * n_probs, nullptr, cc.p);
-    for (int i = 2; i <= degree; ++i) {
+    deg.download(hdeg.data(), (size_t)n_probs, s);
+    CG_CUDA(cudaStreamSynchronize(s));
+    int sweep = 1;
+    for (int p = 0; p < n_probs; ++p)
+      if (!hc[p] && hdeg[p] > sweep) sweep = hdeg[p];
+    gemm_steps += sweep;
+    column(1, al.p + (size_t)1 * n_probs, nullptr, cc.p, 1);
+    for (int i = 2; i <= sweep; ++i) {
       gemm_tn_bf16x3(ctx, gprobs.data(), (int)gprobs.size());
-      column(2, al.p + (size_t)i * n_probs, be.p + (size_t)i * n_probs, cc.p);
+      column(2, al.p + (size_t)i * n_probs, be.p + (size_t)i * n_probs, cc.p, i);
     }
   }
   if (ctx.profile) {
     ctx.stage_ms["reduction.eig.outer_iterations"] += outer_done;
+    ctx.stage_ms["reduction.eig.filter_gemms"] += gemm_steps;
     std::vector<double> hr(n_probs);
     resid.download(hr.data(), (size_t)n_probs, s);
     CG_CUDA(cudaStreamSynchronize(s));

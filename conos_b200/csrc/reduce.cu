@@ -46,6 +46,16 @@ __global__ void interleave_kernel(const double* __restrict__ Va, const double* _
   rot[t] = src[(size_t)(c >> 1) * Gp + g];
 }
 
+// same with a row gather: pair gene g lives in column cols_a[g] / cols_b[g] of its sample's gene universe
+__global__ void interleave_gather_kernel(const double* __restrict__ Va, const double* __restrict__ Vb,
+                                         const int* __restrict__ cols_a, const int* __restrict__ cols_b, int G,
+                                         int Gsa, int Gsb, int r, double* __restrict__ rot) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)G * 2 * r) return;
+  const int g = (int)(t % G), c = (int)(t / G);
+  rot[t] = (c & 1) ? Vb[(size_t)(c >> 1) * Gsb + cols_b[g]] : Va[(size_t)(c >> 1) * Gsa + cols_a[g]];
+}
+
 __global__ void trace_kernel(const double* __restrict__ C, int Gp, double* __restrict__ out) {
   // single block
   double s = 0.0;
@@ -130,15 +140,16 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
     // centred, scaled sample == leading eigenvectors of its scaled covariance; columns interleaved.
     const int r = r_round_half_even(P.ncomps / 2.0);
     CG_CHECK(r >= 1 && r <= 56, "ncomps out of range for the device PCA");
-    // tensor-core path: every pair uses all genes of both samples in storage order (shared gene universe)
+    // tensor-core path: the operator of every pair acts on the per-sample centred Gram matrix over the sample's
+    // whole gene universe; the pair's gene set (any subset, any order) enters through the diagonal scaling (zero
+    // outside the set) and a row gather of the eigenvectors.  The Gram matrix is dense: bounded universe only.
     bool shared = !ctx.exact_reduction && r <= 24;
     for (int q : todo) {
       const cg_pair& pr = pairs[q];
       const Sample& sa = panel.samples[pr.a];
       const Sample& sb = panel.samples[pr.b];
-      if (pr.n_genes != sa.n_genes || pr.n_genes != sb.n_genes || pr.n_genes < 32) shared = false;
-      for (int g = 0; g < pr.n_genes && shared; ++g)
-        if (pr.genes_a[g] != g || pr.genes_b[g] != g) shared = false;
+      if (pr.n_genes < 32 || sa.n_genes < 32 || sb.n_genes < 32 || sa.n_genes > 4096 || sb.n_genes > 4096)
+        shared = false;
       if (!shared) break;
     }
     if (shared) {
@@ -150,6 +161,8 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
       }
       struct PB {
         DevBuf<double> f[2], V[2], theta[2], tr;
+        DevBuf<int> cols[2];
+        std::vector<double> hf[2];  // per pair gene
       };
       std::vector<PB> pbs(todo.size());
       std::vector<TcEigProblem> tp;
@@ -164,23 +177,34 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
           CG_CHECK(!sm[0]->h_qv.empty() && !sm[1]->h_qv.empty() && !sm[0]->h_v.empty() && !sm[1]->h_v.empty(),
                    "var.scale = TRUE needs misc$varinfo$v and $qv for every sample");
           for (int g = 0; g < G; ++g) {
-            const double cqv = std::exp((std::log(sm[0]->h_qv[g]) + std::log(sm[1]->h_qv[g])) / 2.0);
-            const double fa = std::sqrt(cqv / std::exp(sm[0]->h_v[g]));
-            const double fb = std::sqrt(cqv / std::exp(sm[1]->h_v[g]));
+            const int ca = pr.genes_a[g], cb = pr.genes_b[g];  // the gene's column in either sample
+            CG_CHECK(ca >= 0 && ca < sm[0]->n_genes && cb >= 0 && cb < sm[1]->n_genes, "pair gene column out of range");
+            const double cqv = std::exp((std::log(sm[0]->h_qv[ca]) + std::log(sm[1]->h_qv[cb])) / 2.0);
+            const double fa = std::sqrt(cqv / std::exp(sm[0]->h_v[ca]));
+            const double fb = std::sqrt(cqv / std::exp(sm[1]->h_v[cb]));
             f[0][g] = std::isfinite(fa) ? fa : 0.0;
             f[1][g] = std::isfinite(fb) ? fb : 0.0;
           }
         }
         for (int side = 0; side < 2; ++side) {
-          pbs[t].f[side].upload(f[side].data(), (size_t)G, st);
-          pbs[t].V[side].alloc((size_t)G * r);
+          const int Gs = sm[side]->n_genes;
+          const int* cols = side == 0 ? pr.genes_a : pr.genes_b;
+          std::vector<double> fu((size_t)Gs, 0.0);
+          for (int g = 0; g < G; ++g) {
+            CG_CHECK(cols[g] >= 0 && cols[g] < Gs, "pair gene column out of range");
+            fu[cols[g]] = f[side][g];
+          }
+          pbs[t].hf[side] = f[side];
+          pbs[t].f[side].upload(fu.data(), (size_t)Gs, st);
+          pbs[t].cols[side].upload(cols, (size_t)G, st);
+          pbs[t].V[side].alloc((size_t)Gs * r);
           pbs[t].theta[side].alloc((size_t)r);
           tp.push_back(TcEigProblem{side == 0 ? pr.a : pr.b, pbs[t].f[side].p, pbs[t].V[side].p, pbs[t].theta[side].p});
         }
       }
       {
         StageScope sc(ctx, "reduction.eig");
-        top_eigenvectors_shared_gram(ctx, ts.data(), S, tp.data(), (int)tp.size(), r, 1e-5, 12, 10);
+        top_eigenvectors_shared_gram(ctx, ts.data(), S, tp.data(), (int)tp.size(), r, 1e-5, 40, 10);
       }
       for (size_t t = 0; t < todo.size(); ++t) {
         const cg_pair& pr = pairs[todo[t]];
@@ -190,12 +214,14 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
         R.n_cols = 2 * r;
         R.d = P.ncomps < R.n_cols ? P.ncomps : R.n_cols;
         R.rot.alloc((size_t)G * R.n_cols);
-        interleave_kernel<<<nblk((size_t)G * R.n_cols), 256, 0, st>>>(pbs[t].V[0].p, pbs[t].V[1].p, G, G, r, R.rot.p);
+        interleave_gather_kernel<<<nblk((size_t)G * R.n_cols), 256, 0, st>>>(
+            pbs[t].V[0].p, pbs[t].V[1].p, pbs[t].cols[0].p, pbs[t].cols[1].p, G, panel.samples[pr.a].n_genes,
+            panel.samples[pr.b].n_genes, r, R.rot.p);
         ctx.stats.kernels++;
         R.h_rot.resize((size_t)G * R.n_cols);
         R.rot.download(R.h_rot.data(), R.h_rot.size(), st);
         if (P.score_component_variance) {
-          // trace(C) = sum_g f_g^2 (M_gg - n m_g^2) / (n - 1): from the host copies
+          // trace(C) = sum_g f_g^2 (M_cc - n m_c^2) / (n - 1), c = the gene's column: from the host copies
           std::vector<double> th(2 * (size_t)r);
           pbs[t].theta[0].download(th.data(), (size_t)r, st);
           pbs[t].theta[1].download(th.data() + r, (size_t)r, st);
@@ -210,14 +236,14 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
                                         cudaMemcpyDeviceToHost, st));
               CG_CUDA(cudaStreamSynchronize(st));
             }
-            std::vector<double> fh((size_t)G);
-            pbs[t].f[side].download(fh.data(), (size_t)G, st);
-            CG_CUDA(cudaStreamSynchronize(st));
+            const std::vector<double>& fh = pbs[t].hf[side];
+            const int* cols = side == 0 ? pr.genes_a : pr.genes_b;
             const double n = sm.n_cells;
             double tr = 0.0;
             for (int g = 0; g < G; ++g) {
-              const double m = sm.h_colsum[g] / n;
-              tr += fh[g] * fh[g] * (sm.h_gram_diag[g] - n * m * m) / (n - 1.0);
+              const int c = cols[g];
+              const double m = sm.h_colsum[c] / n;
+              tr += fh[g] * fh[g] * (sm.h_gram_diag[c] - n * m * m) / (n - 1.0);
             }
             for (int j = 0; j < r; ++j) R.h_nv[(size_t)side * R.n_cols + j] = th[(size_t)side * r + j] / tr;
           }
