@@ -34,6 +34,15 @@ CONFIGS = {
 }
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the cross-kNN launch of this workload (56 problems of 50k x 50k),
+# main kernel + finish kernel, from the ncu --set full capture summarised in profiles/ (None until captured)
+KNN_DRAM_BYTES_PER_LAUNCH = 0.350210e9 + 0.560675e9 + 1.113106e9 + 0.647829e9
+KNN_DRAM_SOURCE = ("profiles/r01_ncu_knn_tc2_bench_config2.txt: dram read+write of knn_tc2_kernel + "
+                   "knn_tc2_finish_kernel for the cross-kNN launch (56 problems of 50k x 50k); algorithmic bytes of "
+                   "that launch 1.39e9 (fp32 panels in, idx+dist out); the excess is the candidate lists (written by "
+                   "the filter phase, read by the finish kernel) and the fp16 operand copies")
+
+
 def read_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -303,15 +312,20 @@ def main():
     knn_s = kms.value * 1e-3
     flops = 2.0 * kc.value * d
     achieved = flops / knn_s / 1e12 if knn_s > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "knn_tc_kernel (fused cross-kNN: tf32 tcgen05 filter + fp32 re-rank)",
+    roofline = {"bound": "tensor",
+                "kernel": "knn_tc2_kernel + knn_tc2_finish_kernel (exact cross-kNN: fp16 tcgen05 tiles, group-max "
+                          "thresholds, sign-bit filter, fp32 re-score + warp sort)",
                 "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
+                "frac": achieved / peaks["bf16_tflops"], "traffic": KNN_DRAM_BYTES_PER_LAUNCH,
+                "traffic_source": KNN_DRAM_SOURCE, "peak_source": peaks["source"],
                 "launches": int(kl.value), "avg_launch_ms": kms.value / max(int(kl.value), 1),
                 "candidates_per_s": kc.value / knn_s if knn_s > 0 else 0.0,
                 "algorithmic_bytes_per_launch": kb.value / max(int(kl.value), 1),
                 "share_of_step": knn_s / (dev_ms * 1e-3) if dev_ms > 0 else None,
-                "note": "achieved = 2*n_query*n_ref*ncomps per launch / CUDA-event time on the launching stream; "
-                        "the kernel runs kind::tf32 (half the bf16 rate) and is selection-bound, see DESIGN.md"}
+                "note": "achieved = 2*n_query*n_ref*ncomps per launch / CUDA-event time on the launching stream "
+                        "(both kernels and the overflow check); every distance tile is computed twice (threshold "
+                        "phase, filter phase) with K padded 30 -> 32, so the tensor pipe issues 2.13x the algorithmic "
+                        "flops; see DESIGN.md K2"}
     line = {"metric": "buildGraph sample-pairs/s", "value": n_pairs * K / (dev_ms * 1e-3), "unit": "pairs/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -52,14 +52,28 @@ int cg_panel_create(cg_context* ctx, const cg_sample* samples, int n_samples, cg
     pn->samples.resize(n_samples);
     pn->offsets.assign(n_samples + 1, 0);
     StageScope sc(ctx->c, "panel_upload");
+    // all host->device copies go out first on their own stream; the conversions follow sample by sample
+    struct CopyLane {
+      cudaStream_t st = nullptr;
+      std::vector<cudaEvent_t> ev;
+      ~CopyLane() {
+        for (auto e : ev) cudaEventDestroy(e);
+        if (st) cudaStreamDestroy(st);
+      }
+    } lane;
+    CG_CUDA(cudaStreamCreateWithFlags(&lane.st, cudaStreamNonBlocking));
+    lane.ev.resize(n_samples, nullptr);
     for (int s = 0; s < n_samples; ++s) {
       const cg_sample& h = samples[s];
       CG_CHECK(h.p && h.i && h.x, "sample counts matrix missing");
+      CG_CUDA(cudaEventCreateWithFlags(&lane.ev[s], cudaEventDisableTiming));
       sample_upload(ctx->c, pn->samples[s], h.n_cells, h.n_genes, h.p, h.i, h.x, h.var_v, h.var_qv, h.pca, h.n_pcs,
-                    h.pca_ld > 0 ? h.pca_ld : h.n_cells);
+                    h.pca_ld > 0 ? h.pca_ld : h.n_cells, lane.st, lane.ev[s]);
       pn->samples[s].offset = pn->offsets[s];
       pn->offsets[s + 1] = pn->offsets[s] + h.n_cells;
     }
+    for (int s = 0; s < n_samples; ++s) sample_finish(ctx->c, pn->samples[s], lane.ev[s]);
+    CG_CUDA(cudaStreamSynchronize(lane.st));
     *out = pn;
     return 0;
   } catch (const std::exception& e) {

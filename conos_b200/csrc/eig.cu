@@ -69,6 +69,38 @@ __global__ void __launch_bounds__(256) eig_matmul_kernel(const EigWork* __restri
 // S[i][j] = sum_r X[r][i] * Y[r][j]  (B x B, into shared memory), all 256 threads
 template <int B>
 __device__ void block_gram(const double* __restrict__ X, const double* __restrict__ Y, int G, double (*S)[B + 1]) {
+  if constexpr (B == 32) {
+    // rows split over the 8 warps (fixed assignment r = warp, warp + 8, ...), lane l owns column l of S: one coalesced
+    // 256-byte load of each operand per row, x broadcast by shuffles, 32 independent FMA chains per lane; the eight
+    // partial sums are then added in warp order (deterministic).
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int NW = EIG_THREADS / 32;
+    double acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.0;
+    int r = warp;
+    for (; r + NW < G; r += 2 * NW) {  // two rows in flight
+      const double x0 = X[(size_t)r * 32 + lane], y0 = Y[(size_t)r * 32 + lane];
+      const double x1 = X[(size_t)(r + NW) * 32 + lane], y1 = Y[(size_t)(r + NW) * 32 + lane];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] = fma(__shfl_sync(0xffffffffu, x0, i), y0, acc[i]);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] = fma(__shfl_sync(0xffffffffu, x1, i), y1, acc[i]);
+    }
+    if (r < G) {
+      const double x0 = X[(size_t)r * 32 + lane], y0 = Y[(size_t)r * 32 + lane];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] = fma(__shfl_sync(0xffffffffu, x0, i), y0, acc[i]);
+    }
+    for (int w = 0; w < NW; ++w) {
+      if (warp == w) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) S[i][lane] = (w == 0 ? 0.0 : S[i][lane]) + acc[i];
+      }
+      __syncthreads();
+    }
+    return;
+  }
   constexpr int TB = B / 16;
   const int i0 = TB * (threadIdx.x / 16), j0 = TB * (threadIdx.x % 16);
   double acc[TB][TB];
@@ -141,7 +173,7 @@ __device__ void block_jacobi(double (*A)[B + 1], double (*W)[B + 1], double* cs,
     off = 0.0; dg = 0.0;
     for (int wv = 0; wv < 8; ++wv) { off = fmax(off, red[wv]); dg = fmax(dg, red[8 + wv]); }
     __syncthreads();
-    if (off <= 1e-17 * dg || dg == 0.0) break;
+    if (off <= 1e-15 * dg || dg == 0.0) break;
     for (int step = 0; step < B - 1; ++step) {
       if (tid < HP) {
         int p, q;
@@ -187,6 +219,17 @@ __device__ void block_jacobi(double (*A)[B + 1], double (*W)[B + 1], double* cs,
   }
 }
 
+// V = leading r columns of Q (already the sorted Ritz vectors), theta_out = leading r Ritz values
+template <int B>
+__global__ void eig_export_kernel(const EigWork* __restrict__ works, int r) {
+  const EigWork w = works[blockIdx.y];
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < (size_t)w.G * r; t += (size_t)gridDim.x * blockDim.x) {
+    const int row = (int)(t % w.G), c = (int)(t / w.G);
+    w.V[t] = w.Q[(size_t)row * B + c];
+  }
+  if (blockIdx.x == 0 && threadIdx.x < r && w.theta_out) w.theta_out[threadIdx.x] = w.theta[threadIdx.x];
+}
+
 template <int B>
 struct EigSmem {
   double S[B][B + 1];
@@ -197,6 +240,7 @@ struct EigSmem {
   double ev[B];
   int perm[B];
   int flag;
+  int wellcond;  // last Cholesky-QR pass: smallest pivot > 1e-4 * largest diagonal (orthogonality error ~ 1e-12)
 };
 
 // Orthonormalise the columns of Z into Q: Cholesky-QR (Q = Z R^-1 with Z'Z = R'R); when a pivot collapses
@@ -216,9 +260,11 @@ __device__ void orth_pass(const double* __restrict__ src, double* __restrict__ d
     for (int t = lane; t < B * B; t += 32) sm.W[t / B][t % B] = sm.S[t / B][t % B];
     __syncwarp();
     bool ok = maxd > 0.0;
+    double minpiv = maxd;
     for (int k = 0; k < B && ok; ++k) {
       const double piv = sm.W[k][k];
       if (!(piv > 1e-13 * maxd)) { ok = false; break; }
+      minpiv = fmin(minpiv, piv);
       const double dk = sqrt(piv);
       __syncwarp();
       for (int i = k + lane; i < B; i += 32) sm.W[i][k] = (i == k) ? dk : sm.W[i][k] / dk;   // L column k
@@ -229,6 +275,7 @@ __device__ void orth_pass(const double* __restrict__ src, double* __restrict__ d
       }
       __syncwarp();
     }
+    if (lane == 0) sm.wellcond = (ok && minpiv > 1e-4 * maxd) ? 1 : 0;
     if (!ok) {
       if (lane == 0) sm.flag = 1;
     } else {
@@ -272,7 +319,8 @@ __global__ void __launch_bounds__(EIG_THREADS) eig_orth_kernel(const EigWork* __
   const EigWork w = works[blockIdx.x];
   if (w.converged && *w.converged == 2) return;
   orth_pass<B>(w.Z, w.Q, w.G, sm);
-  orth_pass<B>(w.Q, w.Q, w.G, sm);
+  // CholeskyQR2: the second pass only when the first saw an ill-conditioned block
+  if (!sm.wellcond) orth_pass<B>(w.Q, w.Q, w.G, sm);
 }
 
 // Rayleigh-Ritz: T = Q'Z (Z = C Q), eigen-decompose, rotate Q and Z to the Ritz basis (descending values),
@@ -825,7 +873,8 @@ void top_eigenvectors_shared_gram(Context& ctx, const TcEigSample* samples, int 
     ctx.stage_ms["reduction.eig.converged_problems"] += nconv;
     ctx.stage_ms["reduction.eig.problems"] += n_probs;
   }
-  eig_rr_kernel<B><<<n_probs, EIG_THREADS, smem, s>>>(dw.p, r, tol, 1);
+  // the loop always ends right after a Rayleigh-Ritz step: Q holds the sorted Ritz vectors
+  eig_export_kernel<B><<<dim3(8, n_probs), 256, 0, s>>>(dw.p, r);
   ctx.stats.kernels++;
   CG_CUDA(cudaGetLastError());
   CG_CUDA(cudaStreamSynchronize(s));

@@ -159,39 +159,65 @@ void csc_to_csr(Context& ctx, int n_rows, int n_cols, const int* csc_p, const in
   CG_CUDA(cudaStreamSynchronize(st));
 }
 
+// Two halves so that a panel's uploads pipeline: sample_upload enqueues the host->device copies of one sample on
+// `copy_st` (its own stream when the caller has one; the buffers are allocated on the context's stream first and
+// handed over through an event) and records `ready`; sample_finish makes the context's stream wait for `ready` and
+// builds the derived arrays (CSR by cell, column sums).  With pinned host memory the copies of sample s+1 run
+// while sample s is converted.
 void sample_upload(Context& ctx, Sample& s, int n_cells, int n_genes, const int* p, const int* i, const double* x,
-                   const double* var_v, const double* var_qv, const double* pca, int n_pcs, int pca_ld) {
+                   const double* var_v, const double* var_qv, const double* pca, int n_pcs, int pca_ld,
+                   cudaStream_t copy_st, cudaEvent_t ready) {
   cudaStream_t st = ctx.stream;
+  if (!copy_st) copy_st = st;
   CG_CHECK(n_cells > 0 && n_genes > 0, "sample must have cells and genes");
   s.n_cells = n_cells;
   s.n_genes = n_genes;
   s.nnz = p[n_genes];
   for (int g = 0; g < n_genes; ++g) CG_CHECK(p[g + 1] >= p[g], "dgCMatrix @p must be non-decreasing");
-  s.csc_p.upload(p, (size_t)n_genes + 1, st);
-  s.csc_i.upload(i, (size_t)s.nnz, st);
-  s.csc_x.upload(x, (size_t)s.nnz, st);
-  if (var_v) s.h_v.assign(var_v, var_v + n_genes);
-  if (var_qv) s.h_qv.assign(var_qv, var_qv + n_genes);
-  // CSR by cell
+  s.csc_p.alloc((size_t)n_genes + 1);
+  s.csc_i.alloc((size_t)s.nnz);
+  s.csc_x.alloc((size_t)s.nnz);
   s.csr_p.alloc((size_t)n_cells + 1);
   s.csr_i.alloc((size_t)s.nnz);
   s.csr_x.alloc((size_t)s.nnz);
-  csc_to_csr(ctx, n_cells, n_genes, s.csc_p.p, s.csc_i.p, s.csc_x.p, s.nnz, s.csr_p.p, s.csr_i.p, s.csr_x.p);
   s.colsum.alloc((size_t)n_genes);
-  colsum_kernel<<<(n_genes + 7) / 8, 256, 0, st>>>(s.csc_p.p, s.csc_x.p, n_genes, s.colsum.p);
-  ctx.stats.kernels++;
-  s.h_colsum.resize(n_genes);
-  s.colsum.download(s.h_colsum.data(), (size_t)n_genes, st);
   s.n_pcs = 0;
   s.pca_metric = -1;
   if (pca && n_pcs > 0) {
     s.n_pcs = n_pcs;
-    std::vector<double> packed((size_t)n_cells * n_pcs);
-    for (int c = 0; c < n_pcs; ++c)
-      memcpy(&packed[(size_t)c * n_cells], pca + (size_t)c * pca_ld, sizeof(double) * (size_t)n_cells);
-    s.pca.upload(packed.data(), packed.size(), st);
-    CG_CUDA(cudaStreamSynchronize(st));
+    s.pca.alloc((size_t)n_cells * n_pcs);
   }
+  if (copy_st != st) {  // stream-ordered allocations: usable on another stream only after this point of `st`
+    cudaEvent_t ea;
+    CG_CUDA(cudaEventCreateWithFlags(&ea, cudaEventDisableTiming));
+    CG_CUDA(cudaEventRecord(ea, st));
+    CG_CUDA(cudaStreamWaitEvent(copy_st, ea, 0));
+    CG_CUDA(cudaEventDestroy(ea));
+  }
+  s.csc_p.upload(p, (size_t)n_genes + 1, copy_st);
+  s.csc_i.upload(i, (size_t)s.nnz, copy_st);
+  s.csc_x.upload(x, (size_t)s.nnz, copy_st);
+  if (var_v) s.h_v.assign(var_v, var_v + n_genes);
+  if (var_qv) s.h_qv.assign(var_qv, var_qv + n_genes);
+  if (s.n_pcs > 0) {
+    if (pca_ld == n_cells) {
+      s.pca.upload(pca, (size_t)n_cells * n_pcs, copy_st);
+    } else {
+      CG_CUDA(cudaMemcpy2DAsync(s.pca.p, sizeof(double) * (size_t)n_cells, pca, sizeof(double) * (size_t)pca_ld,
+                                sizeof(double) * (size_t)n_cells, (size_t)n_pcs, cudaMemcpyHostToDevice, copy_st));
+    }
+  }
+  if (ready) CG_CUDA(cudaEventRecord(ready, copy_st));
+}
+
+void sample_finish(Context& ctx, Sample& s, cudaEvent_t ready) {
+  cudaStream_t st = ctx.stream;
+  if (ready) CG_CUDA(cudaStreamWaitEvent(st, ready, 0));
+  csc_to_csr(ctx, s.n_cells, s.n_genes, s.csc_p.p, s.csc_i.p, s.csc_x.p, s.nnz, s.csr_p.p, s.csr_i.p, s.csr_x.p);
+  colsum_kernel<<<(s.n_genes + 7) / 8, 256, 0, st>>>(s.csc_p.p, s.csc_x.p, s.n_genes, s.colsum.p);
+  ctx.stats.kernels++;
+  s.h_colsum.resize(s.n_genes);
+  s.colsum.download(s.h_colsum.data(), (size_t)s.n_genes, st);
   CG_CUDA(cudaStreamSynchronize(st));
 }
 

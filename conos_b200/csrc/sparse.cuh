@@ -29,7 +29,9 @@ struct Sample {
 };
 
 void sample_upload(Context& ctx, Sample& s, int n_cells, int n_genes, const int* p, const int* i, const double* x,
-                   const double* var_v, const double* var_qv, const double* pca, int n_pcs, int pca_ld);
+                   const double* var_v, const double* var_qv, const double* pca, int n_pcs, int pca_ld,
+                   cudaStream_t copy_st, cudaEvent_t ready);
+void sample_finish(Context& ctx, Sample& s, cudaEvent_t ready);
 
 // cells x genes CSC (dgCMatrix) -> CSR by cell, columns ascending inside a row (deterministic)
 void csc_to_csr(Context& ctx, int n_rows, int n_cols, const int* csc_p, const int* csc_i, const double* csc_x,

@@ -375,3 +375,30 @@ def test_device_cca_reduction(ctx, oracle, small_panel, exact):
     ref_e = {(min(a, b), max(a, b))
              for a, b in zip(og["vertices"][og["from"]].tolist(), og["vertices"][og["to"]].tolist())}
     assert len(mine_e & ref_e) / len(mine_e | ref_e) > jt
+
+
+@pytest.mark.parametrize("n_types,ncomps", [(2, 30), (6, 20)])
+def test_device_pca_wide_spectrum_default_mode(ctx, n_types, ncomps):
+    """Fewer cell types than components: the wanted eigenvalues span more than a decade and the tail sits in the
+    noise bulk.  The tensor-core solver (bf16x3 GEMMs, fp32 panels) must ramp its Chebyshev degree instead of losing
+    the small directions; its subspaces agree with the FP64 path to irlba's own accuracy.  Samples express
+    different gene subsets, so the pair gene sets are proper, reordered subsets of each sample's genes."""
+    import conos_b200
+    from conos_b200.panel import make_panel
+    panel = make_panel(11, 3, [900, 800, 700], n_genes=400, n_types=n_types, n_pcs=20, use_torch=False)
+    res = {}
+    try:
+        for exact in (1, 0):
+            ctx.lib.cg_set_option(ctx.h, b"exact_reduction", float(exact))
+            con = conos_b200.Conos(panel, ctx=ctx)
+            con.buildGraph(k=10, k_self=5, space="PCA", ncomps=ncomps, n_odgenes=400, score_component_variance=True)
+            res[exact] = con.pairs["PCA"]
+    finally:
+        ctx.lib.cg_set_option(ctx.h, b"exact_reduction", 0.0)
+    for key in res[1]:
+        a, b = res[1][key], res[0][key]
+        assert a["genes"] == b["genes"]
+        for side in (0, 1):
+            cs = _principal_cosines(a["CPC"][:, side::2], b["CPC"][:, side::2])
+            assert cs.min() > 1 - 1e-5, (key, side, cs.min())
+            np.testing.assert_allclose(b["nv"][side], a["nv"][side], rtol=1e-3)
