@@ -1,5 +1,6 @@
 // C ABI, part 2: device-resident panel, per-pair reduction -> projection -> kNN -> matching, local edges.
 #include <cmath>
+#include <map>
 
 #include "api_core.cuh"
 #include "hub.cuh"
@@ -375,15 +376,16 @@ int cg_local_edges(cg_context* ctx, cg_panel* panel, const int32_t* samples, int
   if (!*edges) *edges = new cg_edges();
   if (P.k_self <= 0) return 0;
   const int kp1 = P.k_self + 1;  // +1 accounts for the self edge removed afterwards (R/conos.R:595)
-  // self-kNN of every listed sample in one launch
-  std::vector<KnnProblem> kprobs;
+  // self-kNN of every listed sample: one launch per distinct number of PCA columns (each sample brings its own
+  // reduction, R/conos.R:595 -- the bundled panel has 24 and 33 columns)
   std::vector<DevBuf<int>> idx(n);
   std::vector<DevBuf<float>> dist(n);
-  int d_pad = 0, d_pcs = 0;
+  std::map<int, std::vector<KnnProblem>> by_d;
   for (int t = 0; t < n; ++t) {
     CG_CHECK(samples[t] >= 0 && samples[t] < (int)panel->samples.size(), "no such sample");
     Sample& s = panel->samples[samples[t]];
     CG_CHECK(s.n_pcs > 0, "PCA must be estimated for all samples");
+    CG_CHECK(s.n_pcs <= 64, "at most 64 PCA columns per sample are supported for the local neighbours");
     if (s.pca_metric != P.metric) {
       s.pca_tiled.alloc(KnnPanel::elems(s.n_cells, s.n_pcs));
       KnnPanel pn;
@@ -391,20 +393,19 @@ int cg_local_edges(cg_context* ctx, cg_panel* panel, const int32_t* samples, int
       knn_prep_from_f64_colmajor(c, s.pca.p, s.n_cells, s.n_pcs, s.n_cells, (Metric)P.metric, pn);
       s.pca_metric = P.metric;
     }
-    const int dp = s.n_pcs <= 32 ? 32 : 64;
-    CG_CHECK(d_pad == 0 || (d_pad == dp && d_pcs == s.n_pcs), "per-sample PCAs must have the same number of columns");
-    d_pad = dp;
-    d_pcs = s.n_pcs;
     idx[t].alloc((size_t)s.n_cells * kp1);
     dist[t].alloc((size_t)s.n_cells * kp1);
-    kprobs.push_back(KnnProblem{s.pca_tiled.p, s.pca_tiled.p, s.n_cells, s.n_cells, idx[t].p, dist[t].p});
+    by_d[s.n_pcs].push_back(KnnProblem{s.pca_tiled.p, s.pca_tiled.p, s.n_cells, s.n_cells, idx[t].p, dist[t].p});
   }
-  if (!kprobs.empty()) {
+  {
     StageScope sc(c, "self_knn");
-    DevBuf<KnnProblem> dk;
-    dk.upload(kprobs.data(), kprobs.size(), c.stream);
-    knn_launch(c, dk.p, kprobs.data(), (int)kprobs.size(), kp1, d_pad, d_pcs, (Metric)P.metric);
-    CG_CUDA(cudaStreamSynchronize(c.stream));
+    for (auto& kv : by_d) {
+      DevBuf<KnnProblem> dk;
+      dk.upload(kv.second.data(), kv.second.size(), c.stream);
+      knn_launch(c, dk.p, kv.second.data(), (int)kv.second.size(), kp1, kv.first <= 32 ? 32 : 64, kv.first,
+                 (Metric)P.metric);
+      CG_CUDA(cudaStreamSynchronize(c.stream));
+    }
   }
   StageScope sc_le(c, "local_edges");
   for (int t = 0; t < n; ++t) {

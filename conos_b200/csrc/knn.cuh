@@ -14,8 +14,8 @@
 // i.e. exactly the shared-memory image a K-major, no-swizzle tcgen05 (kind::tf32) operand needs, so a
 // tile of R rows (R % 8 == 0) is one contiguous byte range that a single 1-D bulk copy moves.
 // The panel is stored twice: the exact fp32 values (every exact computation reads these) followed, n_pad * d_pad
-// floats later, by the same values rounded to nearest fp16 in the 16-bit core-matrix layout
-// [row/8][col/8][row%8][col%8] (the kind::f16 tensor-core operand of knn_tc2.cu).
+// floats later, by the same values rounded to nearest fp16 in the swizzled row-major layout of knn_tiled16_offset
+// (the kind::f16 tensor-core operand of knn_tc2.cu).
 // Rows are zero-padded up to a multiple of 256.  When d < d_pad the LAST padded column of every row holds -1:
 // the tensor-core kernel uses it to subtract a per-query threshold inside the MMA; every exact computation
 // (re-rank, SIMT kernel) only touches the d real columns.
@@ -44,9 +44,13 @@ __host__ __device__ inline size_t knn_tiled_offset(int row, int col, int d_pad) 
   return (size_t)(row >> 3) * (size_t)(8 * d_pad) + (size_t)(col >> 2) * 32 + (size_t)(row & 7) * 4 + (col & 3);
 }
 
-// element (row, col) of the fp16 copy: 16-byte chunks of 8 halves, [row/8][col/8][row%8][col%8]
+// element (row, col) of the fp16 copy: row-major rows of d_pad halves (64 or 128 bytes) whose 16-byte chunks are
+// XOR-swizzled inside every 8-row atom -- the SWIZZLE_64B (d_pad 32) / SWIZZLE_128B (d_pad 64) K-major shared-memory
+// image of tcgen05.mma, conflict-free for the tensor core's operand fetch
 __host__ __device__ inline size_t knn_tiled16_offset(int row, int col, int d_pad) {
-  return (size_t)(row >> 3) * (size_t)(8 * d_pad) + (size_t)(col >> 3) * 64 + (size_t)(row & 7) * 8 + (col & 7);
+  const int chunk = col >> 3;
+  const int sw = d_pad == 32 ? (chunk ^ ((row >> 1) & 3)) : (chunk ^ (row & 7));
+  return (size_t)row * (size_t)d_pad + (size_t)sw * 8 + (col & 7);
 }
 
 struct KnnProblem {

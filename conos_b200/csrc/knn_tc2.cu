@@ -41,8 +41,9 @@ constexpr float MMA_MARGIN = 1.1e-3f;
 
 template <int D_PAD>
 struct T2Cfg {
-  // operands are the fp16 copies of the panels: [row/8][k/8][row%8][k%8] halves (16-byte chunks of 8)
+  // operands are the fp16 copies of the panels: rows of D_PAD halves, 16-byte chunks swizzled (knn_tiled16_offset)
   static constexpr int KC = D_PAD / 8;              // 16-byte chunks per row
+  static constexpr int SWZ = D_PAD * 2;             // swizzle span = row bytes: 64 or 128
   static constexpr int ROW_BYTES = D_PAD * 2;
   static constexpr int A_BYTES = QBLOCK * ROW_BYTES;
   static constexpr int B_BYTES = TILE_N * ROW_BYTES;
@@ -144,9 +145,9 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
       for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
         for (int ks = 0; ks < C::KSTEPS; ++ks)
-          adesc[mb][ks] = ptx::umma_desc_kmajor_noswz(ptx::smem_u32(smA) + mb * 128 * C::ROW_BYTES + ks * 256, 128,
-                                                     C::KC * 128);
-      const uint64_t bdesc0 = ptx::umma_desc_kmajor_noswz(ptx::smem_u32(smB), 128, C::KC * 128);
+          adesc[mb][ks] = ptx::umma_desc_kmajor_swz(ptx::smem_u32(smA) + mb * 128 * C::ROW_BYTES + ks * 32, C::SWZ,
+                                                   8 * C::ROW_BYTES);
+      const uint64_t bdesc0 = ptx::umma_desc_kmajor_swz(ptx::smem_u32(smB), C::SWZ, 8 * C::ROW_BYTES);
       uint32_t slot = 0, ph = 0, stage = 0, aph = 0, it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const KnnItem wi = items[item];
@@ -168,7 +169,7 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
 #pragma unroll
               for (int ks = 0; ks < C::KSTEPS; ++ks) {
 #if !defined(TC2_VARIANT) || TC2_VARIANT != 1
-                ptx::mma_f16_ss(d_tmem, adesc[mb][ks], bd + (uint64_t)(ks * 16), idesc, ks > 0 ? 1u : 0u);
+                ptx::mma_f16_ss(d_tmem, adesc[mb][ks], bd + (uint64_t)(ks * 2), idesc, ks > 0 ? 1u : 0u);
 #else
                 (void)d_tmem;
 #endif
@@ -195,8 +196,7 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
     const uint32_t tm_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     float* gm = gmax_s + half * 256 + row_local;  // + g * 512
     // this row's threshold slot in the A tile: last K dimension
-    __half* thr_slot = smA + (size_t)(row_local >> 3) * (8 * D_PAD) + (size_t)((D_PAD - 1) >> 3) * 64 +
-                       (size_t)(row_local & 7) * 8 + ((D_PAD - 1) & 7);
+    __half* thr_slot = smA + knn_tiled16_offset(row_local, D_PAD - 1, D_PAD);
     uint32_t g = 0, it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const KnnItem wi = items[item];
@@ -208,7 +208,7 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
       // ------------------------------------------------ phase A: group maxima of the approximate scores
       {
         float run = -INFINITY;
-        int gi = 0, tcount = 0;
+        int tcount = 0;
         for (int t = 0; t < n_tiles; ++t, ++g) {
           const uint32_t stage = g & 1, aph = (g >> 1) & 1;
           ptx::mbar_wait(acc_full + stage, aph);
@@ -241,20 +241,17 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
           }
           const float m0 = max16(v0), m1 = max16(v1), m2 = max16(v2), m3 = max16(v3);
           if (ax.sg == 16) {
-            gm[(gi + 0) * 512] = m0;
-            gm[(gi + 1) * 512] = m1;
-            gm[(gi + 2) * 512] = m2;
-            gm[(gi + 3) * 512] = m3;
-            gi += 4;
+            gm[(4 * t + 0) * 512] = m0;
+            gm[(4 * t + 1) * 512] = m1;
+            gm[(4 * t + 2) * 512] = m2;
+            gm[(4 * t + 3) * 512] = m3;
           } else if (ax.sg == 32) {
-            gm[(gi + 0) * 512] = fmaxf(m0, m1);
-            gm[(gi + 1) * 512] = fmaxf(m2, m3);
-            gi += 2;
+            gm[(2 * t + 0) * 512] = fmaxf(m0, m1);
+            gm[(2 * t + 1) * 512] = fmaxf(m2, m3);
           } else {
             run = fmaxf(fmaxf(run, fmaxf(m0, m1)), fmaxf(m2, m3));
             if (++tcount == ax.tg || t == n_tiles - 1) {
-              gm[gi * 512] = run;
-              ++gi;
+              gm[(t / ax.tg) * 512] = run;
               run = -INFINITY;
               tcount = 0;
             }

@@ -161,6 +161,20 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_noswz(uint32_t smem_addr, u
   d |= static_cast<uint64_t>(1) << 46;
   return d;
 }
+// Swizzled K-major operand (rows of 64 or 128 bytes, 16-byte chunks XOR-swizzled inside 8-row atoms):
+//   swizzle_bytes 64 or 128; sbo_bytes = distance between 8-row atoms (8 * row bytes); LBO is not used.
+// layout type bits [61,64): 2 = SWIZZLE_128B, 4 = SWIZZLE_64B.  The start address must keep the atom alignment
+// (512 / 1024 bytes) up to the in-row K offset that the k-steps add.
+__device__ __forceinline__ uint64_t umma_desc_kmajor_swz(uint32_t smem_addr, uint32_t swizzle_bytes,
+                                                         uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(swizzle_bytes == 128 ? 2 : 4) << 61;
+  return d;
+}
 // Instruction descriptor: fp32 accumulate, K-major A and B, dense.
 //   fmt: 0 = f16, 1 = bf16, 2 = tf32 (for kind::f16 / kind::tf32)
 __host__ __device__ constexpr uint32_t umma_idesc(uint32_t fmt, uint32_t M, uint32_t N) {

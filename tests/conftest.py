@@ -36,3 +36,23 @@ def small_panel():
 def to_oracle_samples(oracle, panel):
     return {n: oracle.Sample(counts=s.counts, genes=s.genes, cells=s.cells, varinfo_v=s.varinfo_v,
                              varinfo_qv=s.varinfo_qv, pca=s.pca, od_genes=s.od_genes) for n, s in panel.items()}
+
+
+def _golden_loader():
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", "make_golden_vectors.py")
+    spec = importlib.util.spec_from_file_location("make_golden_vectors", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.fixture(scope="session")
+def golden():
+    """(module with load_reference_panel / knn_inputs, the committed oracle vectors)"""
+    import os
+    import numpy as np
+    mod = _golden_loader()
+    vec = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_vectors.npz"))
+    return mod, vec

@@ -198,3 +198,27 @@ def test_build_graph_invariants(oracle, small_panel):
     assert g["weight"][inter].max() <= 1.0 + 1e-12 and g["weight"][~inter].max() <= 0.2 + 1e-12
     a = oracle.adjacency_csr(g)
     assert abs(a - a.T).max() == 0
+
+
+def test_reference_fixture_and_golden_vectors(oracle, golden):
+    """The reference's own panel (data/small_panel.preprocessed.rda, decoded without R) through the oracle:
+    the three quantities tests/testthat/test_functions.R asserts on this path -- 2 samples (:10), 59 cells (:15),
+    59 x 1000 joint count matrix (:20), and one graph vertex per cell after buildGraph(ncomps=25) (:24-33:
+    length(groups) == 59) -- and the oracle's committed output on it, so the oracle cannot drift silently."""
+    mod, vec = golden
+    panel = mod.load_reference_panel(oracle.Sample)
+    assert len(panel) == 2
+    assert sum(s.counts.shape[0] for s in panel.values()) == 59
+    genes = sorted(set(g for s in panel.values() for g in s.genes))
+    assert 59 * len(genes) == 59000
+    ref = oracle.build_graph(panel, ncomps=25)
+    g = ref["graph"]
+    assert len(g["vertices"]) == 59
+    assert np.array_equal(g["vertices"], vec["graph_vertices"])
+    assert np.array_equal(g["from"], vec["graph_from"]) and np.array_equal(g["to"], vec["graph_to"])
+    assert np.array_equal(g["type"], vec["graph_type"])
+    np.testing.assert_allclose(g["weight"], vec["graph_weight"], rtol=1e-10)
+    A, B = mod.knn_inputs()
+    idx, dist = oracle.cross_knn(A, B, 15, "angular")
+    assert np.array_equal(idx, vec["knn_idx"])
+    assert np.array_equal(dist.view(np.uint32), vec["knn_dist"].view(np.uint32))

@@ -402,3 +402,34 @@ def test_device_pca_wide_spectrum_default_mode(ctx, n_types, ncomps):
             cs = _principal_cosines(a["CPC"][:, side::2], b["CPC"][:, side::2])
             assert cs.min() > 1 - 1e-5, (key, side, cs.min())
             np.testing.assert_allclose(b["nv"][side], a["nv"][side], rtol=1e-3)
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_reference_fixture_on_gpu(ctx, golden, exact):
+    """buildGraph(ncomps=25) on the reference's own fixture, as tests/testthat/test_functions.R:24 calls it, against
+    the committed oracle vectors: one vertex per cell (59), and -- with the FP64 reductions -- the oracle's edge
+    set with its weights; the tensor-core reductions agree to irlba's accuracy, so a few near-tied neighbours
+    may differ."""
+    import conos_b200
+    mod, vec = golden
+    panel = mod.load_reference_panel(conos_b200.Pagoda2)
+    con = conos_b200.Conos(panel, ctx=ctx)
+    ctx.lib.cg_set_option(ctx.h, b"exact_reduction", 1.0 if exact else 0.0)
+    try:
+        g = con.buildGraph(ncomps=25)
+    finally:
+        ctx.lib.cg_set_option(ctx.h, b"exact_reduction", 0.0)
+    assert g.vcount() == 59
+    mine = {(min(a, b), max(a, b)): w for a, b, w in zip(g.vertices[g.edge_from].tolist(),
+                                                        g.vertices[g.edge_to].tolist(), g.weight.tolist())}
+    gv = vec["graph_vertices"]
+    ref = {(min(a, b), max(a, b)): w for a, b, w in zip(gv[vec["graph_from"]].tolist(), gv[vec["graph_to"]].tolist(),
+                                                       vec["graph_weight"].tolist())}
+    common = set(mine) & set(ref)
+    jac = len(common) / len(set(mine) | set(ref))
+    if exact:
+        assert np.array_equal(g.vertices, gv)
+        assert set(mine) == set(ref)
+        np.testing.assert_allclose([mine[e] for e in sorted(common)], [ref[e] for e in sorted(common)], rtol=1e-6)
+    else:
+        assert jac > 0.9, jac
