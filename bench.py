@@ -28,6 +28,13 @@ CONFIGS = {
     # BASELINE.json configs[1]: the configuration the metric is quoted on at N = 1
     2: dict(workload="synthetic 8 samples x 50k cells x 2000 od-genes, space=PCA ncomps=30 k=30 (configs[1])",
             n_samples=8, n_cells=50000, n_genes=2000, space="PCA", ncomps=30, k=30, k_self=10),
+    # configs[2]: covariance + common-PCA kernels (profiling / parity runs, not a bench line)
+    3: dict(workload="synthetic 32 samples x 20k cells, space=CPCA ncomps=50 (configs[2])",
+            n_samples=32, n_cells=20000, n_genes=2000, space="CPCA", ncomps=50, k=15, k_self=10),
+    # configs[4]: CCA with alignment.strength = 0.3 (k1 = round(0.09 * max cells) >> k: hub paring ladder)
+    5: dict(workload="synthetic 2 x 40 samples x 25k cells, space=CCA ncomps=30 alignment.strength=0.3 (configs[4])",
+            n_samples=80, n_cells=25000, n_genes=2000, space="CCA", ncomps=30, k=15, k_self=10,
+            alignment_strength=0.3),
     # configs[3]: the atlas, pair-sharded
     4: dict(workload="synthetic atlas 100 samples x 10k cells (4950 pairs), space=PCA k=15 k.self=5 (configs[3])",
             n_samples=100, n_cells=10000, n_genes=2000, space="PCA", ncomps=30, k=15, k_self=5),
@@ -149,13 +156,31 @@ def to_oracle(oracle, panel):
                              varinfo_qv=s.varinfo_qv, pca=s.pca, od_genes=s.od_genes) for n, s in panel.items()}
 
 
+_RESULT_FD = None
+
+
+def guard_stdout():
+    """Library chatter (NCCL prints its version on stdout) must not share the channel of the one JSON line: file
+    descriptor 1 is pointed at stderr for the rest of the process and the result goes to a private duplicate."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--config", type=int, default=2, choices=[2, 4])
     ap.add_argument("--n-samples", type=int, default=None, help="override (debug runs only)")
     ap.add_argument("--n-cells", type=int, default=None, help="override (debug runs only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -207,7 +232,7 @@ def main():
                 "data": "synthetic", "config": {"workload": cfg["workload"]},
                 "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
                 "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ this repository's arm
@@ -348,7 +373,7 @@ def main():
         line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "pairs/s", "cores": os.cpu_count() or 1, "kind": "port",
                                 "sample": f"1 of {n_pairs} pairs at full size (2 x {cfg['n_cells']} cells): reduction "
                                           f"+ projection + exact kNN both ways + matching, {dt:.1f} s"}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 

@@ -287,7 +287,7 @@ void cca_pair(Context& ctx, cg_panel& panel, const cg_pair& pr, const cg_params&
   DevBuf<double> Ucm((size_t)n1 * d), theta((size_t)d);
   {
     StageScope sc(ctx, "reduction.eig");
-    top_eigenvectors_operator(ctx, n1, d, 1e-10, 600, apply, Ucm.p, theta.p);
+    top_eigenvectors_operator(ctx, n1, d, ctx.exact_reduction ? 1e-10 : 1e-5, 600, apply, Ucm.p, theta.p);
   }
   // sigma = sqrt(eigenvalue of A A'); v = Yb (Ya' u) / sigma; both scaled by sqrt(sigma) / max sqrt(sigma)
   std::vector<double> th((size_t)d), su((size_t)d), sv((size_t)d);

@@ -19,6 +19,8 @@ struct EigWork {
   int* converged;  // 1 when the leading r residuals are below tol * theta_1
   double* resid;   // optional: worst relative residual of the leading r pairs
   double* colres = nullptr;  // optional [B]: relative residual of every leading Ritz pair (the filter degree uses it)
+  double* X = nullptr;       // FP64 driver: previous Chebyshev iterate [G][B]
+  int* nlock = nullptr;      // FP64 driver: leading Ritz pairs that met the tolerance (locked: no longer filtered)
 };
 
 __device__ __forceinline__ double hash_unit(unsigned a, unsigned b) {
@@ -251,6 +253,17 @@ __device__ void orth_pass(const double* __restrict__ src, double* __restrict__ d
   block_gram<B>(src, src, G, sm.S);
   const int tid = threadIdx.x, lane = tid & 31;
   if (tid == 0) sm.flag = 0;
+  // equilibrate: the columns of a filtered block differ by many orders of magnitude in norm, which says nothing
+  // about their independence.  S <- D^-1 S D^-1 with D = diag(column norms) (a zero column keeps D = 1 and shows up
+  // as a null direction below); the multiplier is rescaled by D^-1 at the end.
+  if (tid < B) {
+    const double d = sm.S[tid][tid];
+    sm.ev[tid] = d > 0.0 ? 1.0 / sqrt(d) : 1.0;   // D^-1
+  }
+  __syncthreads();
+  for (int t = tid; t < B * B; t += EIG_THREADS) sm.S[t / B][t % B] *= sm.ev[t / B] * sm.ev[t % B];
+  __syncthreads();
+  if (tid < B) sm.rowbuf[0][tid] = sm.ev[tid];  // D^-1 survives the fallback (which reuses ev) here
   __syncthreads();
   if (tid < 32) {
     double maxd = 0.0;
@@ -305,11 +318,25 @@ __device__ void orth_pass(const double* __restrict__ src, double* __restrict__ d
     for (int t = tid; t < B * B; t += EIG_THREADS) {
       const int i = t / B, j = t % B;
       const double l = sm.S[j][j];
-      sm.W[i][j] = (l > 1e-20 * lmax && l > 0.0) ? sm.W[i][j] / sqrt(l) : 0.0;
+      sm.W[i][j] = (l > 1e-14 * lmax && l > 0.0) ? sm.W[i][j] / sqrt(l) : 0.0;
     }
+    if (tid < B) sm.ev[tid] = (sm.S[tid][tid] > 1e-14 * lmax && sm.S[tid][tid] > 0.0) ? 0.0 : 1.0;
     __syncthreads();
   }
+  // undo the equilibration: Q = Z D^-1 W
+  for (int t = tid; t < B * B; t += EIG_THREADS) sm.W[t / B][t % B] *= sm.rowbuf[0][t / B];
+  __syncthreads();
   rows_times_matrix<B>(src, dst, G, sm.W, sm.rowbuf);
+  if (sm.flag) {
+    // a numerically null direction is replaced by a fresh pseudo-random column (the next pass orthonormalises it):
+    // a zero column would stay zero for the rest of the iteration
+    for (size_t t = tid; t < (size_t)G * B; t += EIG_THREADS) {
+      const int j = (int)(t % B);
+      if (sm.ev[j] != 0.0) dst[t] = hash_unit((unsigned)(t / B) + 0x9e37u, (unsigned)j + 4099u);
+    }
+    __syncthreads();
+    if (tid == 0) sm.wellcond = 0;
+  }
 }
 
 template <int B>
@@ -395,6 +422,11 @@ __global__ void __launch_bounds__(EIG_THREADS) eig_rr_kernel(const EigWork* __re
     if (w.resid && !finalize) *w.resid = worst / scale;
     if (w.colres && !finalize)
       for (int j = 0; j < r; ++j) w.colres[j] = sqrt(sm.cs[j]) / scale;
+    if (w.nlock && !finalize) {
+      int nl = 0;
+      while (nl < r && sane && sqrt(sm.cs[nl]) <= tol * scale) ++nl;
+      *w.nlock = nl;
+    }
   }
   if (finalize) {
     for (size_t t = tid; t < (size_t)w.G * r; t += EIG_THREADS) {
@@ -405,11 +437,130 @@ __global__ void __launch_bounds__(EIG_THREADS) eig_rr_kernel(const EigWork* __re
   }
 }
 
-// Generic driver: `matmul(works)` must fill Z = Op(Q) for every problem (Q, Z row-major [G][B] on the device).
+// Chebyshev coefficients of one sweep of the FP64 driver (same recurrence and degree rule as tc_coeff_kernel; FP64
+// panels keep 16 digits, so a wanted column may carry 1e3 times its own size of a better-conditioned direction).
+template <int B>
+__global__ void eig_coeff_kernel(const EigWork* __restrict__ W, int n_probs, int degree, int r, double budget,
+                                 double* __restrict__ al, double* __restrict__ be, double* __restrict__ cc,
+                                 int* __restrict__ deg) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_probs) return;
+  const double* theta = W[p].theta;
+  const int nl = W[p].nlock ? *W[p].nlock : 0;
+  const double a0 = theta[nl < B ? nl : B - 1];  // the filter is scaled at the first pair that is still iterated
+  double b = theta[B - 1];
+  if (!(b > 1e-12 * theta[0])) b = 1e-12 * theta[0];
+  if (!(a0 > b) || nl >= r) {  // nothing left to separate (or a zero matrix): one plain power step
+    for (int i = 1; i <= degree; ++i) { al[(size_t)i * n_probs + p] = 0.0; be[(size_t)i * n_probs + p] = 0.0; }
+    al[(size_t)1 * n_probs + p] = a0 > 0.0 ? 1.0 / a0 : 0.0;
+    cc[p] = 0.0;
+    deg[p] = 1;
+    return;
+  }
+  const double e = b / 2.0, c = b / 2.0;
+  double sigma1 = e / (a0 - c), sigma = sigma1;
+  cc[p] = c;
+  al[(size_t)1 * n_probs + p] = sigma1 / e;
+  be[(size_t)1 * n_probs + p] = 0.0;
+  for (int i = 2; i <= degree; ++i) {
+    const double s2 = 1.0 / (2.0 / sigma1 - sigma);
+    al[(size_t)i * n_probs + p] = 2.0 * s2 / e;
+    be[(size_t)i * n_probs + p] = sigma * s2;
+    sigma = s2;
+  }
+  // degree: eps_i * T_m(x_i) / T_m(x_j) <= budget over the pairs that are still iterated
+  double m_safe = (double)degree;
+  for (int i = nl; i + 1 < r; ++i) {
+    double xi = (theta[i] - c) / e;
+    if (!(xi > 1.0)) xi = 1.0;
+    const double li = log(xi + sqrt(xi * xi - 1.0));
+    double eps = W[p].colres ? W[p].colres[i] : 1.0;
+    if (!(eps > 1e-14)) eps = 1e-14;
+    if (!(eps < 1.0)) eps = 1.0;
+    const double room = log(budget / eps);
+    for (int j = i + 1; j < r; ++j) {
+      double xj = (theta[j] - c) / e;
+      if (!(xj > 1.0)) xj = 1.0;
+      const double dl = li - log(xj + sqrt(xj * xj - 1.0));
+      if (dl > 1e-12) m_safe = fmin(m_safe, room / dl);
+    }
+  }
+  const int m = (int)floor(m_safe);
+  deg[p] = m < 1 ? 1 : (m > degree ? degree : m);
+}
+
+// One step of the scaled three-term recurrence on the whole block of a problem (elementwise):
+//   first:   X = Q;  Y = al (Z - c Q)                         (Z = Op Q from the Rayleigh-Ritz step)
+//   later:   Y = al (Z - c Q) - be X;  X = Q                  (Z = Op Q, Q the current iterate)
+// Y goes to Q (next operand) or, on the problem's last step, to Z (what eig_orth_kernel orthonormalises).
+template <int B>
+__global__ void eig_cheb_kernel(const EigWork* __restrict__ W, const double* __restrict__ al,
+                                const double* __restrict__ be, const double* __restrict__ cc,
+                                const int* __restrict__ deg, int n_probs, int step) {
+  const int p = blockIdx.y;
+  const EigWork w = W[p];
+  if (*w.converged != 0) return;
+  const int m = deg[p];
+  if (step > m) return;
+  const double a = al[(size_t)step * n_probs + p], b = be[(size_t)step * n_probs + p], c = cc[p];
+  const bool last = step == m;
+  const int nl = w.nlock ? *w.nlock : 0;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < (size_t)w.G * B;
+       t += (size_t)gridDim.x * blockDim.x) {
+    if ((int)(t % B) < nl) {  // locked Ritz vector: kept as it is
+      if (last) w.Z[t] = w.Q[t];
+      continue;
+    }
+    const double q = w.Q[t], z = w.Z[t];
+    const double y = a * (z - c * q) - (step == 1 ? 0.0 : b * w.X[t]);
+    w.X[t] = q;
+    if (last) w.Z[t] = y; else w.Q[t] = y;
+  }
+}
+
+// The filter polynomial is huge at the locked eigenvalues, so whatever the iterated columns still hold of the locked
+// directions is removed after every step:  Y <- Y - Q_L (Q_L' Y)  (Q_L = the first nlock columns of Q).
+template <int B>
+__global__ void __launch_bounds__(EIG_THREADS) eig_project_kernel(const EigWork* __restrict__ W,
+                                                                  const int* __restrict__ deg, int step) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  EigSmem<B>& sm = *reinterpret_cast<EigSmem<B>*>(raw);
+  const EigWork w = W[blockIdx.x];
+  if (*w.converged != 0) return;
+  const int m = deg[blockIdx.x];
+  if (step > m) return;
+  const int nl = w.nlock ? *w.nlock : 0;
+  if (nl == 0) return;
+  double* Y = step == m ? w.Z : w.Q;
+  block_gram<B>(w.Q, Y, w.G, sm.S);   // S[l][j] = q_l' y_j
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NC = B / 32;
+  for (int g = warp; g < w.G; g += EIG_THREADS / 32) {
+#pragma unroll
+    for (int u = 0; u < NC; ++u) sm.rowbuf[warp][lane + 32 * u] = w.Q[(size_t)g * B + lane + 32 * u];
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < NC; ++u) {
+      const int j = lane + 32 * u;
+      if (j >= nl) {
+        double acc = Y[(size_t)g * B + j];
+        for (int l = 0; l < nl; ++l) acc = fma(-sm.rowbuf[warp][l], sm.S[l][j], acc);
+        Y[(size_t)g * B + j] = acc;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// Generic FP64 driver: `matmul(works)` must fill Z = Op(Q) for every problem (Q, Z row-major [G][B] on the device).
+// Chebyshev-filtered subspace iteration: Rayleigh-Ritz, residual test (||C q - theta q|| <= tol * theta_1 for the
+// leading r pairs -- irlba's criterion), then a polynomial filter of per-problem degree on the unwanted interval
+// [0, theta_B], CholeskyQR2, repeat.  `max_iter` bounds the number of operator applications.
 template <int B, class MatMul>
 void run_eig_generic(Context& ctx, const int* rows, double* const* Vout, double* const* theta_out, const double* const* Cmat,
                      int n_probs, int r, double tol, int max_iter, MatMul&& matmul) {
   cudaStream_t s = ctx.stream;
+  constexpr int DEGREE = 12;
   std::vector<EigWork> works(n_probs);
   size_t tot = 0;
   int maxG = 0;
@@ -418,14 +569,24 @@ void run_eig_generic(Context& ctx, const int* rows, double* const* Vout, double*
     maxG = rows[p] > maxG ? rows[p] : maxG;
     CG_CHECK(rows[p] >= B, "eigen block wider than the matrix");
   }
-  DevBuf<double> Q(tot), Z(tot), theta((size_t)n_probs * B);
-  DevBuf<int> conv((size_t)n_probs);
+  DevBuf<double> Q(tot), Z(tot), X(tot), theta((size_t)n_probs * B), colres((size_t)n_probs * B);
+  DevBuf<double> al((size_t)(DEGREE + 1) * n_probs), be((size_t)(DEGREE + 1) * n_probs), cc((size_t)n_probs);
+  DevBuf<int> conv((size_t)n_probs), deg((size_t)n_probs), nlock((size_t)n_probs);
   theta.zero(s);
   conv.zero(s);
+  nlock.zero(s);
+  {
+    std::vector<double> ones((size_t)n_probs * B, 1.0);
+    colres.upload(ones.data(), ones.size(), s);
+  }
+  // how far a wanted column may be swamped by a better-conditioned one before the FP64 panel loses the accuracy
+  // the tolerance asks for; the Gram matrix of CholeskyQR squares the condition number, so 1e4 at most
+  const double budget = fmin(1e4, fmax(1e3, tol * 1e13));
   size_t o = 0;
   for (int p = 0; p < n_probs; ++p) {
     works[p] = EigWork{Cmat ? Cmat[p] : nullptr, rows[p], Q.p + o, Z.p + o, theta.p + (size_t)p * B, Vout[p],
-                       theta_out ? theta_out[p] : nullptr, conv.p + p, nullptr};
+                       theta_out ? theta_out[p] : nullptr, conv.p + p, nullptr, colres.p + (size_t)p * B, X.p + o,
+                       nlock.p + p};
     o += (size_t)rows[p] * B;
   }
   DevBuf<EigWork> dw;
@@ -433,49 +594,68 @@ void run_eig_generic(Context& ctx, const int* rows, double* const* Vout, double*
   const size_t smem = sizeof(EigSmem<B>);
   CG_CUDA(cudaFuncSetAttribute(eig_orth_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CG_CUDA(cudaFuncSetAttribute(eig_rr_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CG_CUDA(cudaFuncSetAttribute(eig_project_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 gi((unsigned)(((size_t)maxG * B + 255) / 256), n_probs);
   eig_init_kernel<B><<<gi, 256, 0, s>>>(dw.p);
   eig_orth_kernel<B><<<n_probs, EIG_THREADS, smem, s>>>(dw.p);
   ctx.stats.kernels += 2;
-  std::vector<int> hc(n_probs, 0);
-  const int rr_every = 4;
-  int it_done = 0;
-  for (int it = 1; it <= max_iter; ++it) {
-    it_done = it;
+  std::vector<int> hc(n_probs, 0), hdeg(n_probs, 1);
+  int applied = 0, outer = 0;
+  const unsigned cheb_blocks = (unsigned)std::min<size_t>(((size_t)maxG * B + 255) / 256, 64);
+  while (true) {
+    ++outer;
     {
       StageScope sc(ctx, "reduction.eig.matmul");
       matmul(works, dw.p, maxG);
+      ++applied;
     }
-    if (it % rr_every == 0) {
-      {
-        StageScope sc(ctx, "reduction.eig.rr");
-        eig_rr_kernel<B><<<n_probs, EIG_THREADS, smem, s>>>(dw.p, r, tol, 0);
-      }
+    {
+      StageScope sc(ctx, "reduction.eig.rr");
+      eig_rr_kernel<B><<<n_probs, EIG_THREADS, smem, s>>>(dw.p, r, tol, 0);
       ctx.stats.kernels++;
       conv.download(hc.data(), (size_t)n_probs, s);
       CG_CUDA(cudaStreamSynchronize(s));
-      bool all = true;
-      for (int p = 0; p < n_probs; ++p) all = all && hc[p] != 0;
-      if (all) break;
+    }
+    bool all = true;
+    for (int p = 0; p < n_probs; ++p) all = all && hc[p] != 0;
+    if (all || applied >= max_iter) break;
+    eig_coeff_kernel<B><<<(n_probs + 127) / 128, 128, 0, s>>>(dw.p, n_probs, DEGREE, r, budget, al.p, be.p, cc.p,
+                                                             deg.p);
+    ctx.stats.kernels++;
+    deg.download(hdeg.data(), (size_t)n_probs, s);
+    CG_CUDA(cudaStreamSynchronize(s));
+    int sweep = 1;
+    for (int p = 0; p < n_probs; ++p)
+      if (!hc[p] && hdeg[p] > sweep) sweep = hdeg[p];
+    for (int i = 1; i <= sweep; ++i) {
+      if (i > 1) {
+        StageScope sc(ctx, "reduction.eig.matmul");
+        matmul(works, dw.p, maxG);
+        ++applied;
+      }
+      eig_cheb_kernel<B><<<dim3(cheb_blocks, n_probs), 256, 0, s>>>(dw.p, al.p, be.p, cc.p, deg.p, n_probs, i);
+      eig_project_kernel<B><<<n_probs, EIG_THREADS, smem, s>>>(dw.p, deg.p, i);
+      ctx.stats.kernels += 2;
     }
     {
       StageScope sc(ctx, "reduction.eig.orth");
+      // converged problems keep their Ritz basis: their Z = Op Q is re-orthonormalised, which leaves span(Q)
+      // invariant to the accuracy already reached
       eig_orth_kernel<B><<<n_probs, EIG_THREADS, smem, s>>>(dw.p);
+      ctx.stats.kernels++;
     }
-    ctx.stats.kernels++;
   }
   if (ctx.profile) {
-    ctx.stage_ms["reduction.eig.iterations"] += it_done;
+    ctx.stage_ms["reduction.eig.iterations"] += applied;
+    ctx.stage_ms["reduction.eig.outer_iterations"] += outer;
     int nconv = 0;
     for (int p = 0; p < n_probs; ++p) nconv += hc[p] != 0;
     ctx.stage_ms["reduction.eig.converged_problems"] += nconv;
     ctx.stage_ms["reduction.eig.problems"] += n_probs;
   }
-  // final Rayleigh-Ritz from an orthonormal basis
-  eig_orth_kernel<B><<<n_probs, EIG_THREADS, smem, s>>>(dw.p);
-  matmul(works, dw.p, maxG);
-  eig_rr_kernel<B><<<n_probs, EIG_THREADS, smem, s>>>(dw.p, r, tol, 1);
-  ctx.stats.kernels += 2;
+  // the loop ends right after a Rayleigh-Ritz step: Q holds the sorted Ritz vectors
+  eig_export_kernel<B><<<dim3(8, n_probs), 256, 0, s>>>(dw.p, r);
+  ctx.stats.kernels++;
   CG_CUDA(cudaGetLastError());
   CG_CUDA(cudaStreamSynchronize(s));
 }

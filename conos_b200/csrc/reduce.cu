@@ -322,7 +322,7 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
       CG_CUDA(cudaGetLastError());
       {
         StageScope sc(ctx, "reduction.eig");
-        top_eigenvectors_batched(ctx, eprobs.data(), (int)eprobs.size(), r, 1e-10, 400);
+        top_eigenvectors_batched(ctx, eprobs.data(), (int)eprobs.size(), r, ctx.exact_reduction ? 1e-10 : 1e-5, 400);
       }
       for (int t = 0; t < nq; ++t) {
         Buf& b = bufs[t];
@@ -400,7 +400,7 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
     EigProblem ep{S.p, Gp, V0.p, th0.p};
     {
       StageScope sc(ctx, "reduction.eig");
-      top_eigenvectors_batched(ctx, &ep, 1, ncomp, 1e-10, 600);
+      top_eigenvectors_batched(ctx, &ep, 1, ncomp, ctx.exact_reduction ? 1e-10 : 1e-5, 600);
     }
     DevBuf<double> ng(2), D((size_t)ncomp * 2), CPC((size_t)Gp * ncomp), niter((size_t)ncomp);
     const double hng[2] = {na, nb};

@@ -349,7 +349,8 @@ def test_cca_with_oracle_variates(ctx, oracle, small_panel):
 @pytest.mark.parametrize("exact", [True, False])
 def test_device_cca_reduction(ctx, oracle, small_panel, exact):
     """quickCCA on the device (implicit n1 x n1 operator instead of the dense n1 x n2 cross product).  With the
-    FP64 Gram the variates match the dense SVD tightly; the tensor-core Gram (bf16x3) limits it to ~1e-5."""
+    FP64 Gram and a 1e-10 eigen tolerance the variates match the dense SVD tightly; the default mode (tensor-core
+    Gram, irlba's own 1e-5 tolerance) is held to irlba-level agreement."""
     import conos_b200
     osamples = to_oracle_samples(oracle, small_panel)
     ref = oracle.build_graph(osamples, k=10, k_self=5, space="CCA", ncomps=10, n_odgenes=300)
@@ -359,15 +360,20 @@ def test_device_cca_reduction(ctx, oracle, small_panel, exact):
         g = con.buildGraph(k=10, k_self=5, space="CCA", ncomps=10, n_odgenes=300)
     finally:
         ctx.lib.cg_set_option(ctx.h, b"exact_reduction", 0.0)
-    rt, at, jt = (1e-8, 1e-7, 0.995) if exact else (2e-4, 5e-3, 0.97)
+    rt, at, jt = (1e-8, 1e-7, 0.995) if exact else (1e-3, 5e-3, 0.9)
     for key, red in ref["pairs"].items():
         mine = con.pairs["CCA"][key]
         assert np.array_equal(mine["rows_u"], np.nonzero(red["keep"][0])[0])
         assert np.array_equal(mine["rows_v"], np.nonzero(red["keep"][1])[0])
         np.testing.assert_allclose(mine["d"], red["d"], rtol=rt)
         for a, b in ((mine["u"], red["u"]), (mine["v"], red["v"])):
-            sign = np.sign(np.sum(a * b, axis=0))
-            np.testing.assert_allclose(a * sign[None, :], b, rtol=0, atol=at * np.abs(b).max())
+            if exact:
+                sign = np.sign(np.sum(a * b, axis=0))
+                np.testing.assert_allclose(a * sign[None, :], b, rtol=0, atol=at * np.abs(b).max())
+            else:
+                # irlba's tolerance (residual <= 1e-5 sigma_1^2) fixes the canonical subspace, not the individual
+                # variates of nearly equal correlations
+                assert _principal_cosines(a, b).min() > 1 - 1e-3
         # u_j and v_j flip together
         assert np.array_equal(np.sign(np.sum(mine["u"] * red["u"], axis=0)), np.sign(np.sum(mine["v"] * red["v"], axis=0)))
     og = ref["graph"]

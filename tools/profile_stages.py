@@ -19,6 +19,7 @@ ctx = conos_b200.Context(0)
 panel = make_panel(a.config, cfg["n_samples"], cfg["n_cells"], cfg["n_genes"])
 con = conos_b200.Conos(panel, ctx=ctx)
 kw = dict(k=cfg["k"], k_self=cfg["k_self"], space=cfg["space"], ncomps=cfg["ncomps"], n_odgenes=cfg["n_genes"])
+if "alignment_strength" in cfg: kw["alignment_strength"] = cfg["alignment_strength"]
 con.buildGraph(fetch=False, **kw)  # warm
 for rep in range(a.reps):
     con.pairs = {}
@@ -32,4 +33,6 @@ for rep in range(a.reps):
     st = {kv.split("=")[0]: float(kv.split("=")[1]) for kv in buf.value.decode().split(";") if kv}
     ctx.lib.cg_profile(ctx.h, 0)
     top = {k: v for k, v in st.items() if "." not in k}
-    print(json.dumps({"wall_ms": 1e3 * wall, "lib_ms": sum(top.values()), "stages_ms": st}))
+    print(json.dumps({"config": a.config, "n_samples": cfg["n_samples"], "n_cells": cfg["n_cells"], "space": cfg["space"],
+                      "wall_ms": 1e3 * wall, "lib_ms": sum(top.values()), "edges": getattr(g, "n_edges_device", None),
+                      "stages_ms": st}))
