@@ -314,92 +314,153 @@ void match_one(Context& ctx, const MnnProblem& pb, int k1, const SimParams& sp, 
 }
 
 // reduceEdgesInGraphIteratively on one matched pair (alive flags updated in place)
-void reduce_edges_iteratively(Context& ctx, const MnnProblem& pb, Matched& m, int k) {
+// reduceEdgesInGraphIteratively (R/conos.R:906-933) for a batch of pairs.  The greedy paring of one pair is sequential
+// by definition (every line sees the degrees the previous lines left behind), so the parallelism is across pairs: every
+// pass is ONE pare_kernel launch with a block per pair, the host decisions of the ladder (max degree, number of steps,
+// cleanup pass) are taken for all pairs from one download.
+struct PareState {
+  Matched* m = nullptr;
+  int nA = 0, nB = 0;
+  DevBuf<int> rowN, colN, row_perm;
+  DevBuf<long long> col_ptr, row_ptr, one_seg;
+  DevBuf<u64> scratch, order;
+  std::vector<int> ks;
+  int klow_final = 0;
+  bool active = false;
+};
+
+void reduce_edges_batch(Context& ctx, const MnnProblem* probs, Matched* ms, int n, int k) {
   cudaStream_t s = ctx.stream;
-  if (m.nnz == 0) return;
-  const int nA = pb.nA, nB = pb.nB;
-  DevBuf<int> rowN((size_t)nA), colN((size_t)nB), cursor((size_t)nA), row_perm((size_t)m.nnz), dmax(1);
-  DevBuf<long long> col_ptr((size_t)nB + 1), row_ptr((size_t)nA + 1);
-  exclusive_scan_i32_to_i64(ctx, m.col_cnt.p, col_ptr.p, (size_t)nB, col_ptr.p + nB);
-  auto live_counts = [&]() {
-    rowN.zero(s);
-    colN.zero(s);
-    live_counts_kernel<<<nblk((size_t)m.nnz), 256, 0, s>>>(m.row.p, m.col.p, m.alive.p, m.nnz, rowN.p, colN.p);
+  if (n == 0) return;
+  std::vector<PareState> st((size_t)n);
+  DevBuf<int> dmax((size_t)n);
+  std::vector<int> hmax((size_t)n, 0);
+  auto live_counts = [&](PareState& q) {
+    q.rowN.zero(s);
+    q.colN.zero(s);
+    live_counts_kernel<<<nblk((size_t)q.m->nnz), 256, 0, s>>>(q.m->row.p, q.m->col.p, q.m->alive.p, q.m->nnz, q.rowN.p,
+                                                             q.colN.p);
     ctx.stats.kernels++;
   };
-  auto max_degree = [&]() -> int {
+  auto max_degrees = [&]() {  // live degrees must be current; one download for the whole batch
     dmax.zero(s);
-    max_int_kernel<<<64, 256, 0, s>>>(rowN.p, nA, dmax.p);
-    max_int_kernel<<<64, 256, 0, s>>>(colN.p, nB, dmax.p);
-    int h = 0;
-    dmax.download(&h, 1, s);
-    CG_CUDA(cudaStreamSynchronize(s));
-    ctx.stats.kernels += 2;
-    return h;
-  };
-  live_counts();
-  int maxd = max_degree();
-  if (maxd <= k) return;  // nothing to be done - already below k
-  // CSR permutation (stored entries by row, columns ascending)
-  exclusive_scan_i32_to_i64(ctx, rowN.p, row_ptr.p, (size_t)nA, row_ptr.p + nA);
-  {
-    DevBuf<u64> rk((size_t)m.nnz);
-    cursor.zero(s);
-    row_scatter_kernel<<<nblk((size_t)m.nnz), 256, 0, s>>>(m.row.p, m.col.p, m.nnz, row_ptr.p, cursor.p, rk.p);
-    segmented_sort_u64(ctx, rk.p, row_ptr.p, nA);
-    low32_kernel<<<nblk((size_t)m.nnz), 256, 0, s>>>(rk.p, m.nnz, row_perm.p);
-    ctx.stats.kernels += 2;
-    CG_CUDA(cudaStreamSynchronize(s));
-  }
-  const int max_kdiff = 5;
-  const int klow_final = std::max(std::min(k, 3), k - max_kdiff);
-  int n_steps = std::min(3, r_round((double)maxd / k));
-  std::vector<int> ks;
-  if (n_steps > 1) {
-    // round(exp(seq(log(maxd), log(k), length.out = n.steps + 1))[-1])
-    for (int t = 1; t <= n_steps; ++t) {
-      const double v = std::exp(std::log((double)maxd) + (std::log((double)k) - std::log((double)maxd)) * t / n_steps);
-      ks.push_back(r_round(v));
-    }
-  } else {
-    ks.push_back(k);
-  }
-  int max_line = 2;
-  {
-    // scratch sized for the longest stored line
-    int h1 = 0;
-    dmax.zero(s);
-    max_int_kernel<<<64, 256, 0, s>>>(rowN.p, nA, dmax.p);
-    max_int_kernel<<<64, 256, 0, s>>>(colN.p, nB, dmax.p);
-    dmax.download(&h1, 1, s);
-    CG_CUDA(cudaStreamSynchronize(s));
-    while (max_line < h1) max_line <<= 1;
-  }
-  DevBuf<u64> scratch((size_t)max_line), order((size_t)std::max(nA, nB));
-  DevBuf<long long> one_seg(2);
-  DevBuf<PareProblem> dprob(1);
-  auto one_pass = [&](int kk, int klow) {
-    // reduceEdgesInGraph: column side, then row side (R/conos.R:890-901)
-    for (int side = 0; side < 2; ++side) {
-      live_counts();
-      const int n_lines = side == 0 ? nB : nA;
-      order_keys_kernel<<<nblk((size_t)n_lines), 256, 0, s>>>(side == 0 ? colN.p : rowN.p, n_lines, order.p);
-      long long seg[2] = {0, n_lines};
-      one_seg.upload(seg, 2, s);
-      segmented_sort_u64(ctx, order.p, one_seg.p, 1);
-      PareProblem pp{m.row.p, m.col.p, m.alive.p, m.nnz, nA, nB, col_ptr.p, row_ptr.p, row_perm.p, rowN.p, colN.p,
-                     order.p, scratch.p, kk, klow};
-      dprob.upload(&pp, 1, s);
-      pare_kernel<<<1, PARE_THREADS, 0, s>>>(dprob.p, side);
+    for (int p = 0; p < n; ++p) {
+      if (!st[p].active) continue;
+      max_int_kernel<<<64, 256, 0, s>>>(st[p].rowN.p, st[p].nA, dmax.p + p);
+      max_int_kernel<<<64, 256, 0, s>>>(st[p].colN.p, st[p].nB, dmax.p + p);
       ctx.stats.kernels += 2;
+    }
+    dmax.download(hmax.data(), (size_t)n, s);
+    CG_CUDA(cudaStreamSynchronize(s));
+  };
+  for (int p = 0; p < n; ++p) {
+    PareState& q = st[p];
+    q.m = &ms[p];
+    q.nA = probs[p].nA;
+    q.nB = probs[p].nB;
+    q.active = ms[p].nnz > 0;
+    if (!q.active) continue;
+    q.rowN.alloc((size_t)q.nA);
+    q.colN.alloc((size_t)q.nB);
+    q.col_ptr.alloc((size_t)q.nB + 1);
+    exclusive_scan_i32_to_i64(ctx, q.m->col_cnt.p, q.col_ptr.p, (size_t)q.nB, q.col_ptr.p + q.nB);
+    live_counts(q);
+  }
+  max_degrees();
+  const int max_kdiff = 5;
+  size_t max_steps = 0;
+  for (int p = 0; p < n; ++p) {
+    PareState& q = st[p];
+    if (!q.active) continue;
+    const int maxd = hmax[p];
+    if (maxd <= k) {  // nothing to be done - already below k
+      q.active = false;
+      continue;
+    }
+    // CSR permutation (stored entries by row, columns ascending)
+    q.row_ptr.alloc((size_t)q.nA + 1);
+    q.row_perm.alloc((size_t)q.m->nnz);
+    exclusive_scan_i32_to_i64(ctx, q.rowN.p, q.row_ptr.p, (size_t)q.nA, q.row_ptr.p + q.nA);
+    {
+      DevBuf<u64> rk((size_t)q.m->nnz);
+      DevBuf<int> cursor((size_t)q.nA);
+      cursor.zero(s);
+      row_scatter_kernel<<<nblk((size_t)q.m->nnz), 256, 0, s>>>(q.m->row.p, q.m->col.p, q.m->nnz, q.row_ptr.p, cursor.p,
+                                                               rk.p);
+      segmented_sort_u64(ctx, rk.p, q.row_ptr.p, q.nA);
+      low32_kernel<<<nblk((size_t)q.m->nnz), 256, 0, s>>>(rk.p, q.m->nnz, q.row_perm.p);
+      ctx.stats.kernels += 2;
+    }
+    q.klow_final = std::max(std::min(k, 3), k - max_kdiff);
+    const int n_steps = std::min(3, r_round((double)maxd / k));
+    if (n_steps > 1) {
+      // round(exp(seq(log(maxd), log(k), length.out = n.steps + 1))[-1])
+      for (int t = 1; t <= n_steps; ++t) {
+        const double v = std::exp(std::log((double)maxd) + (std::log((double)k) - std::log((double)maxd)) * t / n_steps);
+        q.ks.push_back(r_round(v));
+      }
+    } else {
+      q.ks.push_back(k);
+    }
+    max_steps = std::max(max_steps, q.ks.size());
+    int max_line = 2;  // scratch sized for the longest stored line
+    while (max_line < maxd) max_line <<= 1;
+    q.scratch.alloc((size_t)max_line);
+    q.order.alloc((size_t)std::max(q.nA, q.nB));
+    q.one_seg.alloc(2);
+  }
+  DevBuf<PareProblem> dprob((size_t)n);
+  std::vector<PareProblem> hprob((size_t)n);
+  auto one_pass = [&](const std::vector<int>& kk, const std::vector<int>& klow) {
+    // reduceEdgesInGraph: column side, then row side (R/conos.R:890-901)
+    bool any = false;
+    for (int p = 0; p < n; ++p) any = any || (st[p].active && kk[p] >= 0);
+    if (!any) return;
+    for (int side = 0; side < 2; ++side) {
+      for (int p = 0; p < n; ++p) {
+        PareState& q = st[p];
+        hprob[p] = PareProblem{};
+        hprob[p].k = -1;
+        if (!q.active || kk[p] < 0) continue;
+        live_counts(q);
+        const int n_lines = side == 0 ? q.nB : q.nA;
+        order_keys_kernel<<<nblk((size_t)n_lines), 256, 0, s>>>(side == 0 ? q.colN.p : q.rowN.p, n_lines, q.order.p);
+        const long long seg[2] = {0, n_lines};
+        q.one_seg.upload(seg, 2, s);
+        segmented_sort_u64(ctx, q.order.p, q.one_seg.p, 1);
+        hprob[p] = PareProblem{q.m->row.p, q.m->col.p, q.m->alive.p, q.m->nnz, q.nA, q.nB, q.col_ptr.p, q.row_ptr.p,
+                               q.row_perm.p, q.rowN.p, q.colN.p, q.order.p, q.scratch.p, kk[p], klow[p]};
+        ctx.stats.kernels++;
+      }
+      dprob.upload(hprob.data(), (size_t)n, s);
+      pare_kernel<<<n, PARE_THREADS, 0, s>>>(dprob.p, side);
+      ctx.stats.kernels++;
       CG_CUDA(cudaGetLastError());
       CG_CUDA(cudaStreamSynchronize(s));
     }
   };
-  for (int ki : ks) one_pass(ki, ki);
-  live_counts();
-  maxd = max_degree();
-  if (maxd - k > max_kdiff) one_pass(k, klow_final);  // cleanup step
+  std::vector<int> kk((size_t)n), kl((size_t)n);
+  for (size_t t = 0; t < max_steps; ++t) {
+    for (int p = 0; p < n; ++p) {
+      kk[p] = (st[p].active && t < st[p].ks.size()) ? st[p].ks[t] : -1;
+      kl[p] = kk[p];
+    }
+    one_pass(kk, kl);
+  }
+  bool any_active = false;
+  for (int p = 0; p < n; ++p)
+    if (st[p].active) {
+      live_counts(st[p]);
+      any_active = true;
+    }
+  if (!any_active) return;
+  max_degrees();
+  for (int p = 0; p < n; ++p) {  // cleanup step
+    const bool need = st[p].active && hmax[p] - k > max_kdiff;
+    kk[p] = need ? k : -1;
+    kl[p] = st[p].klow_final;
+  }
+  one_pass(kk, kl);
 }
 
 }  // namespace
@@ -411,30 +472,46 @@ void match_append_edges(Context& ctx, const MnnProblem* h_probs, int n_probs, in
     return;
   }
   cudaStream_t s = ctx.stream;
-  for (int p = 0; p < n_probs; ++p) {
-    const MnnProblem& pb = h_probs[p];
-    Matched m;
-    match_one(ctx, pb, k1, sp, m);
-    if (k1 > k) reduce_edges_iteratively(ctx, pb, m, k);
-    long long n_alive = 0;
-    if (m.nnz) {
-      DevBuf<long long> pos((size_t)m.nnz + 1);
-      exclusive_scan_i32_to_i64(ctx, m.alive.p, pos.p, (size_t)m.nnz, pos.p + m.nnz);
-      CG_CUDA(cudaMemcpyAsync(&n_alive, pos.p + m.nnz, sizeof(long long), cudaMemcpyDeviceToHost, s));
-      CG_CUDA(cudaStreamSynchronize(s));
-      out.reserve(out.n + (size_t)n_alive, s);
-      if (n_alive) {
-        emit_alive_kernel<<<nblk((size_t)m.nnz), 256, 0, s>>>(m.row.p, m.col.p, m.w.p, m.alive.p, pos.p, m.nnz,
-                                                              pb.rows_a, pb.rows_b, pb.offA, pb.offB,
-                                                              out.from.p + out.n, out.to.p + out.n, out.w.p + out.n,
-                                                              out.type.p + out.n);
-        ctx.stats.kernels++;
-        CG_CUDA(cudaGetLastError());
-        CG_CUDA(cudaStreamSynchronize(s));
-      }
-      out.n += (size_t)n_alive;
+  // sub-batches bounded by the matched structures that are alive at the same time (~24 B per neighbour triple)
+  const size_t budget = (size_t)16 << 30;
+  int p0 = 0;
+  while (p0 < n_probs) {
+    int p1 = p0;
+    size_t used = 0;
+    while (p1 < n_probs && p1 - p0 < 1024) {
+      const size_t need = (size_t)(h_probs[p1].nA + h_probs[p1].nB) * (size_t)k1 * 24;
+      if (p1 > p0 && used + need > budget) break;
+      used += need;
+      ++p1;
     }
-    if (pair_counts) pair_counts[p] = n_alive;
+    const int nb = p1 - p0;
+    std::vector<Matched> ms((size_t)nb);
+    for (int q = 0; q < nb; ++q) match_one(ctx, h_probs[p0 + q], k1, sp, ms[q]);
+    if (k1 > k) reduce_edges_batch(ctx, h_probs + p0, ms.data(), nb, k);
+    for (int q = 0; q < nb; ++q) {
+      const MnnProblem& pb = h_probs[p0 + q];
+      Matched& m = ms[q];
+      long long n_alive = 0;
+      if (m.nnz) {
+        DevBuf<long long> pos((size_t)m.nnz + 1);
+        exclusive_scan_i32_to_i64(ctx, m.alive.p, pos.p, (size_t)m.nnz, pos.p + m.nnz);
+        CG_CUDA(cudaMemcpyAsync(&n_alive, pos.p + m.nnz, sizeof(long long), cudaMemcpyDeviceToHost, s));
+        CG_CUDA(cudaStreamSynchronize(s));
+        out.reserve(out.n + (size_t)n_alive, s);
+        if (n_alive) {
+          emit_alive_kernel<<<nblk((size_t)m.nnz), 256, 0, s>>>(m.row.p, m.col.p, m.w.p, m.alive.p, pos.p, m.nnz,
+                                                                pb.rows_a, pb.rows_b, pb.offA, pb.offB,
+                                                                out.from.p + out.n, out.to.p + out.n, out.w.p + out.n,
+                                                                out.type.p + out.n);
+          ctx.stats.kernels++;
+          CG_CUDA(cudaGetLastError());
+          CG_CUDA(cudaStreamSynchronize(s));
+        }
+        out.n += (size_t)n_alive;
+      }
+      if (pair_counts) pair_counts[p0 + q] = n_alive;
+    }
+    p0 = p1;
   }
 }
 
