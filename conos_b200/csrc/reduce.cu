@@ -354,80 +354,115 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
   }
   // ---- CPCA: quickCPCA (R/conos.R:204-259) -> cpcaFast (:175-191) -> cpcaF (src/cpca.cpp)
   CG_CHECK(P.space == CG_SPACE_CPCA, "unknown space");
-  for (int q : todo) {
-    const cg_pair& pr = pairs[q];
-    const int G = pr.n_genes;
-    const int ncomp = std::min(P.ncomps, G - 1);  // R/conos.R:210
-    CG_CHECK(ncomp >= 1 && ncomp <= 56, "device CPCA supports up to 56 common components");
-    const int B = ncomp <= 24 ? 32 : 64;
-    const int Gp = G > B ? G : B;
-    Sample* sm[2] = {&panel.samples[pr.a], &panel.samples[pr.b]};
-    const int* gcols[2] = {pr.genes_a, pr.genes_b};
-    std::vector<double> f[2];
-    f[0].assign(G, 1.0);
-    f[1].assign(G, 1.0);
-    if (P.var_scale) {
-      CG_CHECK(!sm[0]->h_qv.empty() && !sm[1]->h_qv.empty() && !sm[0]->h_v.empty() && !sm[1]->h_v.empty(),
-               "var.scale = TRUE needs misc$varinfo$v and $qv for every sample");
-      for (int g = 0; g < G; ++g) {
-        const int ca = pr.genes_a[g], cb = pr.genes_b[g];
-        const double cqv = std::exp((std::log(sm[0]->h_qv[ca]) + std::log(sm[1]->h_qv[cb])) / 2.0);
-        const double fa = std::sqrt(cqv / std::exp(sm[0]->h_v[ca]));
-        const double fb = std::sqrt(cqv / std::exp(sm[1]->h_v[cb]));
-        f[0][g] = std::isfinite(fa) ? fa : 0.0;
-        f[1][g] = std::isfinite(fb) ? fb : 0.0;
+  // chunks of pairs: the covariance cubes of a chunk are built first, the initial eigenproblems of the whole chunk
+  // are solved in one batched call (a block per problem), then the common-PCA iteration runs pair by pair
+  struct CpcaBuf {
+    DevBuf<double> cube, S, tr, V0, th0;
+    int G = 0, Gp = 0, ncomp = 0;
+    double na = 0, nb = 0;
+  };
+  const size_t chunk_pairs = 24;
+  for (size_t c0 = 0, c1 = 0; c0 < todo.size(); c0 = c1) {
+    c1 = std::min(todo.size(), c0 + chunk_pairs);
+    std::vector<CpcaBuf> bufs(c1 - c0);
+    std::vector<EigProblem> eprobs;
+    int ncomp_all = -1;
+    for (size_t t = c0; t < c1; ++t) {
+      const cg_pair& pr = pairs[todo[t]];
+      CpcaBuf& b = bufs[t - c0];
+      const int G = pr.n_genes;
+      const int ncomp = std::min(P.ncomps, G - 1);  // R/conos.R:210
+      CG_CHECK(ncomp >= 1 && ncomp <= 56, "device CPCA supports up to 56 common components");
+      if (ncomp_all >= 0 && ncomp != ncomp_all) {  // a batched solve shares the block size: this pair opens the next chunk
+        c1 = t;
+        break;
       }
+      const int B = ncomp <= 24 ? 32 : 64;
+      const int Gp = G > B ? G : B;
+      b.G = G;
+      b.Gp = Gp;
+      b.ncomp = ncomp;
+      Sample* sm[2] = {&panel.samples[pr.a], &panel.samples[pr.b]};
+      const int* gcols[2] = {pr.genes_a, pr.genes_b};
+      std::vector<double> f[2];
+      f[0].assign(G, 1.0);
+      f[1].assign(G, 1.0);
+      if (P.var_scale) {
+        CG_CHECK(!sm[0]->h_qv.empty() && !sm[1]->h_qv.empty() && !sm[0]->h_v.empty() && !sm[1]->h_v.empty(),
+                 "var.scale = TRUE needs misc$varinfo$v and $qv for every sample");
+        for (int g = 0; g < G; ++g) {
+          const int ca = pr.genes_a[g], cb = pr.genes_b[g];
+          const double cqv = std::exp((std::log(sm[0]->h_qv[ca]) + std::log(sm[1]->h_qv[cb])) / 2.0);
+          const double fa = std::sqrt(cqv / std::exp(sm[0]->h_v[ca]));
+          const double fb = std::sqrt(cqv / std::exp(sm[1]->h_v[cb]));
+          f[0][g] = std::isfinite(fa) ? fa : 0.0;
+          f[1][g] = std::isfinite(fb) ? fb : 0.0;
+        }
+      }
+      // covariance slices (spcov of the scaled matrices) as one p x p x 2 cube
+      b.cube.alloc((size_t)2 * Gp * Gp);
+      b.S.alloc((size_t)Gp * Gp);
+      b.tr.alloc(2);
+      DevBuf<double> fd[2];
+      DevBuf<int> cd[2];
+      for (int side = 0; side < 2; ++side) {
+        fd[side].upload(f[side].data(), (size_t)G, st);
+        cd[side].upload(gcols[side], (size_t)G, st);
+        scaled_cov_kernel<<<nblk((size_t)Gp * Gp), 256, 0, st>>>(sm[side]->gram.p, sm[side]->n_genes,
+                                                                  sm[side]->colsum.p, cd[side].p, fd[side].p, G, Gp,
+                                                                  (double)sm[side]->n_cells,
+                                                                  b.cube.p + (size_t)side * Gp * Gp);
+        trace_kernel<<<1, 256, 0, st>>>(b.cube.p + (size_t)side * Gp * Gp, Gp, b.tr.p + side);
+        ctx.stats.kernels += 2;
+      }
+      // initial vectors: leading eigenvectors of the cell-weighted mean covariance (irlba(S, ncomp)$v)
+      b.na = sm[0]->n_cells;
+      b.nb = sm[1]->n_cells;
+      weighted_sum_kernel<<<nblk((size_t)Gp * Gp), 256, 0, st>>>(b.cube.p, b.cube.p + (size_t)Gp * Gp,
+                                                                  b.na / (b.na + b.nb), b.nb / (b.na + b.nb),
+                                                                  (size_t)Gp * Gp, b.S.p);
+      ctx.stats.kernels++;
+      b.V0.alloc((size_t)Gp * ncomp);
+      b.th0.alloc((size_t)ncomp);
+      ncomp_all = ncomp;
+      eprobs.push_back(EigProblem{b.S.p, Gp, b.V0.p, b.th0.p});
+      CG_CUDA(cudaStreamSynchronize(st));  // fd / cd are released at the end of this iteration
     }
-    // covariance slices (spcov of the scaled matrices) as one p x p x 2 cube
-    DevBuf<double> cube((size_t)2 * Gp * Gp), S((size_t)Gp * Gp), fd[2], tr(2);
-    DevBuf<int> cd[2];
-    for (int side = 0; side < 2; ++side) {
-      fd[side].upload(f[side].data(), (size_t)G, st);
-      cd[side].upload(gcols[side], (size_t)G, st);
-      scaled_cov_kernel<<<nblk((size_t)Gp * Gp), 256, 0, st>>>(sm[side]->gram.p, sm[side]->n_genes, sm[side]->colsum.p,
-                                                                cd[side].p, fd[side].p, G, Gp,
-                                                                (double)sm[side]->n_cells,
-                                                                cube.p + (size_t)side * Gp * Gp);
-      trace_kernel<<<1, 256, 0, st>>>(cube.p + (size_t)side * Gp * Gp, Gp, tr.p + side);
-      ctx.stats.kernels += 2;
-    }
-    // initial vectors: leading eigenvectors of the cell-weighted mean covariance (irlba(S, ncomp)$v)
-    const double na = sm[0]->n_cells, nb = sm[1]->n_cells;
-    weighted_sum_kernel<<<nblk((size_t)Gp * Gp), 256, 0, st>>>(cube.p, cube.p + (size_t)Gp * Gp, na / (na + nb),
-                                                                nb / (na + nb), (size_t)Gp * Gp, S.p);
-    ctx.stats.kernels++;
-    DevBuf<double> V0((size_t)Gp * ncomp), th0((size_t)ncomp);
-    EigProblem ep{S.p, Gp, V0.p, th0.p};
     {
       StageScope sc(ctx, "reduction.eig");
-      top_eigenvectors_batched(ctx, &ep, 1, ncomp, ctx.exact_reduction ? 1e-10 : 1e-5, 600);
+      top_eigenvectors_batched(ctx, eprobs.data(), (int)eprobs.size(), ncomp_all, ctx.exact_reduction ? 1e-10 : 1e-5,
+                               600);
     }
-    DevBuf<double> ng(2), D((size_t)ncomp * 2), CPC((size_t)Gp * ncomp), niter((size_t)ncomp);
-    const double hng[2] = {na, nb};
-    ng.upload(hng, 2, st);
-    {
-      StageScope sc(ctx, "reduction.cpca");
-      cpca_device(ctx, cube.p, Gp, 2, ng.p, ncomp, P.cpca_maxit, P.cpca_tol, V0.p, D.p, CPC.p, niter.p);
-    }
-    PairReduction& R = out[q];
-    R.n_rows = G;
-    R.n_cols = ncomp;
-    R.d = P.ncomps < ncomp ? P.ncomps : ncomp;
-    R.rot.alloc((size_t)G * ncomp);
-    CG_CUDA(cudaMemcpy2DAsync(R.rot.p, (size_t)G * sizeof(double), CPC.p, (size_t)Gp * sizeof(double),
-                              (size_t)G * sizeof(double), ncomp, cudaMemcpyDeviceToDevice, st));
-    R.h_rot.resize((size_t)G * ncomp);
-    R.rot.download(R.h_rot.data(), R.h_rot.size(), st);
-    if (P.score_component_variance) {
-      std::vector<double> hD((size_t)ncomp * 2), htr(2);
-      D.download(hD.data(), hD.size(), st);
-      tr.download(htr.data(), 2, st);
+    for (size_t t = c0; t < c1; ++t) {
+      CpcaBuf& b = bufs[t - c0];
+      const int G = b.G, Gp = b.Gp, ncomp = b.ncomp;
+      DevBuf<double> ng(2), D((size_t)ncomp * 2), CPC((size_t)Gp * ncomp), niter((size_t)ncomp);
+      const double hng[2] = {b.na, b.nb};
+      ng.upload(hng, 2, st);
+      {
+        StageScope sc(ctx, "reduction.cpca");
+        cpca_device(ctx, b.cube.p, Gp, 2, ng.p, ncomp, P.cpca_maxit, P.cpca_tol, b.V0.p, D.p, CPC.p, niter.p);
+      }
+      PairReduction& R = out[todo[t]];
+      R.n_rows = G;
+      R.n_cols = ncomp;
+      R.d = P.ncomps < ncomp ? P.ncomps : ncomp;
+      R.rot.alloc((size_t)G * ncomp);
+      CG_CUDA(cudaMemcpy2DAsync(R.rot.p, (size_t)G * sizeof(double), CPC.p, (size_t)Gp * sizeof(double),
+                                (size_t)G * sizeof(double), ncomp, cudaMemcpyDeviceToDevice, st));
+      R.h_rot.resize((size_t)G * ncomp);
+      R.rot.download(R.h_rot.data(), R.h_rot.size(), st);
+      if (P.score_component_variance) {
+        std::vector<double> hD((size_t)ncomp * 2), htr(2);
+        D.download(hD.data(), hD.size(), st);
+        b.tr.download(htr.data(), 2, st);
+        CG_CUDA(cudaStreamSynchronize(st));
+        R.h_nv.assign((size_t)2 * ncomp, 0.0);
+        for (int side = 0; side < 2; ++side)
+          for (int j = 0; j < ncomp; ++j) R.h_nv[(size_t)side * ncomp + j] = hD[(size_t)side * ncomp + j] / htr[side];
+      }
       CG_CUDA(cudaStreamSynchronize(st));
-      R.h_nv.assign((size_t)2 * ncomp, 0.0);
-      for (int side = 0; side < 2; ++side)
-        for (int j = 0; j < ncomp; ++j) R.h_nv[(size_t)side * ncomp + j] = hD[(size_t)side * ncomp + j] / htr[side];
     }
-    CG_CUDA(cudaStreamSynchronize(st));
   }
 }
 
