@@ -169,7 +169,10 @@ void gemm_tn_bf16x3(Context& ctx, const GemmProblem* h_probs, int n_probs) {
              "GEMM operands must be padded (rows to 256, k to 64)");
     const int mts = (g.M + BM - 1) / BM, nts = (g.N + BN - 1) / BN;
     for (int nt = 0; nt < nts; ++nt)
-      for (int mt = 0; mt < mts; ++mt) tiles.push_back(GemmTile{p, mt, nt});
+      for (int mt = 0; mt < mts; ++mt) {
+        if (g.symmetric && mt * BM > nt * BN + BN - 1) continue;  // strictly below the diagonal
+        tiles.push_back(GemmTile{p, mt, nt});
+      }
   }
   if (tiles.empty()) return;
   DevBuf<GemmProblem> dp;

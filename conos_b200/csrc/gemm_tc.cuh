@@ -44,6 +44,7 @@ struct GemmProblem {
   void* C;         // column-major M x N, leading dimension ldc: element (m, n) at n*ldc + m
   long long ldc;
   int out_fp64;    // 1: double output, 0: float
+  int symmetric = 0;  // 1: A == B (X'X): only the tiles that touch the upper triangle (m <= n) are computed
 };
 
 // batched: every problem is cut into 128 x 256 output tiles, one CTA per tile

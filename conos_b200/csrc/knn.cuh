@@ -13,9 +13,10 @@
 //   tiled[(row/8)][chunk = col/4][row%8][col%4],   KC = d_pad/4 chunks, d_pad in {32, 64}
 // i.e. exactly the shared-memory image a K-major, no-swizzle tcgen05 (kind::tf32) operand needs, so a
 // tile of R rows (R % 8 == 0) is one contiguous byte range that a single 1-D bulk copy moves.
-// The panel is stored twice: the exact fp32 values (every exact computation reads these) followed, n_pad * d_pad
-// floats later, by the same values rounded to nearest fp16 in the swizzled row-major layout of knn_tiled16_offset
-// (the kind::f16 tensor-core operand of knn_tc2.cu).
+// The panel is stored three times: the exact fp32 values in the tiled layout (knn_tc.cu, knn_simt.cu); n_pad * d_pad
+// floats later the same values rounded to nearest fp16 in the swizzled row-major layout of knn_tiled16_offset (the
+// kind::f16 tensor-core operand of knn_tc2.cu); 1.5 * n_pad * d_pad floats later the exact fp32 values row-major
+// [row][d_pad] (the re-score of knn_tc2.cu reads whole rows: 128 / 256 contiguous bytes per candidate).
 // Rows are zero-padded up to a multiple of 256.  When d < d_pad the LAST padded column of every row holds -1:
 // the tensor-core kernel uses it to subtract a per-query threshold inside the MMA; every exact computation
 // (re-rank, SIMT kernel) only touches the d real columns.
@@ -36,8 +37,9 @@ struct KnnPanel {
   int d = 0;      // valid columns
   int d_pad = 0;  // 32 or 64
   int n_pad = 0;  // multiple of KNN_ROW_PAD
-  float* tiled = nullptr;  // 1.5 * n_pad * d_pad floats (not owned): the exact fp32 panel, then its fp16 copy
-  static size_t elems(int n, int d) { return round_up(n, KNN_ROW_PAD) * (size_t)(d <= 32 ? 32 : 64) * 3 / 2; }
+  // 2.5 * n_pad * d_pad floats (not owned): the exact fp32 panel (tiled), its fp16 copy, the exact panel row-major
+  float* tiled = nullptr;
+  static size_t elems(int n, int d) { return round_up(n, KNN_ROW_PAD) * (size_t)(d <= 32 ? 32 : 64) * 5 / 2; }
 };
 
 __host__ __device__ inline size_t knn_tiled_offset(int row, int col, int d_pad) {

@@ -16,11 +16,13 @@ __global__ void knn_prep_kernel(const SrcT* __restrict__ src, int n, int d, int 
   const int KC = d_pad >> 2;
   float* dst = tiled + (size_t)(row >> 3) * (size_t)(8 * d_pad) + (size_t)(row & 7) * 4;
   __half* dst16 = reinterpret_cast<__half*>(tiled + (size_t)n_pad * d_pad);  // fp16 copy (knn_tiled16_offset)
+  float* dstrm = tiled + (size_t)n_pad * d_pad * 3 / 2 + (size_t)row * d_pad;  // row-major exact copy
   const bool fold = d < d_pad;  // spare last column: -1 (threshold dimension of the tensor-core kernel)
   if (row >= n) {
     for (int c = 0; c < KC; ++c) {
       const float4 z = make_float4(0.f, 0.f, 0.f, (fold && c == KC - 1) ? -1.0f : 0.f);
       *reinterpret_cast<float4*>(dst + c * 32) = z;
+      *reinterpret_cast<float4*>(dstrm + c * 4) = z;
       __half2* h = reinterpret_cast<__half2*>(dst16 + knn_tiled16_offset(row, c * 4, d_pad));
       h[0] = __floats2half2_rn(z.x, z.y);
       h[1] = __floats2half2_rn(z.z, z.w);
@@ -47,6 +49,7 @@ __global__ void knn_prep_kernel(const SrcT* __restrict__ src, int n, int d, int 
       if (fold && i == d_pad - 1) v[e] = -1.0f;
     }
     *reinterpret_cast<float4*>(dst + c * 32) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(dstrm + c * 4) = make_float4(v[0], v[1], v[2], v[3]);
     __half2* h = reinterpret_cast<__half2*>(dst16 + knn_tiled16_offset(row, c * 4, d_pad));
     h[0] = __floats2half2_rn(v[0], v[1]);
     h[1] = __floats2half2_rn(v[2], v[3]);

@@ -426,21 +426,24 @@ __device__ __forceinline__ void finish_row(const KnnProblem& pb, const int* __re
   int j[U];
   float a0[U], a1[U], a2[U], a3[U];
   const float* rp[U];
+  // whole rows from the row-major exact copies of the panels
+  const float* r_rows = pb.r_tiled + round_up((size_t)pb.nr, KNN_ROW_PAD) * D_PAD * 3 / 2;
+  const float* q_rows = pb.q_tiled + round_up((size_t)pb.nq, KNN_ROW_PAD) * D_PAD * 3 / 2;
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     const int s = u * 32 + lane;
     j[u] = s < c ? (s < c0 ? cand[s] : cand[KNN_TC2_CAND_STRIDE + s - c0]) : -1;
     const int jj = j[u] >= 0 ? j[u] : 0;
-    rp[u] = pb.r_tiled + (size_t)(jj >> 3) * (8 * D_PAD) + (size_t)(jj & 7) * 4;
+    rp[u] = r_rows + (size_t)jj * D_PAD;
     a0[u] = a1[u] = a2[u] = a3[u] = 0.f;
   }
-  const float* qp = pb.q_tiled + (size_t)(qrow >> 3) * (8 * D_PAD) + (size_t)(qrow & 7) * 4;
+  const float* qp = q_rows + (size_t)qrow * D_PAD;
 #pragma unroll
   for (int c4 = 0; c4 < KC; ++c4) {
-    const float4 qv = __ldg(reinterpret_cast<const float4*>(qp + c4 * 32));
+    const float4 qv = __ldg(reinterpret_cast<const float4*>(qp + c4 * 4));
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const float4 rv = __ldg(reinterpret_cast<const float4*>(rp[u] + c4 * 32));
+      const float4 rv = __ldg(reinterpret_cast<const float4*>(rp[u] + c4 * 4));
       a0[u] = fmaf(qv.x, rv.x, a0[u]);
       a1[u] = fmaf(qv.y, rv.y, a1[u]);
       a2[u] = fmaf(qv.z, rv.z, a2[u]);

@@ -83,6 +83,7 @@ int r_round_half_even(double x) { return (int)std::nearbyint(x); }  // default r
 
 // X'X of the whole sample in FP64 (upper triangle accumulated, then mirrored); cached on the sample.
 void ensure_gram(Context& ctx, Sample& s);
+void ensure_grams(Context& ctx, Sample* const* samples, int n);
 
 void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs, int n_pairs, const cg_params& P,
                              std::vector<PairReduction>& out) {
@@ -129,10 +130,12 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
   // ---- per-sample Gram matrices
   {
     StageScope sc(ctx, "reduction.gram");
+    std::vector<Sample*> need;
     for (int q : todo) {
-      ensure_gram(ctx, panel.samples[pairs[q].a]);
-      ensure_gram(ctx, panel.samples[pairs[q].b]);
+      need.push_back(&panel.samples[pairs[q].a]);
+      need.push_back(&panel.samples[pairs[q].b]);
     }
+    ensure_grams(ctx, need.data(), (int)need.size());
   }
 
   if (P.space == CG_SPACE_PCA) {
@@ -467,27 +470,75 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
 }
 
 void ensure_gram(Context& ctx, Sample& s) {
-  if (s.gram.n) return;
-  CG_CHECK(s.n_genes <= 16384, "subset the counts matrix to the od-gene universe before upload (Gram matrix too big)");
-  const size_t G = (size_t)s.n_genes;
-  s.gram.alloc(G * G);
+  Sample* one[1] = {&s};
+  ensure_grams(ctx, one, 1);
+}
+
+// Gram matrices X'X of several samples: the dense bf16 hi/lo operands of a chunk are built first, then ONE batched
+// GEMM computes the tiles that touch the upper triangles (a single 2000 x 2000 product is 128 tiles on 148 SMs --
+// one under-filled wave however few of them are needed), and the lower triangles are mirrored (which also makes the
+// matrix exactly symmetric: the two cross terms of the bf16x3 product are accumulated in a different order at (m, n)
+// and (n, m)).
+void ensure_grams(Context& ctx, Sample* const* samples, int n) {
+  std::vector<Sample*> todo;
+  for (int t = 0; t < n; ++t) {
+    Sample* s = samples[t];
+    if (s->gram.n) continue;
+    bool dup = false;
+    for (Sample* o : todo) dup = dup || o == s;
+    if (!dup) todo.push_back(s);
+  }
+  if (todo.empty()) return;
+  for (Sample* s : todo) {
+    CG_CHECK(s->n_genes <= 16384, "subset the counts matrix to the od-gene universe before upload (Gram matrix too big)");
+    s->gram.alloc((size_t)s->n_genes * s->n_genes);
+  }
   if (ctx.exact_reduction) {
-    s.gram.zero(ctx.stream);
-    gram_upper_from_csr(ctx, s.csr_p.p, s.csr_i.p, s.csr_x.p, s.n_cells, s.n_genes, s.gram.p);
-    mirror_upper_kernel<<<nblk(G * G), 256, 0, ctx.stream>>>(s.gram.p, s.n_genes);
-    ctx.stats.kernels++;
+    for (Sample* s : todo) {
+      const size_t G = (size_t)s->n_genes;
+      s->gram.zero(ctx.stream);
+      gram_upper_from_csr(ctx, s->csr_p.p, s->csr_i.p, s->csr_x.p, s->n_cells, s->n_genes, s->gram.p);
+      mirror_upper_kernel<<<nblk(G * G), 256, 0, ctx.stream>>>(s->gram.p, s->n_genes);
+      ctx.stats.kernels++;
+    }
     CG_CUDA(cudaGetLastError());
     return;
   }
-  // X'X on the tensor cores: the sparse counts become a dense bf16 hi/lo operand (rows = genes, k = cells)
-  DevBuf<__nv_bfloat16> hi(TiledOperand::elems(s.n_genes, s.n_cells)), lo(TiledOperand::elems(s.n_genes, s.n_cells));
-  TiledOperand op;
-  op.hi = hi.p;
-  op.lo = lo.p;
-  tiled_from_csc(ctx, s.csc_p.p, s.csc_i.p, s.csc_x.p, s.n_cells, s.n_genes, op);
-  GemmProblem gp{op.hi, op.lo, op.hi, op.lo, op.rows_pad, op.rows_pad, op.k_pad, s.n_genes, s.n_genes, s.gram.p,
-                 (long long)s.n_genes, 1};
-  gemm_tn_bf16x3(ctx, &gp, 1);
+  // X'X on the tensor cores: the sparse counts become dense bf16 hi/lo operands (rows = genes, k = cells)
+  const size_t budget = (size_t)8 << 30;
+  size_t i0 = 0;
+  while (i0 < todo.size()) {
+    size_t i1 = i0, used = 0;
+    while (i1 < todo.size()) {
+      const size_t need = 2 * TiledOperand::elems(todo[i1]->n_genes, todo[i1]->n_cells) * sizeof(__nv_bfloat16);
+      if (i1 > i0 && used + need > budget) break;
+      used += need;
+      ++i1;
+    }
+    std::vector<DevBuf<__nv_bfloat16>> hi(i1 - i0), lo(i1 - i0);
+    std::vector<GemmProblem> gps;
+    for (size_t t = i0; t < i1; ++t) {
+      Sample* s = todo[t];
+      hi[t - i0].alloc(TiledOperand::elems(s->n_genes, s->n_cells));
+      lo[t - i0].alloc(TiledOperand::elems(s->n_genes, s->n_cells));
+      TiledOperand op;
+      op.hi = hi[t - i0].p;
+      op.lo = lo[t - i0].p;
+      tiled_from_csc(ctx, s->csc_p.p, s->csc_i.p, s->csc_x.p, s->n_cells, s->n_genes, op);
+      GemmProblem gp{op.hi, op.lo, op.hi, op.lo, op.rows_pad, op.rows_pad, op.k_pad, s->n_genes, s->n_genes, s->gram.p,
+                     (long long)s->n_genes, 1, 1};
+      gps.push_back(gp);
+    }
+    gemm_tn_bf16x3(ctx, gps.data(), (int)gps.size());
+    for (size_t t = i0; t < i1; ++t) {
+      const size_t G = (size_t)todo[t]->n_genes;
+      mirror_upper_kernel<<<nblk(G * G), 256, 0, ctx.stream>>>(todo[t]->gram.p, todo[t]->n_genes);
+      ctx.stats.kernels++;
+    }
+    CG_CUDA(cudaGetLastError());
+    CG_CUDA(cudaStreamSynchronize(ctx.stream));
+    i0 = i1;
+  }
 }
 
 }  // namespace cg

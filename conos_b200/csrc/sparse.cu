@@ -125,12 +125,14 @@ __global__ void __launch_bounds__(256) project_kernel(const ProjProblem* __restr
   // exact fp32 panel, then its fp16 copy (the tensor-core operand of the two-phase kNN kernel)
   float* dst = pb.tiled + (size_t)(row >> 3) * (8 * D_PAD) + (size_t)(row & 7) * 4;
   __half* dst16 = reinterpret_cast<__half*>(pb.tiled + (size_t)n_pad * D_PAD);
+  float* dstrm = pb.tiled + (size_t)n_pad * D_PAD * 3 / 2 + (size_t)row * D_PAD;  // row-major exact copy
 #pragma unroll
   for (int u = 0; u < NC; ++u) {
     const int c = lane + 32 * u;
     const float x = (d < D_PAD && c == D_PAD - 1) ? -1.0f : v[u] * inv;
     dst[(c >> 2) * 32 + (c & 3)] = x;
     dst16[knn_tiled16_offset(row, c, D_PAD)] = __float2half_rn(x);
+    dstrm[c] = x;
   }
 }
 
