@@ -158,9 +158,7 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
           if (ph2 == 1) ptx::mbar_wait(thr_ready, it & 1);  // the rows' thresholds are in the A tile (FOLD)
           for (int t = 0; t < n_tiles; ++t) {
             ptx::mbar_wait(b_full + slot, ph);
-#if !defined(TC2_VARIANT) || TC2_VARIANT != 2
             ptx::mbar_wait(acc_empty + stage, aph ^ 1);
-#endif
             ptx::tc_fence_after();
             const uint64_t bd = bdesc0 + (uint64_t)((slot * (uint32_t)C::B_BYTES) >> 4);
 #pragma unroll
@@ -168,11 +166,7 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
               const uint32_t d_tmem = tmem_base + (stage * 2 + mb) * TILE_N;
 #pragma unroll
               for (int ks = 0; ks < C::KSTEPS; ++ks) {
-#if !defined(TC2_VARIANT) || TC2_VARIANT != 1
                 ptx::mma_f16_ss(d_tmem, adesc[mb][ks], bd + (uint64_t)(ks * 2), idesc, ks > 0 ? 1u : 0u);
-#else
-                (void)d_tmem;
-#endif
               }
             }
             ptx::mma_commit(b_empty + slot);
