@@ -39,6 +39,24 @@ class Pagoda2:
         return self.od_genes if n_odgenes is None else self.od_genes[:n_odgenes]
 
 
+class PairEntry(dict):
+    """One entry of self$pairs[[space]] (R/conclass.R:1090-1092).  `genes` (the pair's od-gene names, the rownames of
+    CPC) is materialised from the integer ids on first access: an atlas run caches thousands of these."""
+
+    def __init__(self, od_ids, namer, **kw):
+        super().__init__(**kw)
+        self._od_ids, self._namer = od_ids, namer
+
+    def __missing__(self, key):
+        if key == "genes":
+            self["genes"] = self._namer(self._od_ids)
+            return dict.__getitem__(self, "genes")
+        raise KeyError(key)
+
+    def __contains__(self, key):
+        return key == "genes" or dict.__contains__(self, key)
+
+
 @dataclass
 class ConosGraph:
     """What ``self$graph`` (an igraph) carries for findCommunities / embedGraph (R/conclass.R:336-343)."""
@@ -315,14 +333,14 @@ class Conos:
                 sg = np.zeros(dd.value)
                 self.ctx.check(lib.cg_pair_cca(h, slot, None, None, None, ptr(u, C.c_double), ptr(v, C.c_double),
                                                ptr(ru, C.c_int32), ptr(rv, C.c_int32), ptr(sg, C.c_double)))
-                cache[key] = {"u": u, "v": v, "rows_u": ru, "rows_v": rv, "d": sg, "genes": self._gene_names(od)}
+                cache[key] = PairEntry(od, self._gene_names, u=u, v=v, rows_u=ru, rows_v=rv, d=sg)
                 continue
             nr, nc = C.c_int32(0), C.c_int32(0)
             self.ctx.check(lib.cg_pair_reduction(h, slot, C.byref(nr), C.byref(nc), None, None))
             rot = np.zeros((nr.value, nc.value), order="F")
             nv = np.zeros((2, nc.value)) if score_component_variance else None
             self.ctx.check(lib.cg_pair_reduction(h, slot, None, None, ptr(rot, C.c_double), ptr(nv, C.c_double)))
-            cache[key] = {"CPC": rot, "genes": self._gene_names(od)}
+            cache[key] = PairEntry(od, self._gene_names, CPC=rot)
             if space == "CPCA":
                 cache[key]["ncomp"] = nc.value
             if nv is not None:

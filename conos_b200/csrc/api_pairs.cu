@@ -21,9 +21,9 @@ void pair_scale_factors(const Sample& sa, const Sample& sb, const cg_pair& pr, b
            "var.scale = TRUE needs misc$varinfo$v and $qv for every sample");
   for (int g = 0; g < G; ++g) {
     const int ca = pr.genes_a[g], cb = pr.genes_b[g];
-    const double cqv = std::exp((std::log(sa.h_qv[ca]) + std::log(sb.h_qv[cb])) / 2.0);
-    double a = std::sqrt(cqv / std::exp(sa.h_v[ca]));
-    double b = std::sqrt(cqv / std::exp(sb.h_v[cb]));
+    const double cqv = std::exp((sa.h_logqv[ca] + sb.h_logqv[cb]) / 2.0);
+    double a = std::sqrt(cqv / sa.h_expv[ca]);
+    double b = std::sqrt(cqv / sb.h_expv[cb]);
     fa[g] = std::isfinite(a) ? a : 0.0;
     fb[g] = std::isfinite(b) ? b : 0.0;
   }
@@ -175,6 +175,19 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
       int na = 0, nb = 0, d = 0, d_pad = 32;
     };
     std::vector<PairBuf> pb(nb_pairs);
+    // the small per-pair vectors (scale factors, centering, gene columns) of the whole batch travel in two uploads
+    size_t stage_d = 0, stage_i = 0;
+    if (P.space != CG_SPACE_CCA)
+      for (int q = 0; q < nb_pairs; ++q) {
+        stage_d += 4 * (size_t)pairs[p0 + q].n_genes;
+        stage_i += 2 * (size_t)pairs[p0 + q].n_genes;
+      }
+    std::vector<double> h_stage_d;
+    std::vector<int> h_stage_i;
+    h_stage_d.reserve(stage_d);
+    h_stage_i.reserve(stage_i);
+    DevBuf<double> d_stage_d(stage_d);
+    DevBuf<int> d_stage_i(stage_i);
     std::vector<WBuildProblem> wprobs;
     std::vector<ProjProblem> pprobs;
     std::vector<KnnProblem> kprobs;
@@ -205,7 +218,7 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
       B.tb.alloc(KnnPanel::elems(B.nb, B.d));
       keep.n_rows = R.n_rows;
       keep.n_cols = R.n_cols;
-      keep.rot = R.h_rot;
+      keep.rot = std::move(R.h_rot);
       keep.nv = R.h_nv;
       if (P.space == CG_SPACE_CCA) {
         KnnPanel pa, pbn;
@@ -252,18 +265,23 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
           std::fill(ca.begin(), ca.end(), m0);
           std::fill(cb.begin(), cb.end(), m1);
         }
-        B.fa.upload(fa.data(), G, c.stream);
-        B.fb.upload(fb.data(), G, c.stream);
-        B.ca.upload(ca.data(), G, c.stream);
-        B.cb.upload(cb.data(), G, c.stream);
-        B.cols_a.upload(pr.genes_a, G, c.stream);
-        B.cols_b.upload(pr.genes_b, G, c.stream);
+        const double* dfa = d_stage_d.p + h_stage_d.size();
+        h_stage_d.insert(h_stage_d.end(), fa.begin(), fa.end());
+        const double* dfb = d_stage_d.p + h_stage_d.size();
+        h_stage_d.insert(h_stage_d.end(), fb.begin(), fb.end());
+        const double* dca = d_stage_d.p + h_stage_d.size();
+        h_stage_d.insert(h_stage_d.end(), ca.begin(), ca.end());
+        const double* dcb = d_stage_d.p + h_stage_d.size();
+        h_stage_d.insert(h_stage_d.end(), cb.begin(), cb.end());
+        const int* dga = d_stage_i.p + h_stage_i.size();
+        h_stage_i.insert(h_stage_i.end(), pr.genes_a, pr.genes_a + G);
+        const int* dgb = d_stage_i.p + h_stage_i.size();
+        h_stage_i.insert(h_stage_i.end(), pr.genes_b, pr.genes_b + G);
         B.Wa.alloc((size_t)sa.n_genes * B.d_pad);
         B.Wb.alloc((size_t)sb.n_genes * B.d_pad);
         B.shift.alloc((size_t)2 * B.d_pad);
-        wprobs.push_back(WBuildProblem{R.rot.p, B.fa.p, B.ca.p, B.cols_a.p, B.Wa.p, B.shift.p, G, sa.n_genes});
-        wprobs.push_back(
-            WBuildProblem{R.rot.p, B.fb.p, B.cb.p, B.cols_b.p, B.Wb.p, B.shift.p + B.d_pad, G, sb.n_genes});
+        wprobs.push_back(WBuildProblem{R.rot.p, dfa, dca, dga, B.Wa.p, B.shift.p, G, sa.n_genes});
+        wprobs.push_back(WBuildProblem{R.rot.p, dfb, dcb, dgb, B.Wb.p, B.shift.p + B.d_pad, G, sb.n_genes});
         if (ctx->keep_projections) {
           B.p64a.alloc((size_t)B.na * B.d);
           B.p64b.alloc((size_t)B.nb * B.d);
@@ -281,6 +299,12 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
       mprobs.push_back(MnnProblem{B.i_ab.p, B.d_ab.p, B.i_ba.p, B.d_ba.p,
                                   P.space == CG_SPACE_CCA ? B.rows_u.p : nullptr,
                                   P.space == CG_SPACE_CCA ? B.rows_v.p : nullptr, B.na, B.nb, sa.offset, sb.offset});
+    }
+    if (!h_stage_d.empty()) {
+      CG_CUDA(cudaMemcpyAsync(d_stage_d.p, h_stage_d.data(), h_stage_d.size() * sizeof(double), cudaMemcpyHostToDevice,
+                              c.stream));
+      CG_CUDA(cudaMemcpyAsync(d_stage_i.p, h_stage_i.data(), h_stage_i.size() * sizeof(int), cudaMemcpyHostToDevice,
+                              c.stream));
     }
     delete sc_setup;
     if (!wprobs.empty()) {

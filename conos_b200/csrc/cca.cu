@@ -232,9 +232,9 @@ void cca_pair(Context& ctx, cg_panel& panel, const cg_pair& pr, const cg_params&
              "var.scale = TRUE needs misc$varinfo$v and $qv for every sample");
     for (int g = 0; g < G; ++g) {
       const int ca = pr.genes_a[g], cb = pr.genes_b[g];
-      const double cqv = std::exp((std::log(S[0].s->h_qv[ca]) + std::log(S[1].s->h_qv[cb])) / 2.0);
-      const double fa = std::sqrt(cqv / std::exp(S[0].s->h_v[ca]));
-      const double fb = std::sqrt(cqv / std::exp(S[1].s->h_v[cb]));
+      const double cqv = std::exp((S[0].s->h_logqv[ca] + S[1].s->h_logqv[cb]) / 2.0);
+      const double fa = std::sqrt(cqv / S[0].s->h_expv[ca]);
+      const double fb = std::sqrt(cqv / S[1].s->h_expv[cb]);
       f[0][g] = std::isfinite(fa) ? fa : 0.0;
       f[1][g] = std::isfinite(fb) ? fb : 0.0;
     }

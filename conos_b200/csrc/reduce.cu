@@ -163,12 +163,29 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
         ts[si] = TcEigSample{sm.gram.p, sm.colsum.p, sm.n_cells, sm.n_genes};
       }
       struct PB {
-        DevBuf<double> f[2], V[2], theta[2], tr;
-        DevBuf<int> cols[2];
+        const double* f[2];   // into the staging buffer: scale factor per gene of the sample's universe
+        const int* cols[2];   // into the staging buffer: column of every pair gene
+        double* V[2];         // into the batch buffers below
+        double* theta[2];
         std::vector<double> hf[2];  // per pair gene
       };
       std::vector<PB> pbs(todo.size());
       std::vector<TcEigProblem> tp;
+      // one staging upload and one allocation per kind for the whole batch
+      size_t n_f = 0, n_c = 0, n_v = 0;
+      for (size_t t = 0; t < todo.size(); ++t) {
+        const cg_pair& pr = pairs[todo[t]];
+        n_f += (size_t)panel.samples[pr.a].n_genes + panel.samples[pr.b].n_genes;
+        n_c += 2 * (size_t)pr.n_genes;
+        n_v += ((size_t)panel.samples[pr.a].n_genes + panel.samples[pr.b].n_genes) * r;
+      }
+      std::vector<double> h_f;
+      std::vector<int> h_c;
+      h_f.reserve(n_f);
+      h_c.reserve(n_c);
+      DevBuf<double> d_f(n_f), d_V(n_v), d_theta(2 * (size_t)r * todo.size());
+      DevBuf<int> d_c(n_c);
+      size_t o_v = 0;
       for (size_t t = 0; t < todo.size(); ++t) {
         const cg_pair& pr = pairs[todo[t]];
         const int G = pr.n_genes;
@@ -182,9 +199,9 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
           for (int g = 0; g < G; ++g) {
             const int ca = pr.genes_a[g], cb = pr.genes_b[g];  // the gene's column in either sample
             CG_CHECK(ca >= 0 && ca < sm[0]->n_genes && cb >= 0 && cb < sm[1]->n_genes, "pair gene column out of range");
-            const double cqv = std::exp((std::log(sm[0]->h_qv[ca]) + std::log(sm[1]->h_qv[cb])) / 2.0);
-            const double fa = std::sqrt(cqv / std::exp(sm[0]->h_v[ca]));
-            const double fb = std::sqrt(cqv / std::exp(sm[1]->h_v[cb]));
+            const double cqv = std::exp((sm[0]->h_logqv[ca] + sm[1]->h_logqv[cb]) / 2.0);
+            const double fa = std::sqrt(cqv / sm[0]->h_expv[ca]);
+            const double fb = std::sqrt(cqv / sm[1]->h_expv[cb]);
             f[0][g] = std::isfinite(fa) ? fa : 0.0;
             f[1][g] = std::isfinite(fb) ? fb : 0.0;
           }
@@ -198,13 +215,18 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
             fu[cols[g]] = f[side][g];
           }
           pbs[t].hf[side] = f[side];
-          pbs[t].f[side].upload(fu.data(), (size_t)Gs, st);
-          pbs[t].cols[side].upload(cols, (size_t)G, st);
-          pbs[t].V[side].alloc((size_t)Gs * r);
-          pbs[t].theta[side].alloc((size_t)r);
-          tp.push_back(TcEigProblem{side == 0 ? pr.a : pr.b, pbs[t].f[side].p, pbs[t].V[side].p, pbs[t].theta[side].p});
+          pbs[t].f[side] = d_f.p + h_f.size();
+          h_f.insert(h_f.end(), fu.begin(), fu.end());
+          pbs[t].cols[side] = d_c.p + h_c.size();
+          h_c.insert(h_c.end(), cols, cols + G);
+          pbs[t].V[side] = d_V.p + o_v;
+          o_v += (size_t)Gs * r;
+          pbs[t].theta[side] = d_theta.p + (2 * t + side) * (size_t)r;
+          tp.push_back(TcEigProblem{side == 0 ? pr.a : pr.b, pbs[t].f[side], pbs[t].V[side], pbs[t].theta[side]});
         }
       }
+      CG_CUDA(cudaMemcpyAsync(d_f.p, h_f.data(), h_f.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+      CG_CUDA(cudaMemcpyAsync(d_c.p, h_c.data(), h_c.size() * sizeof(int), cudaMemcpyHostToDevice, st));
       {
         StageScope sc(ctx, "reduction.eig");
         top_eigenvectors_shared_gram(ctx, ts.data(), S, tp.data(), (int)tp.size(), r, 1e-5, 40, 10);
@@ -218,7 +240,7 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
         R.d = P.ncomps < R.n_cols ? P.ncomps : R.n_cols;
         R.rot.alloc((size_t)G * R.n_cols);
         interleave_gather_kernel<<<nblk((size_t)G * R.n_cols), 256, 0, st>>>(
-            pbs[t].V[0].p, pbs[t].V[1].p, pbs[t].cols[0].p, pbs[t].cols[1].p, G, panel.samples[pr.a].n_genes,
+            pbs[t].V[0], pbs[t].V[1], pbs[t].cols[0], pbs[t].cols[1], G, panel.samples[pr.a].n_genes,
             panel.samples[pr.b].n_genes, r, R.rot.p);
         ctx.stats.kernels++;
         R.h_rot.resize((size_t)G * R.n_cols);
@@ -226,8 +248,7 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
         if (P.score_component_variance) {
           // trace(C) = sum_g f_g^2 (M_cc - n m_c^2) / (n - 1), c = the gene's column: from the host copies
           std::vector<double> th(2 * (size_t)r);
-          pbs[t].theta[0].download(th.data(), (size_t)r, st);
-          pbs[t].theta[1].download(th.data() + r, (size_t)r, st);
+          CG_CUDA(cudaMemcpyAsync(th.data(), pbs[t].theta[0], 2 * (size_t)r * sizeof(double), cudaMemcpyDeviceToHost, st));
           CG_CUDA(cudaStreamSynchronize(st));
           R.h_nv.assign(2 * (size_t)R.n_cols, 0.0);
           for (int side = 0; side < 2; ++side) {
@@ -296,9 +317,9 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
                    "var.scale = TRUE needs misc$varinfo$v and $qv for every sample");
           for (int g = 0; g < b.G; ++g) {
             const int ca = pr.genes_a[g], cb = pr.genes_b[g];
-            const double cqv = std::exp((std::log(sm[0]->h_qv[ca]) + std::log(sm[1]->h_qv[cb])) / 2.0);
-            const double fa = std::sqrt(cqv / std::exp(sm[0]->h_v[ca]));
-            const double fb = std::sqrt(cqv / std::exp(sm[1]->h_v[cb]));
+            const double cqv = std::exp((sm[0]->h_logqv[ca] + sm[1]->h_logqv[cb]) / 2.0);
+            const double fa = std::sqrt(cqv / sm[0]->h_expv[ca]);
+            const double fb = std::sqrt(cqv / sm[1]->h_expv[cb]);
             f[0][g] = std::isfinite(fa) ? fa : 0.0;
             f[1][g] = std::isfinite(fb) ? fb : 0.0;
           }
@@ -395,9 +416,9 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
                  "var.scale = TRUE needs misc$varinfo$v and $qv for every sample");
         for (int g = 0; g < G; ++g) {
           const int ca = pr.genes_a[g], cb = pr.genes_b[g];
-          const double cqv = std::exp((std::log(sm[0]->h_qv[ca]) + std::log(sm[1]->h_qv[cb])) / 2.0);
-          const double fa = std::sqrt(cqv / std::exp(sm[0]->h_v[ca]));
-          const double fb = std::sqrt(cqv / std::exp(sm[1]->h_v[cb]));
+          const double cqv = std::exp((sm[0]->h_logqv[ca] + sm[1]->h_logqv[cb]) / 2.0);
+          const double fa = std::sqrt(cqv / sm[0]->h_expv[ca]);
+          const double fb = std::sqrt(cqv / sm[1]->h_expv[cb]);
           f[0][g] = std::isfinite(fa) ? fa : 0.0;
           f[1][g] = std::isfinite(fb) ? fb : 0.0;
         }

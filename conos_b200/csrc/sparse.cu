@@ -1,3 +1,4 @@
+#include <cmath>
 #include "prims.cuh"
 #include <cuda_fp16.h>
 
@@ -201,6 +202,10 @@ void sample_upload(Context& ctx, Sample& s, int n_cells, int n_genes, const int*
   s.csc_x.upload(x, (size_t)s.nnz, copy_st);
   if (var_v) s.h_v.assign(var_v, var_v + n_genes);
   if (var_qv) s.h_qv.assign(var_qv, var_qv + n_genes);
+  s.h_logqv.resize(s.h_qv.size());
+  s.h_expv.resize(s.h_v.size());
+  for (size_t g = 0; g < s.h_qv.size(); ++g) s.h_logqv[g] = std::log(s.h_qv[g]);
+  for (size_t g = 0; g < s.h_v.size(); ++g) s.h_expv[g] = std::exp(s.h_v[g]);
   if (s.n_pcs > 0) {
     if (pca_ld == n_cells) {
       s.pca.upload(pca, (size_t)n_cells * n_pcs, copy_st);

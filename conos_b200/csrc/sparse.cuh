@@ -22,6 +22,7 @@ struct Sample {
   std::vector<double> h_colsum;   // host copy
   std::vector<double> h_gram_diag;  // host copy of diag(X'X), filled on demand
   std::vector<double> h_v, h_qv;  // misc$varinfo$v / $qv (empty when not supplied)
+  std::vector<double> h_logqv, h_expv;  // log(qv), exp(v): the per-pair scale factors need them for every gene
   DevBuf<float> pca_tiled;        // reductions$PCA as a normalised kNN panel (metric dependent, built lazily)
   DevBuf<double> pca;             // column-major n_cells x n_pcs
   int n_pcs = 0;
