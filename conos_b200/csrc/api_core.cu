@@ -103,6 +103,10 @@ int cg_set_option(cg_context* ctx, const char* name, double value) {
     ctx->c.exact_reduction = value != 0.0;
     return 0;
   }
+  if (strcmp(name, "tc_eig_max_sweeps") == 0) {
+    ctx->c.tc_eig_max_sweeps = (int)value;
+    return 0;
+  }
   if (strcmp(name, "knn_engine") == 0) {
     ctx->c.knn_engine = (int)value;
     return 0;

@@ -117,6 +117,7 @@ struct Context {
   uint64_t knn_redo_blocks = 0;   // 256-row blocks the streaming kernel had to recompute
   // 1: FP64 reductions (atomics Gram, explicit covariance, plain subspace iteration) instead of the tensor-core path
   bool exact_reduction = false;
+  int tc_eig_max_sweeps = 40;  // tensor-core eigen solver: sweeps before a problem is handed to the FP64 driver
   // optional per-stage wall-clock profile (stream synchronised at both ends of a stage)
   bool profile = false;
   std::map<std::string, double> stage_ms;

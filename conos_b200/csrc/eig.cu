@@ -880,7 +880,7 @@ void top_eigenvectors_operator(Context& ctx, int n_rows, int r, double tol, int 
 
 void top_eigenvectors_shared_gram(Context& ctx, const TcEigSample* samples, int n_samples,
                                   const TcEigProblem* probs, int n_probs, int r, double tol, int max_outer,
-                                  int degree) {
+                                  int degree, int* h_converged) {
   if (n_probs == 0) return;
   CG_CHECK(r >= 1 && r <= 24, "tensor-core eigen path: 1..24 eigenvectors per problem");
   cudaStream_t s = ctx.stream;
@@ -1053,6 +1053,8 @@ void top_eigenvectors_shared_gram(Context& ctx, const TcEigSample* samples, int 
     ctx.stage_ms["reduction.eig.converged_problems"] += nconv;
     ctx.stage_ms["reduction.eig.problems"] += n_probs;
   }
+  if (h_converged)
+    for (int pi = 0; pi < n_probs; ++pi) h_converged[order[pi]] = hc[pi] != 0 ? 1 : 0;
   // the loop always ends right after a Rayleigh-Ritz step: Q holds the sorted Ritz vectors
   eig_export_kernel<B><<<dim3(8, n_probs), 256, 0, s>>>(dw.p, r);
   ctx.stats.kernels++;

@@ -45,8 +45,9 @@ struct TcEigProblem {
   double* V;        // out: G x r column-major
   double* theta;    // out: [r]
 };
+// h_converged (optional, [n_probs]): 1 where the leading r pairs met the tolerance within max_outer sweeps
 void top_eigenvectors_shared_gram(Context& ctx, const TcEigSample* samples, int n_samples,
                                   const TcEigProblem* probs, int n_probs, int r, double tol, int max_outer,
-                                  int degree);
+                                  int degree, int* h_converged = nullptr);
 
 }  // namespace cg

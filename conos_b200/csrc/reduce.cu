@@ -171,6 +171,7 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
       };
       std::vector<PB> pbs(todo.size());
       std::vector<TcEigProblem> tp;
+      std::vector<int> tc_conv(2 * todo.size(), 1), redo;
       // one staging upload and one allocation per kind for the whole batch
       size_t n_f = 0, n_c = 0, n_v = 0;
       for (size_t t = 0; t < todo.size(); ++t) {
@@ -229,9 +230,14 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
       CG_CUDA(cudaMemcpyAsync(d_c.p, h_c.data(), h_c.size() * sizeof(int), cudaMemcpyHostToDevice, st));
       {
         StageScope sc(ctx, "reduction.eig");
-        top_eigenvectors_shared_gram(ctx, ts.data(), S, tp.data(), (int)tp.size(), r, 1e-5, 40, 10);
+        top_eigenvectors_shared_gram(ctx, ts.data(), S, tp.data(), (int)tp.size(), r, 1e-5, ctx.tc_eig_max_sweeps, 10,
+                                     tc_conv.data());
       }
       for (size_t t = 0; t < todo.size(); ++t) {
+        if (!tc_conv[2 * t] || !tc_conv[2 * t + 1]) {  // not at irlba's tolerance: this pair goes to the FP64 driver
+          redo.push_back(todo[t]);
+          continue;
+        }
         const cg_pair& pr = pairs[todo[t]];
         const int G = pr.n_genes;
         PairReduction& R = out[todo[t]];
@@ -274,7 +280,9 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
         }
       }
       CG_CUDA(cudaStreamSynchronize(st));
-      return;
+      if (redo.empty()) return;
+      if (ctx.profile) ctx.stage_ms["reduction.eig.fp64_redo_pairs"] += (double)redo.size();
+      todo = redo;
     }
     const int B = r <= 24 ? 32 : 64;
     // chunks of pairs bounded by memory (2 covariance matrices per pair)

@@ -439,3 +439,22 @@ def test_reference_fixture_on_gpu(ctx, golden, exact):
         np.testing.assert_allclose([mine[e] for e in sorted(common)], [ref[e] for e in sorted(common)], rtol=1e-6)
     else:
         assert jac > 0.9, jac
+
+
+def test_unconverged_tensor_core_pairs_go_to_fp64(ctx, small_panel):
+    """A pair whose tensor-core eigen solve has not met the tolerance after the allowed sweeps is recomputed by the
+    FP64 driver instead of being returned half-converged (forced here by allowing a single sweep)."""
+    import conos_b200
+    res = {}
+    try:
+        for sweeps in (40, 1):
+            ctx.check(ctx.lib.cg_set_option(ctx.h, b"tc_eig_max_sweeps", float(sweeps)))
+            con = conos_b200.Conos(small_panel, ctx=ctx)
+            con.buildGraph(k=10, k_self=5, space="PCA", ncomps=20, n_odgenes=300)
+            res[sweeps] = con.pairs["PCA"]
+    finally:
+        ctx.lib.cg_set_option(ctx.h, b"tc_eig_max_sweeps", 40.0)
+    for key in res[40]:
+        for side in (0, 1):
+            cs = _principal_cosines(res[40][key]["CPC"][:, side::2], res[1][key]["CPC"][:, side::2])
+            assert cs.min() > 1 - 1e-5, (key, side, cs.min())
