@@ -148,6 +148,8 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
           adesc[mb][ks] = ptx::umma_desc_kmajor_swz(ptx::smem_u32(smA) + mb * 128 * C::ROW_BYTES + ks * 32, C::SWZ,
                                                    8 * C::ROW_BYTES);
       const uint64_t bdesc0 = ptx::umma_desc_kmajor_swz(ptx::smem_u32(smB), C::SWZ, 8 * C::ROW_BYTES);
+      const uint32_t b_full_a = ptx::smem_u32(b_full), b_empty_a = ptx::smem_u32(b_empty);
+      const uint32_t acc_full_a = ptx::smem_u32(acc_full), acc_empty_a = ptx::smem_u32(acc_empty);
       uint32_t slot = 0, ph = 0, stage = 0, aph = 0, it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const KnnItem wi = items[item];
@@ -157,8 +159,8 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
         for (int ph2 = 0; ph2 < 2; ++ph2) {
           if (ph2 == 1) ptx::mbar_wait(thr_ready, it & 1);  // the rows' thresholds are in the A tile (FOLD)
           for (int t = 0; t < n_tiles; ++t) {
-            ptx::mbar_wait(b_full + slot, ph);
-            ptx::mbar_wait(acc_empty + stage, aph ^ 1);
+            ptx::mbar_wait_a(b_full_a + slot * 8, ph);
+            ptx::mbar_wait_a(acc_empty_a + stage * 8, aph ^ 1);
             ptx::tc_fence_after();
             const uint64_t bd = bdesc0 + (uint64_t)((slot * (uint32_t)C::B_BYTES) >> 4);
 #pragma unroll
@@ -169,8 +171,8 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
                 ptx::mma_f16_ss(d_tmem, adesc[mb][ks], bd + (uint64_t)(ks * 2), idesc, ks > 0 ? 1u : 0u);
               }
             }
-            ptx::mma_commit(b_empty + slot);
-            ptx::mma_commit(acc_full + stage);
+            ptx::mma_commit_a(b_empty_a + slot * 8);
+            ptx::mma_commit_a(acc_full_a + stage * 8);
             if (++slot == C::NSTAGE) { slot = 0; ph ^= 1; }
             aph ^= stage;
             stage ^= 1;
@@ -188,6 +190,7 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
     const int mb = sub & 1, half = sub >> 1;
     const int row_local = mb * 128 + quarter * 32 + lane;
     const uint32_t tm_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t acc_full_a = ptx::smem_u32(acc_full), acc_empty_a = ptx::smem_u32(acc_empty);
     float* gm = gmax_s + half * 256 + row_local;  // + g * 512
     // this row's threshold slot in the A tile: last K dimension
     __half* thr_slot = smA + knn_tiled16_offset(row_local, D_PAD - 1, D_PAD);
@@ -205,12 +208,12 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
         int tcount = 0;
         for (int t = 0; t < n_tiles; ++t, ++g) {
           const uint32_t stage = g & 1, aph = (g >> 1) & 1;
-          ptx::mbar_wait(acc_full + stage, aph);
+          ptx::mbar_wait_a(acc_full_a + stage * 8, aph);
           ptx::tc_fence_after();
 #ifdef TC2_MMA_ONLY  // measurement build: tensor pipe + pipeline only, accumulators are dropped
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(acc_empty + stage);
+          if (lane == 0) ptx::mbar_arrive_a(acc_empty_a + stage * 8);
           continue;
 #endif
           const uint32_t taddr = tm_lane + (stage * 2 + mb) * TILE_N + half * 64;
@@ -222,7 +225,7 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
           ptx::tmem_wait_ld();
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(acc_empty + stage);
+          if (lane == 0) ptx::mbar_arrive_a(acc_empty_a + stage * 8);
           const int nv = pb.nr - t * TILE_N - half * 64;  // valid columns of this thread's 64
           if (nv < 64) {  // zero padding rows of the last reference tile never count
 #pragma unroll
@@ -293,12 +296,12 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
         int cnt = 0;
         for (int t = 0; t < n_tiles; ++t, ++g) {
           const uint32_t stage = g & 1, aph = (g >> 1) & 1;
-          ptx::mbar_wait(acc_full + stage, aph);
+          ptx::mbar_wait_a(acc_full_a + stage * 8, aph);
           ptx::tc_fence_after();
 #ifdef TC2_MMA_ONLY
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(acc_empty + stage);
+          if (lane == 0) ptx::mbar_arrive_a(acc_empty_a + stage * 8);
           continue;
 #endif
           const uint32_t taddr = tm_lane + (stage * 2 + mb) * TILE_N + half * 64;
@@ -310,7 +313,7 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
           ptx::tmem_wait_ld();
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(acc_empty + stage);
+          if (lane == 0) ptx::mbar_arrive_a(acc_empty_a + stage * 8);
           uint32_t ma = 0, mb2 = 0;
           if (FOLD) {
             // accumulator = dot - thr: collect the sign bits (highest column first), survivors = NOT sign
