@@ -216,6 +216,7 @@ class Conos:
         """`world` = (rank, world_size, process group or None) shards the sample pairs (and the per-sample
         local-neighbour searches) over one process per GPU; every rank ends with the full graph.
         `fetch=False` keeps the assembled graph on the device (self.graph is a size-only stub)."""
+        t_total = time.perf_counter()
         if space not in SUPPORTED_SPACES:
             raise ValueError("only the following spaces are currently supported: [" + " ".join(SUPPORTED_SPACES) + "]")
         if space not in DEVICE_SPACES:
@@ -386,6 +387,7 @@ class Conos:
         if balance_edge_weights:
             g = self._balance(g, names, same_factor_downweight)
         self.graph = g
+        self.timings["total_ms"] = 1e3 * (time.perf_counter() - t_total)
         return g
 
     def _out(self, key: str, n: int, dtype):
