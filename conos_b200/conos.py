@@ -96,6 +96,7 @@ class Conos:
         self._panel = None
         self._panel_names: List[str] = []
         self._vocab = None
+        self._od_membership = {}
         self._cell_names = None
         self._pinned = {}
         self.timings: Dict[str, float] = {}
@@ -120,6 +121,7 @@ class Conos:
                 raise ValueError(f"sample {n}: counts must be cells x genes")
             self.samples[n] = s
         self._vocab = None
+        self._od_membership = {}
         self._cell_names = None
         self._drop_panel()
 
@@ -182,15 +184,21 @@ class Conos:
     def _common_od_genes(self, na: str, nb: str, n_odgenes: int):
         """commonOverdispersedGenes for the pair + the column of every od gene in both samples:
         table() of the two top-n od lists, sorted by count (decreasing, stable => ties keep name order),
-        restricted to genes present in both samples, first n.odgenes."""
+        restricted to genes present in both samples, first n.odgenes.
+        Gene ids are ranks in sort() order, so "count 2 first, then count 1, names ascending inside a count" is two
+        flatnonzero calls on the per-sample membership vectors of the top-n lists (cached per n.odgenes)."""
         self._ensure_vocab()
         allnames, per = self._vocab
         col_a, od_a = per[na]
         col_b, od_b = per[nb]
-        cat = np.concatenate([od_a[:n_odgenes], od_b[:n_odgenes]])
-        ids, cnt = np.unique(cat, return_counts=True)          # ids ascending == names in sort() order
-        order = np.argsort(-cnt, kind="stable")
-        ids = ids[order]
+        memb = self._od_membership
+        for n, od in ((na, od_a), (nb, od_b)):
+            if (n, n_odgenes) not in memb:
+                m = np.zeros(len(allnames), np.int8)
+                m[od[:n_odgenes]] = 1          # an od list never repeats a gene
+                memb[(n, n_odgenes)] = m
+        cnt = memb[(na, n_odgenes)] + memb[(nb, n_odgenes)]
+        ids = np.concatenate([np.flatnonzero(cnt == 2), np.flatnonzero(cnt == 1)])
         ids = ids[(col_a[ids] >= 0) & (col_b[ids] >= 0)]
         ids = ids[:min(len(ids), n_odgenes)]
         ga = np.ascontiguousarray(col_a[ids], np.int32)
