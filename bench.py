@@ -171,6 +171,28 @@ def pin_panel(panel):
     return out
 
 
+def knn_recall(ctx, k, d):
+    """recall@k of the library's kNN against an FP64 brute force (torch on the GPU, outside every timed region) on
+    the kernel-level micro-input of SURVEY.md 8(d): 20-component Gaussian mixture, 2000 queries x 50000 references."""
+    import torch
+    from conos_b200 import ops
+    rng = np.random.default_rng(SEED_RECALL)
+    cent = rng.normal(0, 3.0, (20, d))
+    A = cent[rng.integers(0, 20, 2000)] + rng.normal(0, 1, (2000, d))
+    B = cent[rng.integers(0, 20, 50000)] + rng.normal(0, 1, (50000, d))
+    idx, _ = ops.crossKnn(A, B, k, "angular", ctx=ctx)
+    ta = torch.as_tensor(A, device="cuda", dtype=torch.float64)
+    tb = torch.as_tensor(B, device="cuda", dtype=torch.float64)
+    ta = ta / ta.norm(dim=1, keepdim=True)
+    tb = tb / tb.norm(dim=1, keepdim=True)
+    true = torch.topk(ta @ tb.T, k, dim=1).indices.cpu().numpy()
+    hit = sum(len(set(a.tolist()) & set(b.tolist())) for a, b in zip(idx, true))
+    return hit / float(idx.size)
+
+
+SEED_RECALL = 20261019
+
+
 def panel_bytes(panel):
     b = 0
     for s in panel.values():
@@ -410,6 +432,8 @@ def main():
                     "d2h_bytes_per_step": graph_bytes(g_host), "steps": K2},
             "e2e_breakdown_ms": {k: round(v, 2) for k, v in con.timings.items()}, "e2e_steps_ms": e2e_each,
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
+    if rank == 0:
+        line["knn_recall_at_k"] = knn_recall(ctx, cfg["k"], cfg["ncomps"])
     if not args.no_cpu_baseline:
         import conos_oracle as oracle
         oracle.build()

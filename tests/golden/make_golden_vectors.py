@@ -3,7 +3,7 @@
 
 The reference asserts no value on this path (parity unpinned), so these vectors pin the ORACLE
 against drift, and give the GPU tests a committed target that does not depend on re-running the oracle:
-  * buildGraph(ncomps=25) on the reference's own fixture (tests/golden/small_panel_preprocessed.npz, decoded from
+  * buildGraph(k=15, k.self=5, ncomps=30) = BASELINE.json configs[0], and buildGraph(ncomps=25) on the reference's own fixture (tests/golden/small_panel_preprocessed.npz, decoded from
     data/small_panel.preprocessed.rda by make_small_panel_fixture.py) -- the call tests/testthat/test_functions.R:24
     makes;
   * exact float32 kNN on a seeded mixture.
@@ -51,11 +51,15 @@ def main():
     panel = load_reference_panel(oracle.Sample)
     ref = oracle.build_graph(panel, ncomps=25)   # defaults k=15, k.self=10, space='PCA', n.odgenes=2000
     g = ref["graph"]
+    # BASELINE.json configs[0]: the same panel with k=15, k.self=5, space='PCA', ncomps=30
+    g0 = oracle.build_graph(panel, k=15, k_self=5, space="PCA", ncomps=30)["graph"]
     A, B = knn_inputs()
     idx, dist = oracle.cross_knn(A, B, 15, "angular")
     dst = os.path.join(HERE, "oracle_vectors.npz")
     np.savez_compressed(dst, graph_vertices=g["vertices"], graph_from=g["from"], graph_to=g["to"],
-                        graph_weight=g["weight"], graph_type=g["type"], knn_idx=idx, knn_dist=dist)
+                        graph_weight=g["weight"], graph_type=g["type"], knn_idx=idx, knn_dist=dist,
+                        c0_vertices=g0["vertices"], c0_from=g0["from"], c0_to=g0["to"], c0_weight=g0["weight"],
+                        c0_type=g0["type"])
     print("wrote", dst, os.path.getsize(dst), "bytes;", len(g["vertices"]), "vertices,", len(g["from"]), "edges")
 
 

@@ -218,6 +218,10 @@ def test_reference_fixture_and_golden_vectors(oracle, golden):
     assert np.array_equal(g["from"], vec["graph_from"]) and np.array_equal(g["to"], vec["graph_to"])
     assert np.array_equal(g["type"], vec["graph_type"])
     np.testing.assert_allclose(g["weight"], vec["graph_weight"], rtol=1e-10)
+    g0 = oracle.build_graph(panel, k=15, k_self=5, space="PCA", ncomps=30)["graph"]   # BASELINE.json configs[0]
+    assert len(g0["vertices"]) == 59
+    assert np.array_equal(g0["from"], vec["c0_from"]) and np.array_equal(g0["to"], vec["c0_to"])
+    np.testing.assert_allclose(g0["weight"], vec["c0_weight"], rtol=1e-10)
     A, B = mod.knn_inputs()
     idx, dist = oracle.cross_knn(A, B, 15, "angular")
     assert np.array_equal(idx, vec["knn_idx"])

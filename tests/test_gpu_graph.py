@@ -458,3 +458,20 @@ def test_unconverged_tensor_core_pairs_go_to_fp64(ctx, small_panel):
         for side in (0, 1):
             cs = _principal_cosines(res[40][key]["CPC"][:, side::2], res[1][key]["CPC"][:, side::2])
             assert cs.min() > 1 - 1e-5, (key, side, cs.min())
+
+
+def test_baseline_config0_on_gpu(ctx, golden):
+    """BASELINE.json configs[0]: the bundled panel, buildGraph(k=15, k.self=5, space='PCA', ncomps=30), FP64 reductions:
+    the oracle's committed graph, vertex order, edges and weights."""
+    import conos_b200
+    mod, vec = golden
+    con = conos_b200.Conos(mod.load_reference_panel(conos_b200.Pagoda2), ctx=ctx)
+    ctx.lib.cg_set_option(ctx.h, b"exact_reduction", 1.0)
+    try:
+        g = con.buildGraph(k=15, k_self=5, space="PCA", ncomps=30)
+    finally:
+        ctx.lib.cg_set_option(ctx.h, b"exact_reduction", 0.0)
+    assert np.array_equal(g.vertices, vec["c0_vertices"])
+    assert np.array_equal(g.edge_from, vec["c0_from"]) and np.array_equal(g.edge_to, vec["c0_to"])
+    assert np.array_equal(g.type, vec["c0_type"])
+    np.testing.assert_allclose(g.weight, vec["c0_weight"], rtol=1e-6)
