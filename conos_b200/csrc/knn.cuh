@@ -104,6 +104,19 @@ bool knn_tc2_plan(int nr, int k, KnnTc2Aux& ax);
 void knn_tc2_run(Context& ctx, const KnnProblem* d_probs, const KnnProblem* h_probs, const std::vector<int>& plist,
                  std::vector<KnnTc2Aux>& aux, int n_probs, int k, int d_pad, int d, std::vector<KnnItem>& redo);
 
+// Large-k tensor-core kernel (knn_tcl.cu): 32 < k <= KNN_TCL_MAXK, angular metric.  Thresholds by counting passes.
+constexpr int KNN_TCL_MAXK = 3072;
+struct KnnTclAux {
+  long long row0 = 0;   // first row of this problem in the chunk's scratch arrays
+  int* cand = nullptr;  // [rows][2][cap / 2]
+  int* cnt = nullptr;   // [rows][2]
+  float* thr = nullptr; // [rows]
+};
+bool knn_tcl_applies(int nr, int k);
+// Runs the problems in `plist`; problems that need the exact SIMT kernel (candidate overflow) are appended to `redo`.
+void knn_tcl_run(Context& ctx, const KnnProblem* d_probs, const KnnProblem* h_probs, const std::vector<int>& plist,
+                 int n_probs, int k, int d_pad, int d, std::vector<int>& redo);
+
 // Dispatch by (k, metric): the tensor-core kernel whenever it applies.
 void knn_launch(Context& ctx, const KnnProblem* d_probs, const KnnProblem* h_probs, int n_probs, int k, int d_pad,
                 int d, Metric metric);

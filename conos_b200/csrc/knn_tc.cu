@@ -561,9 +561,30 @@ void knn_tc_launch(Context& ctx, const KnnProblem* d_probs, const KnnProblem* h_
 
 void knn_launch(Context& ctx, const KnnProblem* d_probs, const KnnProblem* h_probs, int n_probs, int k, int d_pad,
                 int d, Metric metric) {
-  if (metric == METRIC_ANGULAR && k <= KNN_TC_MAXK && ctx.knn_engine != 2)
+  if (metric == METRIC_ANGULAR && k <= KNN_TC_MAXK && ctx.knn_engine != 2) {
     knn_tc_launch(ctx, d_probs, h_probs, n_probs, k, d_pad, d);
-  else knn_simt_launch(ctx, d_probs, h_probs, n_probs, k, d_pad, d, metric);
+    return;
+  }
+  if (metric == METRIC_ANGULAR && k <= KNN_TCL_MAXK && ctx.knn_engine == 0) {
+    // large k (alignment.strength > 0): counting passes on the tensor cores; whatever does not qualify, or
+    // overflows its candidate lists, goes to the exact SIMT kernel
+    std::vector<int> plist, rest;
+    for (int p = 0; p < n_probs; ++p) {
+      if (h_probs[p].nq <= 0) continue;
+      (knn_tcl_applies(h_probs[p].nr, k) ? plist : rest).push_back(p);
+    }
+    if (!plist.empty()) knn_tcl_run(ctx, d_probs, h_probs, plist, n_probs, k, d_pad, d, rest);
+    if (!rest.empty()) {
+      std::vector<KnnProblem> sub;
+      for (int p : rest) sub.push_back(h_probs[p]);
+      DevBuf<KnnProblem> d_sub;
+      d_sub.upload(sub.data(), sub.size(), ctx.stream);
+      knn_simt_launch(ctx, d_sub.p, sub.data(), (int)sub.size(), k, d_pad, d, metric);
+      CG_CUDA(cudaStreamSynchronize(ctx.stream));
+    }
+    return;
+  }
+  knn_simt_launch(ctx, d_probs, h_probs, n_probs, k, d_pad, d, metric);
 }
 
 }  // namespace cg

@@ -178,3 +178,38 @@ def test_two_phase_no_redo_on_regular_data(ctx):
     before = _stat(ctx, "knn_redo_blocks")
     ops.crossKnn(A, B, 30, "angular", ctx=ctx, both=True)
     assert _stat(ctx, "knn_redo_blocks") == before
+
+
+@pytest.mark.parametrize("nA,nB,d,k", [(600, 3000, 30, 100), (300, 5000, 30, 500), (257, 6000, 30, 2250),
+                                       (1000, 2500, 50, 64), (700, 1800, 32, 200), (513, 4000, 64, 333)])
+def test_large_k_tensor_core_kernel(ctx, oracle, nA, nB, d, k):
+    """32 < k <= 3072 (alignment.strength > 0 asks for k1 = a^2 * cells neighbours): thresholds by counting passes on
+    the tensor cores, bit-identical to the oracle and to the SIMT kernel, duplicates (ties) included."""
+    from conos_b200 import ops
+    rng = np.random.default_rng(nA + nB + k)
+    A, B = mixture(rng, nA, d), mixture(rng, nB, d)
+    B[5::23] = B[4::23][:len(B[5::23])]
+    oi, od = oracle.cross_knn(A, B, k, "angular")
+    try:
+        for engine in (0, 2):
+            ctx.check(ctx.lib.cg_set_option(ctx.h, b"knn_engine", float(engine)))
+            idx, dist = ops.crossKnn(A, B, k, "angular", ctx=ctx)
+            assert np.array_equal(idx, oi), engine
+            assert np.array_equal(dist.view(np.uint32), od.view(np.uint32)), engine
+    finally:
+        ctx.lib.cg_set_option(ctx.h, b"knn_engine", 0.0)
+
+
+def test_large_k_mass_duplicates_fall_back(ctx, oracle):
+    """Thousands of copies of one reference tie at the threshold: the candidate lists overflow and the problem is
+    recomputed by the exact SIMT kernel."""
+    from conos_b200 import ops
+    rng = np.random.default_rng(91)
+    A, B = mixture(rng, 300, 30), mixture(rng, 6000, 30)
+    B[1000:5000] = B[999]
+    before = _stat(ctx, "knn_redo_blocks")
+    idx, dist = ops.crossKnn(A, B, 100, "angular", ctx=ctx)
+    oi, od = oracle.cross_knn(A, B, 100, "angular")
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(dist.view(np.uint32), od.view(np.uint32))
+    assert _stat(ctx, "knn_redo_blocks") > before
