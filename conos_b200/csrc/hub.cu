@@ -159,29 +159,31 @@ __global__ void __launch_bounds__(PARE_THREADS) pare_kernel(const PareProblem* _
     const long long b = lptr[line], e = lptr[line + 1];
     const int len = (int)(e - b);
     if (len <= pb.k) continue;  // cannot exceed k live entries
-    // live entries of the line, in line order (position = rank among the stored entries)
+    // the live degree of the line itself is current (live_counts ran before this side; the entries of a line die
+    // only while that line is visited): nothing to pare
+    const int* own = side == 0 ? pb.colN : pb.rowN;  // absent in the standalone pareDownHubEdges entry point
+    if (own && own[line] <= pb.k) continue;
+    // live entries of the line, compacted to the front (the sort below restores the order: the key carries the
+    // position among the stored entries); only the live ones are sorted -- after the first pass of the ladder most
+    // of a hub line is dead
     if (tid == 0) { s_cnt = 0; s_above = 0; }
     __syncthreads();
     u64* keys = len <= PARE_SMEM_KEYS ? skeys : pb.scratch;
-    int np = 2;
-    while (np < len) np <<= 1;
-    int local = 0;
-    for (int t = tid; t < np; t += PARE_THREADS) {
-      u64 key = ~0ull;
-      if (t < len) {
-        const int ent = side == 0 ? (int)(b + t) : pb.row_perm[b + t];
-        if (pb.alive[ent]) {
-          const int opp = side == 0 ? pb.row[ent] : pb.col[ent];
-          const unsigned deg = (unsigned)N[opp];
-          key = ((u64)(0x7fffffffu - deg) << 32) | (u64)(unsigned)t;  // degree descending, position ascending
-          ++local;
-        }
+    for (int t = tid; t < len; t += PARE_THREADS) {
+      const int ent = side == 0 ? (int)(b + t) : pb.row_perm[b + t];
+      if (pb.alive[ent]) {
+        const int opp = side == 0 ? pb.row[ent] : pb.col[ent];
+        const unsigned deg = (unsigned)N[opp];
+        // degree descending, position ascending
+        keys[atomicAdd(&s_cnt, 1)] = ((u64)(0x7fffffffu - deg) << 32) | (u64)(unsigned)t;
       }
-      keys[t] = key;
     }
-    atomicAdd(&s_cnt, local);
     __syncthreads();
     const int nedges = s_cnt;
+    int np = 2;
+    while (np < nedges) np <<= 1;
+    for (int t = nedges + tid; t < np; t += PARE_THREADS) keys[t] = ~0ull;
+    __syncthreads();
     if (nedges > pb.k) {
       block_bitonic(keys, np, tid, PARE_THREADS);
       // removable prefix: entries whose opposite degree exceeds klow (sorted descending => a prefix)
