@@ -103,6 +103,37 @@ __device__ void block_gram(const double* __restrict__ X, const double* __restric
     }
     return;
   }
+  if constexpr (B == 64) {
+    // four 32 x 32 blocks of S, two warps per block (even / odd rows); lane l owns column l of its block
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int blk = warp & 3, par = warp >> 2;
+    const int bi = (blk >> 1) * 32, bj = (blk & 1) * 32;
+    double acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.0;
+    int r = par;
+    for (; r + 2 < G; r += 4) {  // two rows in flight
+      const double x0 = X[(size_t)r * 64 + bi + lane], y0 = Y[(size_t)r * 64 + bj + lane];
+      const double x1 = X[(size_t)(r + 2) * 64 + bi + lane], y1 = Y[(size_t)(r + 2) * 64 + bj + lane];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] = fma(__shfl_sync(0xffffffffu, x0, i), y0, acc[i]);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] = fma(__shfl_sync(0xffffffffu, x1, i), y1, acc[i]);
+    }
+    if (r < G) {
+      const double x0 = X[(size_t)r * 64 + bi + lane], y0 = Y[(size_t)r * 64 + bj + lane];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] = fma(__shfl_sync(0xffffffffu, x0, i), y0, acc[i]);
+    }
+    for (int w = 0; w < 2; ++w) {
+      if (par == w) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) S[bi + i][bj + lane] = (w == 0 ? 0.0 : S[bi + i][bj + lane]) + acc[i];
+      }
+      __syncthreads();
+    }
+    return;
+  }
   constexpr int TB = B / 16;
   const int i0 = TB * (threadIdx.x / 16), j0 = TB * (threadIdx.x % 16);
   double acc[TB][TB];
