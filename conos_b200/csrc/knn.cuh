@@ -93,8 +93,9 @@ void knn_prep_from_f32_rowmajor(Context& ctx, const float* d_src, int n, int d, 
 void knn_simt_launch(Context& ctx, const KnnProblem* d_probs, const KnnProblem* h_probs, int n_probs, int k,
                      int d_pad, int d, Metric metric);
 
-// Tensor-core kernel (angular, k <= KNN_TC_MAXK): TF32 tcgen05 distance tiles in TMEM as a filter,
-// canonical fp32 re-rank of the survivors, per-row sorted top-k lists in shared memory.
+// Tensor-core path for the angular metric, k <= KNN_TC_MAXK: problems that qualify go to the two-phase kernel
+// (knn_tc2.cu); small problems and the 256-row blocks it hands back run through the streaming kernel of knn_tc.cu
+// (TF32 tcgen05 tiles as a filter, canonical fp32 re-rank of the survivors, sorted top-k lists in shared memory).
 void knn_tc_launch(Context& ctx, const KnnProblem* d_probs, const KnnProblem* h_probs, int n_probs, int k,
                    int d_pad, int d);
 

@@ -1,4 +1,6 @@
-// K2 fused exact cross-kNN on the sm_100a tensor cores (angular metric, k <= 32).
+// K2s: streaming exact cross-kNN on the sm_100a tensor cores (angular metric, k <= 32).  The first design of the
+// round; since knn_tc2.cu (two tensor-core phases, no list in the inner loop) it serves the small problems and the
+// 256-row blocks whose candidate lists overflow there, and hosts the dispatch (knn_tc_launch, knn_launch).
 //
 // One persistent CTA per SM walks work items (problem, block of 256 query rows):
 //   warp 0   producer : 1-D bulk async copies (TMA engine) of the query block (A, 256 rows) and of
