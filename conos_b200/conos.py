@@ -95,6 +95,8 @@ class Conos:
         self._device = device
         self._panel = None
         self._panel_names: List[str] = []
+        self._panel_key = None
+        self._panel_col: Dict[str, Optional[np.ndarray]] = {}
         self._vocab = None
         self._od_membership = {}
         self._cell_names = None
@@ -129,6 +131,7 @@ class Conos:
         if self._panel is not None:
             self.ctx.lib.cg_panel_free(self._panel)
             self._panel = None
+            self._panel_key = None
 
     @property
     def ctx(self):
@@ -137,21 +140,47 @@ class Conos:
         return self._ctx
 
     # ------------------------------------------------------------------ device-resident panel
-    def _ensure_panel(self, names: Sequence[str]):
-        if self._panel is not None and self._panel_names == list(names):
+    def _ensure_panel(self, names: Sequence[str], n_odgenes: int = 2000):
+        """Upload the samples.  Only the gene universe the path can touch travels: the union of the samples' top
+        n.odgenes overdispersed genes (every pair's gene set is drawn from two of those lists, R/conos.R:107-117).
+        Real pagoda2 objects carry 20-30 thousand genes of which a few thousand qualify; the synthetic panels use all
+        of theirs, in which case the arrays are passed through untouched (no copy)."""
+        key = (tuple(names), int(n_odgenes))
+        if self._panel is not None and self._panel_key == key:
             return
         self._drop_panel()
+        self._ensure_vocab()
+        allnames, per = self._vocab
+        in_u = np.zeros(len(allnames), bool)
+        for n in names:
+            in_u[per[n][1][:n_odgenes]] = True
         arr = (CgSample * len(names))()
         keep = []
+        self._panel_col = {}
         for t, n in enumerate(names):
             s = self.samples[n]
             m = sp.csc_matrix(s.counts)
+            col_of = per[n][0]                                  # vocabulary id -> column of this sample
+            ids_of_col = np.empty(m.shape[1], np.int64)
+            present = np.flatnonzero(col_of >= 0)
+            ids_of_col[col_of[present]] = present
+            kept = np.flatnonzero(in_u[ids_of_col])             # columns that belong to the universe, ascending
+            v, qv = s.varinfo_v, s.varinfo_qv
+            if len(kept) < m.shape[1]:
+                m = m[:, kept]
+                v = None if v is None else np.asarray(v)[kept]
+                qv = None if qv is None else np.asarray(qv)[kept]
+                pc = np.full(len(ids_of_col), -1, np.int32)
+                pc[kept] = np.arange(len(kept), dtype=np.int32)
+                self._panel_col[n] = pc
+            else:
+                self._panel_col[n] = None
             m.sort_indices()
             p = np.ascontiguousarray(m.indptr, np.int32)
             i = np.ascontiguousarray(m.indices, np.int32)
             x = np.ascontiguousarray(m.data, np.float64)
-            v = None if s.varinfo_v is None else np.ascontiguousarray(s.varinfo_v, np.float64)
-            qv = None if s.varinfo_qv is None else np.ascontiguousarray(s.varinfo_qv, np.float64)
+            v = None if v is None else np.ascontiguousarray(v, np.float64)
+            qv = None if qv is None else np.ascontiguousarray(qv, np.float64)
             pca = None if s.pca is None else np.asfortranarray(s.pca, np.float64)
             keep += [p, i, x, v, qv, pca]
             arr[t].n_cells, arr[t].n_genes = m.shape
@@ -164,6 +193,7 @@ class Conos:
         self.ctx.check(self.ctx.lib.cg_panel_create(self.ctx.h, arr, len(names), C.byref(h)))
         self._panel = h
         self._panel_names = list(names)
+        self._panel_key = key
 
     # ------------------------------------------------------------------ R/conos.R:107-117
     def _ensure_vocab(self):
@@ -201,9 +231,13 @@ class Conos:
         ids = np.concatenate([np.flatnonzero(cnt == 2), np.flatnonzero(cnt == 1)])
         ids = ids[(col_a[ids] >= 0) & (col_b[ids] >= 0)]
         ids = ids[:min(len(ids), n_odgenes)]
-        ga = np.ascontiguousarray(col_a[ids], np.int32)
-        gb = np.ascontiguousarray(col_b[ids], np.int32)
-        return ids, ga, gb
+        ga, gb = col_a[ids], col_b[ids]
+        pca_, pcb_ = self._panel_col.get(na), self._panel_col.get(nb)   # columns of the uploaded (subset) matrices
+        if pca_ is not None:
+            ga = pca_[ga]
+        if pcb_ is not None:
+            gb = pcb_[gb]
+        return ids, np.ascontiguousarray(ga, np.int32), np.ascontiguousarray(gb, np.int32)
 
     def _gene_names(self, ids) -> List[str]:
         allnames = self._vocab[0]
@@ -263,7 +297,7 @@ class Conos:
         if len(pair_names) < 1:
             raise ValueError("insufficient number of comparable pairs")
         t_0 = time.perf_counter()
-        self._ensure_panel(names)
+        self._ensure_panel(names, n_odgenes)
         self.timings["panel_ms"] = 1e3 * (time.perf_counter() - t_0)
         t_0 = time.perf_counter()
         index = {n: t for t, n in enumerate(names)}

@@ -475,3 +475,21 @@ def test_baseline_config0_on_gpu(ctx, golden):
     assert np.array_equal(g.edge_from, vec["c0_from"]) and np.array_equal(g.edge_to, vec["c0_to"])
     assert np.array_equal(g.type, vec["c0_type"])
     np.testing.assert_allclose(g.weight, vec["c0_weight"], rtol=1e-6)
+
+
+def test_gene_universe_subsetting(ctx, oracle, small_panel):
+    """n.odgenes below the number of genes: only the union of the samples' top-n od lists is uploaded (real pagoda2
+    objects carry tens of thousands of genes); gene columns are remapped and the graph equals the oracle's."""
+    import conos_b200
+    osamples = to_oracle_samples(oracle, small_panel)
+    ref = oracle.build_graph(osamples, k=10, k_self=5, space="PCA", ncomps=20, n_odgenes=120)
+    con = conos_b200.Conos(small_panel, ctx=ctx)
+    ctx.lib.cg_set_option(ctx.h, b"exact_reduction", 1.0)
+    try:
+        g = con.buildGraph(k=10, k_self=5, space="PCA", ncomps=20, n_odgenes=120)
+    finally:
+        ctx.lib.cg_set_option(ctx.h, b"exact_reduction", 0.0)
+    assert any(pc is not None for pc in con._panel_col.values()), "the panel was not subset: the test does not bite"
+    for key, red in ref["pairs"].items():
+        assert con.pairs["PCA"][key]["genes"] == red["genes"]
+    _graphs_equal(g, ref["graph"], rtol=1e-6)
