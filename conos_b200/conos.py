@@ -159,7 +159,9 @@ class Conos:
         self._panel_col = {}
         for t, n in enumerate(names):
             s = self.samples[n]
-            m = sp.csc_matrix(s.counts)
+            # the caller's CSC object itself when it is one: scipy caches the sorted-indices check on the object, so
+            # the scan over all non-zeros happens once per sample, not once per upload
+            m = s.counts if sp.isspmatrix_csc(s.counts) else sp.csc_matrix(s.counts)
             col_of = per[n][0]                                  # vocabulary id -> column of this sample
             ids_of_col = np.empty(m.shape[1], np.int64)
             present = np.flatnonzero(col_of >= 0)
@@ -175,7 +177,8 @@ class Conos:
                 self._panel_col[n] = pc
             else:
                 self._panel_col[n] = None
-            m.sort_indices()
+            if not m.has_sorted_indices:
+                m.sort_indices()
             p = np.ascontiguousarray(m.indptr, np.int32)
             i = np.ascontiguousarray(m.indices, np.int32)
             x = np.ascontiguousarray(m.data, np.float64)

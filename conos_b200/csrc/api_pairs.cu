@@ -73,7 +73,16 @@ int cg_panel_create(cg_context* ctx, const cg_sample* samples, int n_samples, cg
       pn->samples[s].offset = pn->offsets[s];
       pn->offsets[s + 1] = pn->offsets[s] + h.n_cells;
     }
-    for (int s = 0; s < n_samples; ++s) sample_finish(ctx->c, pn->samples[s], lane.ev[s]);
+    if (ctx->c.profile) {  // profile mode serialises the two halves to time them separately
+      const auto t0 = std::chrono::steady_clock::now();
+      CG_CUDA(cudaStreamSynchronize(lane.st));
+      ctx->c.stage_ms["panel_upload.copies"] +=
+          std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    {
+      StageScope sc2(ctx->c, "panel_upload.convert");
+      for (int s = 0; s < n_samples; ++s) sample_finish(ctx->c, pn->samples[s], lane.ev[s]);
+    }
     CG_CUDA(cudaStreamSynchronize(lane.st));
     *out = pn;
     return 0;
