@@ -57,6 +57,30 @@ class PairEntry(dict):
         return key == "genes" or dict.__contains__(self, key)
 
 
+class LazyNames:
+    """V(g)$name: cell barcodes in vertex order, gathered from the per-sample lists on first use."""
+
+    def __init__(self, cell_names, vertices):
+        self._cells, self._vertices, self._arr = cell_names, np.array(vertices, copy=True), None
+
+    def _get(self):
+        if self._arr is None:
+            self._arr = self._cells[self._vertices]
+        return self._arr
+
+    def __len__(self):
+        return len(self._vertices)
+
+    def __getitem__(self, i):
+        return self._get()[i]
+
+    def __iter__(self):
+        return iter(self._get())
+
+    def __array__(self, dtype=None, copy=None):
+        return self._get() if dtype is None else self._get().astype(dtype)
+
+
 @dataclass
 class ConosGraph:
     """What ``self$graph`` (an igraph) carries for findCommunities / embedGraph (R/conclass.R:336-343)."""
@@ -479,7 +503,7 @@ class Conos:
         lib.cg_graph_free(gh)
         if self._cell_names is None or self._cell_names[0] != list(names):
             self._cell_names = (list(names), np.array([c for n in names for c in self.samples[n].cells], dtype=object))
-        return ConosGraph(names=self._cell_names[1][vertices], vertices=vertices, edge_from=ef, edge_to=et, weight=w,
+        return ConosGraph(names=LazyNames(self._cell_names[1], vertices), vertices=vertices, edge_from=ef, edge_to=et, weight=w,
                           type=ty, adj_p=ap, adj_i=ai, adj_x=ax)
 
     def _balance(self, g: ConosGraph, names, same_factor_downweight: float) -> ConosGraph:
