@@ -113,3 +113,55 @@ def test_allgatherv_two_ranks_gloo():
         assert gf == want_f and gt == want_t           # rank order == pair order, no interleaving needed
         assert sum(counts) == len(want_f)
         assert np.allclose(gw, np.array(want_f) + np.array(want_t) / 10)
+
+
+def test_lazy_containers():
+    """PairEntry materialises the gene names on first access; LazyNames gathers the barcodes in vertex order and keeps
+    its own copy of the vertex ids (the graph arrays are views into buffers reused by the next buildGraph)."""
+    import numpy as np
+    from conos_b200.conos import LazyNames, PairEntry
+    calls = []
+
+    def namer(ids):
+        calls.append(1)
+        return [f"g{t}" for t in ids]
+
+    e = PairEntry(np.array([3, 1, 2]), namer, CPC=np.zeros((3, 2)))
+    assert "genes" in e and "CPC" in e and not calls
+    assert e["genes"] == ["g3", "g1", "g2"] and e["genes"] == ["g3", "g1", "g2"] and len(calls) == 1
+    cells = np.array(["a", "b", "c", "d"], dtype=object)
+    v = np.array([2, 0, 3], np.int32)
+    ln = LazyNames(cells, v)
+    v[:] = 0                      # the caller's buffer is overwritten by the next call
+    assert len(ln) == 3 and ln[0] == "c" and list(ln) == ["c", "a", "d"]
+    assert np.asarray(ln).tolist() == ["c", "a", "d"]
+
+
+def test_gene_universe_mapping_host_side():
+    """The upload universe is the union of the samples' top-n od lists; pair gene columns are remapped to the columns of
+    the uploaded (subset) matrices.  Pure host logic: checked without a device by stubbing the upload."""
+    import numpy as np
+    import scipy.sparse as sp
+    from conos_b200.conos import Conos, Pagoda2
+    rng = np.random.default_rng(0)
+    genes_a = [f"g{t:02d}" for t in range(10)]
+    genes_b = [f"g{t:02d}" for t in (9, 8, 7, 6, 5, 4, 3, 2, 11, 12)]
+    mk = lambda n, genes, od: Pagoda2(counts=sp.random(n, len(genes), 0.5, "csc", random_state=1), genes=genes,
+                                      cells=[f"c{n}_{t}" for t in range(n)], varinfo_v=np.zeros(len(genes)),
+                                      varinfo_qv=np.ones(len(genes)), pca=rng.normal(size=(n, 3)), od_genes=od)
+    # build the vocabulary and membership without touching the device
+    con = object.__new__(Conos)
+    con.samples = {"A": mk(6, genes_a, ["g03", "g05", "g00", "g09"]), "B": mk(7, genes_b, ["g05", "g12", "g02", "g07"])}
+    con._vocab, con._od_membership, con._panel_col = None, {}, {}
+    ids, ga, gb = con._common_od_genes("A", "B", 3)
+    names = con._gene_names(ids)
+    # top-3 lists: A {g03,g05,g00}, B {g05,g12,g02}; table sorted by count then name; g12 is absent from A, g00 from B
+    assert names == ["g05", "g02", "g03"]
+    assert [genes_a[c] for c in ga] == names and [genes_b[c] for c in gb] == names
+    # with a subset panel the columns are those of the uploaded matrices
+    pc_a = np.full(10, -1, np.int32); pc_a[[0, 2, 3, 5]] = np.arange(4)       # uploaded: g00 g02 g03 g05
+    pc_b = np.full(10, -1, np.int32); pc_b[[4, 6, 7, 9]] = np.arange(4)       # uploaded: g05 g03 g02 g12
+    con._panel_col = {"A": pc_a, "B": pc_b}
+    ids2, ga2, gb2 = con._common_od_genes("A", "B", 3)
+    assert ids2.tolist() == ids.tolist()
+    assert ga2.tolist() == [3, 1, 2] and gb2.tolist() == [0, 2, 1]
