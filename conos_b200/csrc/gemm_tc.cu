@@ -140,6 +140,56 @@ __global__ void tiled_from_csc_kernel(const int* __restrict__ csc_p, const int* 
   }
 }
 
+// Same operand from the CSR (by cell) form, built tile by tile in shared memory: a CTA owns 64 cells (one k-block) x
+// 256 genes, whose image in the operand layout is 32 KB contiguous; the non-zeros of its 64 cell rows that fall into
+// the gene range are dropped into a zeroed shared-memory image, which then leaves with coalesced 16-byte stores.
+// Every element of the padded operand is written exactly once (no memset, no scattered 2-byte stores).
+__global__ void __launch_bounds__(256) tiled_from_csr_kernel(const int* __restrict__ csr_p, const int* __restrict__ csr_i,
+                                                             const double* __restrict__ csr_x, int n_cells, int rows_pad,
+                                                             __nv_bfloat16* __restrict__ hi,
+                                                             __nv_bfloat16* __restrict__ lo) {
+  extern __shared__ __align__(16) unsigned char csr_smem[];
+  __nv_bfloat16* sh = reinterpret_cast<__nv_bfloat16*>(csr_smem);
+  __nv_bfloat16* sl = sh + 256 * 64;
+  const int kb = blockIdx.x, g0 = blockIdx.y * 256;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (int t = tid; t < 256 * 64 / 8; t += 256) {
+    reinterpret_cast<uint4*>(sh)[t] = z;
+    reinterpret_cast<uint4*>(sl)[t] = z;
+  }
+  __syncthreads();
+  for (int cl = warp; cl < 64; cl += 8) {
+    const int c = kb * 64 + cl;
+    if (c >= n_cells) break;
+    const int b = csr_p[c], e = csr_p[c + 1];
+    int lo_i = b, hi_i = e;  // first entry with column >= g0 (columns ascending inside a row)
+    while (lo_i < hi_i) {
+      const int mid = (lo_i + hi_i) >> 1;
+      if (csr_i[mid] < g0) lo_i = mid + 1; else hi_i = mid;
+    }
+    for (int t0 = lo_i; t0 < e; t0 += 32) {
+      const int t = t0 + lane;
+      const int col = t < e ? csr_i[t] : 0x7fffffff;
+      if (col < g0 + 256) {
+        const int gl = col - g0;
+        __nv_bfloat16 h, l;
+        split_bf16((float)csr_x[t], h, l);
+        const int o = ((gl >> 3) * 8 + (cl >> 3)) * 64 + (gl & 7) * 8 + (cl & 7);
+        sh[o] = h;
+        sl[o] = l;
+      }
+      if (__any_sync(0xffffffffu, col >= g0 + 256)) break;
+    }
+  }
+  __syncthreads();
+  const size_t base = ((size_t)kb * (size_t)(rows_pad >> 3) + (size_t)(g0 >> 3)) * 512;
+  for (int t = tid; t < 256 * 64 / 8; t += 256) {
+    reinterpret_cast<uint4*>(hi + base)[t] = reinterpret_cast<const uint4*>(sh)[t];
+    reinterpret_cast<uint4*>(lo + base)[t] = reinterpret_cast<const uint4*>(sl)[t];
+  }
+}
+
 template <class T>
 __global__ void tiled_from_colmajor_kernel(const T* __restrict__ src, int k, int rows, long long ld, int rows_pad,
                                            int k_pad, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
@@ -197,6 +247,21 @@ void tiled_from_csc(Context& ctx, const int* csc_p, const int* csc_i, const doub
   CG_CUDA(cudaMemsetAsync(op.lo, 0, n * sizeof(__nv_bfloat16), ctx.stream));
   tiled_from_csc_kernel<<<(n_genes + 7) / 8, 256, 0, ctx.stream>>>(csc_p, csc_i, csc_x, n_genes, op.rows_pad, op.hi,
                                                                   op.lo);
+  ctx.stats.kernels++;
+  CG_CUDA(cudaGetLastError());
+}
+
+void tiled_from_csr(Context& ctx, const int* csr_p, const int* csr_i, const double* csr_x, int n_cells, int n_genes,
+                    TiledOperand& op) {
+  op.rows = n_genes;
+  op.k = n_cells;
+  op.rows_pad = (int)round_up(n_genes, GEMM_ROW_PAD);
+  op.k_pad = (int)round_up(n_cells, GEMM_K_PAD);
+  static_assert(GEMM_ROW_PAD % 256 == 0 && GEMM_K_PAD == 64, "tile shape of tiled_from_csr_kernel");
+  dim3 grid((unsigned)(op.k_pad / 64), (unsigned)(op.rows_pad / 256));
+  constexpr int smem = 2 * 256 * 64 * (int)sizeof(__nv_bfloat16);
+  CG_CUDA(cudaFuncSetAttribute(tiled_from_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  tiled_from_csr_kernel<<<grid, 256, smem, ctx.stream>>>(csr_p, csr_i, csr_x, n_cells, op.rows_pad, op.hi, op.lo);
   ctx.stats.kernels++;
   CG_CUDA(cudaGetLastError());
 }

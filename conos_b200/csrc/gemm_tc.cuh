@@ -54,6 +54,9 @@ void gemm_tn_bf16x3(Context& ctx, const GemmProblem* h_probs, int n_probs);
 // sparse cells x genes CSC -> operand with rows = genes, k = cells (op.hi/lo pre-allocated, elems(rows, k))
 void tiled_from_csc(Context& ctx, const int* csc_p, const int* csc_i, const double* csc_x, int n_cells, int n_genes,
                     TiledOperand& op);
+// same operand from the CSR-by-cell form (columns ascending inside a row): tile-wise, coalesced, no memset
+void tiled_from_csr(Context& ctx, const int* csr_p, const int* csr_i, const double* csr_x, int n_cells, int n_genes,
+                    TiledOperand& op);
 // dense column-major (k x rows, element (k, r) at r*ld + k) FP64 or FP32 -> operand
 void tiled_from_colmajor_f64(Context& ctx, const double* src, int k, int rows, long long ld, TiledOperand& op);
 void tiled_from_colmajor_f32(Context& ctx, const float* src, int k, int rows, long long ld, TiledOperand& op);

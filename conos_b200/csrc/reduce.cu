@@ -553,7 +553,7 @@ void ensure_grams(Context& ctx, Sample* const* samples, int n) {
       TiledOperand op;
       op.hi = hi[t - i0].p;
       op.lo = lo[t - i0].p;
-      tiled_from_csc(ctx, s->csc_p.p, s->csc_i.p, s->csc_x.p, s->n_cells, s->n_genes, op);
+      tiled_from_csr(ctx, s->csr_p.p, s->csr_i.p, s->csr_x.p, s->n_cells, s->n_genes, op);
       GemmProblem gp{op.hi, op.lo, op.hi, op.lo, op.rows_pad, op.rows_pad, op.k_pad, s->n_genes, s->n_genes, s->gram.p,
                      (long long)s->n_genes, 1, 1};
       gps.push_back(gp);
