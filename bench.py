@@ -337,9 +337,15 @@ def main():
         return con.buildGraph(fetch=True, world=wtuple, **kw)
 
     import ctypes as C
+    import gc
     # ---- device-resident throughput
     for _ in range(W):
         device_step()
+    # the panel holds ~10^6 Python strings (cell barcodes, gene names): a generation-2 collection of the cyclic GC walks
+    # all of them and lands, at random, as a 100-600 ms pause inside a step.  Everything allocated so far is parked in
+    # the permanent generation; the collector stays enabled for what the steps themselves allocate.
+    gc.collect()
+    gc.freeze()
     barrier()
     lib.cg_knn_timing(ctx.h, 1)
     sampler = ClockSampler(local_rank)
