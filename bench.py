@@ -43,7 +43,7 @@ CONFIGS = {
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the cross-kNN launch of this workload (56 problems of 50k x 50k),
 # main kernel + finish kernel, from the ncu --set full capture summarised in profiles/ (None until captured)
-KNN_DRAM_BYTES_PER_LAUNCH = 0.350210e9 + 0.560675e9 + 1.113106e9 + 0.647829e9
+KNN_DRAM_BYTES_PER_LAUNCH = 0.354947e9 + 0.564263e9 + 1.114550e9 + 0.640961e9
 KNN_DRAM_SOURCE = ("profiles/r01_ncu_knn_tc2_bench_config2.txt: dram read+write of knn_tc2_kernel + "
                    "knn_tc2_finish_kernel for the cross-kNN launch (56 problems of 50k x 50k); algorithmic bytes of "
                    "that launch 1.39e9 (fp32 panels in, idx+dist out); the excess is the candidate lists (written by "
