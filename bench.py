@@ -319,11 +319,14 @@ def main():
     kw = dict(k=cfg["k"], k_self=cfg["k_self"], space=cfg["space"], ncomps=cfg["ncomps"], n_odgenes=cfg["n_genes"])
 
     def barrier():
+        t1 = time.perf_counter()
         torch.cuda.synchronize()
         if world > 1:
             import torch.distributed as dist
             dist.barrier()
         torch.cuda.synchronize()
+        if os.environ.get("CONOS_BENCH_STAGES"):
+            sys.stderr.write(f"[barrier rank {rank}] {1e3 * (time.perf_counter() - t1):.1f} ms\n")
 
     def device_step():
         con.pairs = {}                                   # no cached reductions (updatePairs recomputes every pair)
@@ -354,8 +357,13 @@ def main():
     n_launch0 = ctx.kernel_launches()
     lib.cg_timer_start(ctx.h)
     t0 = time.perf_counter()
+    step_ms = []
     for _ in range(K):
+        t1 = time.perf_counter()
         g = device_step()
+        step_ms.append(round(1e3 * (time.perf_counter() - t1), 1))
+    if os.environ.get("CONOS_BENCH_STAGES"):
+        sys.stderr.write(f"[steps rank {rank}] {step_ms}\n")
     ms = C.c_double(0)
     lib.cg_timer_stop(ctx.h, C.byref(ms))
     barrier()
@@ -374,6 +382,19 @@ def main():
         lsum = torch.tensor([float(launches)], device="cuda")
         dist.all_reduce(lsum)
         launches = int(lsum.item())
+    if os.environ.get("CONOS_BENCH_STAGES"):   # debugging aid: one more step with the per-stage profile, every rank
+        sys.stderr.write(f"[timed rank {rank}] last timed step py " +
+                         json.dumps({k: round(v, 1) for k, v in con.timings.items()}) + "\n")
+        lib.cg_profile(ctx.h, 1)
+        t1 = time.perf_counter()
+        device_step()
+        dt = 1e3 * (time.perf_counter() - t1)
+        buf = C.create_string_buffer(8192)
+        lib.cg_profile_dump(ctx.h, buf, 8192)
+        lib.cg_profile(ctx.h, 0)
+        st = {kv.split("=")[0]: float(kv.split("=")[1]) for kv in buf.value.decode().split(";") if kv}
+        sys.stderr.write(f"[stages rank {rank}] wall {dt:.1f} ms " + json.dumps({k: round(v, 1) for k, v in st.items() if "." not in k}) +
+                         " py " + json.dumps({k: round(v, 1) for k, v in con.timings.items()}) + "\n")
     n_inter = con._n_inter_edges
     if world > 1:
         import torch.distributed as dist
