@@ -395,6 +395,8 @@ def main():
         st = {kv.split("=")[0]: float(kv.split("=")[1]) for kv in buf.value.decode().split(";") if kv}
         sys.stderr.write(f"[stages rank {rank}] wall {dt:.1f} ms " + json.dumps({k: round(v, 1) for k, v in st.items() if "." not in k}) +
                          " py " + json.dumps({k: round(v, 1) for k, v in con.timings.items()}) + "\n")
+    if os.environ.get("CONOS_BENCH_TC_PROJECTION"):   # debugging aid: A/B of the projection engine in the e2e loop
+        lib.cg_set_option(ctx.h, b"tc_projection", float(os.environ["CONOS_BENCH_TC_PROJECTION"]))
     n_inter = con._n_inter_edges
     if world > 1:
         import torch.distributed as dist
@@ -406,12 +408,22 @@ def main():
         e2e_step()
     barrier()
     t0 = time.perf_counter()
-    K2 = max(1, min(K, 3))
+    K2 = max(1, min(K, 10))
     e2e_each = []
     for _ in range(K2):
+        if os.environ.get("CONOS_BENCH_E2E_STAGES"):   # debugging aid (adds synchronisation: not a bench number)
+            lib.cg_profile(ctx.h, 1)
+        redo0 = (ctx.stat("knn_redo_blocks"), ctx.stat("eig_redo_pairs"))
         t1 = time.perf_counter()
         g_host = e2e_step()
+        if os.environ.get("CONOS_BENCH_E2E_STAGES"):
+            buf = C.create_string_buffer(8192)
+            lib.cg_profile_dump(ctx.h, buf, 8192)
+            lib.cg_profile(ctx.h, 0)
+            sys.stderr.write(f"[e2e rank {rank}] {1e3 * (time.perf_counter() - t1):.1f} ms " + buf.value.decode() + "\n")
         e2e_each.append({"ms": round(1e3 * (time.perf_counter() - t1), 2),
+                         "knn_redo_blocks": int(ctx.stat("knn_redo_blocks") - redo0[0]),
+                         "eig_redo_pairs": int(ctx.stat("eig_redo_pairs") - redo0[1]),
                          **{k: round(v, 1) for k, v in con.timings.items() if k != "total_ms"}})
     barrier()
     e2e_s = time.perf_counter() - t0

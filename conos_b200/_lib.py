@@ -159,6 +159,13 @@ class Context:
     def kernel_launches(self) -> int:
         return int(self.lib.cg_kernel_launches(self.h))
 
+    def stat(self, name: str) -> float:
+        """Counter of the library context ("knn_redo_blocks", "eig_redo_pairs", "kernel_launches")."""
+        v = C.c_double(0.0)
+        if self.lib.cg_get_stat(self.h, name.encode(), C.byref(v)) != 0:
+            raise KeyError(name)
+        return v.value
+
     def __del__(self):
         try:
             self.close()

@@ -103,6 +103,10 @@ int cg_set_option(cg_context* ctx, const char* name, double value) {
     ctx->c.exact_reduction = value != 0.0;
     return 0;
   }
+  if (strcmp(name, "tc_projection") == 0) {
+    ctx->c.tc_projection = value != 0.0;
+    return 0;
+  }
   if (strcmp(name, "tc_eig_max_sweeps") == 0) {
     ctx->c.tc_eig_max_sweeps = (int)value;
     return 0;
@@ -120,6 +124,10 @@ int cg_set_option(cg_context* ctx, const char* name, double value) {
 
 int cg_get_stat(cg_context* ctx, const char* name, double* value) {
   if (!ctx || !name || !value) return 1;
+  if (strcmp(name, "eig_redo_pairs") == 0) {
+    *value = (double)ctx->c.eig_redo_pairs;
+    return 0;
+  }
   if (strcmp(name, "knn_redo_blocks") == 0) {
     *value = (double)ctx->c.knn_redo_blocks;
     return 0;

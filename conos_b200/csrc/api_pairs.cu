@@ -199,6 +199,7 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
     DevBuf<int> d_stage_i(stage_i);
     std::vector<WBuildProblem> wprobs;
     std::vector<ProjProblem> pprobs;
+    std::vector<int> psample, pgenes;  // sample index and gene count of every projection problem
     std::vector<KnnProblem> kprobs;
     std::vector<MnnProblem> mprobs;
     int d_pad_all = 0, d_all = -1;
@@ -298,6 +299,10 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
         pprobs.push_back(ProjProblem{sa.csr_p.p, sa.csr_i.p, sa.csr_x.p, B.Wa.p, B.shift.p, B.ta.p, B.p64a.p, B.na});
         pprobs.push_back(
             ProjProblem{sb.csr_p.p, sb.csr_i.p, sb.csr_x.p, B.Wb.p, B.shift.p + B.d_pad, B.tb.p, B.p64b.p, B.nb});
+        psample.push_back(pr.a);
+        psample.push_back(pr.b);
+        pgenes.push_back(sa.n_genes);
+        pgenes.push_back(sb.n_genes);
       }
       B.i_ab.alloc((size_t)B.na * P.k1);
       B.d_ab.alloc((size_t)B.na * P.k1);
@@ -319,7 +324,17 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
     if (!wprobs.empty()) {
       StageScope sc(c, "projection");
       build_projection_operands(c, wprobs.data(), (int)wprobs.size(), d_all, d_pad_all);
-      project_and_prep(c, pprobs.data(), (int)pprobs.size(), d_all, d_pad_all, metric);
+      // default mode: one tensor-core GEMM per sample for all of its pair sides (fp32 accumulation, the accuracy class
+      // of the tensor-core rotations it multiplies).  The FP64 SpMM serves the exact mode, rotations the caller
+      // supplied (exact inputs: the projection stays exact too), d > 32, gene universes beyond the dense operand and
+      // callers that want the raw FP64 projections back
+      bool tc_proj = c.tc_projection && !c.exact_reduction && !ctx->keep_projections && d_pad_all == 32;
+      for (int gcount : pgenes) tc_proj = tc_proj && gcount <= 4096;
+      for (int q = 0; q < nb_pairs; ++q) tc_proj = tc_proj && pairs[p0 + q].rot == nullptr;
+      if (tc_proj)
+        project_and_prep_tc(c, pprobs.data(), psample.data(), pgenes.data(), (int)pprobs.size(), d_all, metric);
+      else
+        project_and_prep(c, pprobs.data(), (int)pprobs.size(), d_all, d_pad_all, metric);
       if (ctx->keep_projections) {
         for (int q = 0; q < nb_pairs; ++q) {
           cg_context::PairKeep& keep = ctx->kept[p0 + q];

@@ -114,9 +114,11 @@ struct Context {
   // 1 = streaming tensor-core kernel only, 2 = exact SIMT kernel only
   int knn_engine = 0;
   int knn_cand_cap = 64;          // candidate slots per (row, half) the two-phase kernel may use (tests shrink it)
+  uint64_t eig_redo_pairs = 0;    // pairs the tensor-core eigen solver handed to the FP64 driver
   uint64_t knn_redo_blocks = 0;   // 256-row blocks the streaming kernel had to recompute
   // 1: FP64 reductions (atomics Gram, explicit covariance, plain subspace iteration) instead of the tensor-core path
   bool exact_reduction = false;
+  bool tc_projection = true;   // default mode: project through the tensor-core GEMM (false: FP64 SpMM everywhere)
   int tc_eig_max_sweeps = 40;  // tensor-core eigen solver: sweeps before a problem is handed to the FP64 driver
   // optional per-stage wall-clock profile (stream synchronised at both ends of a stage)
   bool profile = false;

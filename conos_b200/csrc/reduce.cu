@@ -281,6 +281,7 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
       }
       CG_CUDA(cudaStreamSynchronize(st));
       if (redo.empty()) return;
+      ctx.eig_redo_pairs += redo.size();
       if (ctx.profile) ctx.stage_ms["reduction.eig.fp64_redo_pairs"] += (double)redo.size();
       todo = redo;
     }

@@ -3,6 +3,9 @@
 #include <cuda_fp16.h>
 
 #include "sparse.cuh"
+#include "gemm_tc.cuh"
+#include <map>
+#include <algorithm>
 
 namespace cg {
 namespace {
@@ -257,6 +260,191 @@ void project_and_prep(Context& ctx, const ProjProblem* h_probs, int n_probs, int
   }
   CG_CUDA(cudaGetLastError());
   CG_CUDA(cudaStreamSynchronize(ctx.stream));
+}
+
+
+// ---------------------------------------------------------------------------------------- tensor-core projection
+namespace {
+
+// dense bf16 hi/lo operand with rows = cells, k = genes, built tile-wise from the CSR form: a CTA owns 256 cells x
+// 64 genes (32 KB contiguous in the operand layout); every thread drops the non-zeros of one cell row that fall into
+// the gene range into the zeroed shared-memory image, which leaves with coalesced 16-byte stores.
+__global__ void __launch_bounds__(256) cells_operand_kernel(const int* __restrict__ csr_p, const int* __restrict__ csr_i,
+                                                            const double* __restrict__ csr_x, int n_cells, int rows_pad,
+                                                            __nv_bfloat16* __restrict__ hi,
+                                                            __nv_bfloat16* __restrict__ lo) {
+  extern __shared__ __align__(16) unsigned char co_smem[];
+  __nv_bfloat16* sh = reinterpret_cast<__nv_bfloat16*>(co_smem);
+  __nv_bfloat16* sl = sh + 256 * 64;
+  const int kb = blockIdx.y, r0 = blockIdx.x * 256, k0 = kb * 64;
+  const int tid = threadIdx.x;
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (int t = tid; t < 256 * 64 / 8; t += 256) {
+    reinterpret_cast<uint4*>(sh)[t] = z;
+    reinterpret_cast<uint4*>(sl)[t] = z;
+  }
+  __syncthreads();
+  const int c = r0 + tid;
+  if (c < n_cells) {
+    const int b = csr_p[c], e = csr_p[c + 1];
+    int lo_i = b, hi_i = e;  // first entry with column >= k0
+    while (lo_i < hi_i) {
+      const int mid = (lo_i + hi_i) >> 1;
+      if (csr_i[mid] < k0) lo_i = mid + 1; else hi_i = mid;
+    }
+    for (int t = lo_i; t < e; ++t) {
+      const int col = csr_i[t];
+      if (col >= k0 + 64) break;
+      const float x = (float)csr_x[t];
+      const __nv_bfloat16 h = __float2bfloat16_rn(x);
+      const int kk = col - k0;
+      const int o = ((tid >> 3) * 8 + (kk >> 3)) * 64 + (tid & 7) * 8 + (kk & 7);
+      sh[o] = h;
+      sl[o] = __float2bfloat16_rn(x - __bfloat162float(h));
+    }
+  }
+  __syncthreads();
+  const size_t base = ((size_t)kb * (size_t)(rows_pad >> 3) + (size_t)(r0 >> 3)) * 512;
+  for (int t = tid; t < 256 * 64 / 8; t += 256) {
+    reinterpret_cast<uint4*>(hi + base)[t] = reinterpret_cast<const uint4*>(sh)[t];
+    reinterpret_cast<uint4*>(lo + base)[t] = reinterpret_cast<const uint4*>(sl)[t];
+  }
+}
+
+struct WSide {
+  const double* W;  // [n_genes][32]
+};
+
+// B operand of the projection GEMM: rows = 32 * side + component (256 rows = up to 8 sides), k = gene
+__global__ void w_operand_kernel(const WSide* __restrict__ sides, int n_sides, int n_genes, int k_pad,
+                                 __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)256 * k_pad) return;
+  const int r = (int)(t & 255), kk = (int)(t >> 8);
+  const int side = r >> 5, comp = r & 31;
+  float x = 0.f;
+  if (side < n_sides && kk < n_genes) x = (float)sides[side].W[(size_t)kk * 32 + comp];
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  const size_t o = tiled_operand_offset(r, kk, 256);
+  hi[o] = h;
+  lo[o] = __float2bfloat16_rn(x - __bfloat162float(h));
+}
+
+struct ProjFinish {
+  const float* C;       // GEMM output, column-major n_rows x 256: this side's 32 columns start at C
+  const double* shift;  // [32]
+  float* tiled;         // the kNN panel (three copies)
+  int n_rows;
+};
+
+// one thread per cell row: shift, cast, canonical normalisation, the three panel copies (same tail as project_kernel)
+__global__ void __launch_bounds__(128) project_finish_kernel(const ProjFinish* __restrict__ probs, int d, int metric) {
+  constexpr int D_PAD = 32;
+  const ProjFinish pb = probs[blockIdx.y];
+  const int n_pad = (int)((pb.n_rows + KNN_ROW_PAD - 1) / KNN_ROW_PAD * KNN_ROW_PAD);
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_pad) return;
+  float v[D_PAD];
+#pragma unroll
+  for (int c = 0; c < D_PAD; ++c)
+    v[c] = (row < pb.n_rows && c < d) ? (float)((double)pb.C[(size_t)c * pb.n_rows + row] - pb.shift[c]) : 0.0f;
+  float inv = 1.0f;
+  if (metric == METRIC_ANGULAR) {
+    float ss = 0.0f;
+#pragma unroll
+    for (int c = 0; c < D_PAD; ++c)
+      if (c < d) ss = fmaf(v[c], v[c], ss);
+    inv = ss > 0.0f ? 1.0f / sqrtf(ss) : 0.0f;
+  }
+  float* dst = pb.tiled + (size_t)(row >> 3) * (8 * D_PAD) + (size_t)(row & 7) * 4;
+  __half* dst16 = reinterpret_cast<__half*>(pb.tiled + (size_t)n_pad * D_PAD);
+  float* dstrm = pb.tiled + (size_t)n_pad * D_PAD * 3 / 2 + (size_t)row * D_PAD;
+#pragma unroll
+  for (int c = 0; c < D_PAD; ++c) {
+    const float x = (d < D_PAD && c == D_PAD - 1) ? -1.0f : v[c] * inv;
+    dst[(c >> 2) * 32 + (c & 3)] = x;
+    dst16[knn_tiled16_offset(row, c, D_PAD)] = __float2half_rn(x);
+    dstrm[c] = x;
+  }
+}
+
+}  // namespace
+
+void project_and_prep_tc(Context& ctx, const ProjProblem* h_probs, const int* sample_of, const int* n_genes_of,
+                         int n_probs, int d, Metric metric) {
+  if (n_probs == 0) return;
+  cudaStream_t st = ctx.stream;
+  // sides grouped by sample (stable)
+  std::map<int, std::vector<int>> by_sample;
+  for (int p = 0; p < n_probs; ++p) by_sample[sample_of[p]].push_back(p);
+  constexpr int co_smem = 2 * 256 * 64 * (int)sizeof(__nv_bfloat16);
+  CG_CUDA(cudaFuncSetAttribute(cells_operand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, co_smem));
+  // one set of operand / output buffers sized for the largest sample, reused in stream order
+  size_t max_x = 0, max_w = 0, max_c = 0, n_chunks = 0;
+  for (auto& kv : by_sample) {
+    const size_t rp = round_up(h_probs[kv.second[0]].n_rows, GEMM_ROW_PAD);
+    const size_t kp = round_up(n_genes_of[kv.second[0]], GEMM_K_PAD);
+    max_x = std::max(max_x, rp * kp);
+    max_w = std::max(max_w, (size_t)256 * kp);
+    max_c = std::max(max_c, (size_t)h_probs[kv.second[0]].n_rows * 256);
+    n_chunks += (kv.second.size() + 7) / 8;
+  }
+  DevBuf<__nv_bfloat16> xh(max_x), xl(max_x), wh(max_w * n_chunks), wl(max_w * n_chunks);
+  DevBuf<float> Cbuf(max_c);
+  // the side tables of every chunk travel in one upload each
+  std::vector<WSide> hw;
+  std::vector<ProjFinish> hf;
+  for (auto& kv : by_sample)
+    for (size_t s0 = 0; s0 < kv.second.size(); s0 += 8) {
+      const int ns = (int)std::min<size_t>(8, kv.second.size() - s0);
+      for (int j = 0; j < 8; ++j) {
+        if (j < ns) {
+          const ProjProblem& pp = h_probs[kv.second[s0 + j]];
+          hw.push_back(WSide{pp.W});
+          hf.push_back(ProjFinish{Cbuf.p + (size_t)j * 32 * pp.n_rows, pp.shift, pp.tiled, pp.n_rows});
+        } else {
+          hw.push_back(WSide{nullptr});
+          hf.push_back(ProjFinish{nullptr, nullptr, nullptr, 0});
+        }
+      }
+    }
+  DevBuf<WSide> dws;
+  DevBuf<ProjFinish> dfs;
+  dws.upload(hw.data(), hw.size(), st);
+  dfs.upload(hf.data(), hf.size(), st);
+  size_t chunk = 0;
+  for (auto& kv : by_sample) {
+    const std::vector<int>& sides = kv.second;
+    const ProjProblem& first = h_probs[sides[0]];
+    const int n_cells = first.n_rows, n_genes = n_genes_of[sides[0]];
+    TiledOperand opx;
+    opx.rows = n_cells;
+    opx.k = n_genes;
+    opx.rows_pad = (int)round_up(n_cells, GEMM_ROW_PAD);
+    opx.k_pad = (int)round_up(n_genes, GEMM_K_PAD);
+    opx.hi = xh.p;
+    opx.lo = xl.p;
+    cells_operand_kernel<<<dim3((unsigned)(opx.rows_pad / 256), (unsigned)(opx.k_pad / 64)), 256, co_smem, st>>>(
+        first.rp, first.ci, first.xv, n_cells, opx.rows_pad, opx.hi, opx.lo);
+    ctx.stats.kernels++;
+    // the W operands of all chunks of this sample first, so that the GEMMs and finishes run back to back
+    for (size_t s0 = 0; s0 < sides.size(); s0 += 8, ++chunk) {
+      const int ns = (int)std::min<size_t>(8, sides.size() - s0);
+      __nv_bfloat16* whc = wh.p + chunk * max_w;
+      __nv_bfloat16* wlc = wl.p + chunk * max_w;
+      w_operand_kernel<<<(unsigned)(((size_t)256 * opx.k_pad + 255) / 256), 256, 0, st>>>(dws.p + chunk * 8, ns, n_genes,
+                                                                                         opx.k_pad, whc, wlc);
+      ctx.stats.kernels++;
+      GemmProblem gp{opx.hi, opx.lo, whc, wlc, opx.rows_pad, 256, opx.k_pad, n_cells, 32 * ns, Cbuf.p,
+                     (long long)n_cells, 0};
+      gemm_tn_bf16x3(ctx, &gp, 1);
+      const int n_pad = (int)round_up(n_cells, KNN_ROW_PAD);
+      project_finish_kernel<<<dim3((unsigned)((n_pad + 127) / 128), (unsigned)ns), 128, 0, st>>>(dfs.p + chunk * 8, d,
+                                                                                                 (int)metric);
+      ctx.stats.kernels++;
+    }
+  }
+  CG_CUDA(cudaGetLastError());
 }
 
 }  // namespace cg

@@ -49,6 +49,12 @@ struct ProjProblem {
   int n_rows;
 };
 
+// Tensor-core projection (default mode, d_pad = 32): the projections of ALL pair sides of a sample are one bf16x3 GEMM
+// cells x genes  times  genes x (32 * sides); `sample_of[p]` / `n_genes_of[p]` give the sample and its gene count.
+// Same outputs as project_and_prep (the three copies of every kNN panel); fp32 accumulation instead of FP64.
+void project_and_prep_tc(Context& ctx, const ProjProblem* h_probs, const int* sample_of, const int* n_genes_of,
+                         int n_probs, int d, Metric metric);
+
 // W[col, c] = gene_pos[col] >= 0 ? f[gene_pos[col]] * rot[gene_pos[col], c] : 0
 // shift[c]  = sum_g cvec[g] * rot[g, c]     (cvec = the centering the reference subtracts, in od-gene order)
 struct WBuildProblem {

@@ -60,9 +60,13 @@ int cg_timer_stop(cg_context* ctx, double* ms);
  * only.  "knn_cand_cap": candidate slots per (query row, half tile) of the two-phase kernel, 1..64 (tests
  * shrink it to force the overflow path).  Results are identical for every setting.
  * "tc_eig_max_sweeps" (default 40): sweeps of the tensor-core eigen solver before a pair that has not reached
- * irlba's tolerance is handed to the FP64 driver (tests set 1 to force that path). */
+ * irlba's tolerance is handed to the FP64 driver (tests set 1 to force that path).
+ * "tc_projection" (default 1): in the default mode the projections of device-computed rotations run as one bf16x3
+ * tensor-core GEMM per sample (fp32 accumulation); 0 keeps the FP64 sparse product, which the exact mode, cached
+ * rotations and cg_keep_projections always use. */
 int cg_set_option(cg_context* ctx, const char* name, double value);
-/* counters: "knn_redo_blocks" (256-row blocks recomputed by the streaming kernel), "kernel_launches" */
+/* counters: "knn_redo_blocks" (256-row blocks recomputed by the streaming kernel), "eig_redo_pairs" (pairs the
+ * tensor-core eigen solver handed to the FP64 driver), "kernel_launches" */
 int cg_get_stat(cg_context* ctx, const char* name, double* value);
 /* optional per-stage wall-clock profile: enable (resets), then dump "name=ms;name=ms;..." into buf */
 int cg_profile(cg_context* ctx, int enable);

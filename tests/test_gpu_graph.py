@@ -493,3 +493,28 @@ def test_gene_universe_subsetting(ctx, oracle, small_panel):
     for key, red in ref["pairs"].items():
         assert con.pairs["PCA"][key]["genes"] == red["genes"]
     _graphs_equal(g, ref["graph"], rtol=1e-6)
+
+
+def test_tensor_core_projection_matches_fp64_projection(ctx, small_panel):
+    """Default mode projects device-computed rotations with one bf16x3 tensor-core GEMM per sample (fp32 accumulation);
+    with "tc_projection" = 0 the same rotations go through the FP64 sparse product.  The rotations are identical in
+    both runs, so the graphs differ only where a neighbour was tied to ~1e-6: the same edges up to a handful, and
+    the same weights on the common ones (getPcaBasedNeighborMatrix, R/conos.R:776-833)."""
+    import conos_b200
+    graphs = {}
+    try:
+        for tc in (1, 0):
+            ctx.check(ctx.lib.cg_set_option(ctx.h, b"tc_projection", float(tc)))
+            con = conos_b200.Conos(small_panel, ctx=ctx)
+            g = con.buildGraph(k=10, k_self=5, space="PCA", ncomps=20, n_odgenes=300)
+            graphs[tc] = {(a, b): w for a, b, w in zip(g.edge_from.tolist(), g.edge_to.tolist(), g.weight.tolist())}
+            rot = con.pairs["PCA"]
+            graphs[(tc, "rot")] = {key: red["CPC"] for key, red in rot.items()}
+    finally:
+        ctx.lib.cg_set_option(ctx.h, b"tc_projection", 1.0)
+    for key, r in graphs[(1, "rot")].items():
+        assert np.array_equal(r, graphs[(0, "rot")][key])
+    a, b = graphs[1], graphs[0]
+    common = set(a) & set(b)
+    assert len(common) / len(set(a) | set(b)) > 0.995
+    np.testing.assert_allclose([a[e] for e in sorted(common)], [b[e] for e in sorted(common)], rtol=2e-4, atol=1e-6)
