@@ -424,6 +424,8 @@ def main():
         e2e_each.append({"ms": round(1e3 * (time.perf_counter() - t1), 2),
                          "knn_redo_blocks": int(ctx.stat("knn_redo_blocks") - redo0[0]),
                          "eig_redo_pairs": int(ctx.stat("eig_redo_pairs") - redo0[1]),
+                         "scratch_pool_mb": round(ctx.stat("scratch_pool_reserved_bytes") / 2**20),
+                         "panel_pool_mb": round(ctx.stat("panel_pool_reserved_bytes") / 2**20),
                          **{k: round(v, 1) for k, v in con.timings.items() if k != "total_ms"}})
     barrier()
     e2e_s = time.perf_counter() - t0

@@ -407,7 +407,7 @@ class Conos:
                 continue
             nr, nc = C.c_int32(0), C.c_int32(0)
             self.ctx.check(lib.cg_pair_reduction(h, slot, C.byref(nr), C.byref(nc), None, None))
-            rot = np.zeros((nr.value, nc.value), order="F")
+            rot = np.empty((nr.value, nc.value), order="F")
             nv = np.zeros((2, nc.value)) if score_component_variance else None
             self.ctx.check(lib.cg_pair_reduction(h, slot, None, None, ptr(rot, C.c_double), ptr(nv, C.c_double)))
             cache[key] = PairEntry(od, self._gene_names, CPC=rot)

@@ -55,6 +55,15 @@ int cg_init(int device, cg_context** out) {
     CG_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t thr = UINT64_MAX;
     CG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    // resident panel buffers come from their own pool: same sizes every upload, so they recycle exactly and leave
+    // the scratch pool's layout alone
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    CG_CUDA(cudaMemPoolCreate(&ctx->c.panel_pool, &props));
+    CG_CUDA(cudaMemPoolSetAttribute(ctx->c.panel_pool, cudaMemPoolAttrReleaseThreshold, &thr));
   }
   *out = ctx;
   CG_API_END(ctx)
@@ -67,6 +76,7 @@ void cg_shutdown(cg_context* ctx) {
     cudaStreamSynchronize(ctx->c.stream);
     cudaStreamDestroy(ctx->c.stream);
   }
+  if (ctx->c.panel_pool) cudaMemPoolDestroy(ctx->c.panel_pool);
   delete ctx;
 }
 
@@ -124,6 +134,16 @@ int cg_set_option(cg_context* ctx, const char* name, double value) {
 
 int cg_get_stat(cg_context* ctx, const char* name, double* value) {
   if (!ctx || !name || !value) return 1;
+  if (strcmp(name, "scratch_pool_reserved_bytes") == 0 || strcmp(name, "panel_pool_reserved_bytes") == 0) {
+    cudaMemPool_t pool = ctx->c.panel_pool;
+    if (name[0] == 's' && cudaDeviceGetDefaultMemPool(&pool, ctx->c.device) != cudaSuccess)
+      return ::cg::fail(ctx, "no default memory pool");
+    uint64_t v = 0;
+    if (!pool || cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &v) != cudaSuccess)
+      return ::cg::fail(ctx, "memory pool query failed");
+    *value = (double)v;
+    return 0;
+  }
   if (strcmp(name, "eig_redo_pairs") == 0) {
     *value = (double)ctx->c.eig_redo_pairs;
     return 0;

@@ -13,7 +13,8 @@ struct cg_context {
   // reductions / projections kept from the last cg_pairs_edges call (host copies, for the pairs cache and tests)
   struct PairKeep {
     int n_rows = 0, n_cols = 0;
-    std::vector<double> rot;  // column-major n_rows x n_cols
+    std::vector<double> rot;  // column-major n_rows x n_cols (caller-supplied rotations)
+    const double* rot_host = nullptr;  // where the host copy lives: rot.data() or the context's pinned arena
     std::vector<double> nv;   // [2][n_cols] or empty
     int pn[2] = {0, 0};
     std::vector<double> proj[2];  // column-major n x ncomps

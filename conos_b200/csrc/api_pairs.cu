@@ -48,6 +48,7 @@ int cg_panel_create(cg_context* ctx, const cg_sample* samples, int n_samples, cg
     CG_CHECK(ctx && samples && out && n_samples > 0, "bad argument");
     CG_CUDA(cudaSetDevice(ctx->c.device));
   CG_BIND(ctx);
+    ::cg::PoolBinding pool_bind(ctx->c.panel_pool);
     pn = new cg_panel();
     pn->ctx = ctx;
     pn->samples.resize(n_samples);
@@ -137,6 +138,7 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
   if (!*edges) *edges = new cg_edges();
   EdgeTable& out = (*edges)->t;
   ctx->kept.clear();
+  ctx->c.rot_arena.reset();
   ctx->kept.resize(n_pairs);
   const int S = (int)panel->samples.size();
   const Metric metric = (Metric)P.metric;
@@ -229,6 +231,7 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
       keep.n_rows = R.n_rows;
       keep.n_cols = R.n_cols;
       keep.rot = std::move(R.h_rot);
+      keep.rot_host = R.h_rot_pinned ? R.h_rot_pinned : keep.rot.data();
       keep.nv = R.h_nv;
       if (P.space == CG_SPACE_CCA) {
         KnnPanel pa, pbn;
@@ -378,7 +381,7 @@ int cg_pair_reduction(cg_context* ctx, int which, int32_t* n_rows, int32_t* n_co
   const auto& k = ctx->kept[which];
   if (n_rows) *n_rows = k.n_rows;
   if (n_cols) *n_cols = k.n_cols;
-  if (rot && !k.rot.empty()) memcpy(rot, k.rot.data(), k.rot.size() * sizeof(double));
+  if (rot && k.rot_host) memcpy(rot, k.rot_host, (size_t)k.n_rows * k.n_cols * sizeof(double));
   if (nv && !k.nv.empty()) memcpy(nv, k.nv.data(), k.nv.size() * sizeof(double));
   CG_API_END(ctx)
 }

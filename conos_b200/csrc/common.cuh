@@ -42,6 +42,17 @@ inline cudaStream_t& bound_stream() {
   static thread_local cudaStream_t s = nullptr;
   return s;
 }
+// Optional second pool for long-lived buffers (the resident samples of a panel): kept apart from the per-call
+// scratch so that re-uploading a panel every call does not fragment the scratch pool.
+inline cudaMemPool_t& bound_pool() {
+  static thread_local cudaMemPool_t p = nullptr;
+  return p;
+}
+struct PoolBinding {
+  cudaMemPool_t prev;
+  explicit PoolBinding(cudaMemPool_t p) : prev(bound_pool()) { bound_pool() = p; }
+  ~PoolBinding() { bound_pool() = prev; }
+};
 struct StreamBinding {
   cudaStream_t prev;
   explicit StreamBinding(cudaStream_t s) : prev(bound_stream()) { bound_stream() = s; }
@@ -73,7 +84,8 @@ struct DevBuf {
     release();
     if (count == 0) return;
     owner = bound_stream();
-    if (owner) CG_CUDA(cudaMallocAsync(&p, count * sizeof(T), owner));
+    if (owner && bound_pool()) CG_CUDA(cudaMallocFromPoolAsync(&p, count * sizeof(T), bound_pool(), owner));
+    else if (owner) CG_CUDA(cudaMallocAsync(&p, count * sizeof(T), owner));
     else CG_CUDA(cudaMalloc(&p, count * sizeof(T)));
     n = count;
   }
@@ -91,6 +103,31 @@ struct DevBuf {
   void download(T* h, size_t count, cudaStream_t s) const {
     if (count) CG_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
   }
+};
+
+// Page-locked host arena for results that leave the device asynchronously (the rotations of the pairs cache):
+// blocks are kept between calls (grow-only), reset() rewinds the cursor.  A pointer stays valid until the next reset.
+struct PinnedArena {
+  std::vector<char*> blocks;
+  std::vector<size_t> caps;
+  size_t cur = 0, off = 0;
+  void reset() { cur = 0; off = 0; }
+  void* take(size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    while (cur < blocks.size() && off + bytes > caps[cur]) { ++cur; off = 0; }
+    if (cur == blocks.size()) {
+      const size_t cap = bytes > ((size_t)32 << 20) ? bytes : ((size_t)32 << 20);
+      char* b = nullptr;
+      CG_CUDA(cudaHostAlloc(&b, cap, cudaHostAllocDefault));
+      blocks.push_back(b);
+      caps.push_back(cap);
+      off = 0;
+    }
+    void* r = blocks[cur] + off;
+    off += bytes;
+    return r;
+  }
+  ~PinnedArena() { for (char* b : blocks) cudaFreeHost(b); }
 };
 
 // Per-context launch statistics (bench.py reports them as gpu_launches).
@@ -114,6 +151,8 @@ struct Context {
   // 1 = streaming tensor-core kernel only, 2 = exact SIMT kernel only
   int knn_engine = 0;
   int knn_cand_cap = 64;          // candidate slots per (row, half) the two-phase kernel may use (tests shrink it)
+  cudaMemPool_t panel_pool = nullptr;  // resident panel buffers (see PoolBinding)
+  PinnedArena rot_arena;          // host copies of the rotations of the current cg_pairs_edges call
   uint64_t eig_redo_pairs = 0;    // pairs the tensor-core eigen solver handed to the FP64 driver
   uint64_t knn_redo_blocks = 0;   // 256-row blocks the streaming kernel had to recompute
   // 1: FP64 reductions (atomics Gram, explicit covariance, plain subspace iteration) instead of the tensor-core path

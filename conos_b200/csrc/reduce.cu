@@ -85,6 +85,14 @@ int r_round_half_even(double x) { return (int)std::nearbyint(x); }  // default r
 void ensure_gram(Context& ctx, Sample& s);
 void ensure_grams(Context& ctx, Sample* const* samples, int n);
 
+// host copy of a device-computed rotation: asynchronous, into the context's page-locked arena
+static void download_rotation(Context& ctx, PairReduction& R) {
+  const size_t n = (size_t)R.n_rows * R.n_cols;
+  double* h = static_cast<double*>(ctx.rot_arena.take(n * sizeof(double)));
+  CG_CUDA(cudaMemcpyAsync(h, R.rot.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+  R.h_rot_pinned = h;
+}
+
 void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs, int n_pairs, const cg_params& P,
                              std::vector<PairReduction>& out) {
   cudaStream_t st = ctx.stream;
@@ -249,8 +257,7 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
             pbs[t].V[0], pbs[t].V[1], pbs[t].cols[0], pbs[t].cols[1], G, panel.samples[pr.a].n_genes,
             panel.samples[pr.b].n_genes, r, R.rot.p);
         ctx.stats.kernels++;
-        R.h_rot.resize((size_t)G * R.n_cols);
-        R.rot.download(R.h_rot.data(), R.h_rot.size(), st);
+        download_rotation(ctx, R);
         if (P.score_component_variance) {
           // trace(C) = sum_g f_g^2 (M_cc - n m_c^2) / (n - 1), c = the gene's column: from the host copies
           std::vector<double> th(2 * (size_t)r);
@@ -366,8 +373,7 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
         R.rot.alloc((size_t)b.G * R.n_cols);
         interleave_kernel<<<nblk((size_t)b.G * R.n_cols), 256, 0, st>>>(b.V[0].p, b.V[1].p, b.G, b.Gp, r, R.rot.p);
         ctx.stats.kernels++;
-        R.h_rot.resize((size_t)b.G * R.n_cols);
-        R.rot.download(R.h_rot.data(), R.h_rot.size(), st);
+        download_rotation(ctx, R);
         if (P.score_component_variance) {
           // nv_j = var(projection on v_j) / sum of column variances = theta_j / trace(C)   (R/conos.R:289-296)
           std::vector<double> th(2 * (size_t)r), tr(2);
@@ -483,8 +489,7 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
       R.rot.alloc((size_t)G * ncomp);
       CG_CUDA(cudaMemcpy2DAsync(R.rot.p, (size_t)G * sizeof(double), CPC.p, (size_t)Gp * sizeof(double),
                                 (size_t)G * sizeof(double), ncomp, cudaMemcpyDeviceToDevice, st));
-      R.h_rot.resize((size_t)G * ncomp);
-      R.rot.download(R.h_rot.data(), R.h_rot.size(), st);
+      download_rotation(ctx, R);
       if (P.score_component_variance) {
         std::vector<double> hD((size_t)ncomp * 2), htr(2);
         D.download(hD.data(), hD.size(), st);

@@ -10,7 +10,8 @@ struct PairReduction {
   int n_cols = 0;  // columns of the full rotation (self$pairs[[space]]$CPC)
   int d = 0;       // columns used: min(ncomps, n_cols)  (R/conclass.R:254-258)
   DevBuf<double> rot;         // column-major n_rows x n_cols
-  std::vector<double> h_rot;  // host copy for the pairs cache
+  std::vector<double> h_rot;  // host copy for the pairs cache (rotations the caller supplied)
+  const double* h_rot_pinned = nullptr;  // or: host copy inside ctx.rot_arena (filled asynchronously on the stream)
   std::vector<double> h_nv;   // [2][n_cols] when score.component.variance
   // CCA
   DevBuf<double> u, v;        // column-major n_u x d, n_v x d
