@@ -311,6 +311,100 @@ __global__ void __launch_bounds__(576, 1) handshake_probe_kernel(int mode, int p
   if (warp == 1) ptx::tmem_dealloc(tm, 512);
 }
 
+// Time-stamped hand-shake: the two-stage round trip of knn_tc2.cu (mode 1 of handshake_probe_kernel: MMAs, consumers
+// read their slice) with %clock64 samples from the issuing thread and from one consumer warp, all on the same SM.
+//   ts[p][0] issuer: `empty` seen      ts[p][1] issuer: MMAs + commit issued
+//   ts[p][2] consumer (warp 2, lane 0): `full` seen      ts[p][3] consumer: slice read (wait::ld done)
+//   ts[p][4] consumer: arrived on `empty`
+__global__ void __launch_bounds__(576, 1) stamp_probe_kernel(int passes, long long* ts) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base;
+  for (int t = threadIdx.x; t < 2 * 256 * 32; t += blockDim.x)
+    reinterpret_cast<__half*>(smem)[t] = __float2half(((t * 37) % 17 - 8) * 0.01f);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(acc_full + s, 1);
+      ptx::mbar_init(acc_empty + s, 16);
+    }
+    ptx::fence_mbar_init();
+  }
+  ptx::fence_proxy_async();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tmem_alloc(&tmem_base, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tm = tmem_base;
+  const bool rec = blockIdx.x == 0;
+  if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t a0 = ptx::smem_u32(smem), b0 = a0 + 256 * 64;
+      uint64_t ad[2][2], bd[2];
+      for (int mb = 0; mb < 2; ++mb)
+        for (int ks = 0; ks < 2; ++ks) ad[mb][ks] = ptx::umma_desc_kmajor_swz(a0 + mb * 128 * 64 + ks * 32, 64, 512);
+      for (int ks = 0; ks < 2; ++ks) bd[ks] = ptx::umma_desc_kmajor_swz(b0 + ks * 32, 64, 512);
+      constexpr uint32_t id128 = ptx::umma_idesc(0u, 128u, 128u);
+      const uint32_t full_a = ptx::smem_u32(acc_full), empty_a = ptx::smem_u32(acc_empty);
+      for (int p = 0; p < passes; ++p) {
+        const int stage = p & 1;
+        const uint32_t par = (uint32_t)(p >> 1) & 1u;
+        ptx::mbar_wait_a(empty_a + stage * 8, par ^ 1);
+        ptx::tc_fence_after();
+        if (rec) ts[(size_t)p * 8 + 0] = clock64();
+        ptx::mma_f16_ss(tm + stage * 256, ad[0][0], bd[0], id128, 0);
+        ptx::mma_f16_ss(tm + stage * 256, ad[0][1], bd[1], id128, 1);
+        ptx::mma_f16_ss(tm + stage * 256 + 128, ad[1][0], bd[0], id128, 0);
+        ptx::mma_f16_ss(tm + stage * 256 + 128, ad[1][1], bd[1], id128, 1);
+        ptx::mma_commit_a(full_a + stage * 8);
+        if (rec) ts[(size_t)p * 8 + 1] = clock64();
+      }
+      for (int s = 0; s < 2; ++s) {
+        const int last = ((passes - 1 - s) / 2) * 2 + s;
+        ptx::mbar_wait_a(empty_a + s * 8, (uint32_t)(last / 2) & 1u);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 2) {
+    const int e = warp - 2;
+    const int quarter = warp & 3;
+    const int sub = e >> 2;
+    const uint32_t tm_lane = tm + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t full_a = ptx::smem_u32(acc_full), empty_a = ptx::smem_u32(acc_empty);
+    const bool stamp = rec && e == 0 && lane == 0;
+    uint32_t sink = 0;
+    for (int p = 0; p < passes; ++p) {
+      const int stage = p & 1;
+      const uint32_t par = (uint32_t)(p >> 1) & 1u;
+      ptx::mbar_wait_a(full_a + stage * 8, par);
+      ptx::tc_fence_after();
+      if (stamp) ts[(size_t)p * 8 + 2] = clock64();
+      uint32_t v0[16], v1[16], v2[16], v3[16];
+      const uint32_t taddr = tm_lane + stage * 256 + sub * 64;
+      ptx::tmem_ld_32x32b_x16(taddr, v0);
+      ptx::tmem_ld_32x32b_x16(taddr + 16, v1);
+      ptx::tmem_ld_32x32b_x16(taddr + 32, v2);
+      ptx::tmem_ld_32x32b_x16(taddr + 48, v3);
+      ptx::tmem_wait_ld();
+      sink += v0[0] ^ v1[5] ^ v2[7] ^ v3[15];
+      if (stamp) ts[(size_t)p * 8 + 3] = clock64();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_a(empty_a + stage * 8);
+      if (stamp) ts[(size_t)p * 8 + 4] = clock64();
+    }
+    if (sink == 0x12345678u) ts[5] = sink;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  if (warp == 1) ptx::tmem_dealloc(tm, 512);
+}
+
 int main() {
   int dev = 0;
   CK(cudaSetDevice(dev));
@@ -354,5 +448,33 @@ int main() {
                (mode & 2) ? "lane0-poll " : ((mode & 32) ? "spin " : ""), (mode & 4) ? "no-mma " : "", (mode & 8) ? "4x128 " : ((mode & 16) ? "2x256 +ring " : "2x256 "),
                (double)h[0] / (double)h[1], (mode & 8) ? "  (a pass is HALF a kNN tile pass)" : "");
     }
+  {
+    const int passes = 4096;
+    long long* d_ts;
+    CK(cudaMalloc(&d_ts, (size_t)passes * 8 * sizeof(long long)));
+    CK(cudaMemset(d_ts, 0, (size_t)passes * 8 * sizeof(long long)));
+    CK(cudaFuncSetAttribute(stamp_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    stamp_probe_kernel<<<prop.multiProcessorCount, 576, smem>>>(passes, d_ts);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    std::vector<long long> h((size_t)passes * 8);
+    CK(cudaMemcpy(h.data(), d_ts, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    // steady state: passes 1024 .. passes-3
+    double d_issue = 0, d_commit_full = 0, d_read = 0, d_arrive = 0, d_empty_seen = 0, d_pass = 0;
+    int n = 0;
+    for (int p = 1024; p + 2 < passes; ++p, ++n) {
+      const long long* t = &h[(size_t)p * 8];
+      const long long* t2 = &h[(size_t)(p + 2) * 8];  // the next use of the same stage
+      d_issue += (double)(t[1] - t[0]);        // empty seen -> MMAs + commit issued
+      d_commit_full += (double)(t[2] - t[1]);  // commit issued -> consumer sees full (MMA execution + commit latency)
+      d_read += (double)(t[3] - t[2]);         // tcgen05.ld x4 + wait::ld
+      d_arrive += (double)(t[4] - t[3]);       // fence + syncwarp + arrive issued
+      d_empty_seen += (double)(t2[0] - t[4]);  // this warp arrived -> issuer sees the stage empty (all 16 warps)
+      d_pass += (double)(h[(size_t)(p + 1) * 8] - t[0]);
+    }
+    printf("stamped round trip (cycles, mean of %d passes): issue %.0f | commit->full seen %.0f | read %.0f | "
+           "arrive %.0f | arrive->empty seen %.0f | pass %.0f\n",
+           n, d_issue / n, d_commit_full / n, d_read / n, d_arrive / n, d_empty_seen / n, d_pass / n);
+  }
   return 0;
 }
