@@ -1018,6 +1018,8 @@ void top_eigenvectors_shared_gram(Context& ctx, const TcEigSample* samples, int 
     gprobs.push_back(GemmProblem{Mop[si].hi, Mop[si].lo, hs[si].Uh, hs[si].Ul, Mop[si].rows_pad, hs[si].u_rows_pad,
                                  Mop[si].k_pad, G, hs[si].n_cols, hs[si].V, (long long)G, 0});
   }
+  GemmPlan gplan;  // the same batch at every step of every sweep
+  gemm_plan(ctx, gprobs.data(), (int)gprobs.size(), gplan);
   const size_t smem = sizeof(EigSmem<B>);
   CG_CUDA(cudaFuncSetAttribute(eig_orth_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CG_CUDA(cudaFuncSetAttribute(eig_rr_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1046,7 +1048,7 @@ void top_eigenvectors_shared_gram(Context& ctx, const TcEigSample* samples, int 
     ctx.stats.kernels += 2;
     // Rayleigh-Ritz: Z = C Q through the shared Gram GEMM
     column(0, nullptr, nullptr, nullptr, 0);
-    gemm_tn_bf16x3(ctx, gprobs.data(), (int)gprobs.size());
+    gemm_run(ctx, gplan);
     column(3, nullptr, nullptr, nullptr, 0);
     eig_rr_kernel<B><<<n_probs, EIG_THREADS, smem, s>>>(dw.p, r, tol, 0);
     ctx.stats.kernels++;
@@ -1066,7 +1068,7 @@ void top_eigenvectors_shared_gram(Context& ctx, const TcEigSample* samples, int 
     gemm_steps += sweep;
     column(1, al.p + (size_t)1 * n_probs, nullptr, cc.p, 1);
     for (int i = 2; i <= sweep; ++i) {
-      gemm_tn_bf16x3(ctx, gprobs.data(), (int)gprobs.size());
+      gemm_run(ctx, gplan);
       column(2, al.p + (size_t)i * n_probs, be.p + (size_t)i * n_probs, cc.p, i);
     }
   }

@@ -210,7 +210,9 @@ inline unsigned nblk(size_t n, int t = 256) { return (unsigned)((n + t - 1) / t)
 
 }  // namespace
 
-void gemm_tn_bf16x3(Context& ctx, const GemmProblem* h_probs, int n_probs) {
+void gemm_plan(Context& ctx, const GemmProblem* h_probs, int n_probs, GemmPlan& plan) {
+  static_assert(sizeof(GemmTileRef) == sizeof(GemmTile), "tile table layout");
+  plan.n_tiles = 0;
   if (n_probs == 0) return;
   std::vector<GemmTile> tiles;
   for (int p = 0; p < n_probs; ++p) {
@@ -225,14 +227,24 @@ void gemm_tn_bf16x3(Context& ctx, const GemmProblem* h_probs, int n_probs) {
       }
   }
   if (tiles.empty()) return;
-  DevBuf<GemmProblem> dp;
-  DevBuf<GemmTile> dt;
-  dp.upload(h_probs, (size_t)n_probs, ctx.stream);
-  dt.upload(tiles.data(), tiles.size(), ctx.stream);
+  plan.probs.upload(h_probs, (size_t)n_probs, ctx.stream);
+  plan.tiles.upload(reinterpret_cast<const GemmTileRef*>(tiles.data()), tiles.size(), ctx.stream);
+  plan.n_tiles = (unsigned)tiles.size();
   CG_CUDA(cudaFuncSetAttribute(gemm_tn_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
-  gemm_tn_bf16x3_kernel<<<(unsigned)tiles.size(), G_THREADS, G_SMEM, ctx.stream>>>(dp.p, dt.p);
+}
+
+void gemm_run(Context& ctx, const GemmPlan& plan) {
+  if (plan.n_tiles == 0) return;
+  gemm_tn_bf16x3_kernel<<<plan.n_tiles, G_THREADS, G_SMEM, ctx.stream>>>(
+      plan.probs.p, reinterpret_cast<const GemmTile*>(plan.tiles.p));
   ctx.stats.kernels++;
   CG_CUDA(cudaGetLastError());
+}
+
+void gemm_tn_bf16x3(Context& ctx, const GemmProblem* h_probs, int n_probs) {
+  GemmPlan plan;
+  gemm_plan(ctx, h_probs, n_probs, plan);
+  gemm_run(ctx, plan);
   CG_CUDA(cudaStreamSynchronize(ctx.stream));
 }
 

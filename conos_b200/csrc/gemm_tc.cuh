@@ -50,6 +50,17 @@ struct GemmProblem {
 // batched: every problem is cut into 128 x 256 output tiles, one CTA per tile
 void gemm_tn_bf16x3(Context& ctx, const GemmProblem* h_probs, int n_probs);
 
+// The same batch launched many times (the filter steps of the eigen iteration): the problem and tile tables are
+// uploaded once, gemm_run only launches -- no host round trip between the steps of a sweep.
+struct GemmTileRef { int prob, mt, nt; };
+struct GemmPlan {
+  DevBuf<GemmProblem> probs;
+  DevBuf<GemmTileRef> tiles;
+  unsigned n_tiles = 0;
+};
+void gemm_plan(Context& ctx, const GemmProblem* h_probs, int n_probs, GemmPlan& plan);
+void gemm_run(Context& ctx, const GemmPlan& plan);
+
 // ---- operand builders (zero padded, hi/lo split) -------------------------------------------------------------
 // sparse cells x genes CSC -> operand with rows = genes, k = cells (op.hi/lo pre-allocated, elems(rows, k))
 void tiled_from_csc(Context& ctx, const int* csc_p, const int* csc_i, const double* csc_x, int n_cells, int n_genes,
