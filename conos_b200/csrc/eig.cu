@@ -783,8 +783,10 @@ __global__ void __launch_bounds__(256) tc_column_kernel(const TcSampleDev* __res
                                                         const float* __restrict__ al, const float* __restrict__ be,
                                                         const float* __restrict__ cc, const int* __restrict__ deg,
                                                         int step) {
+  // one CTA per column: 256 threads share the G rows (the column sum t is a block reduction)
+  __shared__ double t_part[8];
   const int lane = threadIdx.x & 31;
-  const int gc = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int gc = blockIdx.x;
   if (gc >= n_cols_total) return;
   const TcSampleDev sd = S[col_sample[gc]];
   const int col = col_local[gc];
@@ -796,7 +798,7 @@ __global__ void __launch_bounds__(256) tc_column_kernel(const TcSampleDev* __res
   const double t_old = sd.t[col];
   const float a = al ? al[pidx] : 0.f, b = be ? be[pidx] : 0.f, c = cc ? cc[pidx] : 0.f;
   double tacc = 0.0;
-  for (int g = lane; g < G; g += 32) {
+  for (int g = threadIdx.x; g < G; g += 256) {
     const double f = pd.f[g];
     const double m = sd.colsum ? sd.colsum[g] / n : 0.0;
     const size_t pc = (size_t)col * G + g;
@@ -828,7 +830,14 @@ __global__ void __launch_bounds__(256) tc_column_kernel(const TcSampleDev* __res
   }
   if (mode != 3) {
     tacc = warp_sum_d(tacc);
-    if (lane == 0) sd.t[col] = tacc;
+    if (lane == 0) t_part[threadIdx.x >> 5] = tacc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += t_part[w];
+      sd.t[col] = t;
+    }
   }
 }
 
@@ -1023,7 +1032,7 @@ void top_eigenvectors_shared_gram(Context& ctx, const TcEigSample* samples, int 
   const size_t smem = sizeof(EigSmem<B>);
   CG_CUDA(cudaFuncSetAttribute(eig_orth_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CG_CUDA(cudaFuncSetAttribute(eig_rr_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const unsigned colblocks = (unsigned)((n_cols_total + 7) / 8);
+  const unsigned colblocks = (unsigned)n_cols_total;  // one CTA per column
   DevBuf<int> deg((size_t)n_probs);
   auto column = [&](int mode, const float* a, const float* b, const float* c, int step) {
     tc_column_kernel<<<colblocks, 256, 0, s>>>(dS.p, dP.p, dcs.p, dcl.p, (int)n_cols_total, mode, a, b, c, deg.p,

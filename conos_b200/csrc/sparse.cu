@@ -437,7 +437,9 @@ void project_and_prep_tc(Context& ctx, const ProjProblem* h_probs, const int* sa
       ctx.stats.kernels++;
       GemmProblem gp{opx.hi, opx.lo, whc, wlc, opx.rows_pad, 256, opx.k_pad, n_cells, 32 * ns, Cbuf.p,
                      (long long)n_cells, 0};
-      gemm_tn_bf16x3(ctx, &gp, 1);
+      GemmPlan plan;  // stream-ordered: the tables are freed behind the kernel, no host synchronisation per sample
+      gemm_plan(ctx, &gp, 1, plan);
+      gemm_run(ctx, plan);
       const int n_pad = (int)round_up(n_cells, KNN_ROW_PAD);
       project_finish_kernel<<<dim3((unsigned)((n_pad + 127) / 128), (unsigned)ns), 128, 0, st>>>(dfs.p + chunk * 8, d,
                                                                                                  (int)metric);
