@@ -117,6 +117,11 @@ int cg_set_option(cg_context* ctx, const char* name, double value) {
     ctx->c.tc_projection = value != 0.0;
     return 0;
   }
+  if (strcmp(name, "tc_eig_degree") == 0) {
+    if (value < 2 || value > 64) return ::cg::fail(ctx, "tc_eig_degree must be in 2..64");
+    ctx->c.tc_eig_degree = (int)value;
+    return 0;
+  }
   if (strcmp(name, "tc_eig_max_sweeps") == 0) {
     ctx->c.tc_eig_max_sweeps = (int)value;
     return 0;

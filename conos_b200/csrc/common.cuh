@@ -158,6 +158,7 @@ struct Context {
   // 1: FP64 reductions (atomics Gram, explicit covariance, plain subspace iteration) instead of the tensor-core path
   bool exact_reduction = false;
   bool tc_projection = true;   // default mode: project through the tensor-core GEMM (false: FP64 SpMM everywhere)
+  int tc_eig_degree = 10;      // tensor-core eigen solver: largest Chebyshev degree of a sweep
   int tc_eig_max_sweeps = 40;  // tensor-core eigen solver: sweeps before a problem is handed to the FP64 driver
   // optional per-stage wall-clock profile (stream synchronised at both ends of a stage)
   bool profile = false;

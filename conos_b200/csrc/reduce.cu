@@ -238,7 +238,7 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
       CG_CUDA(cudaMemcpyAsync(d_c.p, h_c.data(), h_c.size() * sizeof(int), cudaMemcpyHostToDevice, st));
       {
         StageScope sc(ctx, "reduction.eig");
-        top_eigenvectors_shared_gram(ctx, ts.data(), S, tp.data(), (int)tp.size(), r, 1e-5, ctx.tc_eig_max_sweeps, 10,
+        top_eigenvectors_shared_gram(ctx, ts.data(), S, tp.data(), (int)tp.size(), r, 1e-5, ctx.tc_eig_max_sweeps, ctx.tc_eig_degree,
                                      tc_conv.data());
       }
       for (size_t t = 0; t < todo.size(); ++t) {

@@ -61,6 +61,8 @@ int cg_timer_stop(cg_context* ctx, double* ms);
  * shrink it to force the overflow path).  Results are identical for every setting.
  * "tc_eig_max_sweeps" (default 40): sweeps of the tensor-core eigen solver before a pair that has not reached
  * irlba's tolerance is handed to the FP64 driver (tests set 1 to force that path).
+ * "tc_eig_degree" (default 10, 2..64): largest Chebyshev degree of one sweep of that solver (8 / 10 / 12 / 14 were
+ * measured on configs[1]: 10.4 / 8.8 / 9.1 / 9.2 ms for the 56 eigenproblems).
  * "tc_projection" (default 1): in the default mode the projections of device-computed rotations run as one bf16x3
  * tensor-core GEMM per sample (fp32 accumulation); 0 keeps the FP64 sparse product, which the exact mode, cached
  * rotations and cg_keep_projections always use. */

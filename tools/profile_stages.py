@@ -11,11 +11,14 @@ ap.add_argument("--config", type=int, default=2)
 ap.add_argument("--n-samples", type=int, default=None)
 ap.add_argument("--n-cells", type=int, default=None)
 ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--option", action="append", default=[], help="name=value for cg_set_option")
 a = ap.parse_args()
 cfg = dict(CONFIGS[a.config])
 if a.n_samples: cfg["n_samples"] = a.n_samples
 if a.n_cells: cfg["n_cells"] = a.n_cells
 ctx = conos_b200.Context(0)
+for ov in a.option:
+    ctx.check(ctx.lib.cg_set_option(ctx.h, ov.split('=')[0].encode(), float(ov.split('=')[1])))
 panel = make_panel(a.config, cfg["n_samples"], cfg["n_cells"], cfg["n_genes"])
 con = conos_b200.Conos(panel, ctx=ctx)
 kw = dict(k=cfg["k"], k_self=cfg["k_self"], space=cfg["space"], ncomps=cfg["ncomps"], n_odgenes=cfg["n_genes"])
