@@ -518,3 +518,20 @@ def test_tensor_core_projection_matches_fp64_projection(ctx, small_panel):
     common = set(a) & set(b)
     assert len(common) / len(set(a) | set(b)) > 0.995
     np.testing.assert_allclose([a[e] for e in sorted(common)], [b[e] for e in sorted(common)], rtol=2e-4, atol=1e-6)
+
+
+def test_options_and_counters(ctx, small_panel):
+    """cg_set_option rejects unknown names and out-of-range values; cg_get_stat exposes the counters and the two
+    memory pools (include/conos_gpu.h); the resident panel lives in its own pool."""
+    import conos_b200
+    assert ctx.lib.cg_set_option(ctx.h, b"no_such_option", 1.0) != 0
+    assert ctx.lib.cg_set_option(ctx.h, b"tc_eig_degree", 1.0) != 0
+    assert ctx.lib.cg_set_option(ctx.h, b"tc_eig_degree", 10.0) == 0
+    with pytest.raises(KeyError):
+        ctx.stat("no_such_counter")
+    launches0 = ctx.stat("kernel_launches")
+    con = conos_b200.Conos(small_panel, ctx=ctx)
+    con.buildGraph(k=10, k_self=5, space="PCA", ncomps=20, n_odgenes=300)
+    assert ctx.stat("kernel_launches") > launches0
+    assert ctx.stat("panel_pool_reserved_bytes") > 0 and ctx.stat("scratch_pool_reserved_bytes") > 0
+    assert ctx.stat("knn_redo_blocks") >= 0 and ctx.stat("eig_redo_pairs") >= 0
