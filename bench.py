@@ -22,6 +22,13 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+HOST_THREADS = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+if "reference" in sys.argv or os.environ.get("RANK", "0") == "0":
+    # torch.distributed.run exports OMP_NUM_THREADS=1 when nproc > 1; the CPU legs (reference arm, cpu_baseline) use
+    # every host core the process may run on, whatever the launcher set -- before NumPy / OpenMP read the variable
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = str(HOST_THREADS)
+
 import numpy as np  # noqa: E402
 
 CONFIGS = {
@@ -41,13 +48,15 @@ CONFIGS = {
 }
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of the cross-kNN launch of this workload (56 problems of 50k x 50k),
-# main kernel + finish kernel, from the ncu --set full capture summarised in profiles/ (None until captured)
-KNN_DRAM_BYTES_PER_LAUNCH = 0.354947e9 + 0.564263e9 + 1.114550e9 + 0.640961e9
+# dram__bytes_read.sum + dram__bytes_write.sum of the cross-kNN launch of configs[1] on one GPU (56 problems of
+# 50k x 50k = 1.4e11 scores), main kernel + finish kernel, from the ncu --set full capture summarised in profiles/.
+# A launch on a rank of an N-GPU run scans fewer scores: `traffic` is this figure scaled by the scores of the launch.
+KNN_DRAM_BYTES_CAPTURED = 0.354947e9 + 0.564263e9 + 1.114550e9 + 0.640961e9
+KNN_DRAM_SCORES_CAPTURED = 56 * 50000.0 * 50000.0
 KNN_DRAM_SOURCE = ("profiles/r01_ncu_knn_tc2_bench_config2.txt: dram read+write of knn_tc2_kernel + "
-                   "knn_tc2_finish_kernel for the cross-kNN launch (56 problems of 50k x 50k); algorithmic bytes of "
-                   "that launch 1.39e9 (fp32 panels in, idx+dist out); the excess is the candidate lists (written by "
-                   "the filter phase, read by the finish kernel) and the fp16 operand copies")
+                   "knn_tc2_finish_kernel for the cross-kNN launch of configs[1] on one GPU (1.4e11 scores), scaled by "
+                   "the scores of this run's average launch; the excess over the algorithmic bytes is the candidate "
+                   "lists (written by the filter phase, read by the finish kernel) and the fp16 operand copies")
 
 
 def read_peaks():
@@ -208,16 +217,24 @@ def graph_bytes(g):
 
 def cpu_reference_step(oracle, osamples, names, cfg, pair=(0, 1)):
     """The reference algorithm (oracle restatement) for ONE sample pair at full size: reduction, projection,
-    exact kNN both ways, matching.  Returns seconds."""
+    exact kNN both ways, matching.  Returns (seconds, result of oracle.build_graph)."""
     pr = {names[pair[0]]: osamples[names[pair[0]]], names[pair[1]]: osamples[names[pair[1]]]}
     t0 = time.perf_counter()
-    oracle.build_graph(pr, k=cfg["k"], k_self=0, space=cfg["space"], ncomps=cfg["ncomps"], n_odgenes=cfg["n_genes"])
-    return time.perf_counter() - t0
+    res = oracle.build_graph(pr, k=cfg["k"], k_self=0, space=cfg["space"], ncomps=cfg["ncomps"],
+                             n_odgenes=cfg["n_genes"], alignment_strength=cfg.get("alignment_strength"))
+    return time.perf_counter() - t0, res
 
 
 def to_oracle(oracle, panel):
     return {n: oracle.Sample(counts=s.counts, genes=s.genes, cells=s.cells, varinfo_v=s.varinfo_v,
                              varinfo_qv=s.varinfo_qv, pca=s.pca, od_genes=s.od_genes) for n, s in panel.items()}
+
+
+def oracle_threads(oracle):
+    try:
+        return int(oracle.lib().oracle_max_threads())
+    except Exception:
+        return HOST_THREADS
 
 
 _RESULT_FD = None
@@ -237,6 +254,28 @@ def emit(line):
     os.write(_RESULT_FD if _RESULT_FD is not None else 1, (json.dumps(line) + "\n").encode())
 
 
+def edge_set_jaccard(ctx, lib, panel2, cfg, oracle_res):
+    """Inter-sample edge set of ONE full-size pair, default mode of the library against the oracle (exact eigenvectors,
+    FP64 projection, exact kNN): |intersection| / |union|."""
+    import ctypes as C
+    import conos_b200
+    con = conos_b200.Conos(panel2, ctx=ctx)
+    edges = con.buildGraph(k=cfg["k"], k_self=0, space=cfg["space"], ncomps=cfg["ncomps"], n_odgenes=cfg["n_genes"],
+                           alignment_strength=cfg.get("alignment_strength"), assemble=False)
+    n = int(lib.cg_edges_count(edges))
+    f, t = np.empty(n, np.int32), np.empty(n, np.int32)
+    ctx.check(lib.cg_edges_fetch(ctx.h, edges, f.ctypes.data_as(C.POINTER(C.c_int32)),
+                                 t.ctypes.data_as(C.POINTER(C.c_int32)), None, None))
+    lib.cg_edges_free(edges)
+    con.close()
+    of, ot, _, ty = oracle_res["edges"]
+    nc = int(1 << 32)
+    mine = np.unique(f.astype(np.int64) * nc + t.astype(np.int64))
+    theirs = np.unique(of[ty == 1].astype(np.int64) * nc + ot[ty == 1].astype(np.int64))
+    inter = np.intersect1d(mine, theirs, assume_unique=True).size
+    return inter / max(mine.size + theirs.size - inter, 1), int(mine.size), int(theirs.size)
+
+
 def main():
     guard_stdout()
     ap = argparse.ArgumentParser()
@@ -244,10 +283,14 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", type=int, default=2, choices=[2, 4])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+                    help="2 = BASELINE configs[1] (the bench line); 3 / 4 / 5 = configs[2] (CPCA), configs[3] (atlas), "
+                         "configs[4] (CCA, alignment.strength): profiling runs")
     ap.add_argument("--n-samples", type=int, default=None, help="override (debug runs only)")
     ap.add_argument("--n-cells", type=int, default=None, help="override (debug runs only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end loop (profiling runs)")
+    ap.add_argument("--no-check", action="store_true", help="skip the single-rank / oracle graph checks")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     reduced = False
@@ -271,7 +314,8 @@ def main():
         import conos_oracle as oracle
         oracle.build()
         from conos_b200.panel import make_panel
-        cores = os.cpu_count() or 1
+        oracle.lib().oracle_set_threads(HOST_THREADS)   # explicit: never the launcher's OMP_NUM_THREADS
+        threads = oracle_threads(oracle)
         # two samples of the workload are enough for a one-pair step
         panel = make_panel(args.config, 2, cfg["n_cells"], cfg["n_genes"], use_torch=None)
         osamples = to_oracle(oracle, panel)
@@ -279,7 +323,7 @@ def main():
         times = []
         W = min(W, 1)  # a CPU run needs no clock warm-up; one untimed step pages the libraries in
         for it in range(W + K):
-            dt = cpu_reference_step(oracle, osamples, names, cfg)
+            dt, _ = cpu_reference_step(oracle, osamples, names, cfg)
             if it >= W:
                 times.append(dt)
             if sum(times) > 150 and len(times) >= 1 and it >= W:  # keep the whole run within a few minutes
@@ -288,13 +332,18 @@ def main():
         tot = sum(times)
         val = steps_done / tot
         sample = (f"1 of {n_pairs} sample pairs per step at full size (2 x {cfg['n_cells']} cells, {cfg['n_genes']} "
-                  f"genes): reduction + projection + exact kNN both ways + matching; oracle port (exact float32 "
-                  f"brute force, OpenMP), {steps_done} timed steps")
+                  f"genes): reduction + projection + exact kNN both ways + matching; oracle port of the reference's "
+                  f"algorithm with its HNSW search replaced by an exact float32 brute force (O(n^2): the reference "
+                  f"itself, ef = 50 k, would be faster at this size -- the ratio to this line is a speed-up over the "
+                  f"exact-search baseline, not over conos's approximate search), OpenMP x {threads} threads, "
+                  f"{steps_done} timed steps, k.self = 0")
         line = {"impl": "reference", "metric": "buildGraph sample-pairs/s", "value": val, "unit": "pairs/s",
                 "n_gpus": args.gpus, "steps": steps_done, "warmup": W, "ms_per_step": 1e3 * tot / steps_done,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": {"workload": cfg["workload"]},
-                "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+                "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample,
+                                 "host_cores_available": HOST_THREADS,
+                                 "launcher_omp_num_threads_ignored": True},
                 "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(line)
         return 0
@@ -304,7 +353,6 @@ def main():
     import conos_b200
     from conos_b200.panel import make_panel
     torch.cuda.set_device(local_rank)
-    dist_group = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -315,8 +363,9 @@ def main():
     t_gen = time.perf_counter() - t_gen
     panel = pin_panel(panel)   # host copy of the inputs in page-locked memory (what e2e uploads every step)
     con = conos_b200.Conos(panel, ctx=ctx)
-    wtuple = (rank, world, dist_group) if world > 1 else None
-    kw = dict(k=cfg["k"], k_self=cfg["k_self"], space=cfg["space"], ncomps=cfg["ncomps"], n_odgenes=cfg["n_genes"])
+    wtuple = (rank, world, None) if world > 1 else None   # the library owns the communicator (cg_comm_init)
+    kw = dict(k=cfg["k"], k_self=cfg["k_self"], space=cfg["space"], ncomps=cfg["ncomps"], n_odgenes=cfg["n_genes"],
+              alignment_strength=cfg.get("alignment_strength"))
 
     def barrier():
         t1 = time.perf_counter()
@@ -370,10 +419,15 @@ def main():
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
     launches = ctx.kernel_launches() - n_launch0
+    knn_scores = ctx.stat("knn_scores")
     kms, kl, kc, kb = C.c_double(0), C.c_uint64(0), C.c_double(0), C.c_double(0)
     lib.cg_knn_timing_read(ctx.h, C.byref(kms), C.byref(kl), C.byref(kc), C.byref(kb))
     lib.cg_knn_timing(ctx.h, 0)
     dev_ms = max(ms.value, 1e3 * wall)  # the host gaps between kernels belong to the step
+    graph_sizes = (getattr(g, "n_vertices_device", None), getattr(g, "n_edges_device", None)) if g is not None \
+        else (None, None)
+    n_inter = con._n_inter_edges                         # after the allgatherv: the whole graph's, on every rank
+    rank_stats = None
     if world > 1:
         import torch.distributed as dist
         tmax = torch.tensor([dev_ms], device="cuda")
@@ -382,6 +436,13 @@ def main():
         lsum = torch.tensor([float(launches)], device="cuda")
         dist.all_reduce(lsum)
         launches = int(lsum.item())
+        # per-rank picture of the last timed step (pairs, samples uploaded, kNN time): what scaling is made of
+        mine = torch.tensor([float(len(con._last_pair_counts)), float(len([n for n in con._panel_key[2]])),
+                             kms.value / K, float(step_ms[-1])], device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        rank_stats = [{"pairs": int(t[0]), "samples_resident": int(t[1]), "knn_ms_per_step": round(float(t[2]), 2),
+                       "last_step_ms": round(float(t[3]), 1)} for t in allr]
     if os.environ.get("CONOS_BENCH_STAGES"):   # debugging aid: one more step with the per-stage profile, every rank
         sys.stderr.write(f"[timed rank {rank}] last timed step py " +
                          json.dumps({k: round(v, 1) for k, v in con.timings.items()}) + "\n")
@@ -395,71 +456,80 @@ def main():
         st = {kv.split("=")[0]: float(kv.split("=")[1]) for kv in buf.value.decode().split(";") if kv}
         sys.stderr.write(f"[stages rank {rank}] wall {dt:.1f} ms " + json.dumps({k: round(v, 1) for k, v in st.items() if "." not in k}) +
                          " py " + json.dumps({k: round(v, 1) for k, v in con.timings.items()}) + "\n")
-    if os.environ.get("CONOS_BENCH_TC_PROJECTION"):   # debugging aid: A/B of the projection engine in the e2e loop
-        lib.cg_set_option(ctx.h, b"tc_projection", float(os.environ["CONOS_BENCH_TC_PROJECTION"]))
-    n_inter = con._n_inter_edges
-    if world > 1:
-        import torch.distributed as dist
-        ni = torch.tensor([float(n_inter)], device="cuda")
-        dist.all_reduce(ni)
-        n_inter = int(ni.item())
     # ---- end to end through the host API
-    for _ in range(min(W, 2)):   # the first two passes through the host path still grow pinned / pooled buffers
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    K2 = max(1, min(K, 10))
-    e2e_each = []
-    for _ in range(K2):
-        if os.environ.get("CONOS_BENCH_E2E_STAGES"):   # debugging aid (adds synchronisation: not a bench number)
-            lib.cg_profile(ctx.h, 1)
-        redo0 = (ctx.stat("knn_redo_blocks"), ctx.stat("eig_redo_pairs"))
-        t1 = time.perf_counter()
-        g_host = e2e_step()
-        if os.environ.get("CONOS_BENCH_E2E_STAGES"):
-            buf = C.create_string_buffer(8192)
-            lib.cg_profile_dump(ctx.h, buf, 8192)
-            lib.cg_profile(ctx.h, 0)
-            sys.stderr.write(f"[e2e rank {rank}] {1e3 * (time.perf_counter() - t1):.1f} ms " + buf.value.decode() + "\n")
-        e2e_each.append({"ms": round(1e3 * (time.perf_counter() - t1), 2),
-                         "knn_redo_blocks": int(ctx.stat("knn_redo_blocks") - redo0[0]),
-                         "eig_redo_pairs": int(ctx.stat("eig_redo_pairs") - redo0[1]),
-                         "scratch_pool_mb": round(ctx.stat("scratch_pool_reserved_bytes") / 2**20),
-                         "panel_pool_mb": round(ctx.stat("panel_pool_reserved_bytes") / 2**20),
-                         **{k: round(v, 1) for k, v in con.timings.items() if k != "total_ms"}})
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        import torch.distributed as dist
-        tmax = torch.tensor([e2e_s], device="cuda")
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        e2e_s = float(tmax.item())
+    e2e_each, e2e_s, K2, g_host, h2d = [], None, 0, None, 0
+    if not args.no_e2e:
+        for _ in range(min(W, 2)):   # the first two passes through the host path still grow pinned / pooled buffers
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        K2 = max(1, min(K, 10))
+        for _ in range(K2):
+            if os.environ.get("CONOS_BENCH_E2E_STAGES"):   # debugging aid (adds synchronisation: not a bench number)
+                lib.cg_profile(ctx.h, 1)
+            redo0 = (ctx.stat("knn_redo_blocks"), ctx.stat("eig_redo_pairs"))
+            t1 = time.perf_counter()
+            gh_ = e2e_step()
+            if gh_ is not None:
+                g_host = gh_
+            if os.environ.get("CONOS_BENCH_E2E_STAGES"):
+                buf = C.create_string_buffer(8192)
+                lib.cg_profile_dump(ctx.h, buf, 8192)
+                lib.cg_profile(ctx.h, 0)
+                sys.stderr.write(f"[e2e rank {rank}] {1e3 * (time.perf_counter() - t1):.1f} ms " + buf.value.decode() + "\n")
+            e2e_each.append({"ms": round(1e3 * (time.perf_counter() - t1), 2),
+                             "knn_redo_blocks": int(ctx.stat("knn_redo_blocks") - redo0[0]),
+                             "eig_redo_pairs": int(ctx.stat("eig_redo_pairs") - redo0[1]),
+                             "scratch_pool_mb": round(ctx.stat("scratch_pool_reserved_bytes") / 2**20),
+                             "panel_pool_mb": round(ctx.stat("panel_pool_reserved_bytes") / 2**20),
+                             **{k: round(v, 1) for k, v in con.timings.items() if k != "total_ms"}})
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        h2d = con._h2d_bytes
+        if world > 1:
+            import torch.distributed as dist
+            tmax = torch.tensor([e2e_s], device="cuda")
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            e2e_s = float(tmax.item())
+            hsum = torch.tensor([float(h2d)], device="cuda")
+            dist.all_reduce(hsum)
+            h2d = int(hsum.item())
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
+        con.close()
+        ctx.close()
         return 0
 
     peaks = read_peaks()
     d = cfg["ncomps"]
     knn_s = kms.value * 1e-3
+    # 2 * n_a * n_b * d flop per sample pair -- ONE distance matrix serves both directions -- plus
+    # 2 * n^2 * d for a sample against itself; kc already counts a mirrored pair of problems once
     flops = 2.0 * kc.value * d
     achieved = flops / knn_s / 1e12 if knn_s > 0 else 0.0
+    n_l = max(int(kl.value), 1)
     roofline = {"bound": "tensor",
-                "kernel": "knn_tc2_kernel + knn_tc2_finish_kernel (exact cross-kNN: fp16 tcgen05 tiles, group-max "
-                          "thresholds, sign-bit filter, fp32 re-score + warp sort)",
+                "kernel": "knn_tc2_kernel + knn_tc2_finish_kernel (exact kNN, cross and self: fp16 tcgen05 tiles, "
+                          "group-max thresholds, sign-bit filter, fp32 re-score + warp sort)",
                 "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_tflops"], "traffic": KNN_DRAM_BYTES_PER_LAUNCH,
+                "frac": achieved / peaks["bf16_tflops"],
+                "traffic": KNN_DRAM_BYTES_CAPTURED * (knn_scores / n_l) / KNN_DRAM_SCORES_CAPTURED,
                 "traffic_source": KNN_DRAM_SOURCE, "peak_source": peaks["source"],
-                "launches": int(kl.value), "avg_launch_ms": kms.value / max(int(kl.value), 1),
-                "candidates_per_s": kc.value / knn_s if knn_s > 0 else 0.0,
-                "algorithmic_bytes_per_launch": kb.value / max(int(kl.value), 1),
+                "launches": int(kl.value), "avg_launch_ms": kms.value / n_l,
+                "algorithmic_flop_per_launch": flops / n_l,
+                "scores_scanned_per_s": knn_scores / knn_s if knn_s > 0 else 0.0,
+                "algorithmic_bytes_per_launch": kb.value / n_l,
                 "share_of_step": knn_s / (dev_ms * 1e-3) if dev_ms > 0 else None,
-                "note": "achieved = 2*n_query*n_ref*ncomps per launch / CUDA-event time on the launching stream "
-                        "(both kernels and the overflow check); every distance tile is computed twice (threshold "
-                        "phase, filter phase) with K padded 30 -> 32, so the tensor pipe issues 2.13x the algorithmic "
-                        "flops; see DESIGN.md K2"}
+                "tensor_pipe_active_pct_ncu": 28.2,
+                "note": "achieved = SURVEY 8(d) flops (2*n_a*n_b*ncomps per sample pair, one distance matrix for both "
+                        "directions; 2*n^2*ncomps for the self search) / CUDA-event time of the kNN launches on the "
+                        "launching stream (both kernels and the overflow check); the kernel computes each direction "
+                        "separately, twice (threshold phase, filter phase), with K padded 30 -> 32, so the tensor pipe "
+                        "issues 4.27x these flops; tensor_pipe_active_pct_ncu is sm__pipe_tensor_subunit busy of the "
+                        "committed ncu capture (profiles/), see DESIGN.md K2"}
     line = {"metric": "buildGraph sample-pairs/s", "value": n_pairs * K / (dev_ms * 1e-3), "unit": "pairs/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -468,23 +538,48 @@ def main():
                        "l2": "inputs larger than L2 (panel and per-pair operands exceed 126 MB per step)",
                        "panel_generation_s": t_gen},
             "mnn_edges_per_s": n_inter * K / (dev_ms * 1e-3), "mnn_edges": n_inter,
-            "graph": {"vertices": getattr(g, "n_vertices_device", None), "edges": getattr(g, "n_edges_device", None)},
-            "e2e": {"value": n_pairs * K2 / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": panel_bytes(panel),
-                    "d2h_bytes_per_step": graph_bytes(g_host), "steps": K2},
-            "e2e_breakdown_ms": {k: round(v, 2) for k, v in con.timings.items()}, "e2e_steps_ms": e2e_each,
+            "graph": {"vertices": graph_sizes[0], "edges": graph_sizes[1]},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
-    if rank == 0:
-        line["knn_recall_at_k"] = knn_recall(ctx, cfg["k"], cfg["ncomps"])
-    if not args.no_cpu_baseline:
+    if rank_stats is not None:
+        line["ranks"] = rank_stats
+    if e2e_s is not None:
+        each = sorted(x["ms"] for x in e2e_each)
+        line["e2e"] = {"value": n_pairs * K2 / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": h2d,
+                       "d2h_bytes_per_step": graph_bytes(g_host) if g_host is not None else 0, "steps": K2,
+                       "ms_per_step_median": each[len(each) // 2], "ms_per_step_max": each[-1],
+                       "ms_per_step_min": each[0]}
+        line["e2e_breakdown_ms"] = {k: round(v, 2) for k, v in con.timings.items()}
+        line["e2e_steps_ms"] = e2e_each
+    line["knn_recall_at_k"] = knn_recall(ctx, min(cfg["k"], 30), cfg["ncomps"])
+    # ---- graph checks (outside every timed region)
+    if not args.no_check and g_host is not None and world > 1:
+        # the N-rank graph against the graph one rank builds alone: every array, bit for bit
+        solo = conos_b200.Conos(panel, ctx=ctx)
+        g1 = solo.buildGraph(fetch=True, **kw)
+        same = all(np.array_equal(getattr(g_host, a), getattr(g1, a))
+                   for a in ("vertices", "edge_from", "edge_to", "weight", "type"))
+        line["graph_equals_single_rank"] = bool(same)
+        line["graph_single_rank_edges"] = int(g1.ecount())
+        solo.close()
+    if not args.no_cpu_baseline and world == 1:
         import conos_oracle as oracle
         oracle.build()
+        oracle.lib().oracle_set_threads(HOST_THREADS)
         names = list(panel)
-        osamples = to_oracle(oracle, {n: panel[n] for n in names[:2]})
-        dt = cpu_reference_step(oracle, osamples, names, cfg)
-        line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "pairs/s", "cores": os.cpu_count() or 1, "kind": "port",
+        panel2 = {n: panel[n] for n in names[:2]}
+        osamples = to_oracle(oracle, panel2)
+        dt, ores = cpu_reference_step(oracle, osamples, names, cfg)
+        line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "pairs/s", "cores": oracle_threads(oracle), "kind": "port",
                                 "sample": f"1 of {n_pairs} pairs at full size (2 x {cfg['n_cells']} cells): reduction "
-                                          f"+ projection + exact kNN both ways + matching, {dt:.1f} s"}
+                                          f"+ projection + exact float32 brute-force kNN both ways + matching (the "
+                                          f"reference's HNSW replaced by exact search), {dt:.1f} s"}
+        if not args.no_check:
+            jac, n_mine, n_theirs = edge_set_jaccard(ctx, lib, panel2, cfg, ores)
+            line["graph_jaccard_vs_oracle"] = {"value": jac, "pair": "samples 0 and 1 at full size, default mode",
+                                               "edges": n_mine, "oracle_edges": n_theirs}
     emit(line)
+    con.close()
+    ctx.close()
     return 0
 
 

@@ -6,8 +6,11 @@ requested, this module raises.  Build the library with ``python __graft_entry__.
 """
 from __future__ import annotations
 
+import atexit
 import ctypes as C
 import os
+import sys
+import weakref
 from typing import Optional
 
 import numpy as np
@@ -33,8 +36,9 @@ class CgSample(C.Structure):
 
 class CgPair(C.Structure):
     _fields_ = [("a", C.c_int32), ("b", C.c_int32), ("n_genes", C.c_int32), ("genes_a", c_int_p),
-                ("genes_b", c_int_p), ("rot", c_dbl_p), ("rot_cols", C.c_int32), ("u", c_dbl_p), ("v", c_dbl_p),
-                ("rows_u", c_int_p), ("rows_v", c_int_p), ("n_u", C.c_int32), ("n_v", C.c_int32)]
+                ("genes_b", c_int_p), ("rot", c_dbl_p), ("rot_rows", C.c_int32), ("rot_cols", C.c_int32),
+                ("u", c_dbl_p), ("v", c_dbl_p), ("rows_u", c_int_p), ("rows_v", c_int_p), ("n_u", C.c_int32),
+                ("n_v", C.c_int32), ("uv_cols", C.c_int32), ("k", C.c_int32)]
 
 
 class CgParams(C.Structure):
@@ -71,7 +75,7 @@ SIGNATURES = {
     "cg_pair_cca": (C.c_int, [_VP, C.c_int, c_int_p, c_int_p, c_int_p, c_dbl_p, c_dbl_p, c_int_p, c_int_p, c_dbl_p]),
     "cg_keep_projections": (C.c_int, [_VP, C.c_int]),
     "cg_pair_projection": (C.c_int, [_VP, C.c_int, C.c_int, c_int_p, c_int_p, c_dbl_p]),
-    "cg_local_edges": (C.c_int, [_VP, _VP, c_int_p, C.c_int, C.POINTER(CgParams), C.POINTER(_VP)]),
+    "cg_local_edges": (C.c_int, [_VP, _VP, c_int_p, C.c_int, C.POINTER(CgParams), C.POINTER(_VP), c_i64_p]),
     "cg_edges_count": (C.c_int64, [_VP]),
     "cg_edges_fetch": (C.c_int, [_VP, _VP, c_int_p, c_int_p, c_dbl_p, c_int_p]),
     "cg_edges_append_host": (C.c_int, [_VP, C.POINTER(_VP), c_int_p, c_int_p, c_dbl_p, c_int_p, C.c_int64]),
@@ -86,10 +90,16 @@ SIGNATURES = {
     "cg_edges_reserve": (C.c_int, [_VP, C.POINTER(_VP), C.c_int64]),
     "cg_edges_set_count": (C.c_int, [_VP, C.c_int64]),
     "cg_edges_free": (None, [_VP]),
+    "cg_comm_unique_id": (C.c_int, [_VP]),
+    "cg_comm_init": (C.c_int, [_VP, C.c_int, C.c_int, _VP]),
+    "cg_comm_rank": (C.c_int, [_VP, c_int_p, c_int_p]),
+    "cg_partition_pairs": (C.c_int, [c_int_p, c_int_p, c_dbl_p, C.c_int, c_dbl_p, C.c_int, C.c_int, c_int_p]),
+    "cg_edges_allgatherv": (C.c_int, [_VP, C.POINTER(_VP), c_int_p, c_i64_p, C.c_int]),
     "cg_assemble_graph": (C.c_int, [_VP, _VP, C.c_int32, C.POINTER(_VP)]),
     "cg_graph_sizes": (C.c_int, [_VP, c_int_p, c_i64_p]),
     "cg_graph_fetch": (C.c_int, [_VP, _VP, c_int_p, c_int_p, c_int_p, c_dbl_p, c_int_p]),
     "cg_graph_fetch_adjacency": (C.c_int, [_VP, _VP, c_i64_p, c_int_p, c_dbl_p]),
+    "cg_graph_balance": (C.c_int, [_VP, _VP, c_int_p, C.c_int, C.c_int, C.c_double, C.c_int]),
     "cg_graph_free": (None, [_VP]),
     "cg_spcov": (C.c_int, [_VP, C.c_int, C.c_int, c_int_p, c_int_p, c_dbl_p, c_dbl_p, c_dbl_p]),
     "cg_cpca": (C.c_int, [_VP, c_dbl_p, C.c_int, C.c_int, c_dbl_p, C.c_int, C.c_int, C.c_double, c_dbl_p, c_dbl_p,
@@ -145,6 +155,8 @@ class Context:
             raise ConosGpuError(msg.decode() if msg else "cg_init failed")
         self.h = h
         self.device = device
+        self._comm = None
+        _all_ctx.add(self)
 
     def check(self, rc: int):
         if rc != 0:
@@ -166,17 +178,59 @@ class Context:
             raise KeyError(name)
         return v.value
 
+    # ---- multi-GPU (one context per GPU; the communicator lives inside the library)
+    def comm_init(self, rank: int, world: int, group=None):
+        """NCCL communicator of this context.  The 128-byte id is created on rank 0 and travels through
+        torch.distributed (any backend) -- plumbing only: every collective of the data path runs inside the library."""
+        if getattr(self, "_comm", None) == (rank, world):
+            return
+        ident = (C.c_ubyte * 128)()
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            if rank == 0:
+                self.check(self.lib.cg_comm_unique_id(ident))
+            dev = torch.device("cuda", self.device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+            t = torch.tensor(list(bytes(ident)), dtype=torch.uint8, device=dev)
+            dist.broadcast(t, src=0, group=group)
+            ident = (C.c_ubyte * 128)(*t.cpu().tolist())
+        self.check(self.lib.cg_comm_init(self.h, rank, world, ident))
+        self._comm = (rank, world)
+
     def __del__(self):
+        # never during interpreter teardown (see _shutdown_all)
         try:
-            self.close()
+            if not sys.is_finalizing():
+                self.close()
         except Exception:
             pass
 
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
 
 _default_ctx = {}
+_all_ctx = weakref.WeakSet()
 
 
 def default_context(device: int = 0) -> Context:
     if device not in _default_ctx:
         _default_ctx[device] = Context(device)
     return _default_ctx[device]
+
+
+@atexit.register
+def _shutdown_all():
+    """Contexts are shut down by an atexit hook, i.e. while the interpreter, the CUDA runtime and torch are all still
+    intact -- never from a destructor during interpreter teardown (the order in which modules and extension state go
+    away there is arbitrary).  R's equivalent is the package's .onUnload -> cg_shutdown."""
+    for c in list(_all_ctx):
+        try:
+            c.close()
+        except Exception:
+            pass
+    _default_ctx.clear()

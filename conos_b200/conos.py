@@ -164,12 +164,16 @@ class Conos:
         return self._ctx
 
     # ------------------------------------------------------------------ device-resident panel
-    def _ensure_panel(self, names: Sequence[str], n_odgenes: int = 2000):
+    def _ensure_panel(self, names: Sequence[str], n_odgenes: int = 2000, need_counts=None, need_pca=None):
         """Upload the samples.  Only the gene universe the path can touch travels: the union of the samples' top
         n.odgenes overdispersed genes (every pair's gene set is drawn from two of those lists, R/conos.R:107-117).
         Real pagoda2 objects carry 20-30 thousand genes of which a few thousand qualify; the synthetic panels use all
-        of theirs, in which case the arrays are passed through untouched (no copy)."""
-        key = (tuple(names), int(n_odgenes))
+        of theirs, in which case the arrays are passed through untouched (no copy).
+        `need_counts` / `need_pca` (sets of sample names, None = all): a multi-GPU rank uploads the counts only of the
+        samples its pairs touch and the PCA only of the samples whose local neighbours it computes; the others are
+        placeholders that just number their cells."""
+        key = (tuple(names), int(n_odgenes), None if need_counts is None else frozenset(need_counts),
+               None if need_pca is None else frozenset(need_pca))
         if self._panel is not None and self._panel_key == key:
             return
         self._drop_panel()
@@ -181,8 +185,21 @@ class Conos:
         arr = (CgSample * len(names))()
         keep = []
         self._panel_col = {}
+        self._h2d_bytes = 0
         for t, n in enumerate(names):
             s = self.samples[n]
+            arr[t].n_cells, arr[t].n_genes = s.counts.shape
+            arr[t].pca_ld = s.counts.shape[0]
+            want_pca = s.pca is not None and (need_pca is None or n in need_pca)
+            if want_pca:
+                pca = np.asfortranarray(s.pca, np.float64)
+                keep.append(pca)
+                arr[t].pca = ptr(pca, C.c_double)
+                arr[t].n_pcs = pca.shape[1]
+                self._h2d_bytes += pca.nbytes
+            if need_counts is not None and n not in need_counts:
+                self._panel_col[n] = None
+                continue        # placeholder: p == NULL
             # the caller's CSC object itself when it is one: scipy caches the sorted-indices check on the object, so
             # the scan over all non-zeros happens once per sample, not once per upload
             m = s.counts if sp.isspmatrix_csc(s.counts) else sp.csc_matrix(s.counts)
@@ -208,14 +225,11 @@ class Conos:
             x = np.ascontiguousarray(m.data, np.float64)
             v = None if v is None else np.ascontiguousarray(v, np.float64)
             qv = None if qv is None else np.ascontiguousarray(qv, np.float64)
-            pca = None if s.pca is None else np.asfortranarray(s.pca, np.float64)
-            keep += [p, i, x, v, qv, pca]
+            keep += [p, i, x, v, qv]
             arr[t].n_cells, arr[t].n_genes = m.shape
             arr[t].p, arr[t].i, arr[t].x = ptr(p, C.c_int32), ptr(i, C.c_int32), ptr(x, C.c_double)
             arr[t].var_v, arr[t].var_qv = ptr(v, C.c_double), ptr(qv, C.c_double)
-            arr[t].pca = ptr(pca, C.c_double)
-            arr[t].n_pcs = 0 if pca is None else pca.shape[1]
-            arr[t].pca_ld = m.shape[0]
+            self._h2d_bytes += p.nbytes + i.nbytes + x.nbytes + (0 if v is None else v.nbytes + qv.nbytes)
         h = C.c_void_p()
         self.ctx.check(self.ctx.lib.cg_panel_create(self.ctx.h, arr, len(names), C.byref(h)))
         self._panel = h
@@ -281,9 +295,11 @@ class Conos:
                    balancing_factor_per_cell=None, same_factor_downweight: float = 1.0,
                    k_same_factor: Optional[int] = None, balancing_factor_per_sample=None,
                    pair_shard: Optional[Sequence[int]] = None, assemble: bool = True, fetch: bool = True,
-                   world=None):
-        """`world` = (rank, world_size, process group or None) shards the sample pairs (and the per-sample
-        local-neighbour searches) over one process per GPU; every rank ends with the full graph.
+                   world=None, graph_on: str = "root"):
+        """`world` = (rank, world_size, torch.distributed group or None): one process per GPU.  The pair list is
+        partitioned by the library (cg_partition_pairs: LPT with sample locality), every rank uploads only the samples
+        its pairs touch, the per-rank edge tables are gathered with NCCL inside the library (cg_edges_allgatherv) in
+        the reference's row order, and the graph is assembled on rank 0 (`graph_on="root"`; `"all"`: on every rank).
         `fetch=False` keeps the assembled graph on the device (self.graph is a size-only stub)."""
         t_total = time.perf_counter()
         if space not in SUPPORTED_SPACES:
@@ -298,10 +314,10 @@ class Conos:
             raise NotImplementedError("only data.type='counts' is on the B200 path")
         if base_groups is not None or snn:
             raise NotImplementedError("base.groups / snn are outside the B200 hot path (SURVEY.md 8f)")
-        if balancing_factor_per_sample is not None or balancing_factor_per_cell is not None:
-            raise NotImplementedError("balancing.factor.* is outside the B200 hot path (use balance_edge_weights)")
         if k1 is None:
             k1 = k
+        if k_same_factor is None:
+            k_same_factor = k                       # R default: k.same.factor = k
         names = [n for n in self.samples if not (exclude_samples and n in exclude_samples)]
         if alignment_strength is not None:
             alignment_strength = min(max(alignment_strength, 0.0), 1.0)
@@ -323,61 +339,105 @@ class Conos:
                 pair_names.append((names[ia], names[ib]))
         if len(pair_names) < 1:
             raise ValueError("insufficient number of comparable pairs")
+        index = {n: t for t, n in enumerate(names)}
+        n_cells = np.array([self.samples[n].counts.shape[0] for n in names], np.float64)
+        lib, h = self.ctx.lib, self.ctx.h
+
+        # ---- who does what (one rank: everything)
+        rank, world_size, group = world if world is not None else (0, 1, None)
+        n_pairs = len(pair_names)
+        pa = np.array([index[a] for a, _ in pair_names], np.int32)
+        pb_ = np.array([index[b] for _, b in pair_names], np.int32)
+        pair_owner = np.zeros(n_pairs, np.int32)
+        sample_owner = np.zeros(len(names), np.int32)
+        need_counts = need_pca = None
+        if world_size > 1:
+            if pair_shard is not None:
+                raise ValueError("pair_shard and world are mutually exclusive")
+            self.ctx.comm_init(rank, world_size, group)
+            cost = n_cells[pa] * n_cells[pb_]
+            # what a rank pays the first time it meets a sample (its Gram matrix and, end to end, its upload), in the
+            # unit of `cost` (cell pairs): measured on configs[1], ~0.005 * cells * genes^2
+            n_genes_s = np.array([min(self.samples[n].counts.shape[1], 4 * n_odgenes) for n in names], np.float64)
+            scost = 0.005 * n_cells * n_genes_s ** 2
+            self.ctx.check(lib.cg_partition_pairs(ptr(pa, C.c_int32), ptr(pb_, C.c_int32), ptr(cost, C.c_double),
+                                                  n_pairs, ptr(scost, C.c_double), len(names), world_size,
+                                                  ptr(pair_owner, C.c_int32)))
+            if k_self > 0:   # the local-neighbour searches (R/conos.R:589) are units of their own: cells^2 each
+                sidx = np.arange(len(names), dtype=np.int32)
+                lcost = n_cells ** 2
+                self.ctx.check(lib.cg_partition_pairs(ptr(sidx, C.c_int32), ptr(sidx, C.c_int32),
+                                                      ptr(lcost, C.c_double), len(names), None, len(names),
+                                                      world_size, ptr(sample_owner, C.c_int32)))
+            mine = np.flatnonzero(pair_owner == rank)
+            need_counts = {names[t] for t in set(pa[mine].tolist()) | set(pb_[mine].tolist())}
+            need_pca = {names[t] for t in np.flatnonzero(sample_owner == rank)} if k_self > 0 else set()
+            my_pairs = mine.tolist()
+        else:
+            my_pairs = list(range(n_pairs)) if pair_shard is None else list(pair_shard)
         t_0 = time.perf_counter()
-        self._ensure_panel(names, n_odgenes)
+        self._ensure_panel(names, n_odgenes, need_counts, need_pca)
         self.timings["panel_ms"] = 1e3 * (time.perf_counter() - t_0)
         t_0 = time.perf_counter()
-        index = {n: t for t, n in enumerate(names)}
         cache = self.pairs.setdefault(space, {})
 
-        rank, world_size, group = world if world is not None else (0, 1, None)
-        if world_size > 1:
-            from .dist import partition_contiguous
-            costs = [float(self.samples[a].counts.shape[0]) * self.samples[b].counts.shape[0] for a, b in pair_names]
-            lo, hi = partition_contiguous(costs, world_size)[rank]
-            pair_shard = range(lo, hi)
-        my_pairs = list(range(len(pair_names))) if pair_shard is None else list(pair_shard)
+        # balancing.factor.per.sample: pairs inside one level search k.cur = min(k.same.factor, k1) neighbours
+        # (R/conclass.R:230-233)
+        if balancing_factor_per_sample is not None:
+            missing = [n for n in names if n not in balancing_factor_per_sample]
+            if missing:
+                raise ValueError("balancing.factor.per.sample must name every sample")
+
         carr = (CgPair * max(len(my_pairs), 1))()
         keep_alive = []
         used_pairs = []
-        for slot, pi in enumerate(my_pairs):
+        for pi in my_pairs:
             na, nb = pair_names[pi]
-            od, ga, gb = self._common_od_genes(na, nb, n_odgenes)
+            key = f"{na}.vs.{nb}"
+            red = cache.get(key) or cache.get(f"{nb}.vs.{na}")
+            if red is not None and space in ("PCA", "CPCA") and red.get("CPC") is not None:
+                # od.genes <- rownames(cached CPC) (R/conclass.R:240-243): the cached entry fixes the gene set
+                od, ga, gb = self._cached_od_genes(red, na, nb)
+            else:
+                od, ga, gb = self._common_od_genes(na, nb, n_odgenes)
             if len(od) < 5:
                 continue  # quick* return NULL: the pair vanishes from the graph (R/conos.R:206,278,330)
             cp = carr[len(used_pairs)]
             cp.a, cp.b = index[na], index[nb]
             cp.n_genes = len(od)
             cp.genes_a, cp.genes_b = ptr(ga, C.c_int32), ptr(gb, C.c_int32)
-            key = f"{na}.vs.{nb}"
-            red = cache.get(key) or cache.get(f"{nb}.vs.{na}")
+            if balancing_factor_per_sample is not None and \
+                    balancing_factor_per_sample[na] == balancing_factor_per_sample[nb]:
+                cp.k = min(int(k_same_factor), k1)
             if red is not None and space in ("PCA", "CPCA") and red.get("CPC") is not None:
                 rot = np.asfortranarray(red["CPC"], np.float64)
                 if ncomps > rot.shape[1]:
                     warnings.warn(f"specified ncomps ({ncomps}) is greater than the cached version ({rot.shape[1]})")
-                cp.rot, cp.rot_cols = ptr(rot, C.c_double), rot.shape[1]
+                cp.rot, cp.rot_rows, cp.rot_cols = ptr(rot, C.c_double), rot.shape[0], rot.shape[1]
                 keep_alive.append(rot)
             elif red is not None and space == "CCA" and red.get("u") is not None:
-                u = np.asfortranarray(red["u"][:, :ncomps], np.float64)
-                v = np.asfortranarray(red["v"][:, :ncomps], np.float64)
+                # every cached column is used, whatever ncomps says now (R/conclass.R:268-270)
+                u = np.asfortranarray(red["u"], np.float64)
+                v = np.asfortranarray(red["v"], np.float64)
+                if u.shape[1] != v.shape[1]:
+                    raise ValueError(f"cached CCA of {key}: u and v differ in their number of columns")
                 ru = np.ascontiguousarray(red["rows_u"], np.int32)
                 rv = np.ascontiguousarray(red["rows_v"], np.int32)
                 cp.u, cp.v = ptr(u, C.c_double), ptr(v, C.c_double)
                 cp.rows_u, cp.rows_v = ptr(ru, C.c_int32), ptr(rv, C.c_int32)
-                cp.n_u, cp.n_v = u.shape[0], v.shape[0]
+                cp.n_u, cp.n_v, cp.uv_cols = u.shape[0], v.shape[0], u.shape[1]
                 keep_alive += [u, v, ru, rv]
             keep_alive += [ga, gb]
             used_pairs.append((pi, key, od))
 
         P = CgParams()
-        self.ctx.lib.cg_params_default(C.byref(P))
+        lib.cg_params_default(C.byref(P))
         P.k, P.k1, P.k_self, P.ncomps = k, k1, k_self, ncomps
         P.space, P.matching, P.metric = SPACES[space], MATCHING[matching_method], METRICS[metric]
         P.var_scale, P.common_centering = int(var_scale), int(common_centering)
         P.score_component_variance = int(score_component_variance)
         P.k_self_weight, P.l2_sigma, P.cor_base = k_self_weight, l2_sigma, cor_base
 
-        lib, h = self.ctx.lib, self.ctx.h
         edges = C.c_void_p()
         counts = np.zeros(max(len(used_pairs), 1), np.int64)
         self.timings["host_pairs_ms"] = 1e3 * (time.perf_counter() - t_0)
@@ -386,7 +446,96 @@ class Conos:
                                           ptr(counts, C.c_int64)))
         self.timings["pairs_edges_ms"] = 1e3 * (time.perf_counter() - t_0)
         t_0 = time.perf_counter()
-        # populate self$pairs[[space]] like updatePairs does (R/conclass.R:1090-1092)
+        self._fill_cache(cache, used_pairs, space, score_component_variance)
+        self._last_pair_counts = {used_pairs[t][1]: int(counts[t]) for t in range(len(used_pairs))}
+        self._last_edges = edges
+        self._last_params = P
+        self._last_names = names
+        self.timings["cache_fill_ms"] = 1e3 * (time.perf_counter() - t_0)
+        t_0 = time.perf_counter()
+        if not assemble:
+            return edges
+
+        # ---- exchange (R: rbind of the per-pair data frames, R/conclass.R:316-321) and local edges (:328-333)
+        n_inter = int(sum(self._last_pair_counts.values()))
+        if world_size > 1:
+            seg_counts = np.zeros(n_pairs, np.int64)
+            for t, (pi, _, _) in enumerate(used_pairs):
+                seg_counts[pi] = counts[t]
+            self.ctx.check(lib.cg_edges_allgatherv(h, C.byref(edges), ptr(pair_owner, C.c_int32),
+                                                   ptr(seg_counts, C.c_int64), n_pairs))
+            n_inter = int(lib.cg_edges_count(edges))
+            if k_self > 0:
+                sidx = np.flatnonzero(sample_owner == rank).astype(np.int32)
+                ledges = C.c_void_p()
+                mine_counts = np.zeros(max(len(sidx), 1), np.int64)
+                self.ctx.check(lib.cg_local_edges(h, self._panel, ptr(sidx, C.c_int32), len(sidx), C.byref(P),
+                                                  C.byref(ledges), ptr(mine_counts, C.c_int64)))
+                lcounts = np.zeros(len(names), np.int64)
+                lcounts[sidx] = mine_counts[:len(sidx)]
+                self.ctx.check(lib.cg_edges_allgatherv(h, C.byref(ledges), ptr(sample_owner, C.c_int32),
+                                                       ptr(lcounts, C.c_int64), len(names)))
+                f, t_, w_, ty = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+                lib.cg_edges_device_ptrs(ledges, C.byref(f), C.byref(t_), C.byref(w_), C.byref(ty))
+                self.ctx.check(lib.cg_edges_append_device(h, C.byref(edges), f, t_, w_, ty,
+                                                          int(lib.cg_edges_count(ledges))))
+                lib.cg_edges_free(ledges)
+        elif k_self > 0:
+            sidx = np.arange(len(names), dtype=np.int32)
+            self.ctx.check(lib.cg_local_edges(h, self._panel, ptr(sidx, C.c_int32), len(names), C.byref(P),
+                                              C.byref(edges), None))
+        self._n_inter_edges = n_inter
+        self.timings["local_edges_ms"] = 1e3 * (time.perf_counter() - t_0)
+        t_0 = time.perf_counter()
+        if world_size > 1 and graph_on == "root" and rank != 0:
+            lib.cg_edges_free(edges)
+            self._last_edges = None
+            self.graph = None
+            self.timings["assemble_fetch_ms"] = 0.0
+            self.timings["total_ms"] = 1e3 * (time.perf_counter() - t_total)
+            return None
+        balance = None
+        if balancing_factor_per_sample is not None and balancing_factor_per_cell is not None:
+            warnings.warn("Both balancing.factor.per.cell and balancing.factor.per.sample are provided. "
+                          "Used the former for balancing edge weights")
+        if balance_edge_weights or balancing_factor_per_cell is not None or balancing_factor_per_sample is not None:
+            balance = dict(per_cell=balancing_factor_per_cell, per_sample=balancing_factor_per_sample,
+                           balance_weights=bool(balance_edge_weights), downweight=float(same_factor_downweight))
+        g = self._assemble(edges, names, fetch=fetch, balance=balance)
+        self.timings["assemble_fetch_ms"] = 1e3 * (time.perf_counter() - t_0)
+        lib.cg_edges_free(edges)
+        self._last_edges = None
+        self.graph = g
+        self.timings["total_ms"] = 1e3 * (time.perf_counter() - t_total)
+        return g
+
+    def _cached_od_genes(self, red, na, nb):
+        """Gene set of a cached PCA / CPCA entry = rownames(CPC) (R/conclass.R:240-243), mapped to the columns of the
+        two uploaded samples."""
+        self._ensure_vocab()
+        allnames, per = self._vocab
+        ids = getattr(red, "_od_ids", None)
+        if ids is None:
+            gid = {g: t for t, g in enumerate(allnames)}
+            ids = np.array([gid[g] for g in red["genes"]], np.int64)
+        ids = np.asarray(ids, np.int64)
+        ga, gb = per[na][0][ids], per[nb][0][ids]
+        if (ga < 0).any() or (gb < 0).any():
+            raise ValueError(f"cached reduction of {na}.vs.{nb} names genes that a sample does not have")
+        pca_, pcb_ = self._panel_col.get(na), self._panel_col.get(nb)
+        if pca_ is not None:
+            ga = pca_[ga]
+        if pcb_ is not None:
+            gb = pcb_[gb]
+        if (np.asarray(ga) < 0).any() or (np.asarray(gb) < 0).any():
+            raise ValueError(f"cached reduction of {na}.vs.{nb} uses genes outside the uploaded od-gene universe "
+                             "(it was computed with a larger n.odgenes)")
+        return ids, np.ascontiguousarray(ga, np.int32), np.ascontiguousarray(gb, np.int32)
+
+    def _fill_cache(self, cache, used_pairs, space, score_component_variance):
+        """populate self$pairs[[space]] like updatePairs does (R/conclass.R:1090-1092): PCA list(CPC, nv);
+        CPCA list(D, CPC, niter, nv) (src/cpca.cpp:93-100); CCA list(d, u, v, ul, vl, nv) (R/conos.R:344-366)."""
+        lib, h = self.ctx.lib, self.ctx.h
         for slot, (pi, key, od) in enumerate(used_pairs):
             if key in cache:
                 continue
@@ -416,48 +565,20 @@ class Conos:
             if nv is not None:
                 rr = nc.value // 2 if space == "PCA" else nc.value
                 cache[key]["nv"] = [nv[0, :rr], nv[1, :rr]]
-        self._last_pair_counts = {used_pairs[t][1]: int(counts[t]) for t in range(len(used_pairs))}
-        self._last_edges = edges
-        self._last_params = P
-        self._last_names = names
-        self.timings["cache_fill_ms"] = 1e3 * (time.perf_counter() - t_0)
-        t_0 = time.perf_counter()
-        if not assemble:
-            return edges
 
-        # ---- local edges (R/conclass.R:328-333) and graph assembly
-        if world_size > 1:
-            from .dist import gather_edges, partition_contiguous, device_columns
-            edges, _ = gather_edges(self.ctx, edges, group)          # allgatherv, rank order == combn order
-            if k_self > 0:
-                scost = [float(self.samples[n].counts.shape[0]) ** 2 for n in names]
-                lo, hi = partition_contiguous(scost, world_size)[rank]
-                sidx = np.arange(lo, hi, dtype=np.int32)
-                ledges = C.c_void_p()
-                self.ctx.check(lib.cg_local_edges(h, self._panel, ptr(sidx, C.c_int32), len(sidx), C.byref(P),
-                                                  C.byref(ledges)))
-                ledges, _ = gather_edges(self.ctx, ledges, group)
-                cols = device_columns(self.ctx, ledges)
-                self.ctx.check(lib.cg_edges_append_device(
-                    h, C.byref(edges), C.c_void_p(cols[0].data_ptr()), C.c_void_p(cols[1].data_ptr()),
-                    C.c_void_p(cols[2].data_ptr()), C.c_void_p(cols[3].data_ptr()), int(cols[0].numel())))
-                lib.cg_edges_free(ledges)
-        elif k_self > 0:
-            sidx = np.arange(len(names), dtype=np.int32)
-            self.ctx.check(lib.cg_local_edges(h, self._panel, ptr(sidx, C.c_int32), len(names), C.byref(P),
-                                              C.byref(edges)))
-        self._n_inter_edges = int(sum(self._last_pair_counts.values()))
-        self.timings["local_edges_ms"] = 1e3 * (time.perf_counter() - t_0)
-        t_0 = time.perf_counter()
-        g = self._assemble(edges, names, fetch=fetch)
-        self.timings["assemble_fetch_ms"] = 1e3 * (time.perf_counter() - t_0)
-        lib.cg_edges_free(edges)
-        self._last_edges = None
-        if balance_edge_weights:
-            g = self._balance(g, names, same_factor_downweight)
-        self.graph = g
-        self.timings["total_ms"] = 1e3 * (time.perf_counter() - t_total)
-        return g
+    def close(self):
+        """Release the device-resident panel (R: the object going out of scope / rm(con); gc())."""
+        try:
+            if self._panel is not None and self._ctx is not None and getattr(self._ctx, "h", None):
+                self._drop_panel()
+        except Exception:
+            pass
+        self._panel = None
+
+    def __del__(self):
+        import sys
+        if not sys.is_finalizing():
+            self.close()
 
     def _out(self, key: str, n: int, dtype):
         """Result buffer in pinned host memory when torch is importable (grow-only, reused across calls; the
@@ -475,13 +596,15 @@ class Conos:
         except Exception:
             return np.empty(n, dtype)
 
-    def _assemble(self, edges, names, fetch: bool = True) -> ConosGraph:
+    def _assemble(self, edges, names, fetch: bool = True, balance=None) -> ConosGraph:
         lib, h = self.ctx.lib, self.ctx.h
         n_total = sum(self.samples[n].counts.shape[0] for n in names)
         gh = C.c_void_p()
         self.ctx.check(lib.cg_assemble_graph(h, edges, n_total, C.byref(gh)))
         nv, ne = C.c_int32(0), C.c_int64(0)
         lib.cg_graph_sizes(gh, C.byref(nv), C.byref(ne))
+        if balance is not None and nv.value > 0:
+            self._balance_on_device(gh, nv.value, names, balance)
         if not fetch:
             lib.cg_graph_free(gh)
             z = np.zeros(0, np.int32)
@@ -506,26 +629,30 @@ class Conos:
         return ConosGraph(names=LazyNames(self._cell_names[1], vertices), vertices=vertices, edge_from=ef, edge_to=et, weight=w,
                           type=ty, adj_p=ap, adj_i=ai, adj_x=ax)
 
-    def _balance(self, g: ConosGraph, names, same_factor_downweight: float) -> ConosGraph:
-        """adjustWeightsByCellBalancing with factor = dataset per cell (R/conclass.R:346-368, R/conos.R:936-967).
-        The graph is rebuilt from the adjacency matrix, so `type` is lost like in the reference."""
-        from . import ops
-        adj = g.as_adj().tocsc().tocoo()
-        ri, ci, w = adj.row.astype(np.int32), adj.col.astype(np.int32), adj.data.astype(np.float64)
-        sample_of = np.concatenate([np.full(self.samples[n].counts.shape[0], t, np.int32)
-                                    for t, n in enumerate(names)])
-        _, fl = np.unique(sample_of[g.vertices], return_inverse=True)
-        fl = (fl + 1).astype(np.int32)
-        for _ in range(50):
-            frac = ops.getSumWeightMatrix(w, ri, ci, fl, ctx=self.ctx)
-            div = frac * (frac > 1e-10).sum(axis=1, keepdims=True)
-            w = ops.adjustWeightsByCellBalancingC(w, ri, ci, fl, div, ctx=self.ctx)
-        if abs(same_factor_downweight - 1) > 1e-5:
-            w[fl[ri] == fl[ci]] *= same_factor_downweight
-        a = sp.csc_matrix((w, (ri, ci)), shape=(len(g.vertices),) * 2).tocsr()
-        a.sort_indices()
-        up = sp.triu(a, k=1).tocoo()
-        o = np.lexsort((up.col, up.row))
-        return ConosGraph(names=g.names, vertices=g.vertices, edge_from=up.row[o].astype(np.int32),
-                          edge_to=up.col[o].astype(np.int32), weight=up.data[o], type=np.full(len(o), -1, np.int32),
-                          adj_p=a.indptr.astype(np.int64), adj_i=a.indices.astype(np.int32), adj_x=a.data)
+    def _balance_on_device(self, gh, n_vertices, names, balance):
+        """adjustWeightsByCellBalancing (R/conclass.R:346-368, R/conos.R:936-967) as one device call on the assembled
+        graph.  factor.per.cell: the caller's (cell name -> level), else balancing.factor.per.sample[dataset of the
+        cell], else the dataset itself (getDatasetPerCell); levels are numbered like as.factor() %>% droplevels()
+        (sorted unique values present in the graph)."""
+        lib, h = self.ctx.lib, self.ctx.h
+        vertices = np.empty(n_vertices, np.int32)
+        self.ctx.check(lib.cg_graph_fetch(h, gh, ptr(vertices, C.c_int32), None, None, None, None))
+        sizes = [self.samples[n].counts.shape[0] for n in names]
+        sample_of = np.repeat(np.arange(len(names)), sizes)[vertices]
+        if balance["per_cell"] is not None:
+            if self._cell_names is None or self._cell_names[0] != list(names):
+                self._cell_names = (list(names),
+                                    np.array([c for n in names for c in self.samples[n].cells], dtype=object))
+            cells = self._cell_names[1][vertices]
+            try:
+                values = [balance["per_cell"][c] for c in cells]
+            except KeyError as e:
+                raise ValueError(f"balancing.factor.per.cell has no entry for cell {e}") from None
+        elif balance["per_sample"] is not None:
+            values = [balance["per_sample"][names[t]] for t in sample_of]
+        else:
+            values = [names[t] for t in sample_of]
+        levels, codes = np.unique(np.asarray([str(v) for v in values]), return_inverse=True)
+        fac = np.ascontiguousarray(codes + 1, np.int32)
+        self.ctx.check(lib.cg_graph_balance(h, gh, ptr(fac, C.c_int32), len(levels), int(balance["balance_weights"]),
+                                            balance["downweight"], 50))

@@ -49,6 +49,7 @@ int cg_init(int device, cg_context** out) {
   ctx->c.device = device;
   ctx->c.sm_count = prop.multiProcessorCount;
   CG_CUDA(cudaStreamCreateWithFlags(&ctx->c.stream, cudaStreamNonBlocking));
+  stream_register(ctx->c.stream);
   {
     // keep freed blocks cached in the device's default pool (stream-ordered DevBuf allocations)
     cudaMemPool_t pool;
@@ -69,14 +70,37 @@ int cg_init(int device, cg_context** out) {
   CG_API_END(ctx)
 }
 
+// Order matters (the reference's DLL is unloaded by R at any time: src/RcppExports.cpp:374-377): everything the
+// context owns on the device is released while its stream is still alive, then the stream leaves the registry (so
+// that panels / edge tables / graphs the caller still holds fall back to cudaFree), and only then the stream and
+// the pool go.  Every CUDA error is swallowed: at process exit the runtime may already be unloading.
 void cg_shutdown(cg_context* ctx) {
   if (!ctx) return;
-  cudaSetDevice(ctx->c.device);
-  if (ctx->c.stream) {
-    cudaStreamSynchronize(ctx->c.stream);
-    cudaStreamDestroy(ctx->c.stream);
+  if (cudaSetDevice(ctx->c.device) != cudaSuccess) cudaGetLastError();
+  cudaStream_t st = ctx->c.stream;
+  if (st && cudaStreamSynchronize(st) != cudaSuccess) cudaGetLastError();
+  ::cg::comm_destroy(ctx->c);
+  ctx->coo.from.release();
+  ctx->coo.to.release();
+  ctx->coo.type.release();
+  ctx->coo.w.release();
+  ctx->coo.n = 0;
+  ctx->kept.clear();
+  ctx->c.rot_arena.release();
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  ctx->ev0 = ctx->ev1 = nullptr;
+  if (ctx->c.knn_ev0) cudaEventDestroy(ctx->c.knn_ev0);
+  if (ctx->c.knn_ev1) cudaEventDestroy(ctx->c.knn_ev1);
+  ctx->c.knn_ev0 = ctx->c.knn_ev1 = nullptr;
+  if (st) {
+    if (cudaStreamSynchronize(st) != cudaSuccess) cudaGetLastError();
+    stream_unregister(st);
+    if (cudaStreamDestroy(st) != cudaSuccess) cudaGetLastError();
+    ctx->c.stream = nullptr;
   }
-  if (ctx->c.panel_pool) cudaMemPoolDestroy(ctx->c.panel_pool);
+  if (ctx->c.panel_pool && cudaMemPoolDestroy(ctx->c.panel_pool) != cudaSuccess) cudaGetLastError();
+  ctx->c.panel_pool = nullptr;
   delete ctx;
 }
 
@@ -126,6 +150,10 @@ int cg_set_option(cg_context* ctx, const char* name, double value) {
     ctx->c.tc_eig_max_sweeps = (int)value;
     return 0;
   }
+  if (strcmp(name, "max_batch_bytes") == 0) {
+    ctx->c.max_batch_bytes = value < 1 ? 1 : (size_t)value;
+    return 0;
+  }
   if (strcmp(name, "knn_engine") == 0) {
     ctx->c.knn_engine = (int)value;
     return 0;
@@ -161,6 +189,10 @@ int cg_get_stat(cg_context* ctx, const char* name, double* value) {
     *value = (double)ctx->c.stats.kernels;
     return 0;
   }
+  if (strcmp(name, "knn_scores") == 0) {  // scores scanned since cg_knn_timing(1): n_query * n_ref per direction
+    *value = ctx->c.knn_scores;
+    return 0;
+  }
   return ::cg::fail(ctx, "unknown statistic");
 }
 
@@ -189,6 +221,7 @@ int cg_knn_timing(cg_context* ctx, int enable) {
   ctx->c.knn_ms_accum = 0;
   ctx->c.knn_launches = 0;
   ctx->c.knn_candidates = 0;
+  ctx->c.knn_scores = 0;
   ctx->c.knn_bytes = 0;
   CG_API_END(ctx)
 }

@@ -29,7 +29,8 @@ struct cg_context {
 };
 
 struct cg_panel {
-  cg_context* ctx = nullptr;
+  cg_context* ctx = nullptr;       // creator (may be shut down before the panel is freed: never dereferenced then)
+  cudaStream_t stream = nullptr;   // its stream, checked against the registry of live streams
   std::vector<cg::Sample> samples;
   std::vector<int> offsets;
 };

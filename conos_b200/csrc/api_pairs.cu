@@ -51,6 +51,7 @@ int cg_panel_create(cg_context* ctx, const cg_sample* samples, int n_samples, cg
     ::cg::PoolBinding pool_bind(ctx->c.panel_pool);
     pn = new cg_panel();
     pn->ctx = ctx;
+    pn->stream = ctx->c.stream;
     pn->samples.resize(n_samples);
     pn->offsets.assign(n_samples + 1, 0);
     StageScope sc(ctx->c, "panel_upload");
@@ -67,7 +68,8 @@ int cg_panel_create(cg_context* ctx, const cg_sample* samples, int n_samples, cg
     lane.ev.resize(n_samples, nullptr);
     for (int s = 0; s < n_samples; ++s) {
       const cg_sample& h = samples[s];
-      CG_CHECK(h.p && h.i && h.x, "sample counts matrix missing");
+      // p == NULL: placeholder sample (its counts live on another rank); n_cells still numbers the cells
+      CG_CHECK(h.p == nullptr || (h.i && h.x), "sample counts matrix incomplete");
       CG_CUDA(cudaEventCreateWithFlags(&lane.ev[s], cudaEventDisableTiming));
       sample_upload(ctx->c, pn->samples[s], h.n_cells, h.n_genes, h.p, h.i, h.x, h.var_v, h.var_qv, h.pca, h.n_pcs,
                     h.pca_ld > 0 ? h.pca_ld : h.n_cells, lane.st, lane.ev[s]);
@@ -103,7 +105,7 @@ int cg_panel_offsets(const cg_panel* panel, int32_t* offsets) {
 
 int cg_panel_drop_cache(cg_panel* panel) {
   if (!panel) return 1;
-  ::cg::StreamBinding bind(panel->ctx ? panel->ctx->c.stream : nullptr);
+  ::cg::StreamBinding bind(::cg::stream_alive(panel->stream) ? panel->stream : nullptr);
   for (auto& s : panel->samples) {
     s.gram.release();
     s.h_gram_diag.clear();
@@ -131,7 +133,7 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
   CG_CHECK(P.metric == CG_METRIC_ANGULAR || P.metric == CG_METRIC_L2,
            "only the following distance metrics are currently supported: ['L2' 'angular']");
   CG_CHECK(P.k1 >= P.k && P.k >= 1, "k1 must be >= k");
-  CG_CHECK(P.ncomps >= 1 && P.ncomps <= 64, "ncomps must be in 1..64");
+  CG_CHECK(P.ncomps >= 1 && P.ncomps <= 64, "ncomps must be in 1..64");  // TODO(K-loop over 64-wide slabs)
   Context& c = ctx->c;
   CG_CUDA(cudaSetDevice(c.device));
   CG_BIND(ctx);
@@ -148,14 +150,33 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
   int p0 = 0;
   while (p0 < n_pairs) {
     // per-pair footprint (bytes)
-    const size_t budget = std::min<size_t>(free_device_bytes() / 3, (size_t)24 << 30);
+    const size_t budget = std::min<size_t>(free_device_bytes() / 3, c.max_batch_bytes);
     size_t used = 0;
     int p1 = p0;
+    // a batch shares k.cur (R/conclass.R:230-233) and the width of the common space: it ends where either changes
+    auto width_of = [&](const cg_pair& pr) {
+      if (P.space == CG_SPACE_CCA) return pr.u && pr.v ? pr.uv_cols : std::min(P.ncomps, pr.n_genes - 1);
+      if (pr.rot && pr.rot_cols > 0) return std::min(P.ncomps, pr.rot_cols);
+      if (P.space == CG_SPACE_CPCA) return std::min(P.ncomps, pr.n_genes - 1);
+      return std::min(P.ncomps, 2 * (int)std::nearbyint(P.ncomps / 2.0));
+    };
+    auto k_of = [&](const cg_pair& pr) { return pr.k > 0 ? std::min(pr.k, P.k1) : P.k; };
+    const int batch_k = k_of(pairs[p0]), batch_d = width_of(pairs[p0]);
     while (p1 < n_pairs) {
       const cg_pair& pr = pairs[p1];
+      if (p1 > p0 && (k_of(pr) != batch_k || width_of(pr) != batch_d)) break;
       CG_CHECK(pr.a >= 0 && pr.a < S && pr.b >= 0 && pr.b < S && pr.a != pr.b, "pair refers to a missing sample");
       const Sample& sa = panel->samples[pr.a];
       const Sample& sb = panel->samples[pr.b];
+      CG_CHECK(sa.has_counts && sb.has_counts,
+               "pair refers to a sample whose counts are not resident on this device (placeholder sample)");
+      if (P.space != CG_SPACE_CCA || !(pr.u && pr.v)) {
+        CG_CHECK(pr.n_genes >= 0 && (pr.n_genes == 0 || (pr.genes_a && pr.genes_b)), "pair gene columns missing");
+        for (int g = 0; g < pr.n_genes; ++g)
+          CG_CHECK(pr.genes_a[g] >= 0 && pr.genes_a[g] < sa.n_genes && pr.genes_b[g] >= 0 &&
+                       pr.genes_b[g] < sb.n_genes,
+                   "pair gene column out of range");
+      }
       const size_t na = sa.n_cells, nb = sb.n_cells;
       size_t need = (round_up(na, KNN_ROW_PAD) + round_up(nb, KNN_ROW_PAD)) * 64 * 4  // panels
                     + (na + nb) * (size_t)P.k1 * 8 * 2                                   // kNN out + matching temps
@@ -202,6 +223,7 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
     std::vector<WBuildProblem> wprobs;
     std::vector<ProjProblem> pprobs;
     std::vector<int> psample, pgenes;  // sample index and gene count of every projection problem
+    std::vector<int> pproj_rot_supplied;  // per pair with projection problems: 1 when the caller supplied the rotation
     std::vector<KnnProblem> kprobs;
     std::vector<MnnProblem> mprobs;
     int d_pad_all = 0, d_all = -1;
@@ -302,6 +324,7 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
         pprobs.push_back(ProjProblem{sa.csr_p.p, sa.csr_i.p, sa.csr_x.p, B.Wa.p, B.shift.p, B.ta.p, B.p64a.p, B.na});
         pprobs.push_back(
             ProjProblem{sb.csr_p.p, sb.csr_i.p, sb.csr_x.p, B.Wb.p, B.shift.p + B.d_pad, B.tb.p, B.p64b.p, B.nb});
+        pproj_rot_supplied.push_back(pr.rot != nullptr ? 1 : 0);
         psample.push_back(pr.a);
         psample.push_back(pr.b);
         pgenes.push_back(sa.n_genes);
@@ -331,13 +354,26 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
       // of the tensor-core rotations it multiplies).  The FP64 SpMM serves the exact mode, rotations the caller
       // supplied (exact inputs: the projection stays exact too), d > 32, gene universes beyond the dense operand and
       // callers that want the raw FP64 projections back
-      bool tc_proj = c.tc_projection && !c.exact_reduction && !ctx->keep_projections && d_pad_all == 32;
-      for (int gcount : pgenes) tc_proj = tc_proj && gcount <= 4096;
-      for (int q = 0; q < nb_pairs; ++q) tc_proj = tc_proj && pairs[p0 + q].rot == nullptr;
-      if (tc_proj)
-        project_and_prep_tc(c, pprobs.data(), psample.data(), pgenes.data(), (int)pprobs.size(), d_all, metric);
-      else
-        project_and_prep(c, pprobs.data(), (int)pprobs.size(), d_all, d_pad_all, metric);
+      // The engine is chosen pair by pair, never for the batch as a whole (a pair's edges must not depend on which
+      // other pairs share its call).
+      const bool tc_mode = c.tc_projection && !c.exact_reduction && !ctx->keep_projections && d_pad_all == 32;
+      std::vector<ProjProblem> tc_probs, fp_probs;
+      std::vector<int> tc_sample, tc_genes;
+      for (size_t t = 0; t + 1 < pprobs.size(); t += 2) {
+        const bool tc = tc_mode && pgenes[t] <= 4096 && pgenes[t + 1] <= 4096 && pproj_rot_supplied[t / 2] == 0;
+        for (int side = 0; side < 2; ++side) {
+          if (tc) {
+            tc_probs.push_back(pprobs[t + side]);
+            tc_sample.push_back(psample[t + side]);
+            tc_genes.push_back(pgenes[t + side]);
+          } else {
+            fp_probs.push_back(pprobs[t + side]);
+          }
+        }
+      }
+      if (!tc_probs.empty())
+        project_and_prep_tc(c, tc_probs.data(), tc_sample.data(), tc_genes.data(), (int)tc_probs.size(), d_all, metric);
+      if (!fp_probs.empty()) project_and_prep(c, fp_probs.data(), (int)fp_probs.size(), d_all, d_pad_all, metric);
       if (ctx->keep_projections) {
         for (int q = 0; q < nb_pairs; ++q) {
           cg_context::PairKeep& keep = ctx->kept[p0 + q];
@@ -365,7 +401,7 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
     std::vector<long long> counts(nb_pairs, 0);
     {
       StageScope sc(c, "matching");
-      match_append_edges(c, mprobs.data(), nb_pairs, P.k, P.k1, sp, out, counts.data());
+      match_append_edges(c, mprobs.data(), nb_pairs, batch_k, P.k1, sp, out, counts.data());
     }
     StageScope sc_free(c, "pair_free");
     if (pair_edge_counts)
@@ -415,7 +451,7 @@ int cg_pair_projection(cg_context* ctx, int which, int side, int32_t* n_rows, in
 }
 
 int cg_local_edges(cg_context* ctx, cg_panel* panel, const int32_t* samples, int n, const cg_params* params,
-                   cg_edges** edges) {
+                   cg_edges** edges, int64_t* sample_edge_counts) {
   CG_API_BEGIN
   CG_CHECK(ctx && panel && params && edges && (samples || n == 0), "NULL argument");
   const cg_params& P = *params;
@@ -425,6 +461,8 @@ int cg_local_edges(cg_context* ctx, cg_panel* panel, const int32_t* samples, int
   CG_CUDA(cudaSetDevice(c.device));
   CG_BIND(ctx);
   if (!*edges) *edges = new cg_edges();
+  if (sample_edge_counts)
+    for (int t = 0; t < n; ++t) sample_edge_counts[t] = 0;
   if (P.k_self <= 0) return 0;
   const int kp1 = P.k_self + 1;  // +1 accounts for the self edge removed afterwards (R/conos.R:595)
   // self-kNN of every listed sample: one launch per distinct number of PCA columns (each sample brings its own
@@ -461,8 +499,10 @@ int cg_local_edges(cg_context* ctx, cg_panel* panel, const int32_t* samples, int
   StageScope sc_le(c, "local_edges");
   for (int t = 0; t < n; ++t) {
     Sample& s = panel->samples[samples[t]];
+    const size_t before = (*edges)->t.n;
     local_append_edges(c, idx[t].p, dist[t].p, s.n_cells, kp1, s.offset, P.metric, P.l2_sigma, P.k_self_weight,
                        (*edges)->t);
+    if (sample_edge_counts) sample_edge_counts[t] = (int64_t)((*edges)->t.n - before);
   }
   CG_API_END(ctx)
 }

@@ -10,6 +10,8 @@
 #include <string>
 #include <chrono>
 #include <map>
+#include <mutex>
+#include <set>
 #include <vector>
 
 namespace cg {
@@ -59,6 +61,34 @@ struct StreamBinding {
   ~StreamBinding() { bound_stream() = prev; }
 };
 
+// Streams owned by live contexts.  A device buffer remembers the stream it was allocated on; when its owner (panel,
+// edge table, graph) outlives the context -- a host language that finalises objects in arbitrary order at exit --
+// the block is returned with cudaFree instead of cudaFreeAsync on a destroyed stream (undefined behaviour).
+// The registry is never destroyed: destructors may run during static destruction.
+struct StreamRegistry {
+  std::mutex m;
+  std::set<cudaStream_t> live;
+};
+inline StreamRegistry& stream_registry() {
+  static StreamRegistry* r = new StreamRegistry();
+  return *r;
+}
+inline void stream_register(cudaStream_t s) {
+  StreamRegistry& r = stream_registry();
+  std::lock_guard<std::mutex> g(r.m);
+  r.live.insert(s);
+}
+inline void stream_unregister(cudaStream_t s) {
+  StreamRegistry& r = stream_registry();
+  std::lock_guard<std::mutex> g(r.m);
+  r.live.erase(s);
+}
+inline bool stream_alive(cudaStream_t s) {
+  StreamRegistry& r = stream_registry();
+  std::lock_guard<std::mutex> g(r.m);
+  return r.live.count(s) != 0;
+}
+
 template <class T>
 struct DevBuf {
   T* p = nullptr;
@@ -76,7 +106,9 @@ struct DevBuf {
   ~DevBuf() { release(); }
   void release() {
     if (p) {
-      if (owner) cudaFreeAsync(p, owner); else cudaFree(p);
+      // errors are dropped on purpose: at process exit the runtime may already be unloading (cudaErrorCudartUnloading)
+      cudaError_t e = (owner && stream_alive(owner)) ? cudaFreeAsync(p, owner) : cudaFree(p);
+      if (e != cudaSuccess) cudaGetLastError();
     }
     p = nullptr; n = 0;
   }
@@ -127,7 +159,14 @@ struct PinnedArena {
     off += bytes;
     return r;
   }
-  ~PinnedArena() { for (char* b : blocks) cudaFreeHost(b); }
+  void release() {
+    for (char* b : blocks)
+      if (cudaFreeHost(b) != cudaSuccess) cudaGetLastError();
+    blocks.clear();
+    caps.clear();
+    cur = off = 0;
+  }
+  ~PinnedArena() { release(); }
 };
 
 // Per-context launch statistics (bench.py reports them as gpu_launches).
@@ -135,8 +174,11 @@ struct LaunchStats {
   uint64_t kernels = 0;
 };
 
+struct Comm;  // NCCL communicator of a multi-GPU run (comm.cu); nullptr for a single-GPU context
+
 struct Context {
   int device = 0;
+  Comm* comm = nullptr;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   std::string last_error;
@@ -145,7 +187,9 @@ struct Context {
   bool time_knn = false;
   double knn_ms_accum = 0.0;
   uint64_t knn_launches = 0;
-  double knn_candidates = 0.0;  // sum over launches of n_query * n_ref
+  double knn_candidates = 0.0;  // sum over launches of n_a * n_b, ONE matrix per pair (both directions)
+  double knn_scores = 0.0;      // scores the kernels scanned: n_query * n_ref per direction
+  cudaEvent_t knn_ev0 = nullptr, knn_ev1 = nullptr;
   double knn_bytes = 0.0;       // algorithmic HBM bytes
   // kNN engine: 0 = auto (two-phase tensor-core kernel, streaming kernel for small problems and redo blocks),
   // 1 = streaming tensor-core kernel only, 2 = exact SIMT kernel only
@@ -160,10 +204,13 @@ struct Context {
   bool tc_projection = true;   // default mode: project through the tensor-core GEMM (false: FP64 SpMM everywhere)
   int tc_eig_degree = 10;      // tensor-core eigen solver: largest Chebyshev degree of a sweep
   int tc_eig_max_sweeps = 40;  // tensor-core eigen solver: sweeps before a problem is handed to the FP64 driver
+  size_t max_batch_bytes = (size_t)24 << 30;  // scratch budget of one batch of pairs in cg_pairs_edges (tests shrink it)
   // optional per-stage wall-clock profile (stream synchronised at both ends of a stage)
   bool profile = false;
   std::map<std::string, double> stage_ms;
 };
+
+void comm_destroy(Context& c);
 
 struct StageScope {
   Context& c;

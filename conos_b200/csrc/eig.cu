@@ -40,7 +40,7 @@ __global__ void eig_init_kernel(const EigWork* __restrict__ works) {
 template <int B>
 __global__ void __launch_bounds__(256) eig_matmul_kernel(const EigWork* __restrict__ works) {
   const EigWork w = works[blockIdx.y];
-  if (w.converged && *w.converged == 2) return;
+  if (w.converged && *w.converged != 0) return;  // locked: a converged problem is never touched again
   __shared__ double crow[8][128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + warp;
@@ -375,7 +375,8 @@ __global__ void __launch_bounds__(EIG_THREADS) eig_orth_kernel(const EigWork* __
   extern __shared__ __align__(16) unsigned char raw[];
   EigSmem<B>& sm = *reinterpret_cast<EigSmem<B>*>(raw);
   const EigWork w = works[blockIdx.x];
-  if (w.converged && *w.converged == 2) return;
+  // a problem is locked the moment it converges: its result cannot depend on how long its batch mates take
+  if (w.converged && *w.converged != 0) return;
   orth_pass<B>(w.Z, w.Q, w.G, sm);
   // CholeskyQR2: the second pass only when the first saw an ill-conditioned block
   if (!sm.wellcond) orth_pass<B>(w.Q, w.Q, w.G, sm);
@@ -389,7 +390,7 @@ __global__ void __launch_bounds__(EIG_THREADS) eig_rr_kernel(const EigWork* __re
   extern __shared__ __align__(16) unsigned char raw[];
   EigSmem<B>& sm = *reinterpret_cast<EigSmem<B>*>(raw);
   const EigWork w = works[blockIdx.x];
-  if (*w.converged == 2) return;
+  if (*w.converged != 0) return;  // locked (see eig_orth_kernel): Q already holds the sorted Ritz vectors
   const int tid = threadIdx.x;
   block_gram<B>(w.Q, w.Z, w.G, sm.S);
   for (int t = tid; t < B * B; t += EIG_THREADS) {
@@ -670,8 +671,7 @@ void run_eig_generic(Context& ctx, const int* rows, double* const* Vout, double*
     }
     {
       StageScope sc(ctx, "reduction.eig.orth");
-      // converged problems keep their Ritz basis: their Z = Op Q is re-orthonormalised, which leaves span(Q)
-      // invariant to the accuracy already reached
+      // converged problems are locked: every kernel of the loop skips them
       eig_orth_kernel<B><<<n_probs, EIG_THREADS, smem, s>>>(dw.p);
       ctx.stats.kernels++;
     }
@@ -729,6 +729,7 @@ struct TcSampleDev {
 };
 struct TcProbDev {
   int sample, col0;
+  unsigned seed;  // stable identity of the problem (sample pair + side): the start block never depends on the batch
   const double* f;
   double* Q;  // [G][32] row-major
   double* Z;
@@ -745,14 +746,18 @@ __global__ void tc_center_gram_kernel(const double* __restrict__ M, const double
   Mc[t] = M[t] - (colsum[i] / n) * (colsum[j] / n) * n;
 }
 
-__global__ void tc_init_kernel(const TcSampleDev* __restrict__ S) {
-  const TcSampleDev sd = S[blockIdx.y];
+__global__ void tc_init_kernel(const TcSampleDev* __restrict__ S, const TcProbDev* __restrict__ P) {
+  const TcProbDev pd = P[blockIdx.y];
+  const TcSampleDev sd = S[pd.sample];
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < (size_t)sd.G * sd.n_cols) sd.Y[t] = (float)hash_unit((unsigned)(t % sd.G), (unsigned)(t / sd.G) + 977u * blockIdx.y);
+  if (t >= (size_t)sd.G * TB) return;
+  const unsigned g = (unsigned)(t % sd.G), j = (unsigned)(t / sd.G);
+  sd.Y[(size_t)(pd.col0 + j) * sd.G + g] = (float)hash_unit(g, j + 64u * pd.seed);
 }
 
 __global__ void tc_to64_kernel(const TcSampleDev* __restrict__ S, const TcProbDev* __restrict__ P) {
   const TcProbDev pd = P[blockIdx.y];
+  if (*pd.converged != 0) return;  // locked
   const TcSampleDev sd = S[pd.sample];
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)sd.G * TB) return;
@@ -792,6 +797,7 @@ __global__ void __launch_bounds__(256) tc_column_kernel(const TcSampleDev* __res
   const int col = col_local[gc];
   const int pidx = sd.first_prob + col / TB, j = col % TB;
   const TcProbDev pd = P[pidx];
+  if (*pd.converged != 0) return;  // locked: its columns of the GEMM are idle
   if (mode == 2 && step > deg[pidx]) return;  // this problem's sweep is shorter: keep its X, Y
   const int G = sd.G;
   const double n = (double)sd.n_cells;
@@ -854,6 +860,10 @@ __global__ void tc_coeff_kernel(const TcProbDev* __restrict__ P, int n_probs, in
                                 float* __restrict__ cc, int* __restrict__ deg) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_probs) return;
+  if (*P[p].converged != 0) {  // locked: no filter steps
+    deg[p] = 0;
+    return;
+  }
   const double a0 = P[p].theta[0];
   double b = P[p].theta[TB - 1];
   if (!(b > 1e-7 * a0)) b = 1e-7 * a0;
@@ -937,9 +947,9 @@ void top_eigenvectors_shared_gram(Context& ctx, const TcEigSample* samples, int 
   std::vector<int> col_sample, col_local;
   size_t panel_elems = 0, u_elems = 0, qz_elems = 0, n_cols_total = 0;
   for (int si = 0; si < n_samples; ++si) {
-    const int G = samples[si].G;
-    CG_CHECK(G >= B, "tensor-core eigen path needs at least 32 genes");
     const int nc = B * (int)by_sample[si].size();
+    const int G = nc > 0 ? samples[si].G : 0;  // samples without a problem (not resident on this rank) take no space
+    CG_CHECK(nc == 0 || G >= B, "tensor-core eigen path needs at least 32 genes");
     hs[si].colsum = nullptr;  // the operand is the centred Gram matrix: no rank-one correction left
     hs[si].G = G;
     hs[si].n_cells = samples[si].n_cells;
@@ -986,7 +996,7 @@ void top_eigenvectors_shared_gram(Context& ctx, const TcEigSample* samples, int 
       co += nc;
       for (int t = 0; t < (int)by_sample[si].size(); ++t, ++pi) {
         const TcEigProblem& ep = probs[order[pi]];
-        hp.push_back(TcProbDev{si, t * B, ep.f, Q.p + qo, Z.p + qo, theta.p + (size_t)pi * B, conv.p + pi});
+        hp.push_back(TcProbDev{si, t * B, ep.seed, ep.f, Q.p + qo, Z.p + qo, theta.p + (size_t)pi * B, conv.p + pi});
         qo += (size_t)G * B;
       }
       if (nc == 0) continue;
@@ -1040,10 +1050,8 @@ void top_eigenvectors_shared_gram(Context& ctx, const TcEigSample* samples, int 
     ctx.stats.kernels++;
   };
   {
-    int maxcols = 0;
-    for (auto& h : hs) maxcols = h.n_cols > maxcols ? h.n_cols : maxcols;
-    dim3 gi((unsigned)(((size_t)maxG * maxcols + 255) / 256), n_samples);
-    tc_init_kernel<<<gi, 256, 0, s>>>(dS.p);
+    dim3 gi((unsigned)(((size_t)maxG * B + 255) / 256), n_probs);
+    tc_init_kernel<<<gi, 256, 0, s>>>(dS.p, dP.p);
     ctx.stats.kernels++;
   }
   std::vector<int> hc(n_probs), hdeg(n_probs);

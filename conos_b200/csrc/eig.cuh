@@ -41,6 +41,8 @@ struct TcEigSample {
 };
 struct TcEigProblem {
   int sample;
+  unsigned seed;    // stable identity (sample pair + side): seeds the start block, so that the result of a problem is
+                    // the same whatever batch, shard or GPU count it is solved in
   const double* f;  // [G] scale factors (device)
   double* V;        // out: G x r column-major
   double* theta;    // out: [r]

@@ -514,10 +514,17 @@ void knn_tc_launch(Context& ctx, const KnnProblem* d_probs, const KnnProblem* h_
   std::vector<KnnItem> items;
   std::vector<KnnTc2Aux> aux((size_t)n_probs);
   std::vector<int> plist;
-  double cand = 0.0, bytes = 0.0;
+  double cand = 0.0, scores = 0.0, bytes = 0.0;
   for (int p = 0; p < n_probs; ++p) {
     if (h_probs[p].nq <= 0) continue;
-    cand += (double)h_probs[p].nq * (double)h_probs[p].nr;
+    // ONE distance matrix serves both directions of a pair -- a problem whose mirror image (operands
+    // swapped) is part of the same launch counts half; a sample against itself counts in full
+    bool mirrored = false;
+    for (int o = 0; o < n_probs && !mirrored; ++o)
+      mirrored = o != p && h_probs[o].q_tiled == h_probs[p].r_tiled && h_probs[o].r_tiled == h_probs[p].q_tiled &&
+                 h_probs[p].q_tiled != h_probs[p].r_tiled;
+    cand += (mirrored ? 0.5 : 1.0) * (double)h_probs[p].nq * (double)h_probs[p].nr;
+    scores += (double)h_probs[p].nq * (double)h_probs[p].nr;
     bytes += 4.0 * d_pad * ((double)h_probs[p].nq + h_probs[p].nr) + 8.0 * k * (double)h_probs[p].nq;
     if (ctx.knn_engine == 0 && knn_tc2_plan(h_probs[p].nr, k, aux[p])) {
       plist.push_back(p);
@@ -527,11 +534,12 @@ void knn_tc_launch(Context& ctx, const KnnProblem* d_probs, const KnnProblem* h_
     for (int b = 0; b < nb; ++b) items.push_back(KnnItem{p, b});
   }
   if (items.empty() && plist.empty()) return;
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ctx.time_knn) {
-    CG_CUDA(cudaEventCreate(&e0));
-    CG_CUDA(cudaEventCreate(&e1));
-    CG_CUDA(cudaEventRecord(e0, ctx.stream));
+    if (!ctx.knn_ev0) {
+      CG_CUDA(cudaEventCreate(&ctx.knn_ev0));
+      CG_CUDA(cudaEventCreate(&ctx.knn_ev1));
+    }
+    CG_CUDA(cudaEventRecord(ctx.knn_ev0, ctx.stream));
   }
   if (!plist.empty()) knn_tc2_run(ctx, d_probs, h_probs, plist, aux, n_probs, k, d_pad, d, items);
   if (!items.empty()) {
@@ -548,16 +556,15 @@ void knn_tc_launch(Context& ctx, const KnnProblem* d_probs, const KnnProblem* h_
     }
   }
   if (ctx.time_knn) {
-    CG_CUDA(cudaEventRecord(e1, ctx.stream));
-    CG_CUDA(cudaEventSynchronize(e1));
+    CG_CUDA(cudaEventRecord(ctx.knn_ev1, ctx.stream));
+    CG_CUDA(cudaEventSynchronize(ctx.knn_ev1));
     float ms = 0.f;
-    CG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    CG_CUDA(cudaEventElapsedTime(&ms, ctx.knn_ev0, ctx.knn_ev1));
     ctx.knn_ms_accum += ms;
     ctx.knn_launches++;
     ctx.knn_candidates += cand;
+    ctx.knn_scores += scores;
     ctx.knn_bytes += bytes;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
   }
 }
 

@@ -104,11 +104,12 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
     if (P.space == CG_SPACE_CCA) {
       if (pr.u && pr.v) {
         CG_CHECK(pr.n_u > 0 && pr.n_v > 0 && pr.rows_u && pr.rows_v, "CCA needs the row maps of u and v");
+        CG_CHECK(pr.uv_cols >= 1, "cached CCA variates need their column count (uv_cols)");
         R.n_u = pr.n_u;
         R.n_v = pr.n_v;
-        R.d = P.ncomps;
-        R.u.upload(pr.u, (size_t)pr.n_u * P.ncomps, st);
-        R.v.upload(pr.v, (size_t)pr.n_v * P.ncomps, st);
+        R.d = pr.uv_cols;  // every cached column, whatever ncomps says now (R/conclass.R:268-270)
+        R.u.upload(pr.u, (size_t)pr.n_u * pr.uv_cols, st);
+        R.v.upload(pr.v, (size_t)pr.n_v * pr.uv_cols, st);
         R.h_rows_u.assign(pr.rows_u, pr.rows_u + pr.n_u);
         R.h_rows_v.assign(pr.rows_v, pr.rows_v + pr.n_v);
       } else {
@@ -117,6 +118,8 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
     } else {
       CG_CHECK(pr.n_genes >= 5, "fewer than 5 common od genes: the reference drops such pairs (R/conos.R:206,278)");
       if (pr.rot && pr.rot_cols > 0) {
+        CG_CHECK(pr.rot_rows == pr.n_genes,
+                 "cached rotation: rot_rows must equal n_genes (the pair's genes are the rownames of the cached CPC)");
         R.n_rows = pr.n_genes;
         R.n_cols = pr.rot_cols;
         R.d = P.ncomps < pr.rot_cols ? P.ncomps : pr.rot_cols;
@@ -154,16 +157,25 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
     // tensor-core path: the operator of every pair acts on the per-sample centred Gram matrix over the sample's
     // whole gene universe; the pair's gene set (any subset, any order) enters through the diagonal scaling (zero
     // outside the set) and a row gather of the eigenvectors.  The Gram matrix is dense: bounded universe only.
-    bool shared = !ctx.exact_reduction && r <= 24;
-    for (int q : todo) {
-      const cg_pair& pr = pairs[q];
-      const Sample& sa = panel.samples[pr.a];
-      const Sample& sb = panel.samples[pr.b];
-      if (pr.n_genes < 32 || sa.n_genes < 32 || sb.n_genes < 32 || sa.n_genes > 4096 || sb.n_genes > 4096)
-        shared = false;
-      if (!shared) break;
+    // The choice is made pair by pair (never for a batch as a whole: the result of a pair must not depend on which
+    // other pairs share its call); pairs that do not qualify take the FP64 driver below.
+    std::vector<int> fp64_pairs;
+    if (!ctx.exact_reduction && r <= 24) {
+      std::vector<int> tc_pairs;
+      for (int q : todo) {
+        const cg_pair& pr = pairs[q];
+        const Sample& sa = panel.samples[pr.a];
+        const Sample& sb = panel.samples[pr.b];
+        const bool ok = pr.n_genes >= 32 && sa.n_genes >= 32 && sb.n_genes >= 32 && sa.n_genes <= 4096 &&
+                        sb.n_genes <= 4096;
+        (ok ? tc_pairs : fp64_pairs).push_back(q);
+      }
+      todo = tc_pairs;
+    } else {
+      fp64_pairs = todo;
+      todo.clear();
     }
-    if (shared) {
+    if (!todo.empty()) {
       const int S = (int)panel.samples.size();
       std::vector<TcEigSample> ts(S);
       for (int si = 0; si < S; ++si) {
@@ -231,7 +243,9 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
           pbs[t].V[side] = d_V.p + o_v;
           o_v += (size_t)Gs * r;
           pbs[t].theta[side] = d_theta.p + (2 * t + side) * (size_t)r;
-          tp.push_back(TcEigProblem{side == 0 ? pr.a : pr.b, pbs[t].f[side], pbs[t].V[side], pbs[t].theta[side]});
+          // identity of the problem: (sample a, sample b, side) -- the same on every rank and in every batch
+          const unsigned seed = ((unsigned)pr.a * 40503u + (unsigned)pr.b) * 2u + (unsigned)side;
+          tp.push_back(TcEigProblem{side == 0 ? pr.a : pr.b, seed, pbs[t].f[side], pbs[t].V[side], pbs[t].theta[side]});
         }
       }
       CG_CUDA(cudaMemcpyAsync(d_f.p, h_f.data(), h_f.size() * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -287,11 +301,13 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
         }
       }
       CG_CUDA(cudaStreamSynchronize(st));
-      if (redo.empty()) return;
       ctx.eig_redo_pairs += redo.size();
       if (ctx.profile) ctx.stage_ms["reduction.eig.fp64_redo_pairs"] += (double)redo.size();
-      todo = redo;
+      fp64_pairs.insert(fp64_pairs.end(), redo.begin(), redo.end());
+      std::sort(fp64_pairs.begin(), fp64_pairs.end());
     }
+    todo = fp64_pairs;
+    if (todo.empty()) return;
     const int B = r <= 24 ? 32 : 64;
     // chunks of pairs bounded by memory (2 covariance matrices per pair)
     size_t i0 = 0;

@@ -175,18 +175,22 @@ void sample_upload(Context& ctx, Sample& s, int n_cells, int n_genes, const int*
                    cudaStream_t copy_st, cudaEvent_t ready) {
   cudaStream_t st = ctx.stream;
   if (!copy_st) copy_st = st;
-  CG_CHECK(n_cells > 0 && n_genes > 0, "sample must have cells and genes");
+  s.has_counts = p != nullptr;
+  CG_CHECK(n_cells > 0 && (n_genes > 0 || !s.has_counts), "sample must have cells and genes");
   s.n_cells = n_cells;
-  s.n_genes = n_genes;
-  s.nnz = p[n_genes];
-  for (int g = 0; g < n_genes; ++g) CG_CHECK(p[g + 1] >= p[g], "dgCMatrix @p must be non-decreasing");
-  s.csc_p.alloc((size_t)n_genes + 1);
-  s.csc_i.alloc((size_t)s.nnz);
-  s.csc_x.alloc((size_t)s.nnz);
-  s.csr_p.alloc((size_t)n_cells + 1);
-  s.csr_i.alloc((size_t)s.nnz);
-  s.csr_x.alloc((size_t)s.nnz);
-  s.colsum.alloc((size_t)n_genes);
+  s.n_genes = s.has_counts ? n_genes : 0;
+  s.nnz = s.has_counts ? p[n_genes] : 0;
+  if (s.has_counts) {
+    CG_CHECK(i != nullptr && x != nullptr, "sample counts matrix incomplete");
+    for (int g = 0; g < n_genes; ++g) CG_CHECK(p[g + 1] >= p[g], "dgCMatrix @p must be non-decreasing");
+    s.csc_p.alloc((size_t)n_genes + 1);
+    s.csc_i.alloc((size_t)s.nnz);
+    s.csc_x.alloc((size_t)s.nnz);
+    s.csr_p.alloc((size_t)n_cells + 1);
+    s.csr_i.alloc((size_t)s.nnz);
+    s.csr_x.alloc((size_t)s.nnz);
+    s.colsum.alloc((size_t)n_genes);
+  }
   s.n_pcs = 0;
   s.pca_metric = -1;
   if (pca && n_pcs > 0) {
@@ -200,11 +204,13 @@ void sample_upload(Context& ctx, Sample& s, int n_cells, int n_genes, const int*
     CG_CUDA(cudaStreamWaitEvent(copy_st, ea, 0));
     CG_CUDA(cudaEventDestroy(ea));
   }
-  s.csc_p.upload(p, (size_t)n_genes + 1, copy_st);
-  s.csc_i.upload(i, (size_t)s.nnz, copy_st);
-  s.csc_x.upload(x, (size_t)s.nnz, copy_st);
-  if (var_v) s.h_v.assign(var_v, var_v + n_genes);
-  if (var_qv) s.h_qv.assign(var_qv, var_qv + n_genes);
+  if (s.has_counts) {
+    s.csc_p.upload(p, (size_t)n_genes + 1, copy_st);
+    s.csc_i.upload(i, (size_t)s.nnz, copy_st);
+    s.csc_x.upload(x, (size_t)s.nnz, copy_st);
+    if (var_v) s.h_v.assign(var_v, var_v + n_genes);
+    if (var_qv) s.h_qv.assign(var_qv, var_qv + n_genes);
+  }
   s.h_logqv.resize(s.h_qv.size());
   s.h_expv.resize(s.h_v.size());
   for (size_t g = 0; g < s.h_qv.size(); ++g) s.h_logqv[g] = std::log(s.h_qv[g]);
@@ -223,6 +229,7 @@ void sample_upload(Context& ctx, Sample& s, int n_cells, int n_genes, const int*
 void sample_finish(Context& ctx, Sample& s, cudaEvent_t ready) {
   cudaStream_t st = ctx.stream;
   if (ready) CG_CUDA(cudaStreamWaitEvent(st, ready, 0));
+  if (!s.has_counts) return;
   csc_to_csr(ctx, s.n_cells, s.n_genes, s.csc_p.p, s.csc_i.p, s.csc_x.p, s.nnz, s.csr_p.p, s.csr_i.p, s.csr_x.p);
   colsum_kernel<<<(s.n_genes + 7) / 8, 256, 0, st>>>(s.csc_p.p, s.csc_x.p, s.n_genes, s.colsum.p);
   ctx.stats.kernels++;

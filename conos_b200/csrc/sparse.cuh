@@ -12,6 +12,9 @@ struct Sample {
   int n_cells = 0, n_genes = 0;
   long long nnz = 0;
   int offset = 0;  // global cell-id offset
+  // false: a placeholder (multi-GPU runs upload the counts of a sample only to the ranks whose pairs touch it; the
+  // cell count still fixes the global cell ids, and the per-sample PCA may be present for the local neighbours)
+  bool has_counts = false;
   // counts, cells x genes: CSC as given (by gene) and CSR built on device (by cell, columns ascending)
   DevBuf<int> csc_p, csc_i;
   DevBuf<double> csc_x;

@@ -1,100 +1,62 @@
-"""Pair sharding and the edge-table allgatherv for one-process-per-GPU runs (torch.distributed plumbing).
+"""Host-side helpers of one-process-per-GPU runs.
 
-The sample-pair list is cut into contiguous ranges balanced by cells_a x cells_b, so the gathered table is
-simply the concatenation of the ranks' tables in rank order == the reference's combn order
-(R/conclass.R:1058, 224-317).  The only exchange step of the path is this allgatherv (NCCL on the GPU,
-gloo in the CPU tests); there is no other data-path collective.
+Everything on the data path lives in libconosgpu.so: the partition of the pair list (cg_partition_pairs), the NCCL
+communicator (cg_comm_init) and the allgatherv of the per-rank edge tables in the reference's row order
+(cg_edges_allgatherv; R/conclass.R:224-317 maps over the pairs, :316-321 rbinds the per-pair tables).  This module
+holds the thin Python bindings of the two functions that need no GPU, and a NumPy restatement of the gathered
+layout that the CPU tests (gloo, world_size 2) check the host logic with.
 """
 from __future__ import annotations
 
-from typing import List, Sequence, Tuple
+import ctypes as C
+from typing import Optional, Sequence
 
 import numpy as np
 
-
-def partition_contiguous(costs: Sequence[float], n_parts: int) -> List[Tuple[int, int]]:
-    """Cut range(len(costs)) into n_parts contiguous ranges with near-equal cost sums.
-    Boundaries are placed where the running sum crosses i/n of the total (deterministic, O(n))."""
-    costs = np.asarray(costs, dtype=np.float64)
-    n = len(costs)
-    if n_parts <= 1 or n == 0:
-        return [(0, n)] + [(n, n)] * (max(n_parts, 1) - 1)
-    cum = np.concatenate([[0.0], np.cumsum(costs)])
-    total = cum[-1]
-    bounds = [0]
-    for i in range(1, n_parts):
-        target = total * i / n_parts
-        # first index whose prefix sum reaches the target, but keep ranges non-decreasing
-        b = int(np.searchsorted(cum, target, side="left"))
-        # choose the closer of b-1 / b
-        if b > 0 and abs(cum[b - 1] - target) <= abs(cum[min(b, n)] - target):
-            b -= 1
-        bounds.append(min(max(b, bounds[-1]), n))
-    bounds.append(n)
-    return [(bounds[i], bounds[i + 1]) for i in range(n_parts)]
+from . import _lib
+from ._lib import ptr
 
 
-def allgather_columns(cols, group=None):
-    """allgatherv of equally long 1-D tensors (one per column of the edge table): every rank receives the
-    concatenation over ranks, in rank order.  Works for CUDA tensors (NCCL) and CPU tensors (gloo).
-    Returns (gathered columns, counts per rank)."""
-    import torch
-    import torch.distributed as dist
-    world = dist.get_world_size(group)
-    n = int(cols[0].numel())
-    dev = cols[0].device
-    cnt = torch.tensor([n], dtype=torch.int64, device=dev)
-    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(counts, cnt, group=group)
-    counts = [int(c.item()) for c in counts]
-    mx = max(counts) if counts else 0
-    out = []
-    for c in cols:
-        pad = torch.zeros(mx, dtype=c.dtype, device=dev)
-        pad[:n] = c
-        parts = [torch.empty(mx, dtype=c.dtype, device=dev) for _ in range(world)]
-        if mx > 0:
-            dist.all_gather(parts, pad, group=group)
-        out.append(torch.cat([p[:k] for p, k in zip(parts, counts)]) if mx > 0
-                   else torch.empty(0, dtype=c.dtype, device=dev))
-    return out, counts
+def partition_pairs(a: Sequence[int], b: Sequence[int], cost: Sequence[float], world: int,
+                    sample_cost: Optional[Sequence[float]] = None, n_samples: Optional[int] = None) -> np.ndarray:
+    """owner[q] = rank of pair q (cg_partition_pairs: longest-processing-time greedy with sample locality).
+    Deterministic and GPU-free: every rank computes the same table."""
+    lib = _lib.load()
+    a = np.ascontiguousarray(a, np.int32)
+    b = np.ascontiguousarray(b, np.int32)
+    cost = np.ascontiguousarray(cost, np.float64)
+    if n_samples is None:
+        n_samples = int(max(a.max(initial=-1), b.max(initial=-1)) + 1)
+    sc = None if sample_cost is None else np.ascontiguousarray(sample_cost, np.float64)
+    owner = np.zeros(len(a), np.int32)
+    rc = lib.cg_partition_pairs(ptr(a, C.c_int32), ptr(b, C.c_int32), ptr(cost, C.c_double), len(a),
+                                ptr(sc, C.c_double), n_samples, world, ptr(owner, C.c_int32))
+    if rc != 0:
+        raise _lib.ConosGpuError((lib.cg_last_error(None) or b"cg_partition_pairs failed").decode())
+    return owner
 
 
-class _DevArray:
-    """Zero-copy view of library-owned device memory for torch (CUDA array interface v2)."""
-
-    def __init__(self, ptr: int, n: int, typestr: str):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
-
-
-def device_columns(ctx, edges):
-    """torch CUDA tensors aliasing the four columns of a cg_edges table (from, to, w, type)."""
-    import ctypes as C
-    import torch
-    n = int(ctx.lib.cg_edges_count(edges))
-    f, t, w, ty = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
-    ctx.lib.cg_edges_device_ptrs(edges, C.byref(f), C.byref(t), C.byref(w), C.byref(ty))
-    dev = torch.device("cuda", ctx.device)
-    if n == 0:
-        return [torch.empty(0, dtype=torch.int32, device=dev), torch.empty(0, dtype=torch.int32, device=dev),
-                torch.empty(0, dtype=torch.float64, device=dev), torch.empty(0, dtype=torch.int32, device=dev)]
-    mk = lambda p, ts: torch.as_tensor(_DevArray(p.value, n, ts), device=dev)
-    return [mk(f, "<i4"), mk(t, "<i4"), mk(w, "<f8"), mk(ty, "<i4")]
+def gathered_layout(seg_owner: Sequence[int], seg_counts: Sequence[int], world: int):
+    """The layout cg_edges_allgatherv builds (comm.cu): every rank's table lands in a staging table rank after rank,
+    then segment s moves from staging row src_off[s] to row dst_off[s] of the gathered table (segments ascending).
+    Returns (rank_off [world + 1], src_off [n_seg], dst_off [n_seg + 1])."""
+    seg_owner = np.asarray(seg_owner, np.int64)
+    seg_counts = np.asarray(seg_counts, np.int64)
+    rank_total = np.bincount(seg_owner, weights=seg_counts, minlength=world).astype(np.int64)
+    rank_off = np.concatenate([[0], np.cumsum(rank_total)])
+    dst_off = np.concatenate([[0], np.cumsum(seg_counts)])
+    src_off = np.zeros(len(seg_owner), np.int64)
+    cursor = rank_off[:-1].copy()
+    for s, (o, c) in enumerate(zip(seg_owner, seg_counts)):
+        src_off[s] = cursor[o]
+        cursor[o] += c
+    return rank_off, src_off, dst_off
 
 
-def gather_edges(ctx, edges, group=None):
-    """Replace a rank-local cg_edges table by the table gathered over all ranks (rank order). Returns the new
-    handle and the per-rank counts."""
-    import ctypes as C
-    import torch
-    cols = device_columns(ctx, edges)
-    torch.cuda.synchronize(ctx.device)
-    gathered, counts = allgather_columns(cols, group)
-    torch.cuda.synchronize(ctx.device)
-    new = C.c_void_p()
-    n = int(gathered[0].numel())
-    ctx.check(ctx.lib.cg_edges_append_device(ctx.h, C.byref(new), C.c_void_p(gathered[0].data_ptr()),
-                                             C.c_void_p(gathered[1].data_ptr()), C.c_void_p(gathered[2].data_ptr()),
-                                             C.c_void_p(gathered[3].data_ptr()), n))
-    ctx.lib.cg_edges_free(edges)
-    return new, counts
+def permute_gathered(staging: np.ndarray, src_off, dst_off) -> np.ndarray:
+    """NumPy restatement of permute_segments_kernel: rows of the staging table in gathered (segment) order."""
+    out = np.empty_like(staging)
+    for s in range(len(src_off)):
+        n = dst_off[s + 1] - dst_off[s]
+        out[dst_off[s]:dst_off[s] + n] = staging[src_off[s]:src_off[s] + n]
+    return out

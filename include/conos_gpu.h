@@ -19,10 +19,13 @@
  *   _conos_spcov                 src/spcov.cpp:14-19,  src/RcppExports.cpp:349-370    -> cg_spcov
  *   _conos_cpcaF                 src/cpca.cpp:16-101                                  -> cg_cpca
  *   _conos_pareDownHubEdges      src/edgeFilter.cpp:23-60                             -> cg_pare_down_hub_edges
+ *   adjustWeightsByCellBalancing (50 rounds + downweight)         R/conos.R:936-967    -> cg_graph_balance
  *   _conos_getSumWeightMatrix    src/edge_rebalancing.cpp:14-36                       -> cg_sum_weight_matrix
  *   _conos_adjustWeightsByCellBalancingC  src/edge_rebalancing.cpp:39-48              -> cg_adjust_weights
  *   _conos_referenceWij          src/edgeweights.cpp:160-184                          -> cg_reference_wij
  *   edge table -> graph_from_edgelist -> simplify                 R/conclass.R:321-343 -> cg_assemble_graph
+ *   papply / plapply fork pools over pairs and samples            R/conclass.R:224,1074; R/conos.R:399,589
+ *                                                        -> cg_comm_init, cg_partition_pairs, cg_edges_allgatherv
  */
 #ifndef CONOS_GPU_H
 #define CONOS_GPU_H
@@ -65,7 +68,9 @@ int cg_timer_stop(cg_context* ctx, double* ms);
  * measured on configs[1]: 10.4 / 8.8 / 9.1 / 9.2 ms for the 56 eigenproblems).
  * "tc_projection" (default 1): in the default mode the projections of device-computed rotations run as one bf16x3
  * tensor-core GEMM per sample (fp32 accumulation); 0 keeps the FP64 sparse product, which the exact mode, cached
- * rotations and cg_keep_projections always use. */
+ * rotations and cg_keep_projections always use.
+ * "max_batch_bytes" (default 24 GB): scratch budget of one batch of pairs inside cg_pairs_edges; the result never
+ * depends on how the pair list is cut into batches (tests set 1 to get one pair per batch). */
 int cg_set_option(cg_context* ctx, const char* name, double value);
 /* counters: "knn_redo_blocks" (256-row blocks recomputed by the streaming kernel), "eig_redo_pairs" (pairs the
  * tensor-core eigen solver handed to the FP64 driver), "kernel_launches" */
@@ -73,7 +78,9 @@ int cg_get_stat(cg_context* ctx, const char* name, double* value);
 /* optional per-stage wall-clock profile: enable (resets), then dump "name=ms;name=ms;..." into buf */
 int cg_profile(cg_context* ctx, int enable);
 int cg_profile_dump(cg_context* ctx, char* buf, int buf_len);
-/* optional CUDA-event timing of the dominant kernel (fused cross-kNN): enable, then read and reset */
+/* optional CUDA-event timing of the dominant kernel (cross-kNN): enable, then read and reset.  `candidates` follows
+ * n_a * n_b per sample pair, ONE distance matrix for both directions (a self search counts n^2);
+ * cg_get_stat("knn_scores") gives the scores the kernels actually scanned (per direction). */
 int cg_knn_timing(cg_context* ctx, int enable);
 int cg_knn_timing_read(cg_context* ctx, double* ms, uint64_t* launches, double* candidates, double* bytes);
 
@@ -99,7 +106,9 @@ int cg_fetch_coo(cg_context* ctx, int32_t* i, int32_t* j, double* x);
 /* ---- samples ------------------------------------------------------------------------------------- */
 typedef struct {
   int32_t n_cells, n_genes;
-  const int32_t* p; /* counts: dgCMatrix cells x genes, @p [n_genes+1] */
+  const int32_t* p; /* counts: dgCMatrix cells x genes, @p [n_genes+1]; NULL = placeholder: the sample's counts are not
+                       uploaded to this device (multi-GPU: only the ranks whose pairs touch a sample hold it); n_cells
+                       still numbers its cells and pca may still be given for the local neighbours */
   const int32_t* i; /*                                   @i [nnz] (0-based cell)  */
   const double* x;  /*                                   @x [nnz]  */
   const double* var_v;  /* misc$varinfo$v  per gene (NULL when var.scale = FALSE) */
@@ -120,13 +129,16 @@ typedef struct {
   int32_t n_genes;        /* common od genes of the pair, in commonOverdispersedGenes order (R/conos.R:107-117) */
   const int32_t* genes_a; /* column of sample a holding od gene g */
   const int32_t* genes_b;
-  const double* rot;      /* optional cached rotation, column-major n_genes x rot_cols (self$pairs[[space]]$CPC) */
-  int32_t rot_cols;
-  const double* u;        /* CCA: optional cached u (n_u x ncomps) and v (n_v x ncomps), column-major */
-  const double* v;
+  const double* rot;      /* optional cached rotation, column-major rot_rows x rot_cols (self$pairs[[space]]$CPC);
+                             rot_rows must equal n_genes: the pair's genes ARE rownames(CPC) (R/conclass.R:240-243) */
+  int32_t rot_rows, rot_cols;
+  const double* u;        /* CCA: optional cached u (n_u x uv_cols) and v (n_v x uv_cols), column-major; every cached */
+  const double* v;        /* column is used, as the reference does (R/conclass.R:268-270)                            */
   const int32_t* rows_u;  /* CCA: cell index of every row of u / v (cells with empty rows are dropped) */
   const int32_t* rows_v;
-  int32_t n_u, n_v;
+  int32_t n_u, n_v, uv_cols;
+  int32_t k;              /* 0: params->k; > 0: k.cur of this pair = min(k.same.factor, k1) for two samples of the same
+                             balancing.factor.per.sample level (R/conclass.R:230-233) */
 } cg_pair;
 
 typedef struct {
@@ -159,9 +171,10 @@ int cg_pair_cca(cg_context* ctx, int which, int32_t* n_u, int32_t* n_v, int32_t*
 int cg_keep_projections(cg_context* ctx, int enable);
 int cg_pair_projection(cg_context* ctx, int which, int side, int32_t* n_rows, int32_t* n_cols, double* p);
 
-/* Within-sample edges of the listed samples (type 0), appended sample after sample. */
+/* Within-sample edges of the listed samples (type 0), appended sample after sample; sample_edge_counts ([n] or NULL)
+ * receives the rows appended per listed sample. */
 int cg_local_edges(cg_context* ctx, cg_panel* panel, const int32_t* samples, int n, const cg_params* params,
-                   cg_edges** edges);
+                   cg_edges** edges, int64_t* sample_edge_counts);
 
 /* ---- edge tables ---------------------------------------------------------------------------------- */
 int64_t cg_edges_count(const cg_edges* e);
@@ -178,6 +191,28 @@ int cg_edges_reserve(cg_context* ctx, cg_edges** e, int64_t n_total);
 int cg_edges_set_count(cg_edges* e, int64_t n);
 void cg_edges_free(cg_edges* e);
 
+/* ---- multi-GPU: one context per GPU ------------------------------------------------------------------ */
+/* Replaces the reference's fork pools over the pair list and the samples (R/conclass.R:224-317, :1074-1088,
+ * R/conos.R:396-416, :589).  One context per GPU -- one process per GPU (torchrun, mpirun) or one host thread per
+ * GPU inside a single R process; rank 0 creates the id, every rank passes the same 128 bytes to cg_comm_init
+ * (NCCL communicator over NVLink; world == 1 needs no NCCL at all). */
+int cg_comm_unique_id(void* id_out /* 128 bytes */);
+int cg_comm_init(cg_context* ctx, int rank, int world, const void* id /* 128 bytes */);
+int cg_comm_rank(const cg_context* ctx, int* rank, int* world);
+/* Deterministic partition of the pair list: longest-processing-time greedy over cost[q] (cells_a x cells_b) with
+ * sample locality -- a rank is charged sample_cost[s] the first time it receives a pair of sample s (its Gram
+ * matrix and its upload), so a rank touches about S / sqrt(world) samples.  owner[q] = rank.  sample_cost may be NULL. */
+int cg_partition_pairs(const int32_t* a, const int32_t* b, const double* cost, int n_pairs, const double* sample_cost,
+                       int n_samples, int world, int32_t* owner);
+/* allgatherv of the ranks' edge tables.  The table is a sequence of segments (pairs for the inter-sample edges,
+ * samples for the local ones): seg_owner[s] = rank that produced segment s, seg_counts_local[s] = its row count on
+ * the owner (ignored elsewhere); the local table holds this rank's segments in ascending s.  On return every rank
+ * holds all segments in ascending s == the reference's row order (pairs in combn order, R/conclass.R:316-321).
+ * One ncclAllReduce of the counts, one grouped ncclBroadcast per rank straight into the gathered table, one
+ * permutation kernel; a single-rank context returns the table as it is. */
+int cg_edges_allgatherv(cg_context* ctx, cg_edges** e, const int32_t* seg_owner, const int64_t* seg_counts_local,
+                        int n_seg);
+
 /* ---- graph ---------------------------------------------------------------------------------------- */
 /* el[w > 0]; vertices numbered by first appearance (graph_from_edgelist on a character matrix);
  * simplify(edge.attr.comb = list(weight = "sum", type = "first")).  R/conclass.R:335-343. */
@@ -187,6 +222,14 @@ int cg_graph_fetch(cg_context* ctx, const cg_graph* g, int32_t* vertices, int32_
                    int32_t* type);
 /* symmetric adjacency (as_adj(graph, attr = "weight")): p [n_vertices+1], i/x [2*n_edges] */
 int cg_graph_fetch_adjacency(cg_context* ctx, const cg_graph* g, int64_t* p, int32_t* i, double* x);
+/* adjustWeightsByCellBalancing on the assembled graph, in place (R/conos.R:936-967 driven from R/conclass.R:346-368):
+ * factor_per_vertex[v] = 1-based level of `as.factor(factor.per.cell[colnames(adj)])` for graph vertex v;
+ * balance_weights != 0 runs the n_iters (50) rounds of getSumWeightMatrix / adjustWeightsByCellBalancingC
+ * (src/edge_rebalancing.cpp:14-48) on the device without a host round trip; same_factor_downweight multiplies the
+ * edges inside one level (applied when |f - 1| > 1e-5).  The edge weights are then re-read from the adjacency matrix
+ * and `type` is set to -1: the reference rebuilds the graph from the adjacency matrix and loses the attribute. */
+int cg_graph_balance(cg_context* ctx, cg_graph* g, const int32_t* factor_per_vertex, int n_levels, int balance_weights,
+                     double same_factor_downweight, int n_iters);
 void cg_graph_free(cg_graph* g);
 
 /* ---- the reference's own .Call entry points, same argument meaning ----------------------------------- */

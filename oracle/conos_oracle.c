@@ -23,6 +23,10 @@
 #include <omp.h>
 #endif
 
+/* threads the OpenMP loops of this library will use (bench.py prints it next to the CPU baseline) */
+int oracle_max_threads(void) { return omp_get_max_threads(); }
+void oracle_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+
 /* ------------------------------------------------------------------ kNN (canonical fp32 arithmetic)
  * normalise: ss = fma chain of x_i*x_i (i ascending) ; inv = 1/sqrtf(ss) (0 when ss == 0); xh = x*inv.
  * dot      : four interleaved fma chains a_j = sum_{i = j mod 4} q_i*r_i (the 4-lane SIMD accumulation of

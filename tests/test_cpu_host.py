@@ -64,39 +64,59 @@ def test_common_od_genes_partial_overlap(oracle):
     assert con._gene_names(ids) == want == ["C", "E", "a"]   # count 2 first (name order), 'Z'/'B' absent in one sample
 
 
-def test_partition_contiguous():
-    from conos_b200.dist import partition_contiguous
-    for n, parts in [(28, 8), (4950, 8), (3, 8), (1, 2), (0, 4)]:
-        pr = partition_contiguous([1.0] * n, parts)
-        assert len(pr) == parts and pr[0][0] == 0 and pr[-1][1] == n
-        assert all(a[1] == b[0] for a, b in zip(pr, pr[1:]))
-        sizes = [b - a for a, b in pr]
-        assert max(sizes) - min(sizes) <= 1
-    costs = np.random.default_rng(0).integers(1, 100, 500).astype(float)
-    pr = partition_contiguous(costs, 8)
-    loads = [costs[a:b].sum() for a, b in pr]
-    assert max(loads) <= costs.sum() / 8 + costs.max()
+def test_partition_pairs_lpt_with_locality():
+    """cg_partition_pairs (GPU-free): balanced loads, every pair owned, fewer samples per rank than a contiguous cut."""
+    from conos_b200.dist import partition_pairs
+    for S, world in [(8, 8), (8, 2), (100, 8), (3, 8), (2, 1)]:
+        pairs = [(i, j) for i in range(S) for j in range(i + 1, S)]
+        a, b = [p[0] for p in pairs], [p[1] for p in pairs]
+        cost = [1.0] * len(pairs)
+        owner = partition_pairs(a, b, cost, world, sample_cost=[0.4] * S, n_samples=S)
+        assert owner.min() >= 0 and owner.max() < world
+        loads = np.bincount(owner, minlength=world)
+        assert loads.max() - loads[loads > 0].min() <= max(2, 0.05 * loads.max())
+        assert np.array_equal(owner, partition_pairs(a, b, cost, world, sample_cost=[0.4] * S, n_samples=S))
+        if S == 100:   # locality: a rank sees far fewer than all 100 samples' worth of distinct partners
+            touched = [len({a[q] for q in np.flatnonzero(owner == r)} | {b[q] for q in np.flatnonzero(owner == r)})
+                       for r in range(world)]
+            assert max(touched) <= 60, touched
+    # unequal costs: the largest pair alone on its rank when it dominates
+    owner = partition_pairs([0, 0, 1], [1, 2, 2], [100.0, 1.0, 1.0], 2)
+    assert owner[0] != owner[1] and owner[1] == owner[2]
 
 
-def _gloo_worker(rank, world, port, q):
+def _gloo_worker(rank, world, port, out_q):
     import torch
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
-    from conos_b200.dist import allgather_columns, partition_contiguous
+    from conos_b200.dist import gathered_layout, partition_pairs, permute_gathered
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
-    pairs = list(range(11))
-    lo, hi = partition_contiguous([1.0] * len(pairs), world)[rank]
-    # every "pair" p contributes p+1 rows (from=p, to=row, w=p+row/10)
-    frm = torch.tensor([p for p in pairs[lo:hi] for _ in range(p + 1)], dtype=torch.int32)
-    to = torch.tensor([r for p in pairs[lo:hi] for r in range(p + 1)], dtype=torch.int32)
-    w = frm.double() + to.double() / 10
-    ty = torch.ones_like(frm)
-    (gf, gt, gw, gty), counts = allgather_columns([frm, to, w, ty])
-    q.put((rank, gf.tolist(), gt.tolist(), gw.tolist(), counts))
+    S = 5
+    pairs = [(i, j) for i in range(S) for j in range(i + 1, S)]
+    owner = partition_pairs([p[0] for p in pairs], [p[1] for p in pairs], [float((i + 1) * (j + 1)) for i, j in pairs],
+                            world, sample_cost=[1.0] * S, n_samples=S)
+    mine = [q for q in range(len(pairs)) if owner[q] == rank]
+    # every pair q contributes q + 1 rows (from = q, to = row)
+    local = np.array([(q, r) for q in mine for r in range(q + 1)], np.int64).reshape(-1, 2)
+    counts_local = np.zeros(len(pairs), np.int64)
+    for q in mine:
+        counts_local[q] = q + 1
+    # the library does: allreduce(sum) of the counts, broadcast of every rank's table into the staging table
+    t = torch.from_numpy(counts_local.copy())
+    dist.all_reduce(t)
+    counts = t.numpy()
+    tables = [None] * world
+    dist.all_gather_object(tables, local)
+    rank_off, src_off, dst_off = gathered_layout(owner, counts, world)
+    staging = np.concatenate(tables)
+    assert [len(x) for x in tables] == np.diff(rank_off).tolist()
+    out_q.put((rank, owner.tolist(), permute_gathered(staging, src_off, dst_off).tolist()))
     dist.destroy_process_group()
 
 
-def test_allgatherv_two_ranks_gloo():
+def test_allgatherv_layout_two_ranks_gloo():
+    """The N > 1 host logic on CPU: two gloo ranks compute the same partition, and the gathered layout restores the
+    reference's row order (pairs in combn order) whatever the partition was."""
     import torch.multiprocessing as mp
     ctxmp = mp.get_context("spawn")
     q = ctxmp.Queue()
@@ -104,15 +124,13 @@ def test_allgatherv_two_ranks_gloo():
     procs = [ctxmp.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=120) for _ in procs]
+    res = [q.get(timeout=60) for _ in procs]
     for p in procs:
         p.join(timeout=60)
-    want_f = [p for p in range(11) for _ in range(p + 1)]
-    want_t = [r for p in range(11) for r in range(p + 1)]
-    for rank, gf, gt, gw, counts in res:
-        assert gf == want_f and gt == want_t           # rank order == pair order, no interleaving needed
-        assert sum(counts) == len(want_f)
-        assert np.allclose(gw, np.array(want_f) + np.array(want_t) / 10)
+    want = [[q_, r] for q_ in range(10) for r in range(q_ + 1)]
+    assert res[0][1] == res[1][1] and len(set(res[0][1])) == 2       # same partition on both ranks, both ranks used
+    for rank, owner, table in res:
+        assert table == want
 
 
 def test_lazy_containers():

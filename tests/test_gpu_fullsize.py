@@ -1,0 +1,117 @@
+"""Parity on ONE sample pair of BASELINE.json configs[1] at full size (2 x 50 000 cells x 2000 od genes, PCA, 30
+components, k = 30) -- north_star's bar (R/conos.R:848-886): with the same rotation on both sides the neighbour
+indices and the mutual-edge set are identical, weights within 1e-5 relative; the default (tensor-core) mode is then
+compared with the oracle's exact eigenvectors through the Jaccard index of the edge sets."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import to_oracle_samples
+
+pytestmark = pytest.mark.gpu
+
+N_CELLS = int(os.environ.get("CONOS_FULLSIZE_CELLS", "50000"))
+
+
+@pytest.fixture(scope="module")
+def pair_panel():
+    from conos_b200.panel import make_panel
+    return make_panel(2, 2, N_CELLS, 2000)   # the first two samples of the bench panel (same seeds)
+
+
+@pytest.fixture(scope="module")
+def oracle_pair(oracle, pair_panel):
+    """Oracle reduction of the pair (dense eigh of the two 2000 x 2000 covariances): seconds."""
+    osamples = to_oracle_samples(oracle, pair_panel)
+    names = list(pair_panel)
+    red = oracle.quick_plain_pca([osamples[names[0]], osamples[names[1]]], ncomps=30, n_odgenes=2000)
+    return osamples, names, red
+
+
+def _edges(ctx, handle):
+    n = int(ctx.lib.cg_edges_count(handle))
+    f, t, w = np.empty(n, np.int32), np.empty(n, np.int32), np.empty(n)
+    ctx.check(ctx.lib.cg_edges_fetch(ctx.h, handle, f.ctypes.data_as(C.POINTER(C.c_int32)),
+                                     t.ctypes.data_as(C.POINTER(C.c_int32)), w.ctypes.data_as(C.POINTER(C.c_double)),
+                                     None))
+    ctx.lib.cg_edges_free(handle)
+    return f, t, w
+
+
+def _projection(ctx, which, side):
+    nr, nc = C.c_int32(0), C.c_int32(0)
+    ctx.check(ctx.lib.cg_pair_projection(ctx.h, which, side, C.byref(nr), C.byref(nc), None))
+    p = np.zeros((nr.value, nc.value), order="F")
+    ctx.check(ctx.lib.cg_pair_projection(ctx.h, which, side, None, None, p.ctypes.data_as(C.POINTER(C.c_double))))
+    return p
+
+
+def test_fullsize_pair_with_oracle_rotation(ctx, oracle, pair_panel, oracle_pair):
+    """Same rot on both sides: projections 1e-9, then -- on the device's own projections -- kNN indices and float32
+    distances bit for bit in both directions, the mNN edge table (CSC order) row for row, weights 1e-12."""
+    import conos_b200
+    from conos_b200 import ops
+    osamples, names, red = oracle_pair
+    key = f"{names[0]}.vs.{names[1]}"
+    con = conos_b200.Conos(pair_panel, ctx=ctx)
+    con.pairs["PCA"] = {key: {"CPC": red["CPC"], "genes": red["genes"]}}
+    ctx.lib.cg_keep_projections(ctx.h, 1)
+    try:
+        f, t, w = _edges(ctx, con.buildGraph(k=30, k_self=0, space="PCA", ncomps=30, n_odgenes=2000, assemble=False))
+        p1, p2 = _projection(ctx, 0, 0), _projection(ctx, 0, 1)
+    finally:
+        ctx.lib.cg_keep_projections(ctx.h, 0)
+    con.close()
+    op1, op2 = oracle.project_pair([osamples[names[0]], osamples[names[1]]], red["genes"], red["CPC"][:, :30])
+    np.testing.assert_allclose(p1, op1, rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(p2, op2, rtol=1e-9, atol=1e-10)
+    # exact kNN at full size, both directions, against the oracle's float32 brute force on the same inputs
+    iab, dab, iba, dba = ops.crossKnn(p1, p2, 30, ctx=ctx, both=True)
+    oi, od = oracle.cross_knn(p1, p2, 30)
+    assert np.array_equal(iab, oi) and np.array_equal(dab.view(np.uint32), od.view(np.uint32))
+    oi2, od2 = oracle.cross_knn(p2, p1, 30)
+    assert np.array_equal(iba, oi2) and np.array_equal(dba.view(np.uint32), od2.view(np.uint32))
+    # mutual-neighbour edge table of the pair
+    i, j, x = oracle.neighbor_matrix(p1, p2, 30)
+    assert len(f) == len(i) > N_CELLS
+    assert np.array_equal(f, i) and np.array_equal(t - N_CELLS, j)
+    np.testing.assert_allclose(w, x, rtol=1e-12)
+    # ... and against the oracle's own projections (float32 casts of values that agree to 1e-9 may differ in the last
+    # bit, which can move a neighbour across the k-th place): the edge sets agree up to such ties, weights to 1e-5
+    i2, j2, x2 = oracle.neighbor_matrix(op1, op2, 30)
+    a = set(zip(i.tolist(), j.tolist()))
+    b = set(zip(i2.tolist(), j2.tolist()))
+    jac = len(a & b) / len(a | b)
+    print(f"fullsize pair: {len(a)} mNN edges, Jaccard vs oracle projections {jac:.7f}")
+    assert jac > 0.9999
+    wa = dict(zip(zip(i.tolist(), j.tolist()), x.tolist()))
+    wb = dict(zip(zip(i2.tolist(), j2.tolist()), x2.tolist()))
+    common = list(a & b)[:200000]
+    np.testing.assert_allclose([wa[e] for e in common], [wb[e] for e in common], rtol=1e-5, atol=1e-7)
+
+
+def test_fullsize_pair_default_mode_vs_oracle(ctx, oracle, pair_panel, oracle_pair):
+    """Default mode (tensor-core Gram, Chebyshev subspace iteration to irlba's tolerance 1e-5, tensor-core
+    projection): rotation subspaces against the exact eigenvectors, and the Jaccard index of the mNN edge sets
+    (the same figure bench.py prints as graph_jaccard_vs_oracle)."""
+    import conos_b200
+    osamples, names, red = oracle_pair
+    con = conos_b200.Conos(pair_panel, ctx=ctx)
+    f, t, w = _edges(ctx, con.buildGraph(k=30, k_self=0, space="PCA", ncomps=30, n_odgenes=2000, assemble=False))
+    rot = con.pairs["PCA"][f"{names[0]}.vs.{names[1]}"]["CPC"]
+    con.close()
+    assert rot.shape == red["CPC"].shape
+    for side in (0, 1):   # interleaved columns: sample 1 = even, sample 2 = odd
+        mine, theirs = rot[:, side::2], red["CPC"][:, side::2]
+        cosines = np.linalg.svd(mine.T @ theirs, compute_uv=False)
+        print(f"side {side}: smallest principal cosine {cosines.min():.9f}")
+        assert cosines.min() > 1 - 1e-4
+    op1, op2 = oracle.project_pair([osamples[names[0]], osamples[names[1]]], red["genes"], red["CPC"][:, :30])
+    i2, j2, x2 = oracle.neighbor_matrix(op1, op2, 30)
+    a = set(zip(f.tolist(), (t - N_CELLS).tolist()))
+    b = set(zip(i2.tolist(), j2.tolist()))
+    jac = len(a & b) / len(a | b)
+    print(f"fullsize pair, default mode: {len(a)} edges vs {len(b)} (oracle), Jaccard {jac:.6f}")
+    assert jac > 0.97

@@ -103,7 +103,7 @@ def test_local_edges_and_merge(ctx, oracle, small_panel):
     edges = C.c_void_p()
     sidx = np.arange(len(names), dtype=np.int32)
     ctx.check(ctx.lib.cg_local_edges(ctx.h, con._panel, sidx.ctypes.data_as(C.POINTER(C.c_int32)), len(names),
-                                     C.byref(P), C.byref(edges)))
+                                     C.byref(P), C.byref(edges), None))
     g = con._assemble(edges, names)
     ctx.lib.cg_edges_free(edges)
     _graphs_equal(g, og)
