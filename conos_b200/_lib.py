@@ -73,6 +73,8 @@ SIGNATURES = {
     "cg_pairs_edges": (C.c_int, [_VP, _VP, C.POINTER(CgPair), C.c_int, C.POINTER(CgParams), C.POINTER(_VP), c_i64_p]),
     "cg_pair_reduction": (C.c_int, [_VP, C.c_int, c_int_p, c_int_p, c_dbl_p, c_dbl_p]),
     "cg_pair_cca": (C.c_int, [_VP, C.c_int, c_int_p, c_int_p, c_int_p, c_dbl_p, c_dbl_p, c_int_p, c_int_p, c_dbl_p]),
+    "cg_pair_cpca": (C.c_int, [_VP, C.c_int, c_int_p, c_dbl_p, c_dbl_p]),
+    "cg_pair_cca_loadings": (C.c_int, [_VP, C.c_int, c_int_p, c_int_p, c_dbl_p, c_dbl_p, c_dbl_p]),
     "cg_keep_projections": (C.c_int, [_VP, C.c_int]),
     "cg_pair_projection": (C.c_int, [_VP, C.c_int, C.c_int, c_int_p, c_int_p, c_dbl_p]),
     "cg_local_edges": (C.c_int, [_VP, _VP, c_int_p, C.c_int, C.POINTER(CgParams), C.POINTER(_VP), c_i64_p]),

@@ -553,6 +553,15 @@ class Conos:
                 self.ctx.check(lib.cg_pair_cca(h, slot, None, None, None, ptr(u, C.c_double), ptr(v, C.c_double),
                                                ptr(ru, C.c_int32), ptr(rv, C.c_int32), ptr(sg, C.c_double)))
                 cache[key] = PairEntry(od, self._gene_names, u=u, v=v, rows_u=ru, rows_v=rv, d=sg)
+                ng, dl = C.c_int32(0), C.c_int32(0)
+                self.ctx.check(lib.cg_pair_cca_loadings(h, slot, C.byref(ng), C.byref(dl), None, None, None))
+                if ng.value > 0:
+                    ul = np.zeros((ng.value, dl.value), order="F")
+                    vl = np.zeros((ng.value, dl.value), order="F")
+                    nv = np.zeros((2, dl.value))
+                    self.ctx.check(lib.cg_pair_cca_loadings(h, slot, None, None, ptr(ul, C.c_double),
+                                                            ptr(vl, C.c_double), ptr(nv, C.c_double)))
+                    cache[key].update(ul=ul, vl=vl, nv=[nv[0], nv[1]])
                 continue
             nr, nc = C.c_int32(0), C.c_int32(0)
             self.ctx.check(lib.cg_pair_reduction(h, slot, C.byref(nr), C.byref(nc), None, None))
@@ -562,6 +571,10 @@ class Conos:
             cache[key] = PairEntry(od, self._gene_names, CPC=rot)
             if space == "CPCA":
                 cache[key]["ncomp"] = nc.value
+                D = np.zeros((nc.value, 2), order="F")   # res$D = t(D): ncomp x k (src/cpca.cpp:97)
+                niter = np.zeros(nc.value)
+                self.ctx.check(lib.cg_pair_cpca(h, slot, None, ptr(D, C.c_double), ptr(niter, C.c_double)))
+                cache[key].update(D=D, niter=niter)
             if nv is not None:
                 rr = nc.value // 2 if space == "PCA" else nc.value
                 cache[key]["nv"] = [nv[0, :rr], nv[1, :rr]]

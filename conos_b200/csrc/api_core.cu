@@ -146,6 +146,15 @@ int cg_set_option(cg_context* ctx, const char* name, double value) {
     ctx->c.tc_eig_degree = (int)value;
     return 0;
   }
+  if (strcmp(name, "gram_chunk_slabs") == 0) {
+    ctx->c.gram_chunk_slabs = value < 0 ? 0 : (int)value;
+    return 0;
+  }
+  if (strcmp(name, "tc_eig_tol") == 0) {
+    if (!(value > 0.0 && value < 1.0)) return ::cg::fail(ctx, "tc_eig_tol must be in (0, 1)");
+    ctx->c.tc_eig_tol = value;
+    return 0;
+  }
   if (strcmp(name, "tc_eig_max_sweeps") == 0) {
     ctx->c.tc_eig_max_sweeps = (int)value;
     return 0;

@@ -19,6 +19,8 @@ struct cg_context {
     int pn[2] = {0, 0};
     std::vector<double> proj[2];  // column-major n x ncomps
     // CCA: scaled canonical variates, kept-cell row maps, singular values
+    std::vector<double> D, niter;  // CPCA: cpcaF's D [2][n_cols] and niter [n_cols]
+    std::vector<double> ul, vl;    // CCA: gene loadings, column-major n_rows x cca_d
     std::vector<double> u, v, sigma;
     std::vector<int> rows_u, rows_v;
     int cca_d = 0;

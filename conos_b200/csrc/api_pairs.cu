@@ -255,6 +255,10 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
       keep.rot = std::move(R.h_rot);
       keep.rot_host = R.h_rot_pinned ? R.h_rot_pinned : keep.rot.data();
       keep.nv = R.h_nv;
+      keep.D = R.h_D;
+      keep.niter = R.h_niter;
+      keep.ul = std::move(R.h_ul);
+      keep.vl = std::move(R.h_vl);
       if (P.space == CG_SPACE_CCA) {
         KnnPanel pa, pbn;
         pa.tiled = B.ta.p;
@@ -436,6 +440,28 @@ int cg_pair_cca(cg_context* ctx, int which, int32_t* n_u, int32_t* n_v, int32_t*
   if (rows_u && !k.rows_u.empty()) memcpy(rows_u, k.rows_u.data(), k.rows_u.size() * sizeof(int));
   if (rows_v && !k.rows_v.empty()) memcpy(rows_v, k.rows_v.data(), k.rows_v.size() * sizeof(int));
   if (sigma && !k.sigma.empty()) memcpy(sigma, k.sigma.data(), k.sigma.size() * sizeof(double));
+  CG_API_END(ctx)
+}
+
+int cg_pair_cpca(cg_context* ctx, int which, int32_t* n_cols, double* D, double* niter) {
+  CG_API_BEGIN
+  CG_CHECK(ctx && which >= 0 && which < (int)ctx->kept.size(), "no such pair in the last cg_pairs_edges call");
+  const auto& k = ctx->kept[which];
+  if (n_cols) *n_cols = (int32_t)k.niter.size();
+  if (D && !k.D.empty()) memcpy(D, k.D.data(), k.D.size() * sizeof(double));
+  if (niter && !k.niter.empty()) memcpy(niter, k.niter.data(), k.niter.size() * sizeof(double));
+  CG_API_END(ctx)
+}
+
+int cg_pair_cca_loadings(cg_context* ctx, int which, int32_t* n_genes, int32_t* d, double* ul, double* vl, double* nv) {
+  CG_API_BEGIN
+  CG_CHECK(ctx && which >= 0 && which < (int)ctx->kept.size(), "no such pair in the last cg_pairs_edges call");
+  const auto& k = ctx->kept[which];
+  if (n_genes) *n_genes = k.ul.empty() ? 0 : k.n_rows;
+  if (d) *d = k.cca_d;
+  if (ul && !k.ul.empty()) memcpy(ul, k.ul.data(), k.ul.size() * sizeof(double));
+  if (vl && !k.vl.empty()) memcpy(vl, k.vl.data(), k.vl.size() * sizeof(double));
+  if (nv && !k.nv.empty()) memcpy(nv, k.nv.data(), k.nv.size() * sizeof(double));
   CG_API_END(ctx)
 }
 

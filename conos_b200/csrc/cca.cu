@@ -320,10 +320,53 @@ void cca_pair(Context& ctx, cg_panel& panel, const cg_pair& pr, const cg_params&
                                                     S[1].rows.p, n2, W1.p, shift.p, Vrm.p);
     ctx.stats.kernels += 5;
   }
+  // gene loadings and variance fractions (R/conos.R:349-357): ul = Ya'u, vl = Yb'v with unit columns (W1 already is
+  // Ya'u; the 1 / sigma of v drops out of the normalisation); nv_s[j] = var(Y_s l_j) / sum of column variances
+  // = l_j' K_s l_j / trace(K_s) with K_s = Y_s'Y_s of the centred kept cells
+  {
+    const Sample& sb = *S[1].s;
+    DevBuf<double> T1((size_t)G * B), T2((size_t)G * B);
+    cca_colsum_kernel<B><<<1, 256, 0, st>>>(Vrm.p, n2, csU.p);
+    cca_yt_u_kernel<B><<<(G + 7) / 8, 256, 0, st>>>(sb.csc_p.p, sb.csc_i.p, sb.csc_x.p, S[1].cols.p, S[1].f.p,
+                                                    S[1].mean.p, S[1].posmap.p, Vrm.p, csU.p, G, W2.p);
+    cca_kw_kernel<B><<<(G + 7) / 8, 256, 0, st>>>(S[0].K.p, W1.p, G, T1.p);
+    cca_kw_kernel<B><<<(G + 7) / 8, 256, 0, st>>>(S[1].K.p, W2.p, G, T2.p);
+    ctx.stats.kernels += 4;
+    std::vector<double> hw[2], ht[2], hd[2];
+    const DevBuf<double>* Wd[2] = {&W1, &W2};
+    const DevBuf<double>* Td[2] = {&T1, &T2};
+    for (int side = 0; side < 2; ++side) {
+      hw[side].resize((size_t)G * B);
+      ht[side].resize((size_t)G * B);
+      hd[side].resize((size_t)G);
+      Wd[side]->download(hw[side].data(), hw[side].size(), st);
+      Td[side]->download(ht[side].data(), ht[side].size(), st);
+      CG_CUDA(cudaMemcpy2DAsync(hd[side].data(), sizeof(double), S[side].K.p, ((size_t)G + 1) * sizeof(double),
+                                sizeof(double), (size_t)G, cudaMemcpyDeviceToHost, st));
+    }
+    CG_CUDA(cudaStreamSynchronize(st));
+    R.h_nv.assign((size_t)2 * d, 0.0);
+    for (int side = 0; side < 2; ++side) {
+      std::vector<double>& L = side == 0 ? R.h_ul : R.h_vl;
+      L.assign((size_t)G * d, 0.0);
+      double tr = 0.0;
+      for (int g = 0; g < G; ++g) tr += hd[side][g];
+      for (int j = 0; j < d; ++j) {
+        double nn = 0.0, q = 0.0;
+        for (int g = 0; g < G; ++g) {
+          nn += hw[side][(size_t)g * B + j] * hw[side][(size_t)g * B + j];
+          q += hw[side][(size_t)g * B + j] * ht[side][(size_t)g * B + j];
+        }
+        const double inv = nn > 0.0 ? 1.0 / std::sqrt(nn) : 0.0;
+        for (int g = 0; g < G; ++g) L[(size_t)j * G + g] = hw[side][(size_t)g * B + j] * inv;
+        R.h_nv[(size_t)side * d + j] = (nn > 0.0 && tr > 0.0) ? q / nn / tr : 0.0;
+      }
+    }
+  }
   R.n_u = n1;
   R.n_v = n2;
   R.d = d;
-  R.n_rows = 0;
+  R.n_rows = G;
   R.n_cols = d;
   R.u.alloc((size_t)n1 * d);
   R.v.alloc((size_t)n2 * d);

@@ -203,6 +203,8 @@ struct Context {
   bool exact_reduction = false;
   bool tc_projection = true;   // default mode: project through the tensor-core GEMM (false: FP64 SpMM everywhere)
   int tc_eig_degree = 10;      // tensor-core eigen solver: largest Chebyshev degree of a sweep
+  int gram_chunk_slabs = 16;   // tensor-core Gram: cells per FP32 accumulation chunk / 64 (chunks are summed in FP64)
+  double tc_eig_tol = 1e-5;    // its stopping rule: residual <= tol * theta_1 (irlba's default tolerance)
   int tc_eig_max_sweeps = 40;  // tensor-core eigen solver: sweeps before a problem is handed to the FP64 driver
   size_t max_batch_bytes = (size_t)24 << 30;  // scratch budget of one batch of pairs in cg_pairs_edges (tests shrink it)
   // optional per-stage wall-clock profile (stream synchronised at both ends of a stage)

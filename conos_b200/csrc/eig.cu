@@ -38,9 +38,13 @@ __global__ void eig_init_kernel(const EigWork* __restrict__ works) {
 
 // Z = C Q.  One warp per row of C (symmetric: row r == column r, contiguous), lanes over the B columns of Q.
 template <int B>
-__global__ void __launch_bounds__(256) eig_matmul_kernel(const EigWork* __restrict__ works) {
+__global__ void __launch_bounds__(256) eig_matmul_kernel(const EigWork* __restrict__ works,
+                                                         const int* __restrict__ deg, int step) {
   const EigWork w = works[blockIdx.y];
   if (w.converged && *w.converged != 0) return;  // locked: a converged problem is never touched again
+  // inside a filter sweep: a problem whose own (shorter) sweep is over already holds its filtered block in Z --
+  // it must not be overwritten because a batch mate runs a higher degree
+  if (step > 0 && step > deg[blockIdx.y] + 0) return;
   __shared__ double crow[8][128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + warp;
@@ -638,7 +642,7 @@ void run_eig_generic(Context& ctx, const int* rows, double* const* Vout, double*
     ++outer;
     {
       StageScope sc(ctx, "reduction.eig.matmul");
-      matmul(works, dw.p, maxG);
+      matmul(works, dw.p, maxG, nullptr, 0);
       ++applied;
     }
     {
@@ -662,7 +666,7 @@ void run_eig_generic(Context& ctx, const int* rows, double* const* Vout, double*
     for (int i = 1; i <= sweep; ++i) {
       if (i > 1) {
         StageScope sc(ctx, "reduction.eig.matmul");
-        matmul(works, dw.p, maxG);
+        matmul(works, dw.p, maxG, deg.p, i);
         ++applied;
       }
       eig_cheb_kernel<B><<<dim3(cheb_blocks, n_probs), 256, 0, s>>>(dw.p, al.p, be.p, cc.p, deg.p, n_probs, i);
@@ -704,9 +708,9 @@ void run_eig(Context& ctx, const EigProblem* h_probs, int n_probs, int r, double
   }
   cudaStream_t s = ctx.stream;
   run_eig_generic<B>(ctx, rows.data(), V.data(), th.data(), Cm.data(), n_probs, r, tol, max_iter,
-                     [&](std::vector<EigWork>&, const EigWork* dw, int maxG) {
+                     [&](std::vector<EigWork>&, const EigWork* dw, int maxG, const int* deg, int step) {
                        dim3 gm((maxG + 7) / 8, n_probs);
-                       eig_matmul_kernel<B><<<gm, 256, 0, s>>>(dw);
+                       eig_matmul_kernel<B><<<gm, 256, 0, s>>>(dw, deg, step);
                        ctx.stats.kernels++;
                      });
 }
@@ -923,7 +927,9 @@ void top_eigenvectors_operator(Context& ctx, int n_rows, int r, double tol, int 
   CG_CHECK(r >= 1 && r <= 56, "1..56 eigenvectors per problem");
   double* Vp[1] = {V};
   double* tp[1] = {theta};
-  auto mm = [&](std::vector<EigWork>& works, const EigWork*, int) { apply(works[0].Q, works[0].Z, r <= 24 ? 32 : 64); };
+  auto mm = [&](std::vector<EigWork>& works, const EigWork*, int, const int*, int) {
+    apply(works[0].Q, works[0].Z, r <= 24 ? 32 : 64);
+  };
   if (r <= 24) run_eig_generic<32>(ctx, &n_rows, Vp, tp, nullptr, 1, r, tol, max_iter, mm);
   else run_eig_generic<64>(ctx, &n_rows, Vp, tp, nullptr, 1, r, tol, max_iter, mm);
 }

@@ -1,3 +1,5 @@
+#include <cuda_fp16.h>
+
 #include "gemm_tc.cuh"
 #include "ptx.cuh"
 
@@ -11,35 +13,48 @@ constexpr int A_BYTES = BM * BK * 2;  // 16 KB per hi / lo tile
 constexpr int B_BYTES = BN * BK * 2;  // 32 KB
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
 constexpr int G_OFF_BAR = G_STAGES * STAGE_BYTES;
-constexpr int G_SMEM = G_OFF_BAR + 64;
+constexpr int G_SMEM = G_OFF_BAR + 128;
 
 struct GemmTile {
   int prob, mt, nt;
 };
 
+// K is consumed in chunks of pb.chunk_slabs 64-wide slabs (0: one chunk = everything).  Every chunk is accumulated in
+// FP32 in its own TMEM accumulator (two accumulators, double buffered) and the chunks are summed in FP64 by the epilogue
+// (C = chunk 0, C += chunk i; a tile belongs to one CTA, so the order is fixed and no atomics are needed).  The tensor
+// core's FP32 accumulator rounds after every K=16 step: over the 50 000-cell contraction of a Gram matrix (9375 steps)
+// that alone costs ~1e-5 relative -- enough to rotate the 15th eigenvector of a covariance with clustered
+// eigenvalues by ~1e-2 and change 2 % of the mutual-neighbour edges; with 1024-cell chunks the FP32 part of every
+// sum is 192 steps long.
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_tn_bf16x3_kernel(const GemmProblem* __restrict__ probs, const GemmTile* __restrict__ tiles) {
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_OFF_BAR);
   uint64_t* full = bars;                 // [2]
   uint64_t* empty = bars + G_STAGES;     // [2]
-  uint64_t* acc_full = bars + 2 * G_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * G_STAGES + 1);
+  uint64_t* acc_full = bars + 2 * G_STAGES;       // [2]
+  uint64_t* acc_empty = bars + 2 * G_STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * G_STAGES + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GemmTile tl = tiles[blockIdx.x];
   const GemmProblem pb = probs[tl.prob];
   const int n_slabs = pb.k_pad / BK;
+  const int chunk = (pb.chunk_slabs > 0 && pb.chunk_slabs < n_slabs) ? pb.chunk_slabs : n_slabs;
+  const int n_chunks = (n_slabs + chunk - 1) / chunk;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < G_STAGES; ++s) {
       ptx::mbar_init(full + s, 1);
       ptx::mbar_init(empty + s, 1);
     }
-    ptx::mbar_init(acc_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(acc_full + s, 1);
+      ptx::mbar_init(acc_empty + s, 4);  // one arrival per epilogue warp
+    }
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, 256);
+    ptx::tmem_alloc(tmem_slot, 512);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
@@ -65,63 +80,92 @@ gemm_tn_bf16x3_kernel(const GemmProblem* __restrict__ probs, const GemmTile* __r
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc(1u, (uint32_t)BM, (uint32_t)BN);  // bf16 x bf16 -> fp32
+      // operands are bf16 (fmt 1) or fp16 (fmt 0) hi + lo pairs; fp32 accumulate
+      const uint32_t idesc = ptx::umma_idesc(pb.fp16 ? 0u : 1u, (uint32_t)BM, (uint32_t)BN);
       const uint32_t s0 = ptx::smem_u32(smem);
-      for (int sl = 0; sl < n_slabs; ++sl) {
-        const int st = sl % G_STAGES, ph = (sl / G_STAGES) & 1;
-        ptx::mbar_wait(full + st, ph);
+      int sl = 0;
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        const int buf = ch & 1;
+        ptx::mbar_wait(acc_empty + buf, ((ch >> 1) & 1) ^ 1);
         ptx::tc_fence_after();
-        const uint32_t a_hi = s0 + st * STAGE_BYTES, a_lo = a_hi + A_BYTES;
-        const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        const int sl_end = sl + chunk < n_slabs ? sl + chunk : n_slabs;
+        for (bool first = true; sl < sl_end; ++sl) {
+          const int st = sl % G_STAGES, ph = (sl / G_STAGES) & 1;
+          ptx::mbar_wait(full + st, ph);
+          ptx::tc_fence_after();
+          const uint32_t a_hi = s0 + st * STAGE_BYTES, a_lo = a_hi + A_BYTES;
+          const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
 #pragma unroll
-        for (int ks = 0; ks < BK / 16; ++ks) {
-          const uint64_t dah = ptx::umma_desc_kmajor_noswz(a_hi + ks * 256, 128, 1024);
-          const uint64_t dal = ptx::umma_desc_kmajor_noswz(a_lo + ks * 256, 128, 1024);
-          const uint64_t dbh = ptx::umma_desc_kmajor_noswz(b_hi + ks * 256, 128, 1024);
-          const uint64_t dbl = ptx::umma_desc_kmajor_noswz(b_lo + ks * 256, 128, 1024);
-          // small terms first
-          ptx::mma_f16_ss(tmem_base, dal, dbh, idesc, (sl > 0 || ks > 0) ? 1u : 0u);
-          ptx::mma_f16_ss(tmem_base, dah, dbl, idesc, 1u);
-          ptx::mma_f16_ss(tmem_base, dah, dbh, idesc, 1u);
+          for (int ks = 0; ks < BK / 16; ++ks) {
+            const uint64_t dah = ptx::umma_desc_kmajor_noswz(a_hi + ks * 256, 128, 1024);
+            const uint64_t dal = ptx::umma_desc_kmajor_noswz(a_lo + ks * 256, 128, 1024);
+            const uint64_t dbh = ptx::umma_desc_kmajor_noswz(b_hi + ks * 256, 128, 1024);
+            const uint64_t dbl = ptx::umma_desc_kmajor_noswz(b_lo + ks * 256, 128, 1024);
+            // small terms first
+            ptx::mma_f16_ss(d_tmem, dal, dbh, idesc, first ? 0u : 1u);
+            ptx::mma_f16_ss(d_tmem, dah, dbl, idesc, 1u);
+            ptx::mma_f16_ss(d_tmem, dah, dbh, idesc, 1u);
+            first = false;
+          }
+          ptx::mma_commit(empty + st);
         }
-        ptx::mma_commit(empty + st);
+        ptx::mma_commit(acc_full + buf);
       }
-      ptx::mma_commit(acc_full);
     }
     __syncwarp();
   } else {
     const int quarter = warp & 3;
-    ptx::mbar_wait(acc_full, 0);
-    ptx::tc_fence_after();
     const int m = tl.mt * BM + quarter * 32 + lane;
-    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      const int buf = ch & 1;
+      ptx::mbar_wait(acc_full + buf, (ch >> 1) & 1);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t v[32];
-      ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
-      ptx::tmem_wait_ld();
-      if (m < pb.M) {
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
+        ptx::tmem_wait_ld();
+        if (m < pb.M) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = tl.nt * BN + c * 32 + j;
-          if (n < pb.N) {
-            const float f = __uint_as_float(v[j]);
-            if (pb.out_fp64) reinterpret_cast<double*>(pb.C)[(size_t)n * pb.ldc + m] = (double)f;
-            else reinterpret_cast<float*>(pb.C)[(size_t)n * pb.ldc + m] = f;
+          for (int j = 0; j < 32; ++j) {
+            const int n = tl.nt * BN + c * 32 + j;
+            if (n < pb.N) {
+              const float f = __uint_as_float(v[j]);
+              if (pb.out_fp64) {
+                double* dst = reinterpret_cast<double*>(pb.C) + (size_t)n * pb.ldc + m;
+                *dst = ch == 0 ? (double)f : *dst + (double)f;
+              } else {
+                float* dst = reinterpret_cast<float*>(pb.C) + (size_t)n * pb.ldc + m;
+                *dst = ch == 0 ? f : *dst + f;
+              }
+            }
           }
         }
       }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(acc_empty + buf);
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, 256);
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------ operand builders
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+// fp16 hi + lo pair in the same 16-bit containers (kind::f16 takes either format): 11 + 11 significant bits instead
+// of 8 + 8, for operands whose range fits fp16 (the expression values of the Gram operand: 0 .. ~6)
+__device__ __forceinline__ void split_fp16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  const __half h = __float2half_rn(x);
+  const __half l = __float2half_rn(x - __half2float(h));
+  hi = *reinterpret_cast<const __nv_bfloat16*>(&h);
+  lo = *reinterpret_cast<const __nv_bfloat16*>(&l);
 }
 
 __global__ void tiled_from_csc_kernel(const int* __restrict__ csc_p, const int* __restrict__ csc_i,
@@ -147,7 +191,7 @@ __global__ void tiled_from_csc_kernel(const int* __restrict__ csc_p, const int* 
 __global__ void __launch_bounds__(256) tiled_from_csr_kernel(const int* __restrict__ csr_p, const int* __restrict__ csr_i,
                                                              const double* __restrict__ csr_x, int n_cells, int rows_pad,
                                                              __nv_bfloat16* __restrict__ hi,
-                                                             __nv_bfloat16* __restrict__ lo) {
+                                                             __nv_bfloat16* __restrict__ lo, int fp16) {
   extern __shared__ __align__(16) unsigned char csr_smem[];
   __nv_bfloat16* sh = reinterpret_cast<__nv_bfloat16*>(csr_smem);
   __nv_bfloat16* sl = sh + 256 * 64;
@@ -174,7 +218,7 @@ __global__ void __launch_bounds__(256) tiled_from_csr_kernel(const int* __restri
       if (col < g0 + 256) {
         const int gl = col - g0;
         __nv_bfloat16 h, l;
-        split_bf16((float)csr_x[t], h, l);
+        if (fp16) split_fp16((float)csr_x[t], h, l); else split_bf16((float)csr_x[t], h, l);
         const int o = ((gl >> 3) * 8 + (cl >> 3)) * 64 + (gl & 7) * 8 + (cl & 7);
         sh[o] = h;
         sl[o] = l;
@@ -264,7 +308,7 @@ void tiled_from_csc(Context& ctx, const int* csc_p, const int* csc_i, const doub
 }
 
 void tiled_from_csr(Context& ctx, const int* csr_p, const int* csr_i, const double* csr_x, int n_cells, int n_genes,
-                    TiledOperand& op) {
+                    TiledOperand& op, bool fp16) {
   op.rows = n_genes;
   op.k = n_cells;
   op.rows_pad = (int)round_up(n_genes, GEMM_ROW_PAD);
@@ -273,7 +317,8 @@ void tiled_from_csr(Context& ctx, const int* csr_p, const int* csr_i, const doub
   dim3 grid((unsigned)(op.k_pad / 64), (unsigned)(op.rows_pad / 256));
   constexpr int smem = 2 * 256 * 64 * (int)sizeof(__nv_bfloat16);
   CG_CUDA(cudaFuncSetAttribute(tiled_from_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  tiled_from_csr_kernel<<<grid, 256, smem, ctx.stream>>>(csr_p, csr_i, csr_x, n_cells, op.rows_pad, op.hi, op.lo);
+  tiled_from_csr_kernel<<<grid, 256, smem, ctx.stream>>>(csr_p, csr_i, csr_x, n_cells, op.rows_pad, op.hi, op.lo,
+                                                         fp16 ? 1 : 0);
   ctx.stats.kernels++;
   CG_CUDA(cudaGetLastError());
 }

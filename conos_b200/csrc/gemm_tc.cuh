@@ -45,6 +45,9 @@ struct GemmProblem {
   long long ldc;
   int out_fp64;    // 1: double output, 0: float
   int symmetric = 0;  // 1: A == B (X'X): only the tiles that touch the upper triangle (m <= n) are computed
+  int chunk_slabs = 0;  // > 0: K is accumulated in FP32 over chunks of this many 64-wide slabs, the chunks are summed
+                        //      in the output type by the epilogue (long contractions: Gram matrices, out_fp64 = 1)
+  int fp16 = 0;         // 1: the operand panels hold fp16 hi + lo pairs (11 + 11 bits) instead of bf16 (8 + 8)
 };
 
 // batched: every problem is cut into 128 x 256 output tiles, one CTA per tile
@@ -66,8 +69,9 @@ void gemm_run(Context& ctx, const GemmPlan& plan);
 void tiled_from_csc(Context& ctx, const int* csc_p, const int* csc_i, const double* csc_x, int n_cells, int n_genes,
                     TiledOperand& op);
 // same operand from the CSR-by-cell form (columns ascending inside a row): tile-wise, coalesced, no memset
+// fp16 = true stores fp16 hi + lo pairs (values must fit fp16's range; GemmProblem::fp16 must be set for both operands)
 void tiled_from_csr(Context& ctx, const int* csr_p, const int* csr_i, const double* csr_x, int n_cells, int n_genes,
-                    TiledOperand& op);
+                    TiledOperand& op, bool fp16 = false);
 // dense column-major (k x rows, element (k, r) at r*ld + k) FP64 or FP32 -> operand
 void tiled_from_colmajor_f64(Context& ctx, const double* src, int k, int rows, long long ld, TiledOperand& op);
 void tiled_from_colmajor_f32(Context& ctx, const float* src, int k, int rows, long long ld, TiledOperand& op);

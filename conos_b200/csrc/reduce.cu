@@ -79,6 +79,41 @@ __global__ void weighted_sum_kernel(const double* __restrict__ A, const double* 
 
 int r_round_half_even(double x) { return (int)std::nearbyint(x); }  // default rounding mode = to nearest even
 
+// S = wa Da Mc_a Da + wb Db Mc_b Db on the pair's od genes (wa = n_a / n / (n_a - 1)): the cell-weighted mean of the two
+// covariance slices, R/conos.R:180-183.  Zero padded to Gp x Gp.
+__global__ void mean_cov_kernel(const double* __restrict__ Ma, int Gsa, const double* __restrict__ Mb, int Gsb,
+                                const int* __restrict__ cols_a, const int* __restrict__ cols_b,
+                                const double* __restrict__ fa, const double* __restrict__ fb, int G, int Gp, double wa,
+                                double wb, double* __restrict__ S) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)Gp * Gp) return;
+  const int i = (int)(t % Gp), j = (int)(t / Gp);
+  double v = 0.0;
+  if (i < G && j < G)
+    v = wa * fa[i] * fa[j] * Ma[(size_t)cols_a[j] * Gsa + cols_a[i]] +
+        wb * fb[i] * fb[j] * Mb[(size_t)cols_b[j] * Gsb + cols_b[i]];
+  S[t] = v;
+}
+
+// scaledMatricesP2 (R/conos.R:18-46): cqv = exp(rowMeans(log qv)), cgsf = sqrt(cqv / exp(v)), non-finite -> 0
+void pair_factors(const Sample& sa, const Sample& sb, const cg_pair& pr, bool var_scale, std::vector<double>& fa,
+                  std::vector<double>& fb) {
+  const int G = pr.n_genes;
+  fa.assign(G, 1.0);
+  fb.assign(G, 1.0);
+  if (!var_scale) return;
+  CG_CHECK(!sa.h_qv.empty() && !sb.h_qv.empty() && !sa.h_v.empty() && !sb.h_v.empty(),
+           "var.scale = TRUE needs misc$varinfo$v and $qv for every sample");
+  for (int g = 0; g < G; ++g) {
+    const int ca = pr.genes_a[g], cb = pr.genes_b[g];
+    const double cqv = std::exp((sa.h_logqv[ca] + sb.h_logqv[cb]) / 2.0);
+    const double a = std::sqrt(cqv / sa.h_expv[ca]);
+    const double b = std::sqrt(cqv / sb.h_expv[cb]);
+    fa[g] = std::isfinite(a) ? a : 0.0;
+    fb[g] = std::isfinite(b) ? b : 0.0;
+  }
+}
+
 }  // namespace
 
 // X'X of the whole sample in FP64 (upper triangle accumulated, then mirrored); cached on the sample.
@@ -252,7 +287,7 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
       CG_CUDA(cudaMemcpyAsync(d_c.p, h_c.data(), h_c.size() * sizeof(int), cudaMemcpyHostToDevice, st));
       {
         StageScope sc(ctx, "reduction.eig");
-        top_eigenvectors_shared_gram(ctx, ts.data(), S, tp.data(), (int)tp.size(), r, 1e-5, ctx.tc_eig_max_sweeps, ctx.tc_eig_degree,
+        top_eigenvectors_shared_gram(ctx, ts.data(), S, tp.data(), (int)tp.size(), r, ctx.tc_eig_tol, ctx.tc_eig_max_sweeps, ctx.tc_eig_degree,
                                      tc_conv.data());
       }
       for (size_t t = 0; t < todo.size(); ++t) {
@@ -409,115 +444,121 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
   }
   // ---- CPCA: quickCPCA (R/conos.R:204-259) -> cpcaFast (:175-191) -> cpcaF (src/cpca.cpp)
   CG_CHECK(P.space == CG_SPACE_CPCA, "unknown space");
-  // chunks of pairs: the covariance cubes of a chunk are built first, the initial eigenproblems of the whole chunk
-  // are solved in one batched call (a block per problem), then the common-PCA iteration runs pair by pair
+  // The covariance slices of a pair are never built: C_s^(pair) = D Mc_s D / (n_s - 1) with the sample's centred Gram
+  // matrix Mc_s shared by all of its pairs.  Initial vectors: leading eigenvectors of the cell-weighted mean covariance
+  // S (explicit G x G, FP64 block iteration, chunks of pairs); then every pair of the call iterates in lock step
+  // (cpca_batch.cu).
+  const int S = (int)panel.samples.size();
+  std::vector<DevBuf<double>> Mc(S);
+  std::vector<const double*> Mc_ptr(S, nullptr);
+  for (int q : todo)
+    for (int si : {pairs[q].a, pairs[q].b})
+      if (!Mc[si].n) {
+        Mc[si].alloc((size_t)panel.samples[si].n_genes * panel.samples[si].n_genes);
+        center_gram(ctx, panel.samples[si], Mc[si].p);
+        Mc_ptr[si] = Mc[si].p;
+      }
   struct CpcaBuf {
-    DevBuf<double> cube, S, tr, V0, th0;
+    DevBuf<double> f[2], V0, CPC, D, niter, tr;
+    DevBuf<int> cols[2];
     int G = 0, Gp = 0, ncomp = 0;
-    double na = 0, nb = 0;
   };
-  const size_t chunk_pairs = 24;
-  for (size_t c0 = 0, c1 = 0; c0 < todo.size(); c0 = c1) {
-    c1 = std::min(todo.size(), c0 + chunk_pairs);
-    std::vector<CpcaBuf> bufs(c1 - c0);
-    std::vector<EigProblem> eprobs;
-    int ncomp_all = -1;
-    for (size_t t = c0; t < c1; ++t) {
-      const cg_pair& pr = pairs[todo[t]];
-      CpcaBuf& b = bufs[t - c0];
-      const int G = pr.n_genes;
-      const int ncomp = std::min(P.ncomps, G - 1);  // R/conos.R:210
-      CG_CHECK(ncomp >= 1 && ncomp <= 56, "device CPCA supports up to 56 common components");
-      if (ncomp_all >= 0 && ncomp != ncomp_all) {  // a batched solve shares the block size: this pair opens the next chunk
-        c1 = t;
-        break;
-      }
-      const int B = ncomp <= 24 ? 32 : 64;
-      const int Gp = G > B ? G : B;
-      b.G = G;
-      b.Gp = Gp;
-      b.ncomp = ncomp;
-      Sample* sm[2] = {&panel.samples[pr.a], &panel.samples[pr.b]};
-      const int* gcols[2] = {pr.genes_a, pr.genes_b};
-      std::vector<double> f[2];
-      f[0].assign(G, 1.0);
-      f[1].assign(G, 1.0);
-      if (P.var_scale) {
-        CG_CHECK(!sm[0]->h_qv.empty() && !sm[1]->h_qv.empty() && !sm[0]->h_v.empty() && !sm[1]->h_v.empty(),
-                 "var.scale = TRUE needs misc$varinfo$v and $qv for every sample");
-        for (int g = 0; g < G; ++g) {
-          const int ca = pr.genes_a[g], cb = pr.genes_b[g];
-          const double cqv = std::exp((sm[0]->h_logqv[ca] + sm[1]->h_logqv[cb]) / 2.0);
-          const double fa = std::sqrt(cqv / sm[0]->h_expv[ca]);
-          const double fb = std::sqrt(cqv / sm[1]->h_expv[cb]);
-          f[0][g] = std::isfinite(fa) ? fa : 0.0;
-          f[1][g] = std::isfinite(fb) ? fb : 0.0;
-        }
-      }
-      // covariance slices (spcov of the scaled matrices) as one p x p x 2 cube
-      b.cube.alloc((size_t)2 * Gp * Gp);
-      b.S.alloc((size_t)Gp * Gp);
-      b.tr.alloc(2);
-      DevBuf<double> fd[2];
-      DevBuf<int> cd[2];
-      for (int side = 0; side < 2; ++side) {
-        fd[side].upload(f[side].data(), (size_t)G, st);
-        cd[side].upload(gcols[side], (size_t)G, st);
-        scaled_cov_kernel<<<nblk((size_t)Gp * Gp), 256, 0, st>>>(sm[side]->gram.p, sm[side]->n_genes,
-                                                                  sm[side]->colsum.p, cd[side].p, fd[side].p, G, Gp,
-                                                                  (double)sm[side]->n_cells,
-                                                                  b.cube.p + (size_t)side * Gp * Gp);
-        trace_kernel<<<1, 256, 0, st>>>(b.cube.p + (size_t)side * Gp * Gp, Gp, b.tr.p + side);
-        ctx.stats.kernels += 2;
-      }
-      // initial vectors: leading eigenvectors of the cell-weighted mean covariance (irlba(S, ncomp)$v)
-      b.na = sm[0]->n_cells;
-      b.nb = sm[1]->n_cells;
-      weighted_sum_kernel<<<nblk((size_t)Gp * Gp), 256, 0, st>>>(b.cube.p, b.cube.p + (size_t)Gp * Gp,
-                                                                  b.na / (b.na + b.nb), b.nb / (b.na + b.nb),
-                                                                  (size_t)Gp * Gp, b.S.p);
-      ctx.stats.kernels++;
-      b.V0.alloc((size_t)Gp * ncomp);
-      b.th0.alloc((size_t)ncomp);
-      ncomp_all = ncomp;
-      eprobs.push_back(EigProblem{b.S.p, Gp, b.V0.p, b.th0.p});
-      CG_CUDA(cudaStreamSynchronize(st));  // fd / cd are released at the end of this iteration
+  std::vector<CpcaBuf> bufs(todo.size());
+  std::vector<CpcaBatchPair> bp(todo.size());
+  for (size_t t = 0; t < todo.size(); ++t) {
+    const cg_pair& pr = pairs[todo[t]];
+    CpcaBuf& b = bufs[t];
+    const int G = pr.n_genes;
+    const int ncomp = std::min(P.ncomps, G - 1);  // R/conos.R:210
+    CG_CHECK(ncomp >= 1 && ncomp <= 56, "device CPCA supports up to 56 common components");
+    const int B = ncomp <= 24 ? 32 : 64;
+    b.G = G;
+    b.Gp = G > B ? G : B;
+    b.ncomp = ncomp;
+    Sample* sm[2] = {&panel.samples[pr.a], &panel.samples[pr.b]};
+    std::vector<double> f[2];
+    pair_factors(*sm[0], *sm[1], pr, P.var_scale != 0, f[0], f[1]);
+    const int* gcols[2] = {pr.genes_a, pr.genes_b};
+    for (int side = 0; side < 2; ++side) {
+      b.f[side].upload(f[side].data(), (size_t)G, st);
+      b.cols[side].upload(gcols[side], (size_t)G, st);
     }
-    {
-      StageScope sc(ctx, "reduction.eig");
-      top_eigenvectors_batched(ctx, eprobs.data(), (int)eprobs.size(), ncomp_all, ctx.exact_reduction ? 1e-10 : 1e-5,
-                               600);
-    }
-    for (size_t t = c0; t < c1; ++t) {
-      CpcaBuf& b = bufs[t - c0];
-      const int G = b.G, Gp = b.Gp, ncomp = b.ncomp;
-      DevBuf<double> ng(2), D((size_t)ncomp * 2), CPC((size_t)Gp * ncomp), niter((size_t)ncomp);
-      const double hng[2] = {b.na, b.nb};
-      ng.upload(hng, 2, st);
+    b.V0.alloc((size_t)b.Gp * ncomp);
+    b.CPC.alloc((size_t)G * ncomp);
+    b.D.alloc((size_t)2 * ncomp);
+    b.niter.alloc((size_t)ncomp);
+    b.tr.alloc(2);
+    bp[t] = CpcaBatchPair{pr.a, pr.b, G, ncomp, b.Gp, {b.cols[0].p, b.cols[1].p}, {b.f[0].p, b.f[1].p}, b.V0.p,
+                          b.CPC.p, b.D.p, b.niter.p, b.tr.p};
+  }
+  CG_CUDA(cudaStreamSynchronize(st));  // the host vectors of the loop above are gone
+  // initial vectors, chunk by chunk (one G x G matrix per pair of the chunk; a batched solve shares the block width)
+  {
+    StageScope sc(ctx, "reduction.cpca_init");
+    size_t c0 = 0;
+    while (c0 < todo.size()) {
+      size_t freeb = 0, totb = 0;
+      cudaMemGetInfo(&freeb, &totb);
+      size_t c1 = c0, used = 0;
+      while (c1 < todo.size()) {
+        if (bufs[c1].ncomp != bufs[c0].ncomp) break;
+        const size_t need = (size_t)bufs[c1].Gp * bufs[c1].Gp * 8 + (size_t)bufs[c1].Gp * 64 * 8 * 4;
+        if (c1 > c0 && used + need > std::min(freeb / 3, ctx.max_batch_bytes)) break;
+        used += need;
+        ++c1;
+      }
+      std::vector<DevBuf<double>> Sm(c1 - c0), th(c1 - c0);
+      std::vector<EigProblem> eprobs;
+      for (size_t t = c0; t < c1; ++t) {
+        const cg_pair& pr = pairs[todo[t]];
+        CpcaBuf& b = bufs[t];
+        const Sample& sa = panel.samples[pr.a];
+        const Sample& sb = panel.samples[pr.b];
+        Sm[t - c0].alloc((size_t)b.Gp * b.Gp);
+        th[t - c0].alloc((size_t)b.ncomp);
+        const double na = sa.n_cells, nb = sb.n_cells;
+        mean_cov_kernel<<<nblk((size_t)b.Gp * b.Gp), 256, 0, st>>>(
+            Mc_ptr[pr.a], sa.n_genes, Mc_ptr[pr.b], sb.n_genes, b.cols[0].p, b.cols[1].p, b.f[0].p, b.f[1].p, b.G, b.Gp,
+            na / (na + nb) / (na - 1.0), nb / (na + nb) / (nb - 1.0), Sm[t - c0].p);
+        ctx.stats.kernels++;
+        eprobs.push_back(EigProblem{Sm[t - c0].p, b.Gp, b.V0.p, th[t - c0].p});
+      }
+      CG_CUDA(cudaGetLastError());
       {
-        StageScope sc(ctx, "reduction.cpca");
-        cpca_device(ctx, b.cube.p, Gp, 2, ng.p, ncomp, P.cpca_maxit, P.cpca_tol, b.V0.p, D.p, CPC.p, niter.p);
+        StageScope sc2(ctx, "reduction.eig");
+        top_eigenvectors_batched(ctx, eprobs.data(), (int)eprobs.size(), bufs[c0].ncomp,
+                                 ctx.exact_reduction ? 1e-10 : 1e-5, 600);
       }
-      PairReduction& R = out[todo[t]];
-      R.n_rows = G;
-      R.n_cols = ncomp;
-      R.d = P.ncomps < ncomp ? P.ncomps : ncomp;
-      R.rot.alloc((size_t)G * ncomp);
-      CG_CUDA(cudaMemcpy2DAsync(R.rot.p, (size_t)G * sizeof(double), CPC.p, (size_t)Gp * sizeof(double),
-                                (size_t)G * sizeof(double), ncomp, cudaMemcpyDeviceToDevice, st));
-      download_rotation(ctx, R);
-      if (P.score_component_variance) {
-        std::vector<double> hD((size_t)ncomp * 2), htr(2);
-        D.download(hD.data(), hD.size(), st);
-        b.tr.download(htr.data(), 2, st);
-        CG_CUDA(cudaStreamSynchronize(st));
-        R.h_nv.assign((size_t)2 * ncomp, 0.0);
-        for (int side = 0; side < 2; ++side)
-          for (int j = 0; j < ncomp; ++j) R.h_nv[(size_t)side * ncomp + j] = hD[(size_t)side * ncomp + j] / htr[side];
-      }
-      CG_CUDA(cudaStreamSynchronize(st));
+      c0 = c1;
     }
   }
+  {
+    StageScope sc(ctx, "reduction.cpca");
+    cpca_batched(ctx, panel, bp.data(), (int)bp.size(), Mc_ptr.data(), P.cpca_maxit, P.cpca_tol);
+  }
+  for (size_t t = 0; t < todo.size(); ++t) {
+    CpcaBuf& b = bufs[t];
+    PairReduction& R = out[todo[t]];
+    R.n_rows = b.G;
+    R.n_cols = b.ncomp;
+    R.d = P.ncomps < b.ncomp ? P.ncomps : b.ncomp;
+    R.rot = std::move(b.CPC);
+    download_rotation(ctx, R);
+    R.h_D.resize((size_t)2 * b.ncomp);
+    R.h_niter.resize((size_t)b.ncomp);
+    b.D.download(R.h_D.data(), R.h_D.size(), st);
+    b.niter.download(R.h_niter.data(), R.h_niter.size(), st);
+    if (P.score_component_variance) {
+      std::vector<double> htr(2);
+      b.tr.download(htr.data(), 2, st);
+      CG_CUDA(cudaStreamSynchronize(st));
+      R.h_nv.assign((size_t)2 * b.ncomp, 0.0);
+      for (int side = 0; side < 2; ++side)
+        for (int j = 0; j < b.ncomp; ++j)
+          R.h_nv[(size_t)side * b.ncomp + j] = R.h_D[(size_t)side * b.ncomp + j] / htr[side];
+    }
+  }
+  CG_CUDA(cudaStreamSynchronize(st));
 }
 
 void ensure_gram(Context& ctx, Sample& s) {
@@ -575,9 +616,14 @@ void ensure_grams(Context& ctx, Sample* const* samples, int n) {
       TiledOperand op;
       op.hi = hi[t - i0].p;
       op.lo = lo[t - i0].p;
-      tiled_from_csr(ctx, s->csr_p.p, s->csr_i.p, s->csr_x.p, s->n_cells, s->n_genes, op);
+      // fp16 hi + lo (22 significant bits) whenever the values fit: expression values are log-scale, 0 .. ~6; the
+      // contraction over the cells runs in 1024-cell FP32 chunks summed in FP64 (see gemm_tc.cu)
+      const bool fp16 = s->max_abs < 3.0e4;
+      tiled_from_csr(ctx, s->csr_p.p, s->csr_i.p, s->csr_x.p, s->n_cells, s->n_genes, op, fp16);
       GemmProblem gp{op.hi, op.lo, op.hi, op.lo, op.rows_pad, op.rows_pad, op.k_pad, s->n_genes, s->n_genes, s->gram.p,
                      (long long)s->n_genes, 1, 1};
+      gp.chunk_slabs = ctx.gram_chunk_slabs;
+      gp.fp16 = fp16 ? 1 : 0;
       gps.push_back(gp);
     }
     gemm_tn_bf16x3(ctx, gps.data(), (int)gps.size());

@@ -47,16 +47,27 @@ __global__ void rowp_narrow_kernel(const long long* __restrict__ in, int n, int*
 }
 
 // deterministic column sums: one warp per column, fixed lane stride and shuffle tree
+// out[g] = column sum, out[n_genes + g] = largest |value| of the column (decides whether the Gram operand fits fp16)
 __global__ void colsum_kernel(const int* __restrict__ csc_p, const double* __restrict__ csc_x, int n_genes,
                               double* __restrict__ out) {
   const int g = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (g >= n_genes) return;
   const int lane = threadIdx.x & 31;
-  double s = 0.0;
-  for (int t = csc_p[g] + lane; t < csc_p[g + 1]; t += 32) s += csc_x[t];
+  double s = 0.0, mx = 0.0;
+  for (int t = csc_p[g] + lane; t < csc_p[g + 1]; t += 32) {
+    const double v = csc_x[t];
+    s += v;
+    mx = fmax(mx, fabs(v));
+  }
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) s += __shfl_down_sync(0xffffffffu, s, d);
-  if (lane == 0) out[g] = s;
+  for (int d = 16; d > 0; d >>= 1) {
+    s += __shfl_down_sync(0xffffffffu, s, d);
+    mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, d));
+  }
+  if (lane == 0) {
+    out[g] = s;
+    out[n_genes + g] = mx;
+  }
 }
 
 // ------------------------------------------------------------------ projection operands
@@ -189,7 +200,7 @@ void sample_upload(Context& ctx, Sample& s, int n_cells, int n_genes, const int*
     s.csr_p.alloc((size_t)n_cells + 1);
     s.csr_i.alloc((size_t)s.nnz);
     s.csr_x.alloc((size_t)s.nnz);
-    s.colsum.alloc((size_t)n_genes);
+    s.colsum.alloc((size_t)2 * n_genes);  // sums, then column maxima
   }
   s.n_pcs = 0;
   s.pca_metric = -1;
@@ -233,9 +244,12 @@ void sample_finish(Context& ctx, Sample& s, cudaEvent_t ready) {
   csc_to_csr(ctx, s.n_cells, s.n_genes, s.csc_p.p, s.csc_i.p, s.csc_x.p, s.nnz, s.csr_p.p, s.csr_i.p, s.csr_x.p);
   colsum_kernel<<<(s.n_genes + 7) / 8, 256, 0, st>>>(s.csc_p.p, s.csc_x.p, s.n_genes, s.colsum.p);
   ctx.stats.kernels++;
-  s.h_colsum.resize(s.n_genes);
-  s.colsum.download(s.h_colsum.data(), (size_t)s.n_genes, st);
+  s.h_colsum.resize((size_t)2 * s.n_genes);
+  s.colsum.download(s.h_colsum.data(), (size_t)2 * s.n_genes, st);
   CG_CUDA(cudaStreamSynchronize(st));
+  s.max_abs = 0.0;
+  for (int g = 0; g < s.n_genes; ++g) s.max_abs = std::max(s.max_abs, s.h_colsum[(size_t)s.n_genes + g]);
+  s.h_colsum.resize(s.n_genes);
 }
 
 void build_projection_operands(Context& ctx, const WBuildProblem* h_probs, int n_probs, int d, int d_pad) {

@@ -20,7 +20,8 @@ struct Sample {
   DevBuf<double> csc_x;
   DevBuf<int> csr_p, csr_i;
   DevBuf<double> csr_x;
-  DevBuf<double> colsum;          // per gene, sum over cells (device)
+  DevBuf<double> colsum;          // per gene, sum over cells (device); [n_genes .. 2 n_genes): column maxima
+  double max_abs = 0.0;           // largest |value| of the counts matrix
   DevBuf<double> gram;            // X'X over all genes, FP64 column-major (built on first use by the reductions)
   std::vector<double> h_colsum;   // host copy
   std::vector<double> h_gram_diag;  // host copy of diag(X'X), filled on demand

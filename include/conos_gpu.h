@@ -64,6 +64,9 @@ int cg_timer_stop(cg_context* ctx, double* ms);
  * shrink it to force the overflow path).  Results are identical for every setting.
  * "tc_eig_max_sweeps" (default 40): sweeps of the tensor-core eigen solver before a pair that has not reached
  * irlba's tolerance is handed to the FP64 driver (tests set 1 to force that path).
+ * "gram_chunk_slabs" (default 16): the tensor-core Gram matrix X'X accumulates the cells in FP32 chunks of 64 x this
+ * many cells and sums the chunks in FP64 (0: one FP32 accumulation over all cells, round 1's behaviour).
+ * "tc_eig_tol" (default 1e-5 = irlba's): residual bound of that solver relative to the largest Ritz value.
  * "tc_eig_degree" (default 10, 2..64): largest Chebyshev degree of one sweep of that solver (8 / 10 / 12 / 14 were
  * measured on configs[1]: 10.4 / 8.8 / 9.1 / 9.2 ms for the 56 eigenproblems).
  * "tc_projection" (default 1): in the default mode the projections of device-computed rotations run as one bf16x3
@@ -166,6 +169,13 @@ int cg_pair_reduction(cg_context* ctx, int which, int32_t* n_rows, int32_t* n_co
  * dropped, :336); sigma = res$d.  Query the sizes with NULL outputs. */
 int cg_pair_cca(cg_context* ctx, int which, int32_t* n_u, int32_t* n_v, int32_t* d, double* u, double* v,
                 int32_t* rows_u, int32_t* rows_v, double* sigma);
+/* CPCA: the other fields of cpcaF's result for pair `which` (src/cpca.cpp:93-100; self$pairs$CPCA keeps them,
+ * R/conos.R:242): D = q'C_i q at convergence, column-major n_cols x 2 like the reference's t(D) (column 0 = sample a);
+ * niter [n_cols]. */
+int cg_pair_cpca(cg_context* ctx, int which, int32_t* n_cols, double* D, double* niter);
+/* CCA: gene loadings ul, vl (n_genes x d column-major, unit columns) and variance fractions nv [2][d] of pair
+ * `which` when it was computed by the most recent call (R/conos.R:349-357).  Query sizes with NULL outputs. */
+int cg_pair_cca_loadings(cg_context* ctx, int which, int32_t* n_genes, int32_t* d, double* ul, double* vl, double* nv);
 /* Projections of pair `which` of the most recent call (column-major n x ncomps doubles), for parity tests;
  * they are only kept after cg_keep_projections(ctx, 1). */
 int cg_keep_projections(cg_context* ctx, int enable);

@@ -326,6 +326,13 @@ def test_device_cpca_rotation(ctx, oracle, small_panel, exact):
         assert dots.min() > 1 - tol, (key, dots.min())
         for side in (0, 1):
             np.testing.assert_allclose(mine["nv"][side], red["nv"][side], rtol=100 * tol)
+        # the other fields of cpcaF's result (src/cpca.cpp:93-100): D (k x ncomp) and niter
+        assert mine["D"].shape == red["D"].shape == (12, 2) and mine["niter"].shape == (12,)
+        np.testing.assert_allclose(mine["D"], red["D"], rtol=1e-6 if exact else 1e-2)
+        if exact:
+            assert np.array_equal(mine["niter"], red["niter"]), (key, mine["niter"], red["niter"])
+        else:
+            assert np.abs(mine["niter"] - red["niter"]).max() <= 3
     og = ref["graph"]
     mine_e = {(min(a, b), max(a, b)) for a, b in zip(g.vertices[g.edge_from].tolist(), g.vertices[g.edge_to].tolist())}
     ref_e = {(min(a, b), max(a, b))
@@ -376,6 +383,19 @@ def test_device_cca_reduction(ctx, oracle, small_panel, exact):
                 assert _principal_cosines(a, b).min() > 1 - 1e-3
         # u_j and v_j flip together
         assert np.array_equal(np.sign(np.sum(mine["u"] * red["u"], axis=0)), np.sign(np.sum(mine["v"] * red["v"], axis=0)))
+        # gene loadings and variance fractions (R/conos.R:349-357)
+        assert mine["ul"].shape == red["ul"].shape and mine["vl"].shape == red["vl"].shape
+        np.testing.assert_allclose(np.linalg.norm(mine["ul"], axis=0), 1.0, rtol=1e-12)
+        if exact:
+            for a, b in ((mine["ul"], red["ul"]), (mine["vl"], red["vl"])):
+                sign = np.sign(np.sum(a * b, axis=0))
+                np.testing.assert_allclose(a * sign[None, :], b, rtol=0, atol=1e-6)
+            for side in (0, 1):
+                np.testing.assert_allclose(mine["nv"][side], red["nv"][side], rtol=1e-6)
+        else:
+            assert _principal_cosines(mine["ul"], red["ul"]).min() > 1 - 1e-3
+            for side in (0, 1):
+                np.testing.assert_allclose(np.sort(mine["nv"][side]), np.sort(red["nv"][side]), rtol=5e-2)
     og = ref["graph"]
     mine_e = {(min(a, b), max(a, b)) for a, b in zip(g.vertices[g.edge_from].tolist(), g.vertices[g.edge_to].tolist())}
     ref_e = {(min(a, b), max(a, b))
