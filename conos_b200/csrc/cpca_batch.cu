@@ -42,48 +42,63 @@ struct SkinnySample {
   int G, ncols;
 };
 
-// Z = Mc U for every sample: CTA = 64 rows x 32 columns of Z, thread = 8 rows x 1 column, k in slabs of 32.
-// Mc is symmetric: row r is the contiguous column r.
+// Z = Mc U for every sample: CTA = 128 rows x 32 columns of Z, thread = 8 rows x 2 columns, k in slabs of 32.
+// Mc is symmetric, so the (rows r0.., k) slab is read as (k, rows r0..): contiguous in the row index, which is also the
+// order the threads want it in shared memory (16-byte vector loads, 5 shared loads per 16 FP64 FMAs).
+constexpr int SK_ROWS = 128, SK_COLS = 32, SK_K = 32;
 __global__ void __launch_bounds__(CP_THREADS) skinny_gemm_kernel(const SkinnySample* __restrict__ S,
                                                                  const int* __restrict__ tile_sample,
                                                                  const int* __restrict__ tile_row0,
                                                                  const int* __restrict__ tile_col0) {
-  __shared__ double As[64][33];
-  __shared__ double Bs[32][33];
+  __shared__ __align__(16) double As[SK_K][SK_ROWS];
+  __shared__ __align__(16) double Bs[SK_K][SK_COLS + 2];
   const SkinnySample sd = S[tile_sample[blockIdx.x]];
   const int row0 = tile_row0[blockIdx.x], col0 = tile_col0[blockIdx.x];
   const int G = sd.G;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  double acc[8];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // columns 2 tx, 2 tx + 1; rows 8 ty .. 8 ty + 7
+  double acc[8][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.0;
-  for (int k0 = 0; k0 < G; k0 += 32) {
-    // A slab: 64 rows x 32 k (coalesced along k), B slab: 32 columns x 32 k
+  for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = 0.0;
+  for (int k0 = 0; k0 < G; k0 += SK_K) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = row0 + ty * 8 + i, k = k0 + tx;
-      As[ty * 8 + i][tx] = (r < G && k < G) ? sd.Mc[(size_t)r * G + k] : 0.0;
+    for (int i = 0; i < SK_K * SK_ROWS / CP_THREADS; ++i) {
+      const int e = threadIdx.x + i * CP_THREADS;
+      const int r = e % SK_ROWS, k = e / SK_ROWS;
+      As[k][r] = (row0 + r < G && k0 + k < G) ? sd.Mc[(size_t)(k0 + k) * G + row0 + r] : 0.0;
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int c = col0 + ty * 4 + i, k = k0 + tx;
-      Bs[ty * 4 + i][tx] = (c < sd.ncols && k < G) ? sd.U[(size_t)c * G + k] : 0.0;
+    for (int i = 0; i < SK_K * SK_COLS / CP_THREADS; ++i) {
+      const int e = threadIdx.x + i * CP_THREADS;
+      const int k = e % SK_K, c = e / SK_K;
+      Bs[k][c] = (col0 + c < sd.ncols && k0 + k < G) ? sd.U[(size_t)(col0 + c) * G + k0 + k] : 0.0;
     }
     __syncthreads();
-#pragma unroll 8
-    for (int k = 0; k < 32; ++k) {
-      const double b = Bs[tx][k];
+#pragma unroll 4
+    for (int k = 0; k < SK_K; ++k) {
+      const double2 b = *reinterpret_cast<const double2*>(&Bs[k][2 * tx]);
+      double a[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = fma(As[ty * 8 + i][k], b, acc[i]);
+      for (int i = 0; i < 4; ++i) {
+        const double2 v = *reinterpret_cast<const double2*>(&As[k][8 * ty + 2 * i]);
+        a[2 * i] = v.x;
+        a[2 * i + 1] = v.y;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[i][0] = fma(a[i], b.x, acc[i][0]);
+        acc[i][1] = fma(a[i], b.y, acc[i][1]);
+      }
     }
     __syncthreads();
   }
-  const int c = col0 + tx;
-  if (c < sd.ncols) {
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int c = col0 + 2 * tx + j;
+    if (c >= sd.ncols) continue;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int r = row0 + ty * 8 + i;
-      if (r < G) sd.Z[(size_t)c * G + r] = acc[i];
+      const int r = row0 + 8 * ty + i;
+      if (r < G) sd.Z[(size_t)c * G + r] = acc[i][j];
     }
   }
 }
@@ -281,8 +296,8 @@ void cpca_batched(Context& ctx, cg_panel& panel, const CpcaBatchPair* pairs, int
     diag[s].alloc((size_t)G);
     extract_diag_kernel<<<(G + 255) / 256, 256, 0, st>>>(Mc[s], G, diag[s].p);
     ctx.stats.kernels++;
-    for (int c0 = 0; c0 < ncols[s]; c0 += 32)
-      for (int r0 = 0; r0 < G; r0 += 64) {
+    for (int c0 = 0; c0 < ncols[s]; c0 += SK_COLS)
+      for (int r0 = 0; r0 < G; r0 += SK_ROWS) {
         t_sample.push_back(s);
         t_row0.push_back(r0);
         t_col0.push_back(c0);

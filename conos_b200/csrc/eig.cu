@@ -594,7 +594,7 @@ __global__ void __launch_bounds__(EIG_THREADS) eig_project_kernel(const EigWork*
 // [0, theta_B], CholeskyQR2, repeat.  `max_iter` bounds the number of operator applications.
 template <int B, class MatMul>
 void run_eig_generic(Context& ctx, const int* rows, double* const* Vout, double* const* theta_out, const double* const* Cmat,
-                     int n_probs, int r, double tol, int max_iter, MatMul&& matmul) {
+                     int n_probs, int r, double tol, int max_iter, MatMul&& matmul, int* h_converged = nullptr) {
   cudaStream_t s = ctx.stream;
   constexpr int DEGREE = 12;
   std::vector<EigWork> works(n_probs);
@@ -688,6 +688,8 @@ void run_eig_generic(Context& ctx, const int* rows, double* const* Vout, double*
     ctx.stage_ms["reduction.eig.converged_problems"] += nconv;
     ctx.stage_ms["reduction.eig.problems"] += n_probs;
   }
+  if (h_converged)
+    for (int p = 0; p < n_probs; ++p) h_converged[p] = hc[p] != 0 ? 1 : 0;
   // the loop ends right after a Rayleigh-Ritz step: Q holds the sorted Ritz vectors
   eig_export_kernel<B><<<dim3(8, n_probs), 256, 0, s>>>(dw.p, r);
   ctx.stats.kernels++;
@@ -934,6 +936,153 @@ void top_eigenvectors_operator(Context& ctx, int n_rows, int r, double tol, int 
   else run_eig_generic<64>(ctx, &n_rows, Vp, tp, nullptr, 1, r, tol, max_iter, mm);
 }
 
+// =================================================================== pair operators  S = wa Da Mc_a Da + wb Db Mc_b Db
+// (the cell-weighted mean covariance whose leading eigenvectors start the common-PCA iteration, R/conos.R:180-185).
+// The FP64 driver above iterates; the operator is applied for ALL pairs at once through one bf16x3 tensor-core GEMM
+// per sample against its centred Gram matrix: a pair contributes a block of B columns to each of its two samples.
+namespace {
+
+struct PairOpDev {
+  const int* cols[2];
+  const double* f[2];
+  double w[2];
+  __nv_bfloat16* Uh[2];  // this pair's B columns inside the samples' operands (tiled, rows = columns of U)
+  __nv_bfloat16* Ul[2];
+  int col0[2];           // first column of the pair's block inside the sample's operand / product
+  int u_rows_pad[2];
+  const float* V[2];     // the samples' products, column-major G_s x ncols_s
+  int Gs[2];
+  int G;                 // od genes of the pair (<= rows of its Q block)
+};
+
+// U_s[:, col0 + j] = D_s Q[:, j] for both samples of every pair (zero outside the pair's gene set: never written)
+template <int B>
+__global__ void pairop_scatter_kernel(const EigWork* __restrict__ W, const PairOpDev* __restrict__ P,
+                                      const int* __restrict__ deg, int step) {
+  const EigWork w = W[blockIdx.y];
+  if (*w.converged != 0) return;
+  if (step > 0 && step > deg[blockIdx.y]) return;
+  const PairOpDev pd = P[blockIdx.y];
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)pd.G * B) return;
+  const int g = (int)(t / B), j = (int)(t % B);
+  const double q = w.Q[t];
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    const float u = (float)(pd.f[side][g] * q);
+    const size_t o = tiled_operand_offset(pd.col0[side] + j, pd.cols[side][g], pd.u_rows_pad[side]);
+    const __nv_bfloat16 h = __float2bfloat16_rn(u);
+    pd.Uh[side][o] = h;
+    pd.Ul[side][o] = __float2bfloat16_rn(u - __bfloat162float(h));
+  }
+}
+
+// Z[g][j] = wa fa[g] V_a[cols_a[g], col0_a + j] + wb fb[g] V_b[cols_b[g], col0_b + j]; padding rows of Q stay zero
+template <int B>
+__global__ void pairop_gather_kernel(const EigWork* __restrict__ W, const PairOpDev* __restrict__ P,
+                                     const int* __restrict__ deg, int step) {
+  const EigWork w = W[blockIdx.y];
+  if (*w.converged != 0) return;
+  if (step > 0 && step > deg[blockIdx.y]) return;
+  const PairOpDev pd = P[blockIdx.y];
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)w.G * B) return;
+  const int g = (int)(t / B), j = (int)(t % B);
+  double z = 0.0;
+  if (g < pd.G) {
+#pragma unroll
+    for (int side = 0; side < 2; ++side)
+      z += pd.w[side] * pd.f[side][g] *
+           (double)pd.V[side][(size_t)(pd.col0[side] + j) * pd.Gs[side] + pd.cols[side][g]];
+  }
+  w.Z[t] = z;
+}
+
+template <int B>
+void run_pair_sum_tc(Context& ctx, const PairOpSample* samples, int n_samples, const PairOpProblem* probs, int n_probs,
+                     int r, double tol, int max_iter, int* h_converged) {
+  cudaStream_t s = ctx.stream;
+  // columns of every sample
+  std::vector<int> ncols(n_samples, 0);
+  std::vector<PairOpDev> hp(n_probs);
+  for (int p = 0; p < n_probs; ++p) {
+    const int sidx[2] = {probs[p].a, probs[p].b};
+    for (int side = 0; side < 2; ++side) {
+      CG_CHECK(sidx[side] >= 0 && sidx[side] < n_samples, "bad sample index");
+      hp[p].col0[side] = ncols[sidx[side]];
+      ncols[sidx[side]] += B;
+    }
+  }
+  std::vector<DevBuf<__nv_bfloat16>> Mh(n_samples), Ml(n_samples), Uh(n_samples), Ul(n_samples);
+  std::vector<DevBuf<float>> V(n_samples);
+  std::vector<TiledOperand> Mop(n_samples);
+  std::vector<int> u_rows_pad(n_samples, 0);
+  std::vector<GemmProblem> gprobs;
+  for (int si = 0; si < n_samples; ++si) {
+    if (ncols[si] == 0) continue;
+    const int G = samples[si].G;
+    Mh[si].alloc(TiledOperand::elems(G, G));
+    Ml[si].alloc(TiledOperand::elems(G, G));
+    Mop[si].hi = Mh[si].p;
+    Mop[si].lo = Ml[si].p;
+    tiled_from_colmajor_f64(ctx, samples[si].Mc, G, G, G, Mop[si]);
+    u_rows_pad[si] = (int)round_up(ncols[si], GEMM_ROW_PAD);
+    const size_t ue = (size_t)u_rows_pad[si] * round_up(G, GEMM_K_PAD);
+    Uh[si].alloc(ue);
+    Ul[si].alloc(ue);
+    Uh[si].zero(s);
+    Ul[si].zero(s);
+    V[si].alloc((size_t)G * ncols[si]);
+    gprobs.push_back(GemmProblem{Mop[si].hi, Mop[si].lo, Uh[si].p, Ul[si].p, Mop[si].rows_pad, u_rows_pad[si],
+                                 Mop[si].k_pad, G, ncols[si], V[si].p, (long long)G, 0});
+  }
+  GemmPlan gplan;
+  gemm_plan(ctx, gprobs.data(), (int)gprobs.size(), gplan);
+  std::vector<int> rows(n_probs);
+  std::vector<double*> Vout(n_probs), th(n_probs);
+  for (int p = 0; p < n_probs; ++p) {
+    const PairOpProblem& pb = probs[p];
+    const int sidx[2] = {pb.a, pb.b};
+    for (int side = 0; side < 2; ++side) {
+      const int si = sidx[side];
+      hp[p].cols[side] = pb.cols[side];
+      hp[p].f[side] = pb.f[side];
+      hp[p].w[side] = pb.w[side];
+      hp[p].Uh[side] = Uh[si].p;
+      hp[p].Ul[side] = Ul[si].p;
+      hp[p].u_rows_pad[side] = u_rows_pad[si];
+      hp[p].V[side] = V[si].p;
+      hp[p].Gs[side] = samples[si].G;
+    }
+    hp[p].G = pb.G;
+    rows[p] = pb.rows;
+    Vout[p] = pb.V;
+    th[p] = pb.theta;
+  }
+  DevBuf<PairOpDev> dP;
+  dP.upload(hp.data(), hp.size(), s);
+  run_eig_generic<B>(
+      ctx, rows.data(), Vout.data(), th.data(), nullptr, n_probs, r, tol, max_iter,
+      [&](std::vector<EigWork>&, const EigWork* dw, int maxG, const int* deg, int step) {
+        dim3 grid((unsigned)(((size_t)maxG * B + 255) / 256), n_probs);
+        pairop_scatter_kernel<B><<<grid, 256, 0, s>>>(dw, dP.p, deg, step);
+        gemm_run(ctx, gplan);
+        pairop_gather_kernel<B><<<grid, 256, 0, s>>>(dw, dP.p, deg, step);
+        ctx.stats.kernels += 2;
+      },
+      h_converged);
+}
+
+}  // namespace
+
+void top_eigenvectors_pair_sum_tc(Context& ctx, const PairOpSample* samples, int n_samples, const PairOpProblem* probs,
+                                  int n_probs, int r, double tol, int max_iter, int* h_converged) {
+  if (n_probs == 0) return;
+  CG_CHECK(r >= 1 && r <= 56, "1..56 eigenvectors per problem");
+  if (r <= 24) run_pair_sum_tc<32>(ctx, samples, n_samples, probs, n_probs, r, tol, max_iter, h_converged);
+  else run_pair_sum_tc<64>(ctx, samples, n_samples, probs, n_probs, r, tol, max_iter, h_converged);
+}
+
 void top_eigenvectors_shared_gram(Context& ctx, const TcEigSample* samples, int n_samples,
                                   const TcEigProblem* probs, int n_probs, int r, double tol, int max_outer,
                                   int degree, int* h_converged) {
@@ -1066,15 +1215,24 @@ void top_eigenvectors_shared_gram(Context& ctx, const TcEigSample* samples, int 
     outer_done = outer;
     // orthonormal basis of the filtered block
     dim3 g64((unsigned)(((size_t)maxG * B + 255) / 256), n_probs);
-    tc_to64_kernel<<<g64, 256, 0, s>>>(dS.p, dP.p);
-    eig_orth_kernel<B><<<n_probs, EIG_THREADS, smem, s>>>(dw.p);
-    ctx.stats.kernels += 2;
+    {
+      StageScope sc(ctx, "reduction.eig.orth");
+      tc_to64_kernel<<<g64, 256, 0, s>>>(dS.p, dP.p);
+      eig_orth_kernel<B><<<n_probs, EIG_THREADS, smem, s>>>(dw.p);
+      ctx.stats.kernels += 2;
+    }
     // Rayleigh-Ritz: Z = C Q through the shared Gram GEMM
-    column(0, nullptr, nullptr, nullptr, 0);
-    gemm_run(ctx, gplan);
-    column(3, nullptr, nullptr, nullptr, 0);
-    eig_rr_kernel<B><<<n_probs, EIG_THREADS, smem, s>>>(dw.p, r, tol, 0);
-    ctx.stats.kernels++;
+    {
+      StageScope sc(ctx, "reduction.eig.rr_product");
+      column(0, nullptr, nullptr, nullptr, 0);
+      gemm_run(ctx, gplan);
+      column(3, nullptr, nullptr, nullptr, 0);
+    }
+    {
+      StageScope sc(ctx, "reduction.eig.rr");
+      eig_rr_kernel<B><<<n_probs, EIG_THREADS, smem, s>>>(dw.p, r, tol, 0);
+      ctx.stats.kernels++;
+    }
     conv.download(hc.data(), (size_t)n_probs, s);
     CG_CUDA(cudaStreamSynchronize(s));
     bool all = true;
@@ -1089,6 +1247,7 @@ void top_eigenvectors_shared_gram(Context& ctx, const TcEigSample* samples, int 
     for (int p = 0; p < n_probs; ++p)
       if (!hc[p] && hdeg[p] > sweep) sweep = hdeg[p];
     gemm_steps += sweep;
+    StageScope sc(ctx, "reduction.eig.filter");
     column(1, al.p + (size_t)1 * n_probs, nullptr, cc.p, 1);
     for (int i = 2; i <= sweep; ++i) {
       gemm_run(ctx, gplan);

@@ -52,4 +52,25 @@ void top_eigenvectors_shared_gram(Context& ctx, const TcEigSample* samples, int 
                                   const TcEigProblem* probs, int n_probs, int r, double tol, int max_outer,
                                   int degree, int* h_converged = nullptr);
 
+// Leading r eigenvectors of  S_p = wa Da Mc_a Da + wb Db Mc_b Db  for many sample pairs p at once (the initial
+// vectors of the common-PCA iteration: irlba(S, ncomp)$v, R/conos.R:180-185).  FP64 block iteration; the operator of
+// all pairs is ONE bf16x3 tensor-core GEMM per sample against its centred Gram matrix Mc_s per application.
+struct PairOpSample {
+  const double* Mc;  // G x G column-major centred Gram matrix (device); may be null for samples without a problem
+  int G;
+};
+struct PairOpProblem {
+  int a, b;             // samples
+  int G;                // od genes of the pair
+  int rows;             // rows of the iterated block (>= G and >= block width; padding rows stay zero)
+  const int* cols[2];   // device [G]: column of gene g in sample a / b
+  const double* f[2];   // device [G]: scale factors
+  double w[2];          // wa = n_a / n / (n_a - 1), wb likewise
+  double* V;            // out: rows x r column-major
+  double* theta;        // out: [r]
+};
+// h_converged (optional, [n_probs]): 0 where the residual bound tol * theta_1 was not reached within max_iter
+void top_eigenvectors_pair_sum_tc(Context& ctx, const PairOpSample* samples, int n_samples, const PairOpProblem* probs,
+                                  int n_probs, int r, double tol, int max_iter, int* h_converged = nullptr);
+
 }  // namespace cg

@@ -128,19 +128,25 @@ gemm_tn_bf16x3_kernel(const GemmProblem* __restrict__ probs, const GemmTile* __r
         ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
         ptx::tmem_wait_ld();
         if (m < pb.M) {
+          const int n0 = tl.nt * BN + c * 32;
+          if (pb.out_fp64) {
+            double* dst = reinterpret_cast<double*>(pb.C) + (size_t)n0 * pb.ldc + m;
+            // all 32 partial sums of the previous chunks are fetched before the first store: the compiler cannot
+            // prove that the 32 addresses (runtime ldc apart) are distinct and would otherwise serialise the round trips
+            double old[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = tl.nt * BN + c * 32 + j;
-            if (n < pb.N) {
-              const float f = __uint_as_float(v[j]);
-              if (pb.out_fp64) {
-                double* dst = reinterpret_cast<double*>(pb.C) + (size_t)n * pb.ldc + m;
-                *dst = ch == 0 ? (double)f : *dst + (double)f;
-              } else {
-                float* dst = reinterpret_cast<float*>(pb.C) + (size_t)n * pb.ldc + m;
-                *dst = ch == 0 ? f : *dst + f;
-              }
-            }
+            for (int j = 0; j < 32; ++j) old[j] = (ch > 0 && n0 + j < pb.N) ? __ldcg(dst + (size_t)j * pb.ldc) : 0.0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < pb.N) __stcg(dst + (size_t)j * pb.ldc, old[j] + (double)__uint_as_float(v[j]));
+          } else {
+            float* dst = reinterpret_cast<float*>(pb.C) + (size_t)n0 * pb.ldc + m;
+            float old[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) old[j] = (ch > 0 && n0 + j < pb.N) ? __ldcg(dst + (size_t)j * pb.ldc) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < pb.N) __stcg(dst + (size_t)j * pb.ldc, old[j] + __uint_as_float(v[j]));
           }
         }
       }

@@ -1,5 +1,6 @@
 #include <algorithm>
 #include <cmath>
+#include <map>
 
 #include "eig.cuh"
 #include "gemm_tc.cuh"
@@ -492,41 +493,86 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
                           b.CPC.p, b.D.p, b.niter.p, b.tr.p};
   }
   CG_CUDA(cudaStreamSynchronize(st));  // the host vectors of the loop above are gone
-  // initial vectors, chunk by chunk (one G x G matrix per pair of the chunk; a batched solve shares the block width)
-  {
+  // initial vectors.  Default mode: S is applied as an operator for all pairs at once (one tensor-core GEMM per sample
+  // and application, eig.cu); pairs that miss irlba's tolerance there -- and every pair in exact mode -- get the
+  // explicit G x G matrix and the FP64 block iteration, chunk by chunk (a batched solve shares the block width).
+  std::vector<size_t> expl;
+  if (!ctx.exact_reduction) {
+    StageScope sc(ctx, "reduction.cpca_init_tc");
+    std::vector<PairOpSample> ps(S);
+    for (int si = 0; si < S; ++si) ps[si] = PairOpSample{Mc_ptr[si], panel.samples[si].n_genes};
+    std::map<int, std::vector<size_t>> by_ncomp;
+    for (size_t t = 0; t < todo.size(); ++t) by_ncomp[bufs[t].ncomp].push_back(t);
+    for (auto& kv : by_ncomp) {
+      std::vector<PairOpProblem> pp;
+      std::vector<DevBuf<double>> th(kv.second.size());
+      for (size_t u = 0; u < kv.second.size(); ++u) {
+        const size_t t = kv.second[u];
+        const cg_pair& pr = pairs[todo[t]];
+        CpcaBuf& b = bufs[t];
+        const double na = panel.samples[pr.a].n_cells, nb = panel.samples[pr.b].n_cells;
+        th[u].alloc((size_t)b.ncomp);
+        PairOpProblem q{};
+        q.a = pr.a;
+        q.b = pr.b;
+        q.G = b.G;
+        q.rows = b.Gp;
+        q.cols[0] = b.cols[0].p;
+        q.cols[1] = b.cols[1].p;
+        q.f[0] = b.f[0].p;
+        q.f[1] = b.f[1].p;
+        q.w[0] = na / (na + nb) / (na - 1.0);
+        q.w[1] = nb / (na + nb) / (nb - 1.0);
+        q.V = b.V0.p;
+        q.theta = th[u].p;
+        pp.push_back(q);
+      }
+      std::vector<int> conv(pp.size(), 1);
+      top_eigenvectors_pair_sum_tc(ctx, ps.data(), S, pp.data(), (int)pp.size(), kv.first, 1e-5, 400, conv.data());
+      for (size_t u = 0; u < kv.second.size(); ++u)
+        if (!conv[u]) expl.push_back(kv.second[u]);
+    }
+    std::sort(expl.begin(), expl.end());
+    ctx.eig_redo_pairs += expl.size();
+    if (ctx.profile) ctx.stage_ms["reduction.eig.fp64_redo_pairs"] += (double)expl.size();
+  } else {
+    for (size_t t = 0; t < todo.size(); ++t) expl.push_back(t);
+  }
+  if (!expl.empty()) {
     StageScope sc(ctx, "reduction.cpca_init");
     size_t c0 = 0;
-    while (c0 < todo.size()) {
+    while (c0 < expl.size()) {
       size_t freeb = 0, totb = 0;
       cudaMemGetInfo(&freeb, &totb);
       size_t c1 = c0, used = 0;
-      while (c1 < todo.size()) {
-        if (bufs[c1].ncomp != bufs[c0].ncomp) break;
-        const size_t need = (size_t)bufs[c1].Gp * bufs[c1].Gp * 8 + (size_t)bufs[c1].Gp * 64 * 8 * 4;
+      while (c1 < expl.size()) {
+        if (bufs[expl[c1]].ncomp != bufs[expl[c0]].ncomp) break;
+        const size_t need = (size_t)bufs[expl[c1]].Gp * bufs[expl[c1]].Gp * 8 + (size_t)bufs[expl[c1]].Gp * 64 * 8 * 4;
         if (c1 > c0 && used + need > std::min(freeb / 3, ctx.max_batch_bytes)) break;
         used += need;
         ++c1;
       }
       std::vector<DevBuf<double>> Sm(c1 - c0), th(c1 - c0);
       std::vector<EigProblem> eprobs;
-      for (size_t t = c0; t < c1; ++t) {
+      for (size_t tt = c0; tt < c1; ++tt) {
+        const size_t t = expl[tt];
         const cg_pair& pr = pairs[todo[t]];
         CpcaBuf& b = bufs[t];
         const Sample& sa = panel.samples[pr.a];
         const Sample& sb = panel.samples[pr.b];
-        Sm[t - c0].alloc((size_t)b.Gp * b.Gp);
-        th[t - c0].alloc((size_t)b.ncomp);
+        Sm[tt - c0].alloc((size_t)b.Gp * b.Gp);
+        th[tt - c0].alloc((size_t)b.ncomp);
         const double na = sa.n_cells, nb = sb.n_cells;
         mean_cov_kernel<<<nblk((size_t)b.Gp * b.Gp), 256, 0, st>>>(
             Mc_ptr[pr.a], sa.n_genes, Mc_ptr[pr.b], sb.n_genes, b.cols[0].p, b.cols[1].p, b.f[0].p, b.f[1].p, b.G, b.Gp,
-            na / (na + nb) / (na - 1.0), nb / (na + nb) / (nb - 1.0), Sm[t - c0].p);
+            na / (na + nb) / (na - 1.0), nb / (na + nb) / (nb - 1.0), Sm[tt - c0].p);
         ctx.stats.kernels++;
-        eprobs.push_back(EigProblem{Sm[t - c0].p, b.Gp, b.V0.p, th[t - c0].p});
+        eprobs.push_back(EigProblem{Sm[tt - c0].p, b.Gp, b.V0.p, th[tt - c0].p});
       }
       CG_CUDA(cudaGetLastError());
       {
         StageScope sc2(ctx, "reduction.eig");
-        top_eigenvectors_batched(ctx, eprobs.data(), (int)eprobs.size(), bufs[c0].ncomp,
+        top_eigenvectors_batched(ctx, eprobs.data(), (int)eprobs.size(), bufs[expl[c0]].ncomp,
                                  ctx.exact_reduction ? 1e-10 : 1e-5, 600);
       }
       c0 = c1;

@@ -16,7 +16,11 @@ op1, op2 = oracle.project_pair([osamples[names[0]], osamples[names[1]]], red["ge
 i2, j2, _ = oracle.neighbor_matrix(op1, op2, 30)
 theirs = np.unique(i2.astype(np.int64) * (1 << 32) + j2)
 ctx = conos_b200.Context(0)
-for tol, deg, sweeps in [(1e-5, 10, 40), (3e-6, 10, 40), (1e-6, 10, 60), (3e-7, 10, 80), (1e-6, 14, 60)]:
+SWEEP = os.environ.get("SWEEP", "tol")
+cases = [(1e-5, 10, 40, 16), (3e-6, 10, 40, 16), (1e-6, 10, 60, 16)] if SWEEP == "tol" else \
+    [(1e-5, 10, 40, c) for c in (0, 128, 64, 32, 16, 8)]
+for tol, deg, sweeps, chunk in cases:
+    ctx.check(ctx.lib.cg_set_option(ctx.h, b"gram_chunk_slabs", float(chunk)))
     ctx.check(ctx.lib.cg_set_option(ctx.h, b"tc_eig_tol", tol))
     ctx.check(ctx.lib.cg_set_option(ctx.h, b"tc_eig_degree", float(deg)))
     ctx.check(ctx.lib.cg_set_option(ctx.h, b"tc_eig_max_sweeps", float(sweeps)))
@@ -37,7 +41,7 @@ for tol, deg, sweeps in [(1e-5, 10, 40), (3e-6, 10, 40), (1e-6, 10, 60), (3e-7, 
     inter = np.intersect1d(mine, theirs, assume_unique=True).size
     rot = con.pairs["PCA"][f"{names[0]}.vs.{names[1]}"]["CPC"]
     cosm = min(np.linalg.svd(rot[:, s::2].T @ red["CPC"][:, s::2], compute_uv=False).min() for s in (0, 1))
-    print(json.dumps({"tol": tol, "degree": deg, "jaccard": inter / (mine.size + theirs.size - inter), "edges": int(mine.size),
+    print(json.dumps({"tol": tol, "degree": deg, "gram_chunk_slabs": chunk, "gram_ms": st.get("reduction.gram"), "jaccard": inter / (mine.size + theirs.size - inter), "edges": int(mine.size),
                       "oracle_edges": int(theirs.size), "min_principal_cos": float(cosm),
                       "eig_ms": st.get("reduction.eig"), "outer": st.get("reduction.eig.outer_iterations"),
                       "gemms": st.get("reduction.eig.filter_gemms"), "redo": ctx.stat("eig_redo_pairs") - redo0,
