@@ -407,10 +407,12 @@ def main():
     lib.cg_timer_start(ctx.h)
     t0 = time.perf_counter()
     step_ms = []
+    gc.disable()    # no collector pauses inside the timed steps (a 35 ms stall on one rank stalls all of them)
     for _ in range(K):
         t1 = time.perf_counter()
         g = device_step()
         step_ms.append(round(1e3 * (time.perf_counter() - t1), 1))
+    gc.enable()
     if os.environ.get("CONOS_BENCH_STAGES"):
         sys.stderr.write(f"[steps rank {rank}] {step_ms}\n")
     ms = C.c_double(0)

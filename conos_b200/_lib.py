@@ -79,6 +79,7 @@ SIGNATURES = {
     "cg_pair_projection": (C.c_int, [_VP, C.c_int, C.c_int, c_int_p, c_int_p, c_dbl_p]),
     "cg_local_edges": (C.c_int, [_VP, _VP, c_int_p, C.c_int, C.POINTER(CgParams), C.POINTER(_VP), c_i64_p]),
     "cg_edges_count": (C.c_int64, [_VP]),
+    "cg_edges_count_type": (C.c_int64, [_VP, _VP, C.c_int32]),
     "cg_edges_fetch": (C.c_int, [_VP, _VP, c_int_p, c_int_p, c_dbl_p, c_int_p]),
     "cg_edges_append_host": (C.c_int, [_VP, C.POINTER(_VP), c_int_p, c_int_p, c_dbl_p, c_int_p, C.c_int64]),
     "cg_edges_append_device": (C.c_int, [_VP, C.POINTER(_VP), _VP, _VP, _VP, _VP, C.c_int64]),
@@ -96,6 +97,15 @@ SIGNATURES = {
     "cg_comm_init": (C.c_int, [_VP, C.c_int, C.c_int, _VP]),
     "cg_comm_rank": (C.c_int, [_VP, c_int_p, c_int_p]),
     "cg_partition_pairs": (C.c_int, [c_int_p, c_int_p, c_dbl_p, C.c_int, c_dbl_p, C.c_int, C.c_int, c_int_p]),
+    "cg_job_create": (C.c_int, [C.c_int, C.POINTER(_VP)]),
+    "cg_job_free": (None, [_VP]),
+    "cg_job_devices": (C.c_int, [_VP]),
+    "cg_job_context": (_VP, [_VP, C.c_int]),
+    "cg_job_last_error": (C.c_char_p, [_VP]),
+    "cg_job_build_graph": (C.c_int, [_VP, C.POINTER(CgSample), C.c_int, C.POINTER(CgPair), C.c_int,
+                                     C.POINTER(CgParams), C.POINTER(_VP)]),
+    "cg_job_pair_location": (C.c_int, [_VP, C.c_int, c_int_p, c_int_p]),
+    "cg_panel_share_grams": (C.c_int, [_VP, _VP, c_int_p, c_int_p]),
     "cg_edges_allgatherv": (C.c_int, [_VP, C.POINTER(_VP), c_int_p, c_i64_p, C.c_int]),
     "cg_assemble_graph": (C.c_int, [_VP, _VP, C.c_int32, C.POINTER(_VP)]),
     "cg_graph_sizes": (C.c_int, [_VP, c_int_p, c_i64_p]),
@@ -215,8 +225,48 @@ class Context:
         return False
 
 
+class BorrowedContext:
+    """A cg_context owned by somebody else (a device of a cg_job): same calling convention, never shut down here."""
+
+    def __init__(self, lib, h, device):
+        self.lib, self.h, self.device = lib, _VP(h), device
+
+    def check(self, rc: int):
+        if rc != 0:
+            msg = self.lib.cg_last_error(self.h)
+            raise ConosGpuError(msg.decode() if msg else f"libconosgpu error {rc}")
+
+
+class Job:
+    """cg_job: one buildGraph over n_devices GPUs from this process (one host thread per device inside the library)."""
+
+    def __init__(self, n_devices: int):
+        self.lib = load()
+        h = _VP()
+        if self.lib.cg_job_create(n_devices, C.byref(h)) != 0:
+            msg = self.lib.cg_last_error(None)
+            raise ConosGpuError(msg.decode() if msg else "cg_job_create failed")
+        self.h = h
+        self.n_devices = n_devices
+        self.contexts = [BorrowedContext(self.lib, self.lib.cg_job_context(h, d), d) for d in range(n_devices)]
+        _all_jobs.add(self)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cg_job_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            if not sys.is_finalizing():
+                self.close()
+        except Exception:
+            pass
+
+
 _default_ctx = {}
 _all_ctx = weakref.WeakSet()
+_all_jobs = weakref.WeakSet()
 
 
 def default_context(device: int = 0) -> Context:
@@ -230,6 +280,11 @@ def _shutdown_all():
     """Contexts are shut down by an atexit hook, i.e. while the interpreter, the CUDA runtime and torch are all still
     intact -- never from a destructor during interpreter teardown (the order in which modules and extension state go
     away there is arbitrary).  R's equivalent is the package's .onUnload -> cg_shutdown."""
+    for j in list(_all_jobs):
+        try:
+            j.close()
+        except Exception:
+            pass
     for c in list(_all_ctx):
         try:
             c.close()

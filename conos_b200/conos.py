@@ -177,6 +177,15 @@ class Conos:
         if self._panel is not None and self._panel_key == key:
             return
         self._drop_panel()
+        arr, keep = self._sample_array(names, n_odgenes, need_counts, need_pca)
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.cg_panel_create(self.ctx.h, arr, len(names), C.byref(h)))
+        self._panel = h
+        self._panel_key = key
+
+    def _sample_array(self, names: Sequence[str], n_odgenes: int, need_counts=None, need_pca=None):
+        """The cg_sample table of the panel (host pointers into the samples' own arrays; `keep` holds the references
+        that must outlive the native call)."""
         self._ensure_vocab()
         allnames, per = self._vocab
         in_u = np.zeros(len(allnames), bool)
@@ -230,11 +239,22 @@ class Conos:
             arr[t].p, arr[t].i, arr[t].x = ptr(p, C.c_int32), ptr(i, C.c_int32), ptr(x, C.c_double)
             arr[t].var_v, arr[t].var_qv = ptr(v, C.c_double), ptr(qv, C.c_double)
             self._h2d_bytes += p.nbytes + i.nbytes + x.nbytes + (0 if v is None else v.nbytes + qv.nbytes)
-        h = C.c_void_p()
-        self.ctx.check(self.ctx.lib.cg_panel_create(self.ctx.h, arr, len(names), C.byref(h)))
-        self._panel = h
         self._panel_names = list(names)
-        self._panel_key = key
+        return arr, keep
+
+    def _uploaded_genes(self, name: str, n_odgenes: int) -> int:
+        """Columns of sample `name` inside the od-gene universe of the panel (what _ensure_panel uploads), known to
+        every rank whether or not it holds the sample."""
+        key = (name, int(n_odgenes), tuple(self._panel_names))
+        cache = self.__dict__.setdefault("_n_uploaded", {})
+        if key not in cache:
+            allnames, per = self._vocab
+            in_u = np.zeros(len(allnames), bool)
+            for n in self._panel_names:
+                in_u[per[n][1][:n_odgenes]] = True
+            col_of = per[name][0]
+            cache[key] = int(np.count_nonzero(in_u[np.flatnonzero(col_of >= 0)]))
+        return cache[key]
 
     # ------------------------------------------------------------------ R/conos.R:107-117
     def _ensure_vocab(self):
@@ -295,12 +315,14 @@ class Conos:
                    balancing_factor_per_cell=None, same_factor_downweight: float = 1.0,
                    k_same_factor: Optional[int] = None, balancing_factor_per_sample=None,
                    pair_shard: Optional[Sequence[int]] = None, assemble: bool = True, fetch: bool = True,
-                   world=None, graph_on: str = "root"):
+                   world=None, graph_on: str = "root", n_devices: Optional[int] = None):
         """`world` = (rank, world_size, torch.distributed group or None): one process per GPU.  The pair list is
         partitioned by the library (cg_partition_pairs: LPT with sample locality), every rank uploads only the samples
         its pairs touch, the per-rank edge tables are gathered with NCCL inside the library (cg_edges_allgatherv) in
         the reference's row order, and the graph is assembled on rank 0 (`graph_on="root"`; `"all"`: on every rank).
-        `fetch=False` keeps the assembled graph on the device (self.graph is a size-only stub)."""
+        `fetch=False` keeps the assembled graph on the device (self.graph is a size-only stub).
+        `n_devices` = N runs the whole call over N GPUs from THIS process (cg_job: one host thread per device inside
+        the library, NCCL between them) -- the form an R session uses; the panel is uploaded by the job on every call."""
         t_total = time.perf_counter()
         if space not in SUPPORTED_SPACES:
             raise ValueError("only the following spaces are currently supported: [" + " ".join(SUPPORTED_SPACES) + "]")
@@ -375,11 +397,33 @@ class Conos:
             my_pairs = mine.tolist()
         else:
             my_pairs = list(range(n_pairs)) if pair_shard is None else list(pair_shard)
+        if n_devices is not None:
+            if world_size > 1 or pair_shard is not None or not assemble:
+                raise ValueError("n_devices excludes world / pair_shard / assemble=False")
+            return self._build_graph_job(int(n_devices), names, pair_names, index, space, ncomps, n_odgenes, k, k1,
+                                         k_self, k_self_weight, matching_method, metric, l2_sigma, cor_base, var_scale,
+                                         common_centering, score_component_variance, balance_edge_weights,
+                                         balancing_factor_per_cell, balancing_factor_per_sample,
+                                         same_factor_downweight, k_same_factor, fetch, t_total)
         t_0 = time.perf_counter()
         self._ensure_panel(names, n_odgenes, need_counts, need_pca)
         self.timings["panel_ms"] = 1e3 * (time.perf_counter() - t_0)
         t_0 = time.perf_counter()
         cache = self.pairs.setdefault(space, {})
+        if world_size > 1 and not all(f"{a}.vs.{b}" in cache or f"{b}.vs.{a}" in cache for a, b in pair_names):
+            # every sample's Gram matrix is computed once in the job, by the least loaded of the ranks that hold the
+            # sample, and broadcast (cg_panel_share_grams); same tables on every rank
+            holders = [sorted(set(pair_owner[(pa == t) | (pb_ == t)].tolist())) for t in range(len(names))]
+            gram_owner = np.full(len(names), -1, np.int32)
+            load = np.zeros(world_size)
+            for t in np.argsort(-n_cells, kind="stable"):
+                if holders[t]:
+                    r = min(holders[t], key=lambda q: (load[q], q))
+                    gram_owner[t] = r
+                    load[r] += n_cells[t]
+            ng = np.array([self._uploaded_genes(n, n_odgenes) for n in names], np.int32)
+            self.ctx.check(lib.cg_panel_share_grams(h, self._panel, ptr(gram_owner, C.c_int32), ptr(ng, C.c_int32)))
+            self.timings["share_grams_ms"] = 1e3 * (time.perf_counter() - t_0)
 
         # balancing.factor.per.sample: pairs inside one level search k.cur = min(k.same.factor, k1) neighbours
         # (R/conclass.R:230-233)
@@ -388,6 +432,74 @@ class Conos:
             if missing:
                 raise ValueError("balancing.factor.per.sample must name every sample")
 
+        carr, keep_alive, used_pairs = self._pair_table(my_pairs, pair_names, index, cache, space, ncomps, n_odgenes,
+                                                        k1, k_same_factor, balancing_factor_per_sample)
+
+        P = self._params(k, k1, k_self, ncomps, space, matching_method, metric, var_scale, common_centering,
+                         score_component_variance, k_self_weight, l2_sigma, cor_base)
+        return self._build_graph_rest(P, carr, keep_alive, used_pairs, cache, names, n_pairs, pair_owner, sample_owner,
+                                      rank, world_size, graph_on, space, score_component_variance, k_self, assemble,
+                                      fetch, balance_edge_weights, balancing_factor_per_cell,
+                                      balancing_factor_per_sample, same_factor_downweight, t_0, t_total)
+
+    def _build_graph_job(self, n_devices, names, pair_names, index, space, ncomps, n_odgenes, k, k1, k_self,
+                         k_self_weight, matching_method, metric, l2_sigma, cor_base, var_scale, common_centering,
+                         score_component_variance, balance_edge_weights, balancing_factor_per_cell,
+                         balancing_factor_per_sample, same_factor_downweight, k_same_factor, fetch, t_total):
+        """The whole buildGraph as ONE native call over n_devices GPUs of this process (cg_job_build_graph)."""
+        lib = self.ctx.lib if self._ctx is not None else _lib.load()
+        job = self.__dict__.get("_job")
+        if job is None or job.n_devices != n_devices or not job.h:
+            job = _lib.Job(n_devices)
+            self._job = job
+        t_0 = time.perf_counter()
+        self._panel_col = {}
+        arr, keep = self._sample_array(names, n_odgenes)
+        cache = self.pairs.setdefault(space, {})
+        if balancing_factor_per_sample is not None:
+            missing = [n for n in names if n not in balancing_factor_per_sample]
+            if missing:
+                raise ValueError("balancing.factor.per.sample must name every sample")
+        carr, keep_alive, used_pairs = self._pair_table(list(range(len(pair_names))), pair_names, index, cache, space,
+                                                        ncomps, n_odgenes, k1, k_same_factor,
+                                                        balancing_factor_per_sample)
+        P = CgParams()
+        lib.cg_params_default(C.byref(P))
+        P.k, P.k1, P.k_self, P.ncomps = k, k1, k_self, ncomps
+        P.space, P.matching, P.metric = SPACES[space], MATCHING[matching_method], METRICS[metric]
+        P.var_scale, P.common_centering = int(var_scale), int(common_centering)
+        P.score_component_variance = int(score_component_variance)
+        P.k_self_weight, P.l2_sigma, P.cor_base = k_self_weight, l2_sigma, cor_base
+        self.timings["host_pairs_ms"] = 1e3 * (time.perf_counter() - t_0)
+        t_0 = time.perf_counter()
+        gh = C.c_void_p()
+        if lib.cg_job_build_graph(job.h, arr, len(names), carr, len(used_pairs), C.byref(P), C.byref(gh)) != 0:
+            raise _lib.ConosGpuError((lib.cg_job_last_error(job.h) or b"cg_job_build_graph failed").decode())
+        self.timings["job_build_graph_ms"] = 1e3 * (time.perf_counter() - t_0)
+        t_0 = time.perf_counter()
+
+        def locate(t):
+            dev, slot = C.c_int32(0), C.c_int32(0)
+            lib.cg_job_pair_location(job.h, t, C.byref(dev), C.byref(slot))
+            return job.contexts[dev.value], slot.value
+        self._fill_cache(cache, used_pairs, space, score_component_variance, locate)
+        self.timings["cache_fill_ms"] = 1e3 * (time.perf_counter() - t_0)
+        t_0 = time.perf_counter()
+        balance = None
+        if balance_edge_weights or balancing_factor_per_cell is not None or balancing_factor_per_sample is not None:
+            balance = dict(per_cell=balancing_factor_per_cell, per_sample=balancing_factor_per_sample,
+                           balance_weights=bool(balance_edge_weights), downweight=float(same_factor_downweight))
+        g = self._graph_out(gh, names, fetch, balance, job.contexts[0])
+        self.timings["assemble_fetch_ms"] = 1e3 * (time.perf_counter() - t_0)
+        self.graph = g
+        self.timings["total_ms"] = 1e3 * (time.perf_counter() - t_total)
+        del keep, keep_alive
+        return g
+
+    def _pair_table(self, my_pairs, pair_names, index, cache, space, ncomps, n_odgenes, k1, k_same_factor,
+                    balancing_factor_per_sample):
+        """cg_pair table of the listed pairs: gene columns, cached reductions (the cache-hit path of updatePairs,
+        R/conclass.R:1062-1071) and k.cur (R/conclass.R:230-233)."""
         carr = (CgPair * max(len(my_pairs), 1))()
         keep_alive = []
         used_pairs = []
@@ -429,15 +541,24 @@ class Conos:
                 keep_alive += [u, v, ru, rv]
             keep_alive += [ga, gb]
             used_pairs.append((pi, key, od))
+        return carr, keep_alive, used_pairs
 
+    def _params(self, k, k1, k_self, ncomps, space, matching_method, metric, var_scale, common_centering,
+                score_component_variance, k_self_weight, l2_sigma, cor_base):
         P = CgParams()
-        lib.cg_params_default(C.byref(P))
+        self.ctx.lib.cg_params_default(C.byref(P))
         P.k, P.k1, P.k_self, P.ncomps = k, k1, k_self, ncomps
         P.space, P.matching, P.metric = SPACES[space], MATCHING[matching_method], METRICS[metric]
         P.var_scale, P.common_centering = int(var_scale), int(common_centering)
         P.score_component_variance = int(score_component_variance)
         P.k_self_weight, P.l2_sigma, P.cor_base = k_self_weight, l2_sigma, cor_base
+        return P
 
+    def _build_graph_rest(self, P, carr, keep_alive, used_pairs, cache, names, n_pairs, pair_owner, sample_owner, rank,
+                          world_size, graph_on, space, score_component_variance, k_self, assemble, fetch,
+                          balance_edge_weights, balancing_factor_per_cell, balancing_factor_per_sample,
+                          same_factor_downweight, t_0, t_total):
+        lib, h = self.ctx.lib, self.ctx.h
         edges = C.c_void_p()
         counts = np.zeros(max(len(used_pairs), 1), np.int64)
         self.timings["host_pairs_ms"] = 1e3 * (time.perf_counter() - t_0)
@@ -456,30 +577,24 @@ class Conos:
         if not assemble:
             return edges
 
-        # ---- exchange (R: rbind of the per-pair data frames, R/conclass.R:316-321) and local edges (:328-333)
+        # ---- local edges (R/conclass.R:328-333) and the exchange (R: rbind of the per-pair data frames, :316-321)
         n_inter = int(sum(self._last_pair_counts.values()))
         if world_size > 1:
-            seg_counts = np.zeros(n_pairs, np.int64)
+            # one allgatherv for everything: segments = the pairs (combn order), then the samples' local edges
+            n_s = len(names)
+            seg_owner = np.concatenate([pair_owner, sample_owner]).astype(np.int32)
+            seg_counts = np.zeros(n_pairs + n_s, np.int64)
             for t, (pi, _, _) in enumerate(used_pairs):
                 seg_counts[pi] = counts[t]
-            self.ctx.check(lib.cg_edges_allgatherv(h, C.byref(edges), ptr(pair_owner, C.c_int32),
-                                                   ptr(seg_counts, C.c_int64), n_pairs))
-            n_inter = int(lib.cg_edges_count(edges))
             if k_self > 0:
                 sidx = np.flatnonzero(sample_owner == rank).astype(np.int32)
-                ledges = C.c_void_p()
                 mine_counts = np.zeros(max(len(sidx), 1), np.int64)
                 self.ctx.check(lib.cg_local_edges(h, self._panel, ptr(sidx, C.c_int32), len(sidx), C.byref(P),
-                                                  C.byref(ledges), ptr(mine_counts, C.c_int64)))
-                lcounts = np.zeros(len(names), np.int64)
-                lcounts[sidx] = mine_counts[:len(sidx)]
-                self.ctx.check(lib.cg_edges_allgatherv(h, C.byref(ledges), ptr(sample_owner, C.c_int32),
-                                                       ptr(lcounts, C.c_int64), len(names)))
-                f, t_, w_, ty = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
-                lib.cg_edges_device_ptrs(ledges, C.byref(f), C.byref(t_), C.byref(w_), C.byref(ty))
-                self.ctx.check(lib.cg_edges_append_device(h, C.byref(edges), f, t_, w_, ty,
-                                                          int(lib.cg_edges_count(ledges))))
-                lib.cg_edges_free(ledges)
+                                                  C.byref(edges), ptr(mine_counts, C.c_int64)))
+                seg_counts[n_pairs + sidx] = mine_counts[:len(sidx)]
+            self.ctx.check(lib.cg_edges_allgatherv(h, C.byref(edges), ptr(seg_owner, C.c_int32),
+                                                   ptr(seg_counts, C.c_int64), n_pairs + n_s))
+            n_inter = self._count_type1(edges) if k_self > 0 else int(lib.cg_edges_count(edges))
         elif k_self > 0:
             sidx = np.arange(len(names), dtype=np.int32)
             self.ctx.check(lib.cg_local_edges(h, self._panel, ptr(sidx, C.c_int32), len(names), C.byref(P),
@@ -509,6 +624,11 @@ class Conos:
         self.timings["total_ms"] = 1e3 * (time.perf_counter() - t_total)
         return g
 
+    def _count_type1(self, edges) -> int:
+        """Inter-sample rows of a gathered edge table = the rows before the first local edge: the local segments follow
+        the pairs' segments, and the library knows the total, so the count comes from the segment totals it returned."""
+        return int(self.ctx.lib.cg_edges_count_type(self.ctx.h, edges, 1))
+
     def _cached_od_genes(self, red, na, nb):
         """Gene set of a cached PCA / CPCA entry = rownames(CPC) (R/conclass.R:240-243), mapped to the columns of the
         two uploaded samples."""
@@ -532,16 +652,18 @@ class Conos:
                              "(it was computed with a larger n.odgenes)")
         return ids, np.ascontiguousarray(ga, np.int32), np.ascontiguousarray(gb, np.int32)
 
-    def _fill_cache(self, cache, used_pairs, space, score_component_variance):
+    def _fill_cache(self, cache, used_pairs, space, score_component_variance, locate=None):
         """populate self$pairs[[space]] like updatePairs does (R/conclass.R:1090-1092): PCA list(CPC, nv);
-        CPCA list(D, CPC, niter, nv) (src/cpca.cpp:93-100); CCA list(d, u, v, ul, vl, nv) (R/conos.R:344-366)."""
-        lib, h = self.ctx.lib, self.ctx.h
-        for slot, (pi, key, od) in enumerate(used_pairs):
+        CPCA list(D, CPC, niter, nv) (src/cpca.cpp:93-100); CCA list(d, u, v, ul, vl, nv) (R/conos.R:344-366).
+        `locate(t)` -> (context, slot) of the t-th used pair (a multi-device job keeps a reduction on its device)."""
+        for t, (pi, key, od) in enumerate(used_pairs):
             if key in cache:
                 continue
+            cx, slot = (self.ctx, t) if locate is None else locate(t)
+            lib, h = cx.lib, cx.h
             if space == "CCA":
                 nu, nvv, dd = C.c_int32(0), C.c_int32(0), C.c_int32(0)
-                self.ctx.check(lib.cg_pair_cca(h, slot, C.byref(nu), C.byref(nvv), C.byref(dd), None, None, None, None,
+                cx.check(lib.cg_pair_cca(h, slot, C.byref(nu), C.byref(nvv), C.byref(dd), None, None, None, None,
                                                None))
                 if nu.value == 0:
                     continue
@@ -550,30 +672,30 @@ class Conos:
                 ru = np.zeros(nu.value, np.int32)
                 rv = np.zeros(nvv.value, np.int32)
                 sg = np.zeros(dd.value)
-                self.ctx.check(lib.cg_pair_cca(h, slot, None, None, None, ptr(u, C.c_double), ptr(v, C.c_double),
+                cx.check(lib.cg_pair_cca(h, slot, None, None, None, ptr(u, C.c_double), ptr(v, C.c_double),
                                                ptr(ru, C.c_int32), ptr(rv, C.c_int32), ptr(sg, C.c_double)))
                 cache[key] = PairEntry(od, self._gene_names, u=u, v=v, rows_u=ru, rows_v=rv, d=sg)
                 ng, dl = C.c_int32(0), C.c_int32(0)
-                self.ctx.check(lib.cg_pair_cca_loadings(h, slot, C.byref(ng), C.byref(dl), None, None, None))
+                cx.check(lib.cg_pair_cca_loadings(h, slot, C.byref(ng), C.byref(dl), None, None, None))
                 if ng.value > 0:
                     ul = np.zeros((ng.value, dl.value), order="F")
                     vl = np.zeros((ng.value, dl.value), order="F")
                     nv = np.zeros((2, dl.value))
-                    self.ctx.check(lib.cg_pair_cca_loadings(h, slot, None, None, ptr(ul, C.c_double),
+                    cx.check(lib.cg_pair_cca_loadings(h, slot, None, None, ptr(ul, C.c_double),
                                                             ptr(vl, C.c_double), ptr(nv, C.c_double)))
                     cache[key].update(ul=ul, vl=vl, nv=[nv[0], nv[1]])
                 continue
             nr, nc = C.c_int32(0), C.c_int32(0)
-            self.ctx.check(lib.cg_pair_reduction(h, slot, C.byref(nr), C.byref(nc), None, None))
+            cx.check(lib.cg_pair_reduction(h, slot, C.byref(nr), C.byref(nc), None, None))
             rot = np.empty((nr.value, nc.value), order="F")
             nv = np.zeros((2, nc.value)) if score_component_variance else None
-            self.ctx.check(lib.cg_pair_reduction(h, slot, None, None, ptr(rot, C.c_double), ptr(nv, C.c_double)))
+            cx.check(lib.cg_pair_reduction(h, slot, None, None, ptr(rot, C.c_double), ptr(nv, C.c_double)))
             cache[key] = PairEntry(od, self._gene_names, CPC=rot)
             if space == "CPCA":
                 cache[key]["ncomp"] = nc.value
                 D = np.zeros((nc.value, 2), order="F")   # res$D = t(D): ncomp x k (src/cpca.cpp:97)
                 niter = np.zeros(nc.value)
-                self.ctx.check(lib.cg_pair_cpca(h, slot, None, ptr(D, C.c_double), ptr(niter, C.c_double)))
+                cx.check(lib.cg_pair_cpca(h, slot, None, ptr(D, C.c_double), ptr(niter, C.c_double)))
                 cache[key].update(D=D, niter=niter)
             if nv is not None:
                 rr = nc.value // 2 if space == "PCA" else nc.value
@@ -610,14 +732,18 @@ class Conos:
             return np.empty(n, dtype)
 
     def _assemble(self, edges, names, fetch: bool = True, balance=None) -> ConosGraph:
-        lib, h = self.ctx.lib, self.ctx.h
         n_total = sum(self.samples[n].counts.shape[0] for n in names)
         gh = C.c_void_p()
-        self.ctx.check(lib.cg_assemble_graph(h, edges, n_total, C.byref(gh)))
+        self.ctx.check(self.ctx.lib.cg_assemble_graph(self.ctx.h, edges, n_total, C.byref(gh)))
+        return self._graph_out(gh, names, fetch, balance, self.ctx)
+
+    def _graph_out(self, gh, names, fetch, balance, cx) -> ConosGraph:
+        """Optional balancing, then the host copy of an assembled graph that lives on context `cx`."""
+        lib, h = cx.lib, cx.h
         nv, ne = C.c_int32(0), C.c_int64(0)
         lib.cg_graph_sizes(gh, C.byref(nv), C.byref(ne))
         if balance is not None and nv.value > 0:
-            self._balance_on_device(gh, nv.value, names, balance)
+            self._balance_on_device(gh, nv.value, names, balance, cx)
         if not fetch:
             lib.cg_graph_free(gh)
             z = np.zeros(0, np.int32)
@@ -630,26 +756,27 @@ class Conos:
         et = self._out("et", ne.value, np.int32)
         w = self._out("w", ne.value, np.float64)
         ty = self._out("ty", ne.value, np.int32)
-        self.ctx.check(lib.cg_graph_fetch(h, gh, ptr(vertices, C.c_int32), ptr(ef, C.c_int32), ptr(et, C.c_int32),
+        cx.check(lib.cg_graph_fetch(h, gh, ptr(vertices, C.c_int32), ptr(ef, C.c_int32), ptr(et, C.c_int32),
                                           ptr(w, C.c_double), ptr(ty, C.c_int32)))
         ap = self._out("ap", nv.value + 1, np.int64)
         ai = self._out("ai", 2 * ne.value, np.int32)
         ax = self._out("ax", 2 * ne.value, np.float64)
-        self.ctx.check(lib.cg_graph_fetch_adjacency(h, gh, ptr(ap, C.c_int64), ptr(ai, C.c_int32), ptr(ax, C.c_double)))
+        cx.check(lib.cg_graph_fetch_adjacency(h, gh, ptr(ap, C.c_int64), ptr(ai, C.c_int32), ptr(ax, C.c_double)))
         lib.cg_graph_free(gh)
         if self._cell_names is None or self._cell_names[0] != list(names):
             self._cell_names = (list(names), np.array([c for n in names for c in self.samples[n].cells], dtype=object))
         return ConosGraph(names=LazyNames(self._cell_names[1], vertices), vertices=vertices, edge_from=ef, edge_to=et, weight=w,
                           type=ty, adj_p=ap, adj_i=ai, adj_x=ax)
 
-    def _balance_on_device(self, gh, n_vertices, names, balance):
+    def _balance_on_device(self, gh, n_vertices, names, balance, cx=None):
         """adjustWeightsByCellBalancing (R/conclass.R:346-368, R/conos.R:936-967) as one device call on the assembled
         graph.  factor.per.cell: the caller's (cell name -> level), else balancing.factor.per.sample[dataset of the
         cell], else the dataset itself (getDatasetPerCell); levels are numbered like as.factor() %>% droplevels()
         (sorted unique values present in the graph)."""
-        lib, h = self.ctx.lib, self.ctx.h
+        cx = cx or self.ctx
+        lib, h = cx.lib, cx.h
         vertices = np.empty(n_vertices, np.int32)
-        self.ctx.check(lib.cg_graph_fetch(h, gh, ptr(vertices, C.c_int32), None, None, None, None))
+        cx.check(lib.cg_graph_fetch(h, gh, ptr(vertices, C.c_int32), None, None, None, None))
         sizes = [self.samples[n].counts.shape[0] for n in names]
         sample_of = np.repeat(np.arange(len(names)), sizes)[vertices]
         if balance["per_cell"] is not None:
@@ -667,5 +794,5 @@ class Conos:
             values = [names[t] for t in sample_of]
         levels, codes = np.unique(np.asarray([str(v) for v in values]), return_inverse=True)
         fac = np.ascontiguousarray(codes + 1, np.int32)
-        self.ctx.check(lib.cg_graph_balance(h, gh, ptr(fac, C.c_int32), len(levels), int(balance["balance_weights"]),
+        cx.check(lib.cg_graph_balance(h, gh, ptr(fac, C.c_int32), len(levels), int(balance["balance_weights"]),
                                             balance["downweight"], 50))

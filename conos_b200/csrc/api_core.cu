@@ -426,6 +426,34 @@ int cg_edges_fetch(cg_context* ctx, const cg_edges* e, int32_t* from, int32_t* t
   CG_API_END(ctx)
 }
 
+namespace {
+__global__ void count_type_kernel(const int* __restrict__ type, long long n, int want, unsigned long long* out) {
+  unsigned long long c = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    c += type[i] == want ? 1 : 0;
+  for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+}  // namespace
+
+int64_t cg_edges_count_type(cg_context* ctx, const cg_edges* e, int32_t type) {
+  if (!ctx || !e || e->t.n == 0) return 0;
+  try {
+    CG_BIND(ctx);
+    DevBuf<unsigned long long> d(1);
+    d.zero(ctx->c.stream);
+    count_type_kernel<<<256, 256, 0, ctx->c.stream>>>(e->t.type.p, (long long)e->t.n, type, d.p);
+    ctx->c.stats.kernels++;
+    unsigned long long h = 0;
+    d.download(&h, 1, ctx->c.stream);
+    CG_CUDA(cudaStreamSynchronize(ctx->c.stream));
+    return (int64_t)h;
+  } catch (const std::exception& ex) {
+    fail(ctx, ex);
+    return -1;
+  }
+}
+
 int cg_edges_reserve(cg_context* ctx, cg_edges** e, int64_t n_total) {
   CG_API_BEGIN
   CG_BIND(ctx);

@@ -51,7 +51,11 @@ int fail(cg_context* ctx, const std::exception& e);
 int fail(cg_context* ctx, const char* msg);
 
 #define CG_API_BEGIN try {
-#define CG_BIND(ctxptr) ::cg::StreamBinding _cg_binding((ctxptr) ? (ctxptr)->c.stream : nullptr)
+// binds the context's stream for stream-ordered allocations of the calling thread and makes its device current (a
+// multi-device job drives several contexts from one process)
+#define CG_BIND(ctxptr)                                                               \
+  ::cg::StreamBinding _cg_binding((ctxptr) ? (ctxptr)->c.stream : nullptr);           \
+  if (ctxptr) CG_CUDA(cudaSetDevice((ctxptr)->c.device))
 #define CG_API_END(ctxptr)                                    \
   return 0;                                                   \
   }                                                           \

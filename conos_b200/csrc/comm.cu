@@ -5,8 +5,8 @@
 // Replaces the reference's fork pools over pairs and samples (R/conclass.R:224-317 `papply` over the pair list,
 // :1074-1088 inside updatePairs, R/conos.R:396-416 / :589 over samples): pairs are independent units, the only
 // exchange step is the concatenation of the per-pair edge data frames (`rbind`, R/conclass.R:316-321), which here is
-// a grouped ncclBroadcast of every rank's table straight into the gathered table, followed by a segment permutation
-// that restores the reference's row order (pairs in combn order) whatever the partition was.
+// ONE ncclAllGather of every rank's packed table, unpacked straight into the reference's row order (pairs in combn
+// order, then the samples' local edges) whatever the partition was.
 //
 // NCCL is bound at run time (dlopen of libnccl.so.2, the copy a host process such as torch has already mapped is
 // reused): a single-GPU caller never needs the library.
@@ -31,6 +31,7 @@ struct Comm {
   ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -68,19 +69,23 @@ void bind_nccl(Comm& cm) {
   cm.CommAbort = reinterpret_cast<decltype(cm.CommAbort)>(sym("ncclCommAbort"));
   cm.AllReduce = reinterpret_cast<decltype(cm.AllReduce)>(sym("ncclAllReduce"));
   cm.Broadcast = reinterpret_cast<decltype(cm.Broadcast)>(sym("ncclBroadcast"));
+  cm.AllGather = reinterpret_cast<decltype(cm.AllGather)>(sym("ncclAllGather"));
   cm.GroupStart = reinterpret_cast<decltype(cm.GroupStart)>(sym("ncclGroupStart"));
   cm.GroupEnd = reinterpret_cast<decltype(cm.GroupEnd)>(sym("ncclGroupEnd"));
   cm.GetErrorString = reinterpret_cast<decltype(cm.GetErrorString)>(sym("ncclGetErrorString"));
 }
 
-// dst row i belongs to the segment s with dst_off[s] <= i < dst_off[s + 1]; its source row is src_off[s] + (i - dst_off[s])
-__global__ void __launch_bounds__(256) permute_segments_kernel(const long long* __restrict__ dst_off,
-                                                               const long long* __restrict__ src_off, int n_seg,
-                                                               long long n_rows, const int* __restrict__ sf,
-                                                               const int* __restrict__ st, const int* __restrict__ sty,
-                                                               const double* __restrict__ sw, int* __restrict__ df,
-                                                               int* __restrict__ dt, int* __restrict__ dty,
-                                                               double* __restrict__ dw) {
+// Every rank's table travels as ONE packed block [from | to | type | w] of `stride` bytes (n_pad rows per column, the
+// largest rank's count rounded up to even) in a single ncclAllGather; this kernel unpacks the gathered blocks straight
+// into the output table in segment order: dst row i belongs to the segment s with dst_off[s] <= i < dst_off[s + 1];
+// it is row src_row[s] + (i - dst_off[s]) of the table of rank seg_owner[s].
+__global__ void __launch_bounds__(256) unpack_segments_kernel(const long long* __restrict__ dst_off,
+                                                              const long long* __restrict__ src_row,
+                                                              const int* __restrict__ seg_owner, int n_seg,
+                                                              long long n_rows, const unsigned char* __restrict__ packed,
+                                                              long long stride, long long n_pad, int* __restrict__ df,
+                                                              int* __restrict__ dt, int* __restrict__ dty,
+                                                              double* __restrict__ dw) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows;
        i += (long long)gridDim.x * blockDim.x) {
     int lo = 0, hi = n_seg;  // last segment with dst_off <= i
@@ -88,11 +93,12 @@ __global__ void __launch_bounds__(256) permute_segments_kernel(const long long* 
       const int mid = (lo + hi) >> 1;
       if (dst_off[mid] <= i) lo = mid; else hi = mid;
     }
-    const long long s = src_off[lo] + (i - dst_off[lo]);
-    df[i] = sf[s];
-    dt[i] = st[s];
-    dty[i] = sty[s];
-    dw[i] = sw[s];
+    const long long r = src_row[lo] + (i - dst_off[lo]);
+    const unsigned char* base = packed + (long long)seg_owner[lo] * stride;
+    df[i] = reinterpret_cast<const int*>(base)[r];
+    dt[i] = reinterpret_cast<const int*>(base + 4 * n_pad)[r];
+    dty[i] = reinterpret_cast<const int*>(base + 8 * n_pad)[r];
+    dw[i] = reinterpret_cast<const double*>(base + 12 * n_pad)[r];
   }
 }
 
@@ -232,60 +238,99 @@ void edges_allgatherv(Context& c, EdgeTable& t, const int* seg_owner, const long
     d_counts.download(counts.data(), (size_t)n_seg, st);
     CG_CUDA(cudaStreamSynchronize(st));  // the one host round trip of the exchange: the gathered size
   }
-  // ---- layout: staging = rank after rank (each rank's table as it is), final = segments ascending
-  std::vector<long long> rank_total(world, 0), rank_off(world + 1, 0);
+  // ---- layout: every rank's table as one packed block, final = segments ascending
+  std::vector<long long> rank_total(world, 0);
   for (int s = 0; s < n_seg; ++s) rank_total[seg_owner[s]] += counts[s];
-  for (int r = 0; r < world; ++r) rank_off[r + 1] = rank_off[r] + rank_total[r];
-  const long long total = rank_off[world];
-  std::vector<long long> dst_off(n_seg + 1, 0), src_off(n_seg, 0), cursor(rank_off.begin(), rank_off.end() - 1);
-  bool identity = true;
+  long long total = 0, n_pad = 0;
+  for (int r = 0; r < world; ++r) {
+    total += rank_total[r];
+    n_pad = std::max(n_pad, rank_total[r]);
+  }
+  n_pad = (n_pad + 1) & ~1ll;  // the double column of a block stays 8-byte aligned
+  const long long stride = 20 * n_pad;
+  std::vector<long long> dst_off(n_seg + 1, 0), src_row(n_seg, 0), cursor(world, 0);
   for (int s = 0; s < n_seg; ++s) {
     dst_off[s + 1] = dst_off[s] + counts[s];
-    src_off[s] = cursor[seg_owner[s]];
+    src_row[s] = cursor[seg_owner[s]];
     cursor[seg_owner[s]] += counts[s];
-    identity = identity && src_off[s] == dst_off[s];
-  }
-  EdgeTable stage;
-  stage.reserve((size_t)total, st);
-  if (mine) {
-    CG_CUDA(cudaMemcpyAsync(stage.from.p + rank_off[me], t.from.p, (size_t)mine * 4, cudaMemcpyDeviceToDevice, st));
-    CG_CUDA(cudaMemcpyAsync(stage.to.p + rank_off[me], t.to.p, (size_t)mine * 4, cudaMemcpyDeviceToDevice, st));
-    CG_CUDA(cudaMemcpyAsync(stage.type.p + rank_off[me], t.type.p, (size_t)mine * 4, cudaMemcpyDeviceToDevice, st));
-    CG_CUDA(cudaMemcpyAsync(stage.w.p + rank_off[me], t.w.p, (size_t)mine * 8, cudaMemcpyDeviceToDevice, st));
-  }
-  // every rank's table travels once, in place into the gathered table (NVLink through NVSwitch)
-  CG_NCCL(cm, cm.GroupStart());
-  for (int r = 0; r < world; ++r) {
-    const size_t n = (size_t)rank_total[r];
-    if (!n) continue;
-    const long long o = rank_off[r];
-    CG_NCCL(cm, cm.Broadcast(stage.from.p + o, stage.from.p + o, n, ncclInt32, r, cm.comm, st));
-    CG_NCCL(cm, cm.Broadcast(stage.to.p + o, stage.to.p + o, n, ncclInt32, r, cm.comm, st));
-    CG_NCCL(cm, cm.Broadcast(stage.type.p + o, stage.type.p + o, n, ncclInt32, r, cm.comm, st));
-    CG_NCCL(cm, cm.Broadcast(stage.w.p + o, stage.w.p + o, n, ncclFloat64, r, cm.comm, st));
-  }
-  CG_NCCL(cm, cm.GroupEnd());
-  stage.n = (size_t)total;
-  if (identity) {
-    t = std::move(stage);
-    return;
   }
   EdgeTable out;
   out.reserve((size_t)total, st);
   out.n = (size_t)total;
-  if (total) {
+  if (total == 0) {
+    t = std::move(out);
+    return;
+  }
+  DevBuf<unsigned char> packed((size_t)stride * world);
+  unsigned char* my = packed.p + (size_t)me * stride;
+  if (mine) {
+    CG_CUDA(cudaMemcpyAsync(my, t.from.p, (size_t)mine * 4, cudaMemcpyDeviceToDevice, st));
+    CG_CUDA(cudaMemcpyAsync(my + 4 * n_pad, t.to.p, (size_t)mine * 4, cudaMemcpyDeviceToDevice, st));
+    CG_CUDA(cudaMemcpyAsync(my + 8 * n_pad, t.type.p, (size_t)mine * 4, cudaMemcpyDeviceToDevice, st));
+    CG_CUDA(cudaMemcpyAsync(my + 12 * n_pad, t.w.p, (size_t)mine * 8, cudaMemcpyDeviceToDevice, st));
+  }
+  // one collective over NVLink / NVSwitch, in place
+  CG_NCCL(cm, cm.AllGather(my, packed.p, (size_t)stride, ncclChar, cm.comm, st));
+  {
     DevBuf<long long> d_dst((size_t)n_seg + 1), d_src((size_t)n_seg);
+    DevBuf<int> d_own((size_t)n_seg);
     d_dst.upload(dst_off.data(), dst_off.size(), st);
-    d_src.upload(src_off.data(), src_off.size(), st);
+    d_src.upload(src_row.data(), src_row.size(), st);
+    d_own.upload(seg_owner, (size_t)n_seg, st);
     const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, (long long)c.sm_count * 16);
-    permute_segments_kernel<<<blocks, 256, 0, st>>>(d_dst.p, d_src.p, n_seg, total, stage.from.p, stage.to.p,
-                                                    stage.type.p, stage.w.p, out.from.p, out.to.p, out.type.p,
-                                                    out.w.p);
+    unpack_segments_kernel<<<blocks, 256, 0, st>>>(d_dst.p, d_src.p, d_own.p, n_seg, total, packed.p, stride, n_pad,
+                                                   out.from.p, out.to.p, out.type.p, out.w.p);
     c.stats.kernels++;
     CG_CUDA(cudaGetLastError());
-    CG_CUDA(cudaStreamSynchronize(st));  // dst_off / src_off host vectors and `stage` go out of scope
+    CG_CUDA(cudaStreamSynchronize(st));  // the host tables and `packed` go out of scope
   }
   t = std::move(out);
+}
+
+// X'X of every sample is computed ONCE in the whole job -- by its owner rank -- and broadcast over NVLink to the ranks
+// whose pairs use the sample (everybody takes part in the broadcast; ranks that do not need a matrix receive it into
+// a scratch buffer).  Without this every rank builds the Gram matrix of every sample it touches: at 8 GPUs and 8
+// samples that is ~5 of them per rank, work that does not shrink with the GPU count.
+void ensure_grams(Context& ctx, Sample* const* samples, int n);
+
+void share_grams(Context& c, cg_panel& panel, const int* owner, const int* n_genes) {
+  const int S = (int)panel.samples.size();
+  const int world = c.comm ? c.comm->world : 1;
+  const int me = c.comm ? c.comm->rank : 0;
+  cudaStream_t st = c.stream;
+  std::vector<Sample*> mine;
+  for (int s = 0; s < S; ++s) {
+    CG_CHECK(owner[s] >= -1 && owner[s] < world, "gram owner out of range");
+    if (owner[s] == me) {
+      CG_CHECK(panel.samples[s].has_counts, "the owner of a Gram matrix must hold the sample's counts");
+      mine.push_back(&panel.samples[s]);
+    }
+  }
+  ensure_grams(c, mine.data(), (int)mine.size());
+  if (world == 1) return;
+  Comm& cm = *c.comm;
+  size_t scratch_elems = 0;
+  for (int s = 0; s < S; ++s) {
+    if (owner[s] < 0) continue;
+    Sample& sm = panel.samples[s];
+    const size_t n = (size_t)n_genes[s] * n_genes[s];
+    if (sm.has_counts) {
+      CG_CHECK(sm.n_genes == n_genes[s], "gene count of a shared Gram matrix does not match the resident sample");
+      if (!sm.gram.n) sm.gram.alloc(n);
+    } else {
+      scratch_elems = std::max(scratch_elems, n);
+    }
+  }
+  DevBuf<double> scratch(scratch_elems);
+  CG_NCCL(cm, cm.GroupStart());
+  for (int s = 0; s < S; ++s) {
+    if (owner[s] < 0) continue;
+    Sample& sm = panel.samples[s];
+    double* buf = sm.has_counts ? sm.gram.p : scratch.p;
+    CG_NCCL(cm, cm.Broadcast(buf, buf, (size_t)n_genes[s] * n_genes[s], ncclFloat64, owner[s], cm.comm, st));
+  }
+  CG_NCCL(cm, cm.GroupEnd());
+  CG_CUDA(cudaStreamSynchronize(st));  // `scratch` is released on return
 }
 
 }  // namespace cg
@@ -293,6 +338,16 @@ void edges_allgatherv(Context& c, EdgeTable& t, const int* seg_owner, const long
 using namespace cg;
 
 extern "C" {
+
+int cg_panel_share_grams(cg_context* ctx, cg_panel* panel, const int32_t* owner, const int32_t* n_genes) {
+  CG_API_BEGIN
+  CG_CHECK(ctx && panel && owner && n_genes, "NULL argument");
+  CG_CUDA(cudaSetDevice(ctx->c.device));
+  CG_BIND(ctx);
+  StageScope sc(ctx->c, "share_grams");
+  share_grams(ctx->c, *panel, owner, n_genes);
+  CG_API_END(ctx)
+}
 
 int cg_comm_unique_id(void* id_out) {
   CG_API_BEGIN

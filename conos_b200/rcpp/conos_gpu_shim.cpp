@@ -1,48 +1,111 @@
-// Rcpp shim a conos maintainer would add to src/ (NOT compiled in this repository: R and Rcpp are not
-// installed here).  It keeps the reference's registered .Call entry points (src/RcppExports.cpp:349-370) and
-// routes the hot-path ones to libconosgpu.so through its C ABI (include/conos_gpu.h).  Marshalling only: dense
-// matrices are passed as R's column-major doubles, dgCMatrix by its p/i/x slots, errors become R errors.
+// Rcpp shim a conos maintainer adds to src/ (NOT compiled in this repository: R and Rcpp are not installed here; the
+// same C entry points are exercised by tests/cuda/job_test.cpp -- a C++ program without Python -- and by every GPU
+// test through ctypes).  It keeps the reference's registered .Call entry points (src/RcppExports.cpp:349-370), routes
+// the hot-path ones to libconosgpu.so through its C ABI (include/conos_gpu.h) and adds the entries that replace the
+// N2R calls and the per-pair R loops.  Marshalling only: dense matrices are R's column-major doubles, dgCMatrix
+// travels by its p / i / x slots, errors become R errors (Rcpp::stop, like BEGIN_RCPP / END_RCPP in the reference).
 //
 // Build: PKG_LIBS += -L$(CONOS_GPU_LIB) -lconosgpu ; PKG_CPPFLAGS += -I$(CONOS_GPU_INCLUDE)
 #include <Rcpp.h>
+
+#include <string>
+#include <vector>
+
 #include "conos_gpu.h"
 
 using namespace Rcpp;
 
-static cg_context* ctx_get() {
-  // one context per R process, created lazily in the PARENT process: CUDA contexts do not survive fork(), so the
-  // GPU path replaces the mclapply / plapply loops over pairs (R/conclass.R:224, 1074) by one batched call
-  static cg_context* ctx = nullptr;
-  if (!ctx && cg_init(0, &ctx) != 0) stop(cg_last_error(nullptr));
-  return ctx;
+// One job per R process, created lazily in the PARENT process (a CUDA context does not survive fork(): the GPU path
+// replaces the mclapply / plapply loops over pairs, R/conclass.R:224 and :1074, by one batched native call).
+static cg_job* g_job = nullptr;
+static int g_job_devices = 0;
+static cg_job* job_get(int n_devices) {
+  if (g_job && g_job_devices != n_devices) {
+    cg_job_free(g_job);
+    g_job = nullptr;
+  }
+  if (!g_job) {
+    if (cg_job_create(n_devices, &g_job) != 0) stop(cg_last_error(nullptr));
+    g_job_devices = n_devices;
+  }
+  return g_job;
 }
-static void check(int rc) {
-  if (rc != 0) stop(cg_last_error(ctx_get()));
+static cg_context* ctx_get() { return cg_job_context(job_get(g_job ? g_job_devices : 1), 0); }
+static void check(int rc, cg_context* ctx = nullptr) {
+  if (rc != 0) stop(cg_last_error(ctx ? ctx : ctx_get()));
+}
+static int metric_id(const std::string& t) {
+  if (t == "angular") return CG_METRIC_ANGULAR;
+  if (t == "L2") return CG_METRIC_L2;
+  stop("only the following distance metrics are currently supported: ['L2' 'angular']");
+  return 0;
 }
 
-// [[Rcpp::export]]   replaces N2R::crossKnn(mA, mB, k, 1, FALSE, indexType) at R/conos.R:851-855
-List crossKnnExact(NumericMatrix mA, NumericMatrix mB, int k, std::string indexType) {
-  const int metric = indexType == "angular" ? CG_METRIC_ANGULAR : CG_METRIC_L2;
-  IntegerMatrix idx(k, mA.nrow());   // column q = neighbours of query row q  (t() of the C layout [nA][k])
+// dgCMatrix from kNN lists: column q = query q, rows = its neighbours (ascending row index inside a column, as
+// Matrix stores it), x = distance -- the layout N2R::crossKnn / N2R::Knn return (nrow(index) x nrow(queries))
+static S4 knn_to_dgc(const std::vector<int32_t>& idx, const std::vector<float>& dist, int n_query, int n_index, int k) {
+  std::vector<int> p(n_query + 1, 0);
+  for (int q = 0; q < n_query; ++q) {
+    int c = 0;
+    for (int t = 0; t < k; ++t) c += idx[(size_t)q * k + t] >= 0;
+    p[q + 1] = p[q] + c;
+  }
+  IntegerVector ri(p[n_query]);
+  NumericVector rx(p[n_query]);
+  for (int q = 0; q < n_query; ++q) {
+    std::vector<std::pair<int, double>> col;
+    for (int t = 0; t < k; ++t)
+      if (idx[(size_t)q * k + t] >= 0) col.emplace_back(idx[(size_t)q * k + t], (double)dist[(size_t)q * k + t]);
+    std::sort(col.begin(), col.end());
+    for (size_t t = 0; t < col.size(); ++t) {
+      ri[p[q] + t] = col[t].first;
+      rx[p[q] + t] = col[t].second;
+    }
+  }
+  S4 m("dgCMatrix");
+  m.slot("i") = ri;
+  m.slot("p") = IntegerVector(p.begin(), p.end());
+  m.slot("x") = rx;
+  m.slot("Dim") = IntegerVector::create(n_index, n_query);
+  return m;
+}
+
+// [[Rcpp::export]]   replaces N2R::crossKnn(mA, mB, k, 1, FALSE, indexType) at R/conos.R:851-855 (exact search)
+S4 crossKnnExact(NumericMatrix mA, NumericMatrix mB, int k, std::string indexType = "angular") {
+  std::vector<int32_t> idx((size_t)k * mA.nrow());
   std::vector<float> dist((size_t)k * mA.nrow());
   check(cg_cross_knn(ctx_get(), mA.begin(), mA.nrow(), mA.nrow(), mB.begin(), mB.nrow(), mB.nrow(), mA.ncol(), k,
-                     metric, idx.begin(), dist.data(), nullptr, nullptr));
-  // triplets (neighbour, query, dist) -> dgCMatrix nrow(mB) x nrow(mA), the layout N2R returns
-  return List::create(_["i"] = idx, _["x"] = NumericVector(dist.begin(), dist.end()));
+                     metric_id(indexType), idx.data(), dist.data(), nullptr, nullptr));
+  return knn_to_dgc(idx, dist, mA.nrow(), mB.nrow(), k);
+}
+
+// [[Rcpp::export]]   replaces N2R::Knn(m, k, 1, verbose = FALSE, indexType) at R/conos.R:595 (self included)
+S4 knnExact(NumericMatrix m, int k, std::string indexType = "angular") {
+  std::vector<int32_t> idx((size_t)k * m.nrow());
+  std::vector<float> dist((size_t)k * m.nrow());
+  check(cg_self_knn(ctx_get(), m.begin(), m.nrow(), m.nrow(), m.ncol(), k, metric_id(indexType), idx.data(),
+                    dist.data()));
+  return knn_to_dgc(idx, dist, m.nrow(), m.nrow(), k);
 }
 
 // [[Rcpp::export]]   getNeighborMatrix(p1, p2, k, k1, matching, metric, l2.sigma, cor.base)  R/conos.R:848-886
-List getNeighborMatrixGPU(NumericMatrix p1, NumericMatrix p2, int k, int k1, std::string matching,
-                          std::string metric, double l2_sigma, double cor_base, double min_similarity = 1e-5) {
+S4 getNeighborMatrixGPU(NumericMatrix p1, NumericMatrix p2, int k, int k1, std::string matching, std::string metric,
+                        double l2_sigma, double cor_base, double min_similarity = 1e-5) {
+  if (matching != "mNN" && matching != "NN") stop("Unrecognized type of NN matching:" + matching);
   int64_t nnz = 0;
   check(cg_neighbor_matrix(ctx_get(), p1.begin(), p1.nrow(), p1.nrow(), p2.begin(), p2.nrow(), p2.nrow(), p1.ncol(),
-                           k, k1, matching == "mNN" ? CG_MATCH_MNN : CG_MATCH_NN,
-                           metric == "angular" ? CG_METRIC_ANGULAR : CG_METRIC_L2, l2_sigma, cor_base,
-                           min_similarity, &nnz));
+                           k, k1, matching == "mNN" ? CG_MATCH_MNN : CG_MATCH_NN, metric_id(metric), l2_sigma,
+                           cor_base, min_similarity, &nnz));
   IntegerVector i(nnz), j(nnz);
   NumericVector x(nnz);
   check(cg_fetch_coo(ctx_get(), i.begin(), j.begin(), x.begin()));
-  return List::create(_["i"] = i, _["j"] = j, _["x"] = x, _["Dim"] = IntegerVector::create(p1.nrow(), p2.nrow()));
+  S4 m("dgTMatrix");  // triplets in CSC order, like as(adj, 'TsparseMatrix') at R/conos.R:880-884
+  m.slot("i") = i;
+  m.slot("j") = j;
+  m.slot("x") = x;
+  m.slot("Dim") = IntegerVector::create(p1.nrow(), p2.nrow());
+  m.slot("Dimnames") = List::create(rownames(p1), rownames(p2));
+  return m;
 }
 
 // [[Rcpp::export]]   same name and arguments as src/spcov.cpp:14
@@ -94,21 +157,46 @@ NumericVector adjustWeightsByCellBalancingC(NumericVector weights, IntegerVector
   return w;
 }
 
-// [[Rcpp::export]]   the one native call Conos$buildGraph makes instead of its two papply loops
-// samples: list of list(p, i, x, Dim, v, qv, pca); pairs: list of list(a, b, genes_a, genes_b [, rot]); params: list
-List buildGraphGPU(List samples, List pairs, List params) {
+// [[Rcpp::export]]   same name and arguments as src/edgeweights.cpp:160 (threads is ignored: the device is the pool)
+S4 referenceWij(IntegerVector i, IntegerVector j, NumericVector d, int threads, double perplexity) {
+  const int64_t n = i.size();
+  std::vector<int32_t> of(2 * n), ot(2 * n);
+  std::vector<double> ow(2 * n);
+  int64_t n_out = 0;
+  check(cg_reference_wij(ctx_get(), i.begin(), j.begin(), d.begin(), n, perplexity, of.data(), ot.data(), ow.data(),
+                         &n_out));
+  // setFromTriplets sums duplicates (src/edgeweights.cpp:178-181): Matrix::sparseMatrix does the same
+  int nv = 0;
+  for (int64_t t = 0; t < n; ++t) nv = std::max(nv, std::max(i[t], j[t]) + 1);
+  Environment Matrix = Environment::namespace_env("Matrix");
+  Function sparseMatrix = Matrix["sparseMatrix"];
+  IntegerVector ri(of.begin(), of.begin() + n_out), rj(ot.begin(), ot.begin() + n_out);
+  NumericVector rx(ow.begin(), ow.begin() + n_out);
+  return sparseMatrix(_["i"] = ri + 1, _["j"] = rj + 1, _["x"] = rx, _["dims"] = IntegerVector::create(nv, nv));
+}
+
+// [[Rcpp::export]]   the one native call Conos$buildGraph makes instead of updatePairs + its two papply loops + rbind +
+// graph_from_edgelist + simplify + adjustWeightsByCellBalancing (R/conclass.R:199-368).
+// samples: list of list(p, i, x, Dim, v, qv, pca); pairs: list of list(a, b, genes_a, genes_b [, k] [, rot] [, u, v,
+// rows_u, rows_v]) in combn order; params: list; n_devices: GPUs of this node to use.
+// Returns the graph and, per pair, the reduction with every field of self$pairs[[space]] (R/conclass.R:1090-1092).
+List buildGraphGPU(List samples, List pairs, List params, int n_devices = 1) {
+  cg_job* job = job_get(n_devices);
+  cg_context* ctx0 = cg_job_context(job, 0);
   const int S = samples.size();
   std::vector<cg_sample> cs(S);
   for (int s = 0; s < S; ++s) {
     List sm = samples[s];
     IntegerVector dim = sm["Dim"], p = sm["p"], i = sm["i"];
     NumericVector x = sm["x"], v = sm["v"], qv = sm["qv"];
-    NumericMatrix pca = sm["pca"];
-    cs[s] = cg_sample{dim[0], dim[1], p.begin(), i.begin(), x.begin(), v.begin(), qv.begin(), pca.begin(),
-                      (int32_t)pca.ncol(), (int32_t)pca.nrow()};
+    cs[s] = cg_sample{dim[0], dim[1], p.begin(), i.begin(), x.begin(), v.begin(), qv.begin(), nullptr, 0, dim[0]};
+    if (sm.containsElementNamed("pca") && !Rf_isNull(sm["pca"])) {
+      NumericMatrix pca = sm["pca"];
+      cs[s].pca = pca.begin();
+      cs[s].n_pcs = pca.ncol();
+      cs[s].pca_ld = pca.nrow();
+    }
   }
-  cg_panel* panel = nullptr;
-  check(cg_panel_create(ctx_get(), cs.data(), S, &panel));
   const int P = pairs.size();
   std::vector<cg_pair> cp(P);
   for (int q = 0; q < P; ++q) {
@@ -120,10 +208,23 @@ List buildGraphGPU(List samples, List pairs, List params) {
     cp[q].n_genes = ga.size();
     cp[q].genes_a = ga.begin();
     cp[q].genes_b = gb.begin();
-    if (pr.containsElementNamed("rot")) {  // cached self$pairs[[space]][[name]]$CPC
+    if (pr.containsElementNamed("k")) cp[q].k = as<int>(pr["k"]);  // k.cur, R/conclass.R:230-233
+    if (pr.containsElementNamed("rot")) {  // cached self$pairs[[space]][[name]]$CPC: its rownames ARE the pair's genes
       NumericMatrix rot = pr["rot"];
       cp[q].rot = rot.begin();
+      cp[q].rot_rows = rot.nrow();
       cp[q].rot_cols = rot.ncol();
+    }
+    if (pr.containsElementNamed("u")) {    // cached self$pairs$CCA[[name]]$u / $v (R/conclass.R:268-270)
+      NumericMatrix u = pr["u"], v = pr["v"];
+      IntegerVector ru = pr["rows_u"], rv = pr["rows_v"];
+      cp[q].u = u.begin();
+      cp[q].v = v.begin();
+      cp[q].rows_u = ru.begin();
+      cp[q].rows_v = rv.begin();
+      cp[q].n_u = u.nrow();
+      cp[q].n_v = v.nrow();
+      cp[q].uv_cols = u.ncol();
     }
   }
   cg_params par;
@@ -141,27 +242,95 @@ List buildGraphGPU(List samples, List pairs, List params) {
   par.k_self_weight = as<double>(params["k.self.weight"]);
   par.l2_sigma = as<double>(params["l2.sigma"]);
   par.cor_base = as<double>(params["cor.base"]);
-  cg_edges* edges = nullptr;
-  std::vector<int64_t> counts(P);
-  check(cg_pairs_edges(ctx_get(), panel, cp.data(), P, &par, &edges, counts.data()));
-  std::vector<int32_t> sidx(S);
-  for (int s = 0; s < S; ++s) sidx[s] = s;
-  check(cg_local_edges(ctx_get(), panel, sidx.data(), S, &par, &edges));
-  std::vector<int32_t> offs(S + 1);
-  cg_panel_offsets(panel, offs.data());
   cg_graph* g = nullptr;
-  check(cg_assemble_graph(ctx_get(), edges, offs[S], &g));
+  if (cg_job_build_graph(job, cs.data(), S, cp.data(), P, &par, &g) != 0) stop(cg_job_last_error(job));
   int32_t nv = 0;
   int64_t ne = 0;
   cg_graph_sizes(g, &nv, &ne);
+  // balancing (R/conclass.R:346-368): factor.per.vertex = 1-based level of every graph vertex, computed by the R side
+  // from balancing.factor.per.cell / per.sample / getDatasetPerCell once the vertex order is known
+  if (params.containsElementNamed("balance") && as<bool>(params["balance"])) {
+    IntegerVector vertices0(nv);
+    check(cg_graph_fetch(ctx0, g, vertices0.begin(), nullptr, nullptr, nullptr, nullptr), ctx0);
+    IntegerVector level_of_cell = params["factor.level.per.cell"];  // 1-based levels in global cell order
+    IntegerVector fac(nv);
+    for (int v = 0; v < nv; ++v) fac[v] = level_of_cell[vertices0[v]];
+    check(cg_graph_balance(ctx0, g, fac.begin(), max(level_of_cell), as<bool>(params["balance.edge.weights"]),
+                           as<double>(params["same.factor.downweight"]), 50), ctx0);
+  }
   IntegerVector vertices(nv), from(ne), to(ne), type(ne);
   NumericVector weight(ne);
-  check(cg_graph_fetch(ctx_get(), g, vertices.begin(), from.begin(), to.begin(), weight.begin(), type.begin()));
+  check(cg_graph_fetch(ctx0, g, vertices.begin(), from.begin(), to.begin(), weight.begin(), type.begin()), ctx0);
   cg_graph_free(g);
-  cg_edges_free(edges);
-  cg_panel_free(panel);
-  // R side: g <- igraph::graph_from_edgelist(cbind(from, to) + 1L, directed = FALSE); V(g)$name <- cells[vertices+1]
-  //         E(g)$weight <- weight; E(g)$type <- type      (already simplified: no call to simplify())
+  // ---- self$pairs[[space]] write-back: every field the reference keeps
+  List reductions(P);
+  for (int q = 0; q < P; ++q) {
+    int32_t dev = 0, slot = 0;
+    cg_job_pair_location(job, q, &dev, &slot);
+    cg_context* cx = cg_job_context(job, dev);
+    if (par.space == CG_SPACE_CCA) {
+      int32_t nu = 0, nvv = 0, d = 0, ng = 0, dl = 0;
+      check(cg_pair_cca(cx, slot, &nu, &nvv, &d, nullptr, nullptr, nullptr, nullptr, nullptr), cx);
+      if (nu == 0) continue;  // supplied by the caller: nothing new
+      NumericMatrix u(nu, d), v(nvv, d);
+      IntegerVector ru(nu), rv(nvv);
+      NumericVector sigma(d);
+      check(cg_pair_cca(cx, slot, nullptr, nullptr, nullptr, u.begin(), v.begin(), ru.begin(), rv.begin(),
+                        sigma.begin()), cx);
+      check(cg_pair_cca_loadings(cx, slot, &ng, &dl, nullptr, nullptr, nullptr), cx);
+      NumericMatrix ul(ng, dl), vl(ng, dl), nvm(dl, 2);
+      check(cg_pair_cca_loadings(cx, slot, nullptr, nullptr, ul.begin(), vl.begin(), nvm.begin()), cx);
+      reductions[q] = List::create(_["d"] = sigma, _["u"] = u, _["v"] = v, _["ul"] = ul, _["vl"] = vl,
+                                   _["nv"] = List::create(nvm(_, 0), nvm(_, 1)), _["rows_u"] = ru, _["rows_v"] = rv);
+      continue;
+    }
+    int32_t nr = 0, nc = 0;
+    check(cg_pair_reduction(cx, slot, &nr, &nc, nullptr, nullptr), cx);
+    NumericMatrix rot(nr, nc), nvm(nc, 2);
+    check(cg_pair_reduction(cx, slot, nullptr, nullptr, rot.begin(), par.score_component_variance ? nvm.begin() : nullptr),
+          cx);
+    List red = List::create(_["CPC"] = rot);   // R side: rownames(CPC) <- od.genes of the pair
+    if (par.score_component_variance) red["nv"] = List::create(nvm(_, 0), nvm(_, 1));
+    if (par.space == CG_SPACE_CPCA) {
+      NumericMatrix D(nc, 2);   // t(D), src/cpca.cpp:97
+      NumericVector niter(nc);
+      check(cg_pair_cpca(cx, slot, nullptr, D.begin(), niter.begin()), cx);
+      red["D"] = D;
+      red["niter"] = niter;
+    }
+    reductions[q] = red;
+  }
+  // R side: g <- igraph::make_graph(rbind(from, to) + 1L, n = length(vertices), directed = FALSE);
+  //         V(g)$name <- cells[vertices + 1]; E(g)$weight <- weight; E(g)$type <- type   (already simplified)
   return List::create(_["vertices"] = vertices, _["from"] = from, _["to"] = to, _["weight"] = weight,
-                      _["type"] = type);
+                      _["type"] = type, _["pairs"] = reductions);
+}
+
+// ---- registration (what Rcpp::compileAttributes() generates into src/RcppExports.cpp for the entries above; the 16
+// untouched entries of the reference's table -- src/RcppExports.cpp:349-370 -- stay as they are)
+//
+//   static const R_CallMethodDef CallEntries[] = {
+//       {"_conos_spcov", (DL_FUNC) &_conos_spcov, 2},
+//       {"_conos_cpcaF", (DL_FUNC) &_conos_cpcaF, 7},
+//       {"_conos_pareDownHubEdges", (DL_FUNC) &_conos_pareDownHubEdges, 4},
+//       {"_conos_getSumWeightMatrix", (DL_FUNC) &_conos_getSumWeightMatrix, 5},
+//       {"_conos_adjustWeightsByCellBalancingC", (DL_FUNC) &_conos_adjustWeightsByCellBalancingC, 5},
+//       {"_conos_referenceWij", (DL_FUNC) &_conos_referenceWij, 5},
+//       {"_conos_crossKnnExact", (DL_FUNC) &_conos_crossKnnExact, 4},          // new
+//       {"_conos_knnExact", (DL_FUNC) &_conos_knnExact, 3},                    // new
+//       {"_conos_getNeighborMatrixGPU", (DL_FUNC) &_conos_getNeighborMatrixGPU, 9},  // new
+//       {"_conos_buildGraphGPU", (DL_FUNC) &_conos_buildGraphGPU, 4},          // new
+//       ... the reference's other 16 entries ...
+//       {NULL, NULL, 0}};
+//   RcppExport void R_init_conos(DllInfo* dll) {
+//     R_registerRoutines(dll, NULL, CallEntries, NULL, NULL);
+//     R_useDynamicSymbols(dll, FALSE);
+//   }
+//   // R/zzz.R: .onUnload <- function(libpath) { .Call('_conos_gpuShutdown'); library.dynam.unload('conos', libpath) }
+
+// [[Rcpp::export]]   called from .onUnload: contexts, streams and the NCCL communicator go before the DLL does
+void gpuShutdown() {
+  if (g_job) cg_job_free(g_job);
+  g_job = nullptr;
+  g_job_devices = 0;
 }

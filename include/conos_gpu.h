@@ -188,6 +188,8 @@ int cg_local_edges(cg_context* ctx, cg_panel* panel, const int32_t* samples, int
 
 /* ---- edge tables ---------------------------------------------------------------------------------- */
 int64_t cg_edges_count(const cg_edges* e);
+/* rows whose type equals `type` (1 = inter-sample: the "mNN edges" of the metric; 0 = within-sample); -1 on error */
+int64_t cg_edges_count_type(cg_context* ctx, const cg_edges* e, int32_t type);
 int cg_edges_fetch(cg_context* ctx, const cg_edges* e, int32_t* from, int32_t* to, double* w, int32_t* type);
 /* append host rows (used to merge shards gathered from other ranks) */
 int cg_edges_append_host(cg_context* ctx, cg_edges** e, const int32_t* from, const int32_t* to, const double* w,
@@ -214,14 +216,41 @@ int cg_comm_rank(const cg_context* ctx, int* rank, int* world);
  * matrix and its upload), so a rank touches about S / sqrt(world) samples.  owner[q] = rank.  sample_cost may be NULL. */
 int cg_partition_pairs(const int32_t* a, const int32_t* b, const double* cost, int n_pairs, const double* sample_cost,
                        int n_samples, int world, int32_t* owner);
+/* Gram matrices X'X of the samples, computed once per job: owner[s] = rank that computes the matrix of sample s (it
+ * must hold the sample's counts; -1: nobody needs it), n_genes[s] = its gene count (known to every rank).  Every
+ * rank calls this with the same tables before cg_pairs_edges; the matrices travel by ncclBroadcast over NVLink.
+ * Replaces the per-pair spcov calls of quickCPCA / the per-sample irlba of quickPlainPCA inside the reference's
+ * fork pool (R/conclass.R:1074-1088): there every worker recomputes what it needs. */
+int cg_panel_share_grams(cg_context* ctx, cg_panel* panel, const int32_t* owner, const int32_t* n_genes);
 /* allgatherv of the ranks' edge tables.  The table is a sequence of segments (pairs for the inter-sample edges,
  * samples for the local ones): seg_owner[s] = rank that produced segment s, seg_counts_local[s] = its row count on
  * the owner (ignored elsewhere); the local table holds this rank's segments in ascending s.  On return every rank
- * holds all segments in ascending s == the reference's row order (pairs in combn order, R/conclass.R:316-321).
- * One ncclAllReduce of the counts, one grouped ncclBroadcast per rank straight into the gathered table, one
- * permutation kernel; a single-rank context returns the table as it is. */
+ * holds all segments in ascending s == the reference's row order (pairs in combn order, then the samples' local
+ * edges: R/conclass.R:316-321, 328-332).  One ncclAllReduce of the counts, ONE ncclAllGather of the packed tables
+ * (from | to | type | w per rank), one kernel that unpacks into segment order; a single-rank context returns the
+ * table as it is. */
 int cg_edges_allgatherv(cg_context* ctx, cg_edges** e, const int32_t* seg_owner, const int64_t* seg_counts_local,
                         int n_seg);
+
+/* ---- one buildGraph over several GPUs from ONE host process ------------------------------------------ */
+/* What an R session needs (no fork with a CUDA context, no torchrun): cg_job_create starts one context per device
+ * 0 .. n_devices-1 and an NCCL communicator between them (n_devices == 1: no NCCL); cg_job_build_graph runs, with
+ * one host thread per device, partition -> resident samples -> shared Gram matrices -> cg_pairs_edges on the
+ * device's pairs -> cg_edges_allgatherv -> cg_local_edges on the device's samples -> cg_edges_allgatherv -> graph
+ * assembly on device 0.  `samples` / `pairs` are the full tables (every pair is computed once, on the device the
+ * partition gives it).  The graph belongs to cg_job_context(job, 0): fetch it with cg_graph_fetch on that context.
+ * The reduction of pair q stays on its device: cg_job_pair_location tells which context and which slot to pass to
+ * cg_pair_reduction / cg_pair_cpca / cg_pair_cca / cg_pair_cca_loadings.
+ * Replaces R/conclass.R:224-343 (both papply loops, rbind, graph_from_edgelist, simplify) and :1074-1088. */
+typedef struct cg_job cg_job;
+int cg_job_create(int n_devices, cg_job** out);
+void cg_job_free(cg_job* job);
+int cg_job_devices(const cg_job* job);
+cg_context* cg_job_context(cg_job* job, int device);
+const char* cg_job_last_error(const cg_job* job);
+int cg_job_build_graph(cg_job* job, const cg_sample* samples, int n_samples, const cg_pair* pairs, int n_pairs,
+                       const cg_params* params, cg_graph** graph);
+int cg_job_pair_location(const cg_job* job, int pair, int32_t* device, int32_t* slot);
 
 /* ---- graph ---------------------------------------------------------------------------------------- */
 /* el[w > 0]; vertices numbered by first appearance (graph_from_edgelist on a character matrix);

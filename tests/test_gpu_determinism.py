@@ -131,3 +131,39 @@ def test_two_rank_graph_equals_single_rank(space):
     r = _run_ranks(2, ["--space", space])
     assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-6000:])
     assert "MP_GRAPH_EQUAL" in r.stdout, (r.stdout[-3000:], r.stderr[-3000:])
+
+
+def test_cpp_host_sequence_and_job():
+    """tests/cuda/job_test.cpp: a C++ program that links libconosgpu.so through include/conos_gpu.h only, runs the call
+    sequence of the Rcpp shim's buildGraphGPU and the same work as one cg_job call (1 device, 2 when present)."""
+    exe = os.path.join(ROOT, "build", "job_test")
+    if not os.path.exists(exe):
+        import __graft_entry__
+        __graft_entry__.build()
+    r = subprocess.run([exe], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "JOB_TEST_OK" in r.stdout, (r.returncode, r.stdout[-2000:], r.stderr[-2000:])
+
+
+@pytest.mark.parametrize("space,ncomps", [("PCA", 20), ("CCA", 10)])
+def test_job_path_equals_context_path(ctx, space, ncomps):
+    """Conos.buildGraph(n_devices=N): ONE native call (cg_job_build_graph) -- same graph and same pairs cache as the
+    call-by-call path; N = 2 when the box has two GPUs."""
+    import conos_b200
+    import torch
+    panel = _panel(4)
+    kw = dict(k=10, k_self=5, space=space, ncomps=ncomps, n_odgenes=400, score_component_variance=(space == "PCA"))
+    con = conos_b200.Conos(panel, ctx=ctx)
+    g0 = con.buildGraph(**kw)
+    ref = {a: np.array(getattr(g0, a), copy=True) for a in ("vertices", "edge_from", "edge_to", "weight", "type")}
+    for nd in ([1, 2] if torch.cuda.device_count() >= 2 else [1]):
+        cj = conos_b200.Conos(panel, ctx=ctx)
+        g1 = cj.buildGraph(n_devices=nd, **kw)
+        for a, v in ref.items():
+            assert np.array_equal(getattr(g1, a), v), (nd, a)
+        assert set(cj.pairs[space]) == set(con.pairs[space])
+        for key, red in con.pairs[space].items():
+            for f in ("CPC", "u", "v", "ul"):
+                if f in red and isinstance(red[f], np.ndarray):
+                    assert np.array_equal(cj.pairs[space][key][f], red[f]), (nd, key, f)
+        cj.close()
+    con.close()
