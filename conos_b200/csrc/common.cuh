@@ -194,7 +194,7 @@ struct Context {
   // kNN engine: 0 = auto (two-phase tensor-core kernel, streaming kernel for small problems and redo blocks),
   // 1 = streaming tensor-core kernel only, 2 = exact SIMT kernel only
   int knn_engine = 0;
-  int knn_cand_cap = 64;          // candidate slots per (row, half) the two-phase kernel may use (tests shrink it)
+  int knn_cand_cap = 96;          // candidate slots per (row, half) the two-phase kernel may use (tests shrink it)
   cudaMemPool_t panel_pool = nullptr;  // resident panel buffers (see PoolBinding)
   PinnedArena rot_arena;          // host copies of the rotations of the current cg_pairs_edges call
   uint64_t eig_redo_pairs = 0;    // pairs the tensor-core eigen solver handed to the FP64 driver
@@ -206,7 +206,7 @@ struct Context {
   int gram_chunk_slabs = 16;   // tensor-core Gram: cells per FP32 accumulation chunk / 64 (chunks are summed in FP64)
   double tc_eig_tol = 1e-5;    // its stopping rule: residual <= tol * theta_1 (irlba's default tolerance)
   int tc_eig_max_sweeps = 40;  // tensor-core eigen solver: sweeps before a problem is handed to the FP64 driver
-  size_t max_batch_bytes = (size_t)24 << 30;  // scratch budget of one batch of pairs in cg_pairs_edges (tests shrink it)
+  size_t max_batch_bytes = (size_t)48 << 30;  // scratch budget of one batch of pairs in cg_pairs_edges (tests shrink it)
   // optional per-stage wall-clock profile (stream synchronised at both ends of a stage)
   bool profile = false;
   std::map<std::string, double> stage_ms;

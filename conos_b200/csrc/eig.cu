@@ -1,3 +1,5 @@
+#include <cooperative_groups.h>
+
 #include <functional>
 
 #include "eig.cuh"
@@ -73,8 +75,11 @@ __global__ void __launch_bounds__(256) eig_matmul_kernel(const EigWork* __restri
 }
 
 // S[i][j] = sum_r X[r][i] * Y[r][j]  (B x B, into shared memory), all 256 threads
+// Rows [r0, r1) only: a problem is shared by the CTAs of a thread-block cluster, each owning a slice of the rows
+// (RowSlice below); the partial Gram matrices are summed over the cluster by cluster_sum.
 template <int B>
-__device__ void block_gram(const double* __restrict__ X, const double* __restrict__ Y, int G, double (*S)[B + 1]) {
+__device__ void block_gram_rows(const double* __restrict__ X, const double* __restrict__ Y, int r0, int G,
+                                double (*S)[B + 1]) {
   if constexpr (B == 32) {
     // rows split over the 8 warps (fixed assignment r = warp, warp + 8, ...), lane l owns column l of S: one coalesced
     // 256-byte load of each operand per row, x broadcast by shuffles, 32 independent FMA chains per lane; the eight
@@ -84,7 +89,7 @@ __device__ void block_gram(const double* __restrict__ X, const double* __restric
     double acc[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) acc[i] = 0.0;
-    int r = warp;
+    int r = r0 + warp;
     for (; r + NW < G; r += 2 * NW) {  // two rows in flight
       const double x0 = X[(size_t)r * 32 + lane], y0 = Y[(size_t)r * 32 + lane];
       const double x1 = X[(size_t)(r + NW) * 32 + lane], y1 = Y[(size_t)(r + NW) * 32 + lane];
@@ -115,7 +120,7 @@ __device__ void block_gram(const double* __restrict__ X, const double* __restric
     double acc[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) acc[i] = 0.0;
-    int r = par;
+    int r = r0 + par;
     for (; r + 2 < G; r += 4) {  // two rows in flight
       const double x0 = X[(size_t)r * 64 + bi + lane], y0 = Y[(size_t)r * 64 + bj + lane];
       const double x1 = X[(size_t)(r + 2) * 64 + bi + lane], y1 = Y[(size_t)(r + 2) * 64 + bj + lane];
@@ -145,7 +150,7 @@ __device__ void block_gram(const double* __restrict__ X, const double* __restric
   for (int a = 0; a < TB; ++a)
 #pragma unroll
     for (int b = 0; b < TB; ++b) acc[a][b] = 0.0;
-  for (int r = 0; r < G; ++r) {
+  for (int r = r0; r < G; ++r) {
     double xv[TB], yv[TB];
 #pragma unroll
     for (int a = 0; a < TB; ++a) { xv[a] = X[(size_t)r * B + i0 + a]; yv[a] = Y[(size_t)r * B + j0 + a]; }
@@ -163,11 +168,11 @@ __device__ void block_gram(const double* __restrict__ X, const double* __restric
 
 // dst[r][:] = src[r][:] * W  (W B x B in shared memory), one warp per row; src may equal dst
 template <int B>
-__device__ void rows_times_matrix(const double* __restrict__ src, double* __restrict__ dst, int G,
+__device__ void rows_times_matrix(const double* __restrict__ src, double* __restrict__ dst, int r0, int G,
                                   double (*W)[B + 1], double (*rowbuf)[B]) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int NC = B / 32;
-  for (int r = warp; r < G; r += EIG_THREADS / 32) {
+  for (int r = r0 + warp; r < G; r += EIG_THREADS / 32) {
 #pragma unroll
     for (int u = 0; u < NC; ++u) rowbuf[warp][lane + 32 * u] = src[(size_t)r * B + lane + 32 * u];
     __syncwarp();
@@ -280,12 +285,76 @@ struct EigSmem {
   int wellcond;  // last Cholesky-QR pass: smallest pivot > 1e-4 * largest diagonal (orthogonality error ~ 1e-12)
 };
 
+// A problem may be shared by the CTAs of one thread-block cluster (EIG_CLUSTER of them): the O(G) parts -- block Gram
+// products, row updates, residuals -- are split by rows, the B x B factorisations are repeated by every CTA on the
+// same (cluster-summed) matrix.  One CTA per problem leaves most of the 148 SMs idle and makes the orthonormalisation
+// and Rayleigh-Ritz steps the latency floor of the eigen stage whatever the number of problems.
+constexpr int EIG_CLUSTER = 4;
+struct RowSlice {
+  int r0, r1;       // rows of this CTA
+  unsigned rank, size;
+};
+__device__ __forceinline__ RowSlice row_slice(int G, int csize) {
+  RowSlice sl;
+  sl.size = (unsigned)csize;
+  sl.rank = csize > 1 ? cooperative_groups::this_cluster().block_rank() : 0u;
+  // slices are multiples of 8 rows (the warp-strided loops of the helpers start at r0 + warp)
+  const int per = ((G + csize - 1) / csize + 7) & ~7;
+  sl.r0 = min(G, (int)sl.rank * per);
+  sl.r1 = min(G, sl.r0 + per);
+  return sl;
+}
+// problem of this CTA: clusters are consecutive CTAs
+__device__ __forceinline__ int cluster_problem(int csize) { return (int)blockIdx.x / csize; }
+
+// S = X'Y over all rows of the problem: every CTA of the cluster forms the partial product of its slice in `part`
+// (shared memory the caller does not need at this point), then adds the partials of all CTAs in rank order through
+// distributed shared memory -- the same order in every CTA, so all of them hold bit-identical S.
+template <int B>
+__device__ void block_gram(const double* __restrict__ X, const double* __restrict__ Y, const RowSlice& sl,
+                           double (*S)[B + 1], double (*part)[B + 1]) {
+  if (sl.size == 1) {
+    block_gram_rows<B>(X, Y, sl.r0, sl.r1, S);
+    return;
+  }
+  namespace cgr = cooperative_groups;
+  cgr::cluster_group cluster = cgr::this_cluster();
+  block_gram_rows<B>(X, Y, sl.r0, sl.r1, part);
+  cluster.sync();
+  for (int t = threadIdx.x; t < B * B; t += EIG_THREADS) {
+    double acc = 0.0;
+    for (unsigned r = 0; r < sl.size; ++r) {
+      const double* remote = cluster.map_shared_rank(&part[0][0], r);
+      acc += remote[(t / B) * (B + 1) + (t % B)];
+    }
+    S[t / B][t % B] = acc;
+  }
+  cluster.sync();  // nobody overwrites its partial while a neighbour still reads it
+}
+
+// sum of one shared-memory vector over the cluster, same order everywhere (v is overwritten by the total)
+__device__ void cluster_sum_vector(double* v, int n, double* scratch, const RowSlice& sl) {
+  if (sl.size == 1) return;
+  namespace cgr = cooperative_groups;
+  cgr::cluster_group cluster = cgr::this_cluster();
+  cluster.sync();
+  if ((int)threadIdx.x < n) {
+    double acc = 0.0;
+    for (unsigned r = 0; r < sl.size; ++r) acc += cluster.map_shared_rank(v, r)[threadIdx.x];
+    scratch[threadIdx.x] = acc;
+  }
+  cluster.sync();
+  if ((int)threadIdx.x < n) v[threadIdx.x] = scratch[threadIdx.x];
+  __syncthreads();
+}
+
 // Orthonormalise the columns of Z into Q: Cholesky-QR (Q = Z R^-1 with Z'Z = R'R); when a pivot collapses
 // (rank-deficient block) the symmetric eigen-decomposition Z'Z = U L U' is used instead, Q = Z U L^-1/2,
 // and the numerically null directions are zeroed.
 template <int B>
-__device__ void orth_pass(const double* __restrict__ src, double* __restrict__ dst, int G, EigSmem<B>& sm) {
-  block_gram<B>(src, src, G, sm.S);
+__device__ void orth_pass(const double* __restrict__ src, double* __restrict__ dst, const RowSlice& sl,
+                          EigSmem<B>& sm) {
+  block_gram<B>(src, src, sl, sm.S, sm.W);
   const int tid = threadIdx.x, lane = tid & 31;
   if (tid == 0) sm.flag = 0;
   // equilibrate: the columns of a filtered block differ by many orders of magnitude in norm, which says nothing
@@ -361,42 +430,50 @@ __device__ void orth_pass(const double* __restrict__ src, double* __restrict__ d
   // undo the equilibration: Q = Z D^-1 W
   for (int t = tid; t < B * B; t += EIG_THREADS) sm.W[t / B][t % B] *= sm.rowbuf[0][t / B];
   __syncthreads();
-  rows_times_matrix<B>(src, dst, G, sm.W, sm.rowbuf);
+  rows_times_matrix<B>(src, dst, sl.r0, sl.r1, sm.W, sm.rowbuf);
   if (sm.flag) {
     // a numerically null direction is replaced by a fresh pseudo-random column (the next pass orthonormalises it):
     // a zero column would stay zero for the rest of the iteration
-    for (size_t t = tid; t < (size_t)G * B; t += EIG_THREADS) {
+    for (size_t t = (size_t)sl.r0 * B + tid; t < (size_t)sl.r1 * B; t += EIG_THREADS) {
       const int j = (int)(t % B);
       if (sm.ev[j] != 0.0) dst[t] = hash_unit((unsigned)(t / B) + 0x9e37u, (unsigned)j + 4099u);
     }
     __syncthreads();
     if (tid == 0) sm.wellcond = 0;
   }
+  // the second pass (and the caller's next kernel) reads rows other CTAs of the cluster have just written
+  if (sl.size > 1) {
+    __threadfence();
+    cooperative_groups::this_cluster().sync();
+  }
 }
 
 template <int B>
-__global__ void __launch_bounds__(EIG_THREADS) eig_orth_kernel(const EigWork* __restrict__ works) {
+__global__ void __launch_bounds__(EIG_THREADS) eig_orth_kernel(const EigWork* __restrict__ works, int csize) {
   extern __shared__ __align__(16) unsigned char raw[];
   EigSmem<B>& sm = *reinterpret_cast<EigSmem<B>*>(raw);
-  const EigWork w = works[blockIdx.x];
+  const EigWork w = works[cluster_problem(csize)];
   // a problem is locked the moment it converges: its result cannot depend on how long its batch mates take
+  // (every CTA of the cluster takes the same branch: the flag is only written by the Rayleigh-Ritz kernel)
   if (w.converged && *w.converged != 0) return;
-  orth_pass<B>(w.Z, w.Q, w.G, sm);
+  const RowSlice sl = row_slice(w.G, csize);
+  orth_pass<B>(w.Z, w.Q, sl, sm);
   // CholeskyQR2: the second pass only when the first saw an ill-conditioned block
-  if (!sm.wellcond) orth_pass<B>(w.Q, w.Q, w.G, sm);
+  if (!sm.wellcond) orth_pass<B>(w.Q, w.Q, sl, sm);
 }
 
 // Rayleigh-Ritz: T = Q'Z (Z = C Q), eigen-decompose, rotate Q and Z to the Ritz basis (descending values),
 // test stagnation of the leading r Ritz values.
 template <int B>
 __global__ void __launch_bounds__(EIG_THREADS) eig_rr_kernel(const EigWork* __restrict__ works, int r, double tol,
-                                                             int finalize) {
+                                                             int finalize, int csize) {
   extern __shared__ __align__(16) unsigned char raw[];
   EigSmem<B>& sm = *reinterpret_cast<EigSmem<B>*>(raw);
-  const EigWork w = works[blockIdx.x];
+  const EigWork w = works[cluster_problem(csize)];
   if (*w.converged != 0) return;  // locked (see eig_orth_kernel): Q already holds the sorted Ritz vectors
   const int tid = threadIdx.x;
-  block_gram<B>(w.Q, w.Z, w.G, sm.S);
+  const RowSlice sl = row_slice(w.G, csize);
+  block_gram<B>(w.Q, w.Z, sl, sm.S, sm.W);
   for (int t = tid; t < B * B; t += EIG_THREADS) {
     const int i = t / B, j = t % B;
     if (i < j) {
@@ -427,28 +504,35 @@ __global__ void __launch_bounds__(EIG_THREADS) eig_rr_kernel(const EigWork* __re
   __syncthreads();
   for (int t = tid; t < B * B; t += EIG_THREADS) sm.W[t / B][t % B] = sm.S[t / B][t % B];
   __syncthreads();
-  if (tid < B) {
-    w.theta[tid] = sm.ev[tid];
-    sm.cs[tid] = 0.0;  // residual accumulators (cs holds 3*B/2 >= B doubles)
-  }
+  if (tid < B && sl.rank == 0) w.theta[tid] = sm.ev[tid];
   __syncthreads();
-  rows_times_matrix<B>(w.Q, w.Q, w.G, sm.W, sm.rowbuf);
-  rows_times_matrix<B>(w.Z, w.Z, w.G, sm.W, sm.rowbuf);
-  // residuals ||C q_j - theta_j q_j||^2 of the leading r Ritz pairs
+  rows_times_matrix<B>(w.Q, w.Q, sl.r0, sl.r1, sm.W, sm.rowbuf);
+  rows_times_matrix<B>(w.Z, w.Z, sl.r0, sl.r1, sm.W, sm.rowbuf);
+  // residuals ||C q_j - theta_j q_j||^2 of the leading r Ritz pairs: EIG_THREADS / B partial sums per column over the
+  // rows of this CTA (S is free by now), added in a fixed order, then summed over the cluster in rank order
   {
-    const int j = tid % B;
+    constexpr int NP = EIG_THREADS / B;
+    const int j = tid % B, part = tid / B;
     double acc = 0.0;
     if (j < r) {
       const double th = sm.ev[j];
-      for (int row = tid / B; row < w.G; row += EIG_THREADS / B) {
+      for (int row = sl.r0 + part; row < sl.r1; row += NP) {
         const double d = w.Z[(size_t)row * B + j] - th * w.Q[(size_t)row * B + j];
         acc = fma(d, d, acc);
       }
-      atomicAdd(&sm.cs[j], acc);
     }
+    sm.S[part][j] = acc;
+    __syncthreads();
+    if (tid < B) {
+      double tot = 0.0;
+#pragma unroll
+      for (int q = 0; q < NP; ++q) tot += sm.S[q][tid];
+      sm.cs[tid] = tot;  // cs holds 3 * B / 2 >= B doubles
+    }
+    __syncthreads();
+    cluster_sum_vector(sm.cs, B, &sm.rowbuf[0][0], sl);
   }
-  __syncthreads();
-  if (tid == 0) {
+  if (tid == 0 && sl.rank == 0) {
     double worst = 0.0;
     for (int j = 0; j < r; ++j) worst = fmax(worst, sqrt(sm.cs[j]));
     const double scale = fmax(fabs(sm.ev[0]), 1e-300);
@@ -467,9 +551,9 @@ __global__ void __launch_bounds__(EIG_THREADS) eig_rr_kernel(const EigWork* __re
   if (finalize) {
     for (size_t t = tid; t < (size_t)w.G * r; t += EIG_THREADS) {
       const int row = (int)(t % w.G), c = (int)(t / w.G);
-      w.V[t] = w.Q[(size_t)row * B + c];
+      if (row >= sl.r0 && row < sl.r1) w.V[t] = w.Q[(size_t)row * B + c];
     }
-    if (tid < r && w.theta_out) w.theta_out[tid] = sm.ev[tid];
+    if (tid < r && w.theta_out && sl.rank == 0) w.theta_out[tid] = sm.ev[tid];
   }
 }
 
@@ -558,20 +642,22 @@ __global__ void eig_cheb_kernel(const EigWork* __restrict__ W, const double* __r
 // directions is removed after every step:  Y <- Y - Q_L (Q_L' Y)  (Q_L = the first nlock columns of Q).
 template <int B>
 __global__ void __launch_bounds__(EIG_THREADS) eig_project_kernel(const EigWork* __restrict__ W,
-                                                                  const int* __restrict__ deg, int step) {
+                                                                  const int* __restrict__ deg, int step, int csize) {
   extern __shared__ __align__(16) unsigned char raw[];
   EigSmem<B>& sm = *reinterpret_cast<EigSmem<B>*>(raw);
-  const EigWork w = W[blockIdx.x];
+  const int prob = cluster_problem(csize);
+  const EigWork w = W[prob];
   if (*w.converged != 0) return;
-  const int m = deg[blockIdx.x];
+  const int m = deg[prob];
   if (step > m) return;
   const int nl = w.nlock ? *w.nlock : 0;
   if (nl == 0) return;
   double* Y = step == m ? w.Z : w.Q;
-  block_gram<B>(w.Q, Y, w.G, sm.S);   // S[l][j] = q_l' y_j
+  const RowSlice sl = row_slice(w.G, csize);
+  block_gram<B>(w.Q, Y, sl, sm.S, sm.W);   // S[l][j] = q_l' y_j
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int NC = B / 32;
-  for (int g = warp; g < w.G; g += EIG_THREADS / 32) {
+  for (int g = sl.r0 + warp; g < sl.r1; g += EIG_THREADS / 32) {
 #pragma unroll
     for (int u = 0; u < NC; ++u) sm.rowbuf[warp][lane + 32 * u] = w.Q[(size_t)g * B + lane + 32 * u];
     __syncwarp();
@@ -586,6 +672,31 @@ __global__ void __launch_bounds__(EIG_THREADS) eig_project_kernel(const EigWork*
     }
     __syncwarp();
   }
+}
+
+// <<<n_probs clusters of csize CTAs>>>
+template <class... KArgs, class... Args>
+void launch_clustered(void (*kernel)(KArgs...), int n_probs, int csize, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(n_probs * csize));
+  cfg.blockDim = dim3(EIG_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = csize > 1 ? 1 : 0;
+  CG_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
+// cluster width for problems of G rows: slices below ~250 rows are not worth the cluster barriers
+// and with hundreds of problems the single-CTA form already fills the machine (the repeated B x B factorisations of a
+// cluster would only add work: 496 CPCA problems ran 1.5x slower clustered)
+inline int eig_cluster_size(int maxG, int n_probs) {
+  if (maxG < 1024) return 1;
+  return n_probs <= 96 ? EIG_CLUSTER : (n_probs <= 192 ? 2 : 1);
 }
 
 // Generic FP64 driver: `matmul(works)` must fill Z = Op(Q) for every problem (Q, Z row-major [G][B] on the device).
@@ -632,8 +743,9 @@ void run_eig_generic(Context& ctx, const int* rows, double* const* Vout, double*
   CG_CUDA(cudaFuncSetAttribute(eig_rr_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CG_CUDA(cudaFuncSetAttribute(eig_project_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 gi((unsigned)(((size_t)maxG * B + 255) / 256), n_probs);
+  const int csize = eig_cluster_size(maxG, n_probs);
   eig_init_kernel<B><<<gi, 256, 0, s>>>(dw.p);
-  eig_orth_kernel<B><<<n_probs, EIG_THREADS, smem, s>>>(dw.p);
+  launch_clustered(eig_orth_kernel<B>, n_probs, csize, smem, s, (const EigWork*)dw.p, csize);
   ctx.stats.kernels += 2;
   std::vector<int> hc(n_probs, 0), hdeg(n_probs, 1);
   int applied = 0, outer = 0;
@@ -647,7 +759,7 @@ void run_eig_generic(Context& ctx, const int* rows, double* const* Vout, double*
     }
     {
       StageScope sc(ctx, "reduction.eig.rr");
-      eig_rr_kernel<B><<<n_probs, EIG_THREADS, smem, s>>>(dw.p, r, tol, 0);
+      launch_clustered(eig_rr_kernel<B>, n_probs, csize, smem, s, (const EigWork*)dw.p, r, tol, 0, csize);
       ctx.stats.kernels++;
       conv.download(hc.data(), (size_t)n_probs, s);
       CG_CUDA(cudaStreamSynchronize(s));
@@ -670,13 +782,13 @@ void run_eig_generic(Context& ctx, const int* rows, double* const* Vout, double*
         ++applied;
       }
       eig_cheb_kernel<B><<<dim3(cheb_blocks, n_probs), 256, 0, s>>>(dw.p, al.p, be.p, cc.p, deg.p, n_probs, i);
-      eig_project_kernel<B><<<n_probs, EIG_THREADS, smem, s>>>(dw.p, deg.p, i);
+      launch_clustered(eig_project_kernel<B>, n_probs, csize, smem, s, (const EigWork*)dw.p, (const int*)deg.p, i, csize);
       ctx.stats.kernels += 2;
     }
     {
       StageScope sc(ctx, "reduction.eig.orth");
       // converged problems are locked: every kernel of the loop skips them
-      eig_orth_kernel<B><<<n_probs, EIG_THREADS, smem, s>>>(dw.p);
+      launch_clustered(eig_orth_kernel<B>, n_probs, csize, smem, s, (const EigWork*)dw.p, csize);
       ctx.stats.kernels++;
     }
   }
@@ -1198,6 +1310,7 @@ void top_eigenvectors_shared_gram(Context& ctx, const TcEigSample* samples, int 
   CG_CUDA(cudaFuncSetAttribute(eig_orth_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CG_CUDA(cudaFuncSetAttribute(eig_rr_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned colblocks = (unsigned)n_cols_total;  // one CTA per column
+  const int csize = eig_cluster_size(maxG, n_probs);
   DevBuf<int> deg((size_t)n_probs);
   auto column = [&](int mode, const float* a, const float* b, const float* c, int step) {
     tc_column_kernel<<<colblocks, 256, 0, s>>>(dS.p, dP.p, dcs.p, dcl.p, (int)n_cols_total, mode, a, b, c, deg.p,
@@ -1218,7 +1331,7 @@ void top_eigenvectors_shared_gram(Context& ctx, const TcEigSample* samples, int 
     {
       StageScope sc(ctx, "reduction.eig.orth");
       tc_to64_kernel<<<g64, 256, 0, s>>>(dS.p, dP.p);
-      eig_orth_kernel<B><<<n_probs, EIG_THREADS, smem, s>>>(dw.p);
+      launch_clustered(eig_orth_kernel<B>, n_probs, csize, smem, s, (const EigWork*)dw.p, csize);
       ctx.stats.kernels += 2;
     }
     // Rayleigh-Ritz: Z = C Q through the shared Gram GEMM
@@ -1230,7 +1343,7 @@ void top_eigenvectors_shared_gram(Context& ctx, const TcEigSample* samples, int 
     }
     {
       StageScope sc(ctx, "reduction.eig.rr");
-      eig_rr_kernel<B><<<n_probs, EIG_THREADS, smem, s>>>(dw.p, r, tol, 0);
+      launch_clustered(eig_rr_kernel<B>, n_probs, csize, smem, s, (const EigWork*)dw.p, r, tol, 0, csize);
       ctx.stats.kernels++;
     }
     conv.download(hc.data(), (size_t)n_probs, s);

@@ -143,10 +143,119 @@ __device__ void block_bitonic(u64* s, int np, int tid, int nthreads) {
 
 constexpr int PARE_THREADS = 512;
 constexpr int PARE_SMEM_KEYS = 4096;
+constexpr int PARE_BINS = 4096;      // counting select: degrees below this many are binned in shared memory
+constexpr int PARE_LINE_MAX = 4096;  // ... for lines of at most this many stored entries
+
+// The entries a line loses are the m live ones with the highest opposite degree (ties: lowest position first).  That is
+// a selection, not a sort: degrees are small integers, so a histogram gives the cut degree d* (everything above it goes,
+// of the entries AT d* the first m - #above in position order go), and one ordered pass over the line removes them.
+// ~10 CTA barriers per line instead of the ~80 of a 4096-key bitonic sort; same result, tie rule included.
+// Returns false when the line does not qualify (too long / degrees too large): the caller sorts instead.
+__device__ bool pare_line_by_counting(const PareProblem& pb, int side, long long b, int len, int* __restrict__ N,
+                                      int* s_deg, int* s_hist, int* s_misc) {
+  if (len > PARE_LINE_MAX) return false;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = PARE_THREADS / 32;
+  // ---- degrees of the live entries (dead: -1), their number and maximum
+  __syncthreads();               // the previous line's readers of s_misc are done
+  if (tid < 4) s_misc[tid] = 0;  // [0] live, [1] max degree, [2] above klow, [3] scratch
+  __syncthreads();
+  int live = 0, dmax = 0, above = 0;
+  for (int t = tid; t < len; t += PARE_THREADS) {
+    const int ent = side == 0 ? (int)(b + t) : pb.row_perm[b + t];
+    int d = -1;
+    if (pb.alive[ent]) {
+      d = N[side == 0 ? pb.row[ent] : pb.col[ent]];
+      ++live;
+      dmax = max(dmax, d);
+      above += d > pb.klow ? 1 : 0;
+    }
+    s_deg[t] = d;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    live += __shfl_xor_sync(0xffffffffu, live, o);
+    above += __shfl_xor_sync(0xffffffffu, above, o);
+    dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+  }
+  if (lane == 0) {
+    atomicAdd(&s_misc[0], live);
+    atomicAdd(&s_misc[2], above);
+    atomicMax(&s_misc[1], dmax);
+  }
+  __syncthreads();
+  live = s_misc[0];
+  dmax = s_misc[1];
+  above = s_misc[2];
+  if (dmax >= PARE_BINS) return false;  // uniform: every thread read the same shared values
+  int m = live - pb.k;
+  if (above < m) m = above;
+  if (m <= 0) return true;  // nothing to remove (also uniform)
+  // ---- histogram of the degrees, cut degree d* = largest d with #(deg >= d) >= m
+  const int nb = dmax + 1;
+  for (int t = tid; t < nb; t += PARE_THREADS) s_hist[t] = 0;
+  __syncthreads();
+  for (int t = tid; t < len; t += PARE_THREADS)
+    if (s_deg[t] >= 0) atomicAdd(&s_hist[s_deg[t]], 1);
+  __syncthreads();
+  // suffix sums: thread t owns the bins [t * per, (t + 1) * per) counted from the TOP (bin index dmax - i)
+  const int per = (nb + PARE_THREADS - 1) / PARE_THREADS;
+  int mine = 0;
+  for (int i = tid * per; i < min(nb, (tid + 1) * per); ++i) mine += s_hist[dmax - i];
+  // exclusive prefix of `mine` over the threads (warp scan + warp totals)
+  int incl = mine;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  __shared__ int s_wtot[NW];
+  if (lane == 31) s_wtot[warp] = incl;
+  __syncthreads();
+  int base = 0;
+  for (int w2 = 0; w2 < warp; ++w2) base += s_wtot[w2];
+  int run = base + incl - mine;  // entries with degree above this thread's first bin
+  for (int i = tid * per; i < min(nb, (tid + 1) * per); ++i) {
+    const int d = dmax - i, c = s_hist[d];
+    if (run < m && run + c >= m) {  // exactly one (thread, bin) satisfies this
+      s_misc[1] = d;                // d*
+      s_misc[3] = m - run;          // how many entries at d* go
+    }
+    run += c;
+  }
+  __syncthreads();
+  const int dstar = s_misc[1], take_eq = s_misc[3];
+  // ---- ordered removal: every warp owns a contiguous piece of the line; entries at d* are ranked by position
+  const int piece = (len + NW - 1) / NW;
+  const int p0 = warp * piece, p1 = min(len, p0 + piece);
+  int eq = 0;
+  for (int t = p0 + lane; t < p1; t += 32) eq += s_deg[t] == dstar ? 1 : 0;
+  for (int o = 16; o > 0; o >>= 1) eq += __shfl_xor_sync(0xffffffffu, eq, o);
+  if (lane == 0) s_wtot[warp] = eq;
+  __syncthreads();
+  int before = 0;
+  for (int w2 = 0; w2 < warp; ++w2) before += s_wtot[w2];
+  for (int t0 = p0; t0 < p1; t0 += 32) {
+    const int t = t0 + lane;
+    const int d = t < p1 ? s_deg[t] : -1;
+    const unsigned eqm = __ballot_sync(0xffffffffu, d == dstar);
+    const int rank = before + __popc(eqm & ((1u << lane) - 1u));
+    if (d > dstar || (d == dstar && rank < take_eq)) {
+      const int ent = side == 0 ? (int)(b + t) : pb.row_perm[b + t];
+      pb.alive[ent] = 0;
+      N[side == 0 ? pb.row[ent] : pb.col[ent]] -= 1;  // opposite vertices are distinct inside a line
+    }
+    before += __popc(eqm);
+  }
+  __syncthreads();
+  return true;
+}
 
 // side 0: lines = columns, opposite = rows (N = rowN); side 1: lines = rows, opposite = columns (N = colN)
 __global__ void __launch_bounds__(PARE_THREADS) pare_kernel(const PareProblem* __restrict__ probs, int side) {
+  // sort keys; the counting select uses the same 32 KB as histogram (first PARE_BINS ints) + degree cache (the rest)
   __shared__ u64 skeys[PARE_SMEM_KEYS];
+  static_assert(PARE_SMEM_KEYS * 2 >= PARE_BINS + PARE_LINE_MAX, "shared memory of the counting select");
+  int* s_deg = reinterpret_cast<int*>(skeys) + PARE_BINS;
+  __shared__ int s_misc[4];
   __shared__ int s_cnt, s_above;
   const PareProblem pb = probs[blockIdx.x];
   if (pb.k < 0) return;
@@ -163,6 +272,8 @@ __global__ void __launch_bounds__(PARE_THREADS) pare_kernel(const PareProblem* _
     // only while that line is visited): nothing to pare
     const int* own = side == 0 ? pb.colN : pb.rowN;  // absent in the standalone pareDownHubEdges entry point
     if (own && own[line] <= pb.k) continue;
+    // selection by counting (the common case); the sort below serves very long lines and degrees >= PARE_BINS
+    if (pare_line_by_counting(pb, side, b, len, N, s_deg, reinterpret_cast<int*>(skeys), s_misc)) continue;
     // live entries of the line, compacted to the front (the sort below restores the order: the key carries the
     // position among the stored entries); only the live ones are sorted -- after the first pass of the ladder most
     // of a hub line is dead
@@ -475,13 +586,16 @@ void match_append_edges(Context& ctx, const MnnProblem* h_probs, int n_probs, in
   }
   cudaStream_t s = ctx.stream;
   // sub-batches bounded by the matched structures that are alive at the same time (~24 B per neighbour triple)
-  const size_t budget = (size_t)16 << 30;
+  // what stays alive per pair is the matched matrix (row, col, w, alive + the row permutation: 24 B per entry, at most
+  // (nA + nB) k1 / 2 entries); the triples of match_one are temporaries of one pair.  The greedy paring of a pair is
+  // sequential, so the throughput of the stage is the number of pairs a launch works on side by side.
+  const size_t budget = (size_t)40 << 30;
   int p0 = 0;
   while (p0 < n_probs) {
     int p1 = p0;
     size_t used = 0;
     while (p1 < n_probs && p1 - p0 < 1024) {
-      const size_t need = (size_t)(h_probs[p1].nA + h_probs[p1].nB) * (size_t)k1 * 24;
+      const size_t need = (size_t)(h_probs[p1].nA + h_probs[p1].nB) * (size_t)k1 * 12;
       if (p1 > p0 && used + need > budget) break;
       used += need;
       ++p1;

@@ -60,7 +60,7 @@ int cg_timer_stop(cg_context* ctx, double* ms);
  * Chebyshev-filtered iteration to irlba's own tolerance 1e-5) -- used by the parity tests */
 /* "knn_engine": 0 = automatic (two-phase tensor-core kernel; the streaming tensor-core kernel for small problems
  * and for blocks whose candidate lists overflow), 1 = streaming tensor-core kernel only, 2 = exact SIMT kernel
- * only.  "knn_cand_cap": candidate slots per (query row, half tile) of the two-phase kernel, 1..64 (tests
+ * only.  "knn_cand_cap": candidate slots per (query row, half tile) of the two-phase kernel, 1..96 (tests
  * shrink it to force the overflow path).  Results are identical for every setting.
  * "tc_eig_max_sweeps" (default 40): sweeps of the tensor-core eigen solver before a pair that has not reached
  * irlba's tolerance is handed to the FP64 driver (tests set 1 to force that path).
@@ -72,7 +72,7 @@ int cg_timer_stop(cg_context* ctx, double* ms);
  * "tc_projection" (default 1): in the default mode the projections of device-computed rotations run as one bf16x3
  * tensor-core GEMM per sample (fp32 accumulation); 0 keeps the FP64 sparse product, which the exact mode, cached
  * rotations and cg_keep_projections always use.
- * "max_batch_bytes" (default 24 GB): scratch budget of one batch of pairs inside cg_pairs_edges; the result never
+ * "max_batch_bytes" (default 48 GB): scratch budget of one batch of pairs inside cg_pairs_edges; the result never
  * depends on how the pair list is cut into batches (tests set 1 to get one pair per batch). */
 int cg_set_option(cg_context* ctx, const char* name, double value);
 /* counters: "knn_redo_blocks" (256-row blocks recomputed by the streaming kernel), "eig_redo_pairs" (pairs the

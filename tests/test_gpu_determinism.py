@@ -66,7 +66,7 @@ def test_graph_independent_of_batches(ctx):
         ctx.lib.cg_panel_drop_cache(con._panel)
         g1 = con.buildGraph(k=10, k_self=5, space="PCA", ncomps=20, n_odgenes=400)
     finally:
-        ctx.lib.cg_set_option(ctx.h, b"max_batch_bytes", float(24 << 30))
+        ctx.lib.cg_set_option(ctx.h, b"max_batch_bytes", float(48 << 30))
     assert np.array_equal(g1.vertices, ref[0]) and np.array_equal(g1.edge_from, ref[1])
     assert np.array_equal(g1.edge_to, ref[2]) and np.array_equal(g1.weight, ref[3])
     con.close()

@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1500 python -X faulthandler -m pytest tests/test_gpu_graph.py -q -x > gpurun_out/j_pytest.log 2>&1; echo "PYTEST_EXIT=$?" >> gpurun_out/j_pytest.log
+tail -4 gpurun_out/j_pytest.log
+timeout 900 python tools/profile_stages.py --config 2 --reps 2 2>/dev/null | tail -1 > gpurun_out/j_prof_config2.json
+python -c "
+import json; d=json.load(open('gpurun_out/j_prof_config2.json')); print('wall', round(d['wall_ms'],1), {k: round(v,2) for k,v in d['stages_ms'].items() if k.startswith('reduction')})"
