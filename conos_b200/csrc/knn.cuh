@@ -70,12 +70,12 @@ struct KnnItem {
 };
 
 // Two-phase tensor-core kernel (knn_tc2.cu): per-problem plan and scratch
-constexpr int KNN_TC2_CAND_STRIDE = 96;  // candidate slots per (query row, 64-column half)
+constexpr int KNN_TC2_CAND_STRIDE = 64;  // candidate slots per (query row, 64-column half)
 struct KnnTc2Aux {
   int sg = 0;   // columns per group inside a tile half: 64 (whole half), 32 or 16
-  int tg = 0;   // (sampled) tiles per group (sg == 64 only)
+  int tg = 0;   // tiles per group (sg == 64 only)
   int ngt = 0;  // groups per (row, half)
-  int astride = 1;  // the threshold phase looks at every astride-th reference tile (1 or 2)
+  int pad = 0;
   long long row0 = 0;   // first row of this problem in the chunk's scratch arrays
   int* cand = nullptr;  // [rows][2][KNN_TC2_CAND_STRIDE] reference indices that passed the filter
   int* cnt = nullptr;   // [rows][2] survivors seen (may exceed the capacity: overflow)

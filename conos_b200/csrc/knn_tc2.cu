@@ -9,9 +9,6 @@
 //            the groups partition the references.  tau = the k-th largest group maximum of a row: at least
 //            k references (one per group) have approximate score >= tau, hence the exact k-th best dot
 //            product is >= tau - eps, hence every true neighbour has approximate score >= tau - 2*eps.
-//            On large problems phase A only looks at every second reference tile: the k-th largest group maximum of
-//            that half still has k references above it (so nothing changes in the argument), the threshold is a
-//            little lower and the candidate lists about 1.5x longer -- a quarter of all tile passes for that.
 //   phase B  the same tensor-core products again, now with thr = tau - 2*margin riding in the spare K
 //            dimension (acc = dot - thr): ONE funnel shift per candidate collects the sign bits, and the few
 //            survivors (~1.2 k per row) are appended to the row's candidate list in HBM.  No feedback.
@@ -25,8 +22,6 @@
 // M=128 x N=128 accumulators per tile, double buffered = 512 TMEM columns), warps 2-17 epilogue: thread =
 // (query row, 64-column half), tcgen05.ld 32x32b.x16.
 #include <cuda_fp16.h>
-
-#include <algorithm>
 
 #include "knn.cuh"
 #include "ptx.cuh"
@@ -128,9 +123,8 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
         const __half* r_mma = reinterpret_cast<const __half*>(pb.r_tiled + round_up((size_t)pb.nr, KNN_ROW_PAD) * D_PAD);
         ptx::bulk_g2s(smA, q_mma + (size_t)wi.qblock * QBLOCK * D_PAD, C::A_BYTES, a_full);
         const int n_tiles = (pb.nr + TILE_N - 1) / TILE_N;
-        const int astride = auxs[wi.prob].astride;
         for (int ph2 = 0; ph2 < 2; ++ph2) {
-          for (int t = 0; t < n_tiles; t += (ph2 == 0 ? astride : 1)) {
+          for (int t = 0; t < n_tiles; ++t) {
             ptx::mbar_wait(b_empty + slot, ph ^ 1);
             ptx::mbar_arrive_expect_tx(b_full + slot, C::B_BYTES);
             ptx::bulk_g2s(smB + (size_t)slot * C::B_BYTES, r_mma + (size_t)t * TILE_N * D_PAD, C::B_BYTES,
@@ -161,11 +155,10 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
         const KnnItem wi = items[item];
         const int nr = probs[wi.prob].nr;
         const int n_tiles = (nr + TILE_N - 1) / TILE_N;
-        const int astride = auxs[wi.prob].astride;
         ptx::mbar_wait(a_full, it & 1);
         for (int ph2 = 0; ph2 < 2; ++ph2) {
           if (ph2 == 1) ptx::mbar_wait(thr_ready, it & 1);  // the rows' thresholds are in the A tile (FOLD)
-          for (int t = 0; t < n_tiles; t += (ph2 == 0 ? astride : 1)) {
+          for (int t = 0; t < n_tiles; ++t) {
             ptx::mbar_wait_a(b_full_a + slot * 8, ph);
             ptx::mbar_wait_a(acc_empty_a + stage * 8, aph ^ 1);
             ptx::tc_fence_after();
@@ -213,9 +206,7 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
       {
         float run = -INFINITY;
         int tcount = 0;
-        const int n_samp = (n_tiles + ax.astride - 1) / ax.astride;  // sampled tiles: ta-th is tile ta * astride
-        for (int ta = 0; ta < n_samp; ++ta, ++g) {
-          const int t = ta * ax.astride;
+        for (int t = 0; t < n_tiles; ++t, ++g) {
           const uint32_t stage = g & 1, aph = (g >> 1) & 1;
           ptx::mbar_wait_a(acc_full_a + stage * 8, aph);
           ptx::tc_fence_after();
@@ -247,17 +238,17 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
           }
           const float m0 = max16(v0), m1 = max16(v1), m2 = max16(v2), m3 = max16(v3);
           if (ax.sg == 16) {
-            gm[(4 * ta + 0) * 512] = m0;
-            gm[(4 * ta + 1) * 512] = m1;
-            gm[(4 * ta + 2) * 512] = m2;
-            gm[(4 * ta + 3) * 512] = m3;
+            gm[(4 * t + 0) * 512] = m0;
+            gm[(4 * t + 1) * 512] = m1;
+            gm[(4 * t + 2) * 512] = m2;
+            gm[(4 * t + 3) * 512] = m3;
           } else if (ax.sg == 32) {
-            gm[(2 * ta + 0) * 512] = fmaxf(m0, m1);
-            gm[(2 * ta + 1) * 512] = fmaxf(m2, m3);
+            gm[(2 * t + 0) * 512] = fmaxf(m0, m1);
+            gm[(2 * t + 1) * 512] = fmaxf(m2, m3);
           } else {
             run = fmaxf(fmaxf(run, fmaxf(m0, m1)), fmaxf(m2, m3));
-            if (++tcount == ax.tg || ta == n_samp - 1) {
-              gm[(ta / ax.tg) * 512] = run;
+            if (++tcount == ax.tg || t == n_tiles - 1) {
+              gm[(t / ax.tg) * 512] = run;
               run = -INFINITY;
               tcount = 0;
             }
@@ -496,8 +487,7 @@ knn_tc2_finish_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __r
     const int c = c0 + c1;
     if (c <= 32) finish_row<D_PAD, 1>(pb, cand, c0, c1, qrow, k, fold != 0, thr, lane, ok);
     else if (c <= 64) finish_row<D_PAD, 2>(pb, cand, c0, c1, qrow, k, fold != 0, thr, lane, ok);
-    else if (c <= 128) finish_row<D_PAD, 4>(pb, cand, c0, c1, qrow, k, fold != 0, thr, lane, ok);
-    else finish_row<D_PAD, 8>(pb, cand, c0, c1, qrow, k, fold != 0, thr, lane, ok);
+    else finish_row<D_PAD, 4>(pb, cand, c0, c1, qrow, k, fold != 0, thr, lane, ok);
   }
   if (!ok && lane == 0) blk_fail[item] = 1;
 }
@@ -518,42 +508,29 @@ void launch_main(Context& ctx, const KnnProblem* d_probs, const KnnTc2Aux* d_aux
 
 }  // namespace
 
-// groups of the threshold phase over `ns` sampled tiles whose last one has nvl valid columns
-static bool tc2_plan_groups(int ns, int nvl, int k, KnnTc2Aux& ax) {
+bool knn_tc2_plan(int nr, int k, KnnTc2Aux& ax) {
+  const int n_tiles = (nr + TILE_N - 1) / TILE_N;
   int valid;
-  if (ns >= 24) {
+  if (n_tiles >= 24) {
     ax.sg = 64;
-    ax.tg = (ns + NGT_MAX - 1) / NGT_MAX;
-    ax.ngt = (ns + ax.tg - 1) / ax.tg;
-    const int last_tiles = ns - (ax.ngt - 1) * ax.tg;
-    valid = 2 * ax.ngt - ((last_tiles == 1 && nvl <= 64) ? 1 : 0);
-  } else if (ns >= 12) {
+    ax.tg = (n_tiles + NGT_MAX - 1) / NGT_MAX;
+    ax.ngt = (n_tiles + ax.tg - 1) / ax.tg;
+    const int last_tiles = n_tiles - (ax.ngt - 1) * ax.tg;
+    const int nv_last = nr - (n_tiles - 1) * TILE_N;
+    valid = 2 * ax.ngt - ((last_tiles == 1 && nv_last <= 64) ? 1 : 0);
+  } else if (n_tiles >= 12) {
     ax.sg = 32;
     ax.tg = 1;
-    ax.ngt = 2 * ns;
-    valid = 4 * (ns - 1) + (nvl + 31) / 32;
+    ax.ngt = 2 * n_tiles;
+    valid = (nr + 31) / 32;
   } else {
     ax.sg = 16;
     ax.tg = 1;
-    ax.ngt = 4 * ns;
-    valid = 8 * (ns - 1) + (nvl + 15) / 16;
+    ax.ngt = 4 * n_tiles;
+    valid = (nr + 15) / 16;
   }
-  // at least 1.25 k non-empty groups keeps the candidate lists short and leaves >= 3 tiles per phase
-  return ns >= 3 && ax.ngt <= NGT_MAX && 4 * valid >= 5 * k;
-}
-
-bool knn_tc2_plan(int nr, int k, KnnTc2Aux& ax) {
-  const int n_tiles = (nr + TILE_N - 1) / TILE_N;
-  // large problems: thresholds from every second tile (see the header); the k-th largest group maximum of the sampled
-  // half is still backed by k references, so exactness is untouched -- only the candidate lists grow (~2 k per row)
-  if (n_tiles >= 48) {
-    const int ns = (n_tiles + 1) / 2, last = 2 * (ns - 1);
-    const int nvl = std::min(TILE_N, nr - last * TILE_N);
-    ax.astride = 2;
-    if (tc2_plan_groups(ns, nvl, k, ax)) return true;
-  }
-  ax.astride = 1;
-  return tc2_plan_groups(n_tiles, nr - (n_tiles - 1) * TILE_N, k, ax);
+  // at least 1.25 k non-empty groups keeps the candidate lists near 1.6 k and leaves >= 3 tiles per phase
+  return n_tiles >= 3 && ax.ngt <= NGT_MAX && 4 * valid >= 5 * k;
 }
 
 void knn_tc2_run(Context& ctx, const KnnProblem* d_probs, const KnnProblem* h_probs, const std::vector<int>& plist,
@@ -561,7 +538,7 @@ void knn_tc2_run(Context& ctx, const KnnProblem* d_probs, const KnnProblem* h_pr
   const bool fold = d < d_pad;
   int cap = ctx.knn_cand_cap;
   if (cap < 1 || cap > KNN_TC2_CAND_STRIDE) cap = KNN_TC2_CAND_STRIDE;
-  const size_t row_budget = (size_t)4 << 20;  // candidate lists: 768 B per query row
+  const size_t row_budget = (size_t)4 << 20;  // candidate lists: 512 B per query row
   size_t p0 = 0;
   while (p0 < plist.size()) {
     size_t rows = 0, p1 = p0;

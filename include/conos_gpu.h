@@ -60,7 +60,7 @@ int cg_timer_stop(cg_context* ctx, double* ms);
  * Chebyshev-filtered iteration to irlba's own tolerance 1e-5) -- used by the parity tests */
 /* "knn_engine": 0 = automatic (two-phase tensor-core kernel; the streaming tensor-core kernel for small problems
  * and for blocks whose candidate lists overflow), 1 = streaming tensor-core kernel only, 2 = exact SIMT kernel
- * only.  "knn_cand_cap": candidate slots per (query row, half tile) of the two-phase kernel, 1..96 (tests
+ * only.  "knn_cand_cap": candidate slots per (query row, half tile) of the two-phase kernel, 1..64 (tests
  * shrink it to force the overflow path).  Results are identical for every setting.
  * "tc_eig_max_sweeps" (default 40): sweeps of the tensor-core eigen solver before a pair that has not reached
  * irlba's tolerance is handed to the FP64 driver (tests set 1 to force that path).

@@ -582,7 +582,9 @@ def build_graph(samples: Dict[str, Sample], k: int = 15, k_self: int = 10, k_sel
                 metric: str = "angular", k1: Optional[int] = None, l2_sigma: float = 1e5, var_scale: bool = True,
                 ncomps: int = 40, n_odgenes: int = 2000, common_centering: bool = True,
                 score_component_variance: bool = False, balance_edge_weights: bool = False,
-                same_factor_downweight: float = 1.0, rotations: Optional[dict] = None):
+                same_factor_downweight: float = 1.0, rotations: Optional[dict] = None,
+                balancing_factor_per_cell: Optional[dict] = None, balancing_factor_per_sample: Optional[dict] = None,
+                k_same_factor: Optional[int] = None):
     """Returns dict(graph=assemble_graph(...), pairs={name: reduction}, edges=(from, to, w, type) pre-merge).
     `rotations` may supply per-pair reductions (keyed 'A.vs.B') so that the kNN stage can be compared with
     the same rot/u/v on both sides (hard part 3)."""
@@ -628,7 +630,12 @@ def build_graph(samples: Dict[str, Sample], k: int = 15, k_self: int = 10, k_sel
                 p1, p2 = red["u"], red["v"]
                 r1 = np.nonzero(red["keep"][0])[0]
                 r2 = np.nonzero(red["keep"][1])[0]
-            i, j, x = neighbor_matrix(p1, p2, k, k1, matching_method, metric, l2_sigma, cor_base)
+            # k.cur (R/conclass.R:230-233): pairs inside one balancing.factor.per.sample level use k.same.factor
+            k_cur = k
+            if balancing_factor_per_sample is not None and \
+                    balancing_factor_per_sample[na] == balancing_factor_per_sample[nb]:
+                k_cur = min(k if k_same_factor is None else k_same_factor, k1)
+            i, j, x = neighbor_matrix(p1, p2, k_cur, k1, matching_method, metric, l2_sigma, cor_base)
             ef.append(r1[i] + offs[na])
             et.append(r2[j] + offs[nb])
             ew.append(x)
@@ -647,8 +654,17 @@ def build_graph(samples: Dict[str, Sample], k: int = 15, k_self: int = 10, k_sel
     typ = np.concatenate(typ)
     g = assemble_graph(frm, to, w, typ)
     out = {"graph": g, "pairs": pairs, "edges": (frm, to, w, typ), "k1": k1, "cor_base": cor_base, "offsets": offs}
-    if balance_edge_weights:
+    # R/conclass.R:346-368: factor.per.cell = the caller's, else balancing.factor.per.sample[dataset], else the dataset
+    if balance_edge_weights or balancing_factor_per_cell is not None or balancing_factor_per_sample is not None:
         adj = adjacency_csr(g)
-        fac = np.concatenate([np.full(samples[n].counts.shape[0], t) for t, n in enumerate(names)])
-        out["balanced"] = adjust_weights_by_cell_balancing(adj, fac[g["vertices"]], True, same_factor_downweight)
+        if balancing_factor_per_cell is not None:
+            cells = np.concatenate([np.asarray(samples[n].cells, dtype=object) for n in names])
+            fac = np.array([str(balancing_factor_per_cell[c]) for c in cells], dtype=object)
+        elif balancing_factor_per_sample is not None:
+            fac = np.concatenate([np.full(samples[n].counts.shape[0], str(balancing_factor_per_sample[n]), dtype=object)
+                                  for n in names])
+        else:
+            fac = np.concatenate([np.full(samples[n].counts.shape[0], str(n), dtype=object) for n in names])
+        out["balanced"] = adjust_weights_by_cell_balancing(adj, fac[g["vertices"]].astype(str), balance_edge_weights,
+                                                           same_factor_downweight)
     return out

@@ -183,6 +183,41 @@ def test_balance_edge_weights(ctx, oracle, small_panel):
     np.testing.assert_allclose(b.data, a.data, rtol=1e-5)
 
 
+@pytest.mark.parametrize("mode", ["per_sample", "per_cell"])
+def test_balancing_factors_and_k_same_factor(ctx, oracle, small_panel, mode):
+    """balancing.factor.per.sample (with k.same.factor: k.cur of the pairs inside one level, R/conclass.R:230-233),
+    balancing.factor.per.cell and same.factor.downweight (R/conclass.R:346-368, R/conos.R:936-967) through
+    buildGraph: the 50 balancing rounds run as one device call."""
+    import conos_b200
+    osamples = to_oracle_samples(oracle, small_panel)
+    names = list(small_panel)
+    kw = dict(k=10, k_self=5, space="PCA", ncomps=20, n_odgenes=300, same_factor_downweight=0.5)
+    if mode == "per_sample":
+        extra = dict(balancing_factor_per_sample={names[0]: "x", names[1]: "x", names[2]: "y"}, k_same_factor=4,
+                     balance_edge_weights=True)
+    else:
+        per_cell = {c: ("a" if t % 3 else "b") for n in names for t, c in enumerate(small_panel[n].cells)}
+        extra = dict(balancing_factor_per_cell=per_cell, balance_edge_weights=False)
+    ref = oracle.build_graph(osamples, **kw, **extra)
+    con = conos_b200.Conos(small_panel, ctx=ctx)
+    con.pairs["PCA"] = {key: {"CPC": red["CPC"], "genes": red["genes"]} for key, red in ref["pairs"].items()}
+    g = con.buildGraph(**kw, **extra)
+    ri, ci, w = ref["balanced"]
+    a = sp.csc_matrix((w, (ri, ci)), shape=(len(g.vertices),) * 2).tocsr()
+    a.sort_indices()
+    b = g.as_adj()
+    assert np.array_equal(g.vertices, ref["graph"]["vertices"])
+    assert np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices)
+    np.testing.assert_allclose(b.data, a.data, rtol=1e-6)
+    # the edge list follows the adjacency matrix, the type attribute is gone (graph rebuilt from the matrix)
+    up = sp.triu(b, k=1).tocoo()
+    o = np.lexsort((up.col, up.row))
+    assert np.array_equal(g.edge_from, up.row[o]) and np.array_equal(g.edge_to, up.col[o])
+    np.testing.assert_allclose(g.weight, up.data[o], rtol=0, atol=0)
+    assert (g.type == -1).all()
+    con.close()
+
+
 def test_reference_wij(ctx, oracle, small_panel):
     import conos_b200
     from conos_b200 import ops

@@ -149,7 +149,7 @@ def test_two_phase_overflow_blocks_are_recomputed(ctx, oracle):
         ctx.check(ctx.lib.cg_set_option(ctx.h, b"knn_cand_cap", 4.0))
         idx, dist = ops.crossKnn(A, B, 30, "angular", ctx=ctx)
     finally:
-        ctx.lib.cg_set_option(ctx.h, b"knn_cand_cap", 96.0)
+        ctx.lib.cg_set_option(ctx.h, b"knn_cand_cap", 64.0)
     assert _stat(ctx, "knn_redo_blocks") > before
     assert np.array_equal(idx, oi)
     assert np.array_equal(dist.view(np.uint32), od.view(np.uint32))
