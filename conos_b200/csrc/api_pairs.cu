@@ -133,7 +133,9 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
   CG_CHECK(P.metric == CG_METRIC_ANGULAR || P.metric == CG_METRIC_L2,
            "only the following distance metrics are currently supported: ['L2' 'angular']");
   CG_CHECK(P.k1 >= P.k && P.k >= 1, "k1 must be >= k");
-  CG_CHECK(P.ncomps >= 1 && P.ncomps <= 64, "ncomps must be in 1..64");  // TODO(K-loop over 64-wide slabs)
+  // the common space: up to 64 components on the tensor cores, 65..112 through the exact SIMT kNN kernel (the device
+  // eigen solvers deliver at most 56 vectors per sample: PCA r = round(ncomps / 2) <= 56, CPCA / CCA ncomps <= 56)
+  CG_CHECK(P.ncomps >= 1 && P.ncomps <= 112, "ncomps must be in 1..112");
   Context& c = ctx->c;
   CG_CUDA(cudaSetDevice(c.device));
   CG_BIND(ctx);
@@ -244,7 +246,7 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
         B.nb = sb.n_cells;
         B.d = R.d;  // min(ncomps, ncol(rot)) -- R/conclass.R:254-258
       }
-      B.d_pad = B.d <= 32 ? 32 : 64;
+      B.d_pad = knn_d_pad(B.d);
       CG_CHECK(d_all < 0 || d_all == B.d, "all pairs of one call must share the number of components");
       d_all = B.d;
       d_pad_all = B.d_pad;
@@ -500,7 +502,9 @@ int cg_local_edges(cg_context* ctx, cg_panel* panel, const int32_t* samples, int
     CG_CHECK(samples[t] >= 0 && samples[t] < (int)panel->samples.size(), "no such sample");
     Sample& s = panel->samples[samples[t]];
     CG_CHECK(s.n_pcs > 0, "PCA must be estimated for all samples");
-    CG_CHECK(s.n_pcs <= 64, "at most 64 PCA columns per sample are supported for the local neighbours");
+    // pagoda2's default nPcs is 100 (R/access_wrappers.R:9 hands over whatever the sample carries): up to 64 columns run
+    // on the tensor cores, 65..128 through the exact SIMT kernel
+    CG_CHECK(s.n_pcs <= KNN_MAX_D, "at most 128 PCA columns per sample are supported for the local neighbours");
     if (s.pca_metric != P.metric) {
       s.pca_tiled.alloc(KnnPanel::elems(s.n_cells, s.n_pcs));
       KnnPanel pn;
@@ -517,7 +521,7 @@ int cg_local_edges(cg_context* ctx, cg_panel* panel, const int32_t* samples, int
     for (auto& kv : by_d) {
       DevBuf<KnnProblem> dk;
       dk.upload(kv.second.data(), kv.second.size(), c.stream);
-      knn_launch(c, dk.p, kv.second.data(), (int)kv.second.size(), kp1, kv.first <= 32 ? 32 : 64, kv.first,
+      knn_launch(c, dk.p, kv.second.data(), (int)kv.second.size(), kp1, knn_d_pad(kv.first), kv.first,
                  (Metric)P.metric);
       CG_CUDA(cudaStreamSynchronize(c.stream));
     }

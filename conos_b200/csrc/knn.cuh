@@ -28,6 +28,9 @@
 namespace cg {
 
 constexpr int KNN_ROW_PAD = 256;  // panel rows are padded to a multiple of this
+constexpr int KNN_MAX_D = 128;    // widest panel: the tensor-core kernels serve d <= 64, the exact SIMT kernel d <= 128
+// padded width of a d-column panel
+__host__ __device__ inline int knn_d_pad(int d) { return d <= 32 ? 32 : (d <= 64 ? 64 : 128); }
 constexpr int KNN_TC_MAXK = 32;   // largest k served by the tensor-core kernel
 
 enum Metric : int { METRIC_ANGULAR = 0, METRIC_L2 = 1 };
@@ -35,11 +38,11 @@ enum Metric : int { METRIC_ANGULAR = 0, METRIC_L2 = 1 };
 struct KnnPanel {
   int n = 0;      // valid rows
   int d = 0;      // valid columns
-  int d_pad = 0;  // 32 or 64
+  int d_pad = 0;  // 32, 64 or 128
   int n_pad = 0;  // multiple of KNN_ROW_PAD
   // 2.5 * n_pad * d_pad floats (not owned): the exact fp32 panel (tiled), its fp16 copy, the exact panel row-major
   float* tiled = nullptr;
-  static size_t elems(int n, int d) { return round_up(n, KNN_ROW_PAD) * (size_t)(d <= 32 ? 32 : 64) * 5 / 2; }
+  static size_t elems(int n, int d) { return round_up(n, KNN_ROW_PAD) * (size_t)knn_d_pad(d) * 5 / 2; }
 };
 
 __host__ __device__ inline size_t knn_tiled_offset(int row, int col, int d_pad) {

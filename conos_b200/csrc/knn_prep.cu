@@ -61,7 +61,8 @@ void prep(Context& ctx, const SrcT* d_src, int n, int d, int ld, Metric metric, 
   CG_CHECK(d >= 1 && d <= 64, "kNN supports 1..64 components");
   out.n = n;
   out.d = d;
-  out.d_pad = d <= 32 ? 32 : 64;
+  CG_CHECK(d >= 1 && d <= KNN_MAX_D, "kNN panels hold 1..128 columns");
+  out.d_pad = knn_d_pad(d);
   out.n_pad = (int)round_up(n, KNN_ROW_PAD);
   CG_CHECK(out.tiled != nullptr, "panel storage missing");
   int threads = 128;

@@ -124,10 +124,13 @@ void knn_simt_launch(Context& ctx, const KnnProblem* d_probs, const KnnProblem* 
     if (d_pad == 32) {
       CG_CUDA(cudaFuncSetAttribute(knn_simt_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       knn_simt_kernel<32><<<grid, SIMT_WARPS * 32, smem, ctx.stream>>>(d_probs + p0, k, (int)metric, d);
-    } else {
-      CG_CHECK(d_pad == 64, "d_pad must be 32 or 64");
+    } else if (d_pad == 64) {
       CG_CUDA(cudaFuncSetAttribute(knn_simt_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       knn_simt_kernel<64><<<grid, SIMT_WARPS * 32, smem, ctx.stream>>>(d_probs + p0, k, (int)metric, d);
+    } else {
+      CG_CHECK(d_pad == 128, "d_pad must be 32, 64 or 128");
+      CG_CUDA(cudaFuncSetAttribute(knn_simt_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      knn_simt_kernel<128><<<grid, SIMT_WARPS * 32, smem, ctx.stream>>>(d_probs + p0, k, (int)metric, d);
     }
     ctx.stats.kernels++;
     CG_CUDA(cudaGetLastError());

@@ -570,6 +570,10 @@ void knn_tc_launch(Context& ctx, const KnnProblem* d_probs, const KnnProblem* h_
 
 void knn_launch(Context& ctx, const KnnProblem* d_probs, const KnnProblem* h_probs, int n_probs, int k, int d_pad,
                 int d, Metric metric) {
+  if (d_pad > 64) {  // wider than the tensor-core kernels' operand tiles: exact SIMT search
+    knn_simt_launch(ctx, d_probs, h_probs, n_probs, k, d_pad, d, metric);
+    return;
+  }
   if (metric == METRIC_ANGULAR && k <= KNN_TC_MAXK && ctx.knn_engine != 2) {
     knn_tc_launch(ctx, d_probs, h_probs, n_probs, k, d_pad, d);
     return;

@@ -276,7 +276,8 @@ void project_and_prep(Context& ctx, const ProjProblem* h_probs, int n_probs, int
     int np = n_probs - p0 < 65535 ? n_probs - p0 : 65535;
     dim3 grid((max_pad + 7) / 8, np);
     if (d_pad == 32) project_kernel<32><<<grid, 256, 0, ctx.stream>>>(dp.p + p0, d, (int)metric);
-    else project_kernel<64><<<grid, 256, 0, ctx.stream>>>(dp.p + p0, d, (int)metric);
+    else if (d_pad == 64) project_kernel<64><<<grid, 256, 0, ctx.stream>>>(dp.p + p0, d, (int)metric);
+    else project_kernel<128><<<grid, 256, 0, ctx.stream>>>(dp.p + p0, d, (int)metric);
     ctx.stats.kernels++;
   }
   CG_CUDA(cudaGetLastError());

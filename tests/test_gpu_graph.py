@@ -110,6 +110,34 @@ def test_local_edges_and_merge(ctx, oracle, small_panel):
     assert (g.type == 0).all()
 
 
+def test_local_edges_with_100_pcs_and_wide_common_space(ctx, oracle):
+    """Per-sample PCA with pagoda2's default 100 columns (local neighbours through the exact SIMT kNN kernel) and a
+    common space of 70 components (PCA, r = 35 per sample: FP64 eigen driver, projection and kNN with 128-wide
+    panels): the whole graph against the oracle with the oracle's rotations."""
+    import conos_b200
+    from conos_b200.panel import make_panel
+    panel = make_panel(13, 2, [500, 420], n_genes=300, n_types=5, n_pcs=100, use_torch=False)
+    osamples = to_oracle_samples(oracle, panel)
+    ref = oracle.build_graph(osamples, k=10, k_self=6, space="PCA", ncomps=70, n_odgenes=300)
+    con = conos_b200.Conos(panel, ctx=ctx)
+    con.pairs["PCA"] = {key: {"CPC": red["CPC"], "genes": red["genes"]} for key, red in ref["pairs"].items()}
+    g = con.buildGraph(k=10, k_self=6, space="PCA", ncomps=70, n_odgenes=300)
+    _graphs_equal(g, ref["graph"], rtol=1e-6)
+    # and with the rotation computed on the device (exact mode): 35 eigenvectors per sample
+    con2 = conos_b200.Conos(panel, ctx=ctx)
+    ctx.lib.cg_set_option(ctx.h, b"exact_reduction", 1.0)
+    try:
+        g2 = con2.buildGraph(k=10, k_self=6, space="PCA", ncomps=70, n_odgenes=300)
+    finally:
+        ctx.lib.cg_set_option(ctx.h, b"exact_reduction", 0.0)
+    assert con2.pairs["PCA"][list(ref["pairs"])[0]]["CPC"].shape == (300, 70)
+    a = {(x, y) for x, y in zip(g2.vertices[g2.edge_from].tolist(), g2.vertices[g2.edge_to].tolist())}
+    b = {(x, y) for x, y in zip(g.vertices[g.edge_from].tolist(), g.vertices[g.edge_to].tolist())}
+    assert len(a & b) / len(a | b) > 0.98
+    con.close()
+    con2.close()
+
+
 def test_assemble_graph_semantics(ctx, oracle):
     """w <= 0 rows dropped before vertex numbering, loops removed, multi-edges summed in table order, type = first."""
     rng = np.random.default_rng(4)

@@ -213,3 +213,21 @@ def test_large_k_mass_duplicates_fall_back(ctx, oracle):
     assert np.array_equal(idx, oi)
     assert np.array_equal(dist.view(np.uint32), od.view(np.uint32))
     assert _stat(ctx, "knn_redo_blocks") > before
+
+
+@pytest.mark.parametrize("nA,nB,d,k,metric", [(700, 1500, 100, 15, "angular"), (300, 900, 128, 11, "angular"),
+                                               (400, 600, 65, 6, "L2")])
+def test_wide_panels_simt_path(ctx, oracle, nA, nB, d, k, metric):
+    """65..128 columns (pagoda2's default nPcs is 100; N2R::Knn takes whatever getPca returns, R/conos.R:595):
+    wider than the tensor-core operand tiles, served by the exact SIMT kernel -- bit-exact like every other path."""
+    from conos_b200 import ops
+    rng = np.random.default_rng(d * 1000 + k)
+    A, B = rng.normal(size=(nA, d)), rng.normal(size=(nB, d))
+    iab, dab, iba, dba = ops.crossKnn(A, B, k, metric, ctx=ctx, both=True)
+    oi, od = oracle.cross_knn(A, B, k, metric)
+    assert np.array_equal(iab, oi) and np.array_equal(dab.view(np.uint32), od.view(np.uint32))
+    oi, od = oracle.cross_knn(B, A, k, metric)
+    assert np.array_equal(iba, oi) and np.array_equal(dba.view(np.uint32), od.view(np.uint32))
+    si, sd = ops.Knn(A, k, metric, ctx=ctx)
+    oi, od = oracle.self_knn(A, k, metric)
+    assert np.array_equal(si, oi) and np.array_equal(sd.view(np.uint32), od.view(np.uint32))
