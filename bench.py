@@ -51,9 +51,9 @@ CONFIGS = {
 # dram__bytes_read.sum + dram__bytes_write.sum of the cross-kNN launch of configs[1] on one GPU (56 problems of
 # 50k x 50k = 1.4e11 scores), main kernel + finish kernel, from the ncu --set full capture summarised in profiles/.
 # A launch on a rank of an N-GPU run scans fewer scores: `traffic` is this figure scaled by the scores of the launch.
-KNN_DRAM_BYTES_CAPTURED = 0.354947e9 + 0.564263e9 + 1.114550e9 + 0.640961e9
+KNN_DRAM_BYTES_CAPTURED = 0.352433e9 + 0.561278e9 + 1.113896e9 + 0.642316e9
 KNN_DRAM_SCORES_CAPTURED = 56 * 50000.0 * 50000.0
-KNN_DRAM_SOURCE = ("profiles/r01_ncu_knn_tc2_bench_config2.txt: dram read+write of knn_tc2_kernel + "
+KNN_DRAM_SOURCE = ("profiles/r02_ncu_knn_tc2_config2.txt: dram read+write of knn_tc2_kernel + "
                    "knn_tc2_finish_kernel for the cross-kNN launch of configs[1] on one GPU (1.4e11 scores), scaled by "
                    "the scores of this run's average launch; the excess over the algorithmic bytes is the candidate "
                    "lists (written by the filter phase, read by the finish kernel) and the fp16 operand copies")
@@ -291,6 +291,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end loop (profiling runs)")
     ap.add_argument("--no-check", action="store_true", help="skip the single-rank / oracle graph checks")
+    ap.add_argument("--no-atlas", action="store_true",
+                    help="skip the atlas sub-record (configs[3]: 100 samples x 10k cells, the scaling workload)")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     reduced = False
@@ -496,6 +498,47 @@ def main():
             hsum = torch.tensor([float(h2d)], device="cuda")
             dist.all_reduce(hsum)
             h2d = int(hsum.item())
+    # ---- atlas sub-record: BASELINE configs[3], the workload north_star names for 1 -> 8 GPU scaling
+    atlas = None
+    if args.config == 2 and not args.no_atlas and not reduced:
+        acfg = CONFIGS[4]
+        con._drop_panel()
+        t_a = time.perf_counter()
+        apanel = make_panel(4, acfg["n_samples"], acfg["n_cells"], acfg["n_genes"])
+        t_a = time.perf_counter() - t_a
+        acon = conos_b200.Conos(apanel, ctx=ctx)
+        akw = dict(k=acfg["k"], k_self=acfg["k_self"], space=acfg["space"], ncomps=acfg["ncomps"],
+                   n_odgenes=acfg["n_genes"])
+
+        def atlas_step():
+            acon.pairs = {}
+            if acon._panel is not None:
+                lib.cg_panel_drop_cache(acon._panel)
+            return acon.buildGraph(fetch=False, world=wtuple, **akw)
+        atlas_step()
+        barrier()
+        gc.disable()
+        t0 = time.perf_counter()
+        KA = 2
+        for _ in range(KA):
+            ga = atlas_step()
+        barrier()
+        a_s = time.perf_counter() - t0
+        gc.enable()
+        if world > 1:
+            import torch.distributed as dist
+            tmax = torch.tensor([a_s], device="cuda")
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            a_s = float(tmax.item())
+        n_ap = acfg["n_samples"] * (acfg["n_samples"] - 1) // 2
+        atlas = {"workload": acfg["workload"], "value": n_ap * KA / a_s, "unit": "pairs/s", "steps": KA, "warmup": 1,
+                 "ms_per_step": 1e3 * a_s / KA, "n_gpus": world, "pairs": n_ap,
+                 "graph_edges": getattr(ga, "n_edges_device", None) if ga is not None else None,
+                 "samples_resident_rank0": None if acon._panel_key[2] is None else len(acon._panel_key[2]),
+                 "panel_generation_s": t_a,
+                 "note": "device-resident, one buildGraph per step, wall clock between barriers, max over ranks"}
+        acon.close()
+        del apanel
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
@@ -525,13 +568,13 @@ def main():
                 "scores_scanned_per_s": knn_scores / knn_s if knn_s > 0 else 0.0,
                 "algorithmic_bytes_per_launch": kb.value / n_l,
                 "share_of_step": knn_s / (dev_ms * 1e-3) if dev_ms > 0 else None,
-                "tensor_pipe_active_pct_ncu": 28.2,
+                "tensor_pipe_active_pct_ncu": 28.3,
                 "note": "achieved = SURVEY 8(d) flops (2*n_a*n_b*ncomps per sample pair, one distance matrix for both "
                         "directions; 2*n^2*ncomps for the self search) / CUDA-event time of the kNN launches on the "
                         "launching stream (both kernels and the overflow check); the kernel computes each direction "
                         "separately, twice (threshold phase, filter phase), with K padded 30 -> 32, so the tensor pipe "
                         "issues 4.27x these flops; tensor_pipe_active_pct_ncu is sm__pipe_tensor_subunit busy of the "
-                        "committed ncu capture (profiles/), see DESIGN.md K2"}
+                        "committed ncu capture (profiles/r02_ncu_knn_tc2_config2.txt), see DESIGN.md K2"}
     line = {"metric": "buildGraph sample-pairs/s", "value": n_pairs * K / (dev_ms * 1e-3), "unit": "pairs/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -544,6 +587,8 @@ def main():
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
     if rank_stats is not None:
         line["ranks"] = rank_stats
+    if atlas is not None:
+        line["atlas"] = atlas
     if e2e_s is not None:
         each = sorted(x["ms"] for x in e2e_each)
         line["e2e"] = {"value": n_pairs * K2 / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": h2d,

@@ -58,7 +58,6 @@ __global__ void knn_prep_kernel(const SrcT* __restrict__ src, int n, int d, int 
 
 template <class SrcT, bool COLMAJOR>
 void prep(Context& ctx, const SrcT* d_src, int n, int d, int ld, Metric metric, KnnPanel& out) {
-  CG_CHECK(d >= 1 && d <= 64, "kNN supports 1..64 components");
   out.n = n;
   out.d = d;
   CG_CHECK(d >= 1 && d <= KNN_MAX_D, "kNN panels hold 1..128 columns");

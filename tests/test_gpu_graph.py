@@ -30,6 +30,33 @@ def test_neighbor_matrix_mnn(ctx, oracle, n1, n2, d, k, cor_base):
     assert len(i) > 0 and x.min() >= 1e-5
 
 
+@pytest.mark.parametrize("matching,k,k1", [("mNN", 12, 12), ("NN", 8, 8), ("mNN", 6, 30)])
+def test_neighbor_matrix_l2_metric(ctx, oracle, matching, k, k1):
+    """metric = 'L2': squared Euclidean distances, similarity exp(-d / l2.sigma) (R/conos.R:767-773) -- matching,
+    the min.similarity cut and hub paring on L2 similarities, against the oracle."""
+    from conos_b200 import ops
+    rng = np.random.default_rng(31 + k)
+    p1, p2 = rng.normal(size=(450, 25)), rng.normal(size=(380, 25)) + 0.2
+    for sigma in (1e5, 30.0):
+        i, j, x = ops.getNeighborMatrix(p1, p2, k, k1, matching, "L2", l2_sigma=sigma, ctx=ctx)
+        oi, oj, ox = oracle.neighbor_matrix(p1, p2, k, k1, matching, "L2", sigma)
+        assert np.array_equal(i, oi) and np.array_equal(j, oj)
+        np.testing.assert_allclose(x, ox, rtol=1e-12)
+
+
+def test_build_graph_l2_metric(ctx, oracle, small_panel):
+    """buildGraph(metric = 'L2') end to end with the oracle's rotations: inter-sample and local edges carry
+    exp(-d / l2.sigma) similarities."""
+    import conos_b200
+    osamples = to_oracle_samples(oracle, small_panel)
+    ref = oracle.build_graph(osamples, k=10, k_self=5, space="PCA", ncomps=20, n_odgenes=300, metric="L2", l2_sigma=50.0)
+    con = conos_b200.Conos(small_panel, ctx=ctx)
+    con.pairs["PCA"] = {key: {"CPC": red["CPC"], "genes": red["genes"]} for key, red in ref["pairs"].items()}
+    g = con.buildGraph(k=10, k_self=5, space="PCA", ncomps=20, n_odgenes=300, metric="L2", l2_sigma=50.0)
+    _graphs_equal(g, ref["graph"], rtol=1e-6)
+    con.close()
+
+
 def test_neighbor_matrix_negative_correlation_dropped(ctx, oracle):
     """distance >= cor.base gives similarity 0: such pairs are dropped even when mutual (drop0)."""
     from conos_b200 import ops
@@ -130,7 +157,9 @@ def test_local_edges_with_100_pcs_and_wide_common_space(ctx, oracle):
         g2 = con2.buildGraph(k=10, k_self=6, space="PCA", ncomps=70, n_odgenes=300)
     finally:
         ctx.lib.cg_set_option(ctx.h, b"exact_reduction", 0.0)
-    assert con2.pairs["PCA"][list(ref["pairs"])[0]]["CPC"].shape == (300, 70)
+    key0 = list(ref["pairs"])[0]
+    assert con2.pairs["PCA"][key0]["CPC"].shape == ref["pairs"][key0]["CPC"].shape
+    assert con2.pairs["PCA"][key0]["CPC"].shape[1] == 70
     a = {(x, y) for x, y in zip(g2.vertices[g2.edge_from].tolist(), g2.vertices[g2.edge_to].tolist())}
     b = {(x, y) for x, y in zip(g.vertices[g.edge_from].tolist(), g.vertices[g.edge_to].tolist())}
     assert len(a & b) / len(a | b) > 0.98
