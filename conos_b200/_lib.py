@@ -73,6 +73,7 @@ SIGNATURES = {
     "cg_pairs_edges": (C.c_int, [_VP, _VP, C.POINTER(CgPair), C.c_int, C.POINTER(CgParams), C.POINTER(_VP), c_i64_p]),
     "cg_pair_reduction": (C.c_int, [_VP, C.c_int, c_int_p, c_int_p, c_dbl_p, c_dbl_p]),
     "cg_pair_cca": (C.c_int, [_VP, C.c_int, c_int_p, c_int_p, c_int_p, c_dbl_p, c_dbl_p, c_int_p, c_int_p, c_dbl_p]),
+    "cg_pair_reductions_all": (C.c_int, [_VP, c_int_p, c_int_p, c_i64_p, c_dbl_p, C.c_int64]),
     "cg_pair_cpca": (C.c_int, [_VP, C.c_int, c_int_p, c_dbl_p, c_dbl_p]),
     "cg_pair_cca_loadings": (C.c_int, [_VP, C.c_int, c_int_p, c_int_p, c_dbl_p, c_dbl_p, c_dbl_p]),
     "cg_keep_projections": (C.c_int, [_VP, C.c_int]),
@@ -106,6 +107,7 @@ SIGNATURES = {
                                      C.POINTER(CgParams), C.POINTER(_VP)]),
     "cg_job_pair_location": (C.c_int, [_VP, C.c_int, c_int_p, c_int_p]),
     "cg_panel_share_grams": (C.c_int, [_VP, _VP, c_int_p, c_int_p]),
+    "cg_partition_units": (C.c_int, [c_dbl_p, C.c_int, C.c_int, c_dbl_p, c_int_p]),
     "cg_edges_allgatherv": (C.c_int, [_VP, C.POINTER(_VP), c_int_p, c_i64_p, C.c_int]),
     "cg_assemble_graph": (C.c_int, [_VP, _VP, C.c_int32, C.POINTER(_VP)]),
     "cg_graph_sizes": (C.c_int, [_VP, c_int_p, c_i64_p]),

@@ -385,12 +385,12 @@ class Conos:
             self.ctx.check(lib.cg_partition_pairs(ptr(pa, C.c_int32), ptr(pb_, C.c_int32), ptr(cost, C.c_double),
                                                   n_pairs, ptr(scost, C.c_double), len(names), world_size,
                                                   ptr(pair_owner, C.c_int32)))
-            if k_self > 0:   # the local-neighbour searches (R/conos.R:589) are units of their own: cells^2 each
-                sidx = np.arange(len(names), dtype=np.int32)
-                lcost = n_cells ** 2
-                self.ctx.check(lib.cg_partition_pairs(ptr(sidx, C.c_int32), ptr(sidx, C.c_int32),
-                                                      ptr(lcost, C.c_double), len(names), None, len(names),
-                                                      world_size, ptr(sample_owner, C.c_int32)))
+            if k_self > 0:   # the local-neighbour searches (R/conos.R:589) are units of their own (~0.4 cells^2 in
+                # pair-cost units: one direction, no reduction / projection); they go to the ranks the pairs left light
+                lcost = 0.4 * n_cells ** 2
+                pload = np.bincount(pair_owner, weights=cost, minlength=world_size).astype(np.float64)
+                self.ctx.check(lib.cg_partition_units(ptr(lcost, C.c_double), len(names), world_size,
+                                                      ptr(pload, C.c_double), ptr(sample_owner, C.c_int32)))
             mine = np.flatnonzero(pair_owner == rank)
             need_counts = {names[t] for t in set(pa[mine].tolist()) | set(pb_[mine].tolist())}
             need_pca = {names[t] for t in np.flatnonzero(sample_owner == rank)} if k_self > 0 else set()
@@ -656,6 +656,21 @@ class Conos:
         """populate self$pairs[[space]] like updatePairs does (R/conclass.R:1090-1092): PCA list(CPC, nv);
         CPCA list(D, CPC, niter, nv) (src/cpca.cpp:93-100); CCA list(d, u, v, ul, vl, nv) (R/conos.R:344-366).
         `locate(t)` -> (context, slot) of the t-th used pair (a multi-device job keeps a reduction on its device)."""
+        # PCA without variance scores on one context (the atlas case: thousands of pairs): all rotations in two calls
+        if space == "PCA" and not score_component_variance and locate is None and len(used_pairs) > 8:
+            cx = self.ctx
+            n = len(used_pairs)
+            nr, nc = np.zeros(n, np.int32), np.zeros(n, np.int32)
+            off = np.zeros(n + 1, np.int64)
+            cx.check(cx.lib.cg_pair_reductions_all(cx.h, ptr(nr, C.c_int32), ptr(nc, C.c_int32), ptr(off, C.c_int64),
+                                                   None, 0))
+            buf = np.empty(int(off[n]), np.float64)
+            cx.check(cx.lib.cg_pair_reductions_all(cx.h, None, None, None, ptr(buf, C.c_double), buf.size))
+            for t, (pi, key, od) in enumerate(used_pairs):
+                if key not in cache:
+                    rot = buf[off[t]:off[t + 1]].reshape((nr[t], nc[t]), order="F")
+                    cache[key] = PairEntry(od, self._gene_names, CPC=rot)
+            return
         for t, (pi, key, od) in enumerate(used_pairs):
             if key in cache:
                 continue

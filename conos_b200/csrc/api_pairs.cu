@@ -445,6 +445,29 @@ int cg_pair_cca(cg_context* ctx, int which, int32_t* n_u, int32_t* n_v, int32_t*
   CG_API_END(ctx)
 }
 
+// All rotations of the last call in one go (an atlas run caches thousands of pairs: one call instead of two per pair)
+int cg_pair_reductions_all(cg_context* ctx, int32_t* n_rows, int32_t* n_cols, int64_t* offsets, double* rot,
+                           int64_t rot_capacity) {
+  CG_API_BEGIN
+  CG_CHECK(ctx, "NULL context");
+  CG_CUDA(cudaStreamSynchronize(ctx->c.stream));  // the asynchronous copies into the pinned arena have landed
+  int64_t off = 0;
+  for (size_t q = 0; q < ctx->kept.size(); ++q) {
+    const auto& k = ctx->kept[q];
+    const int64_t n = (int64_t)k.n_rows * k.n_cols;
+    if (n_rows) n_rows[q] = k.n_rows;
+    if (n_cols) n_cols[q] = k.n_cols;
+    if (offsets) offsets[q] = off;
+    if (rot && k.rot_host && n > 0) {
+      CG_CHECK(off + n <= rot_capacity, "rotation buffer too small");
+      memcpy(rot + off, k.rot_host, (size_t)n * sizeof(double));
+    }
+    off += n;
+  }
+  if (offsets) offsets[ctx->kept.size()] = off;
+  CG_API_END(ctx)
+}
+
 int cg_pair_cpca(cg_context* ctx, int which, int32_t* n_cols, double* D, double* niter) {
   CG_API_BEGIN
   CG_CHECK(ctx && which >= 0 && which < (int)ctx->kept.size(), "no such pair in the last cg_pairs_edges call");

@@ -213,6 +213,25 @@ void partition_pairs(const int* a, const int* b, const double* cost, int n_pairs
   }
 }
 
+// Longest-processing-time assignment of independent units (the samples' local-neighbour searches) onto ranks that
+// already carry `initial_load` (their pairs): the ranks the pair quantisation left light take the local work.
+void partition_units(const double* cost, int n, int world, const double* initial_load, int* owner) {
+  CG_CHECK(world >= 1 && n >= 0, "bad partition arguments");
+  std::vector<double> load(world, 0.0);
+  if (initial_load)
+    for (int r = 0; r < world; ++r) load[r] = initial_load[r];
+  std::vector<int> order(n);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[x] > cost[y]; });
+  for (int u : order) {
+    int best = 0;
+    for (int r = 1; r < world; ++r)
+      if (load[r] < load[best]) best = r;
+    owner[u] = best;
+    load[best] += cost[u];
+  }
+}
+
 void edges_allgatherv(Context& c, EdgeTable& t, const int* seg_owner, const long long* seg_counts_local, int n_seg) {
   const int world = c.comm ? c.comm->world : 1;
   const int me = c.comm ? c.comm->rank : 0;
@@ -392,6 +411,13 @@ int cg_partition_pairs(const int32_t* a, const int32_t* b, const double* cost, i
   CG_API_BEGIN
   CG_CHECK((a && b && cost && owner) || n_pairs == 0, "NULL argument");
   partition_pairs(a, b, cost, n_pairs, sample_cost, n_samples, world, owner);
+  CG_API_END(nullptr)
+}
+
+int cg_partition_units(const double* cost, int n, int world, const double* initial_load, int32_t* owner) {
+  CG_API_BEGIN
+  CG_CHECK((cost && owner) || n == 0, "NULL argument");
+  partition_units(cost, n, world, initial_load, owner);
   CG_API_END(nullptr)
 }
 

@@ -20,6 +20,7 @@ struct cg_job {
 namespace cg {
 void partition_pairs(const int* a, const int* b, const double* cost, int n_pairs, const double* sample_cost,
                      int n_samples, int world, int* owner);
+void partition_units(const double* cost, int n, int world, const double* initial_load, int* owner);
 }
 
 using namespace cg;
@@ -105,7 +106,7 @@ int cg_job_build_graph(cg_job* job, const cg_sample* samples, int n_samples, con
     for (int s = 0; s < n_samples; ++s) {
       const double g = std::min<double>(samples[s].n_genes, 8000.0);
       scost[s] = 0.005 * samples[s].n_cells * g * g;  // Gram matrix + upload, in cell pairs (measured on configs[1])
-      lcost[s] = (double)samples[s].n_cells * samples[s].n_cells;
+      lcost[s] = 0.4 * (double)samples[s].n_cells * samples[s].n_cells;
     }
     for (int q = 0; q < n_pairs; ++q) {
       pa[q] = pairs[q].a;
@@ -113,10 +114,10 @@ int cg_job_build_graph(cg_job* job, const cg_sample* samples, int n_samples, con
       cost[q] = (double)samples[pa[q]].n_cells * samples[pb[q]].n_cells;
     }
     partition_pairs(pa.data(), pb.data(), cost.data(), n_pairs, scost.data(), n_samples, world, owner.data());
-    if (P.k_self > 0) {
-      std::vector<int> ids(n_samples);
-      for (int s = 0; s < n_samples; ++s) ids[s] = s;
-      partition_pairs(ids.data(), ids.data(), lcost.data(), n_samples, nullptr, n_samples, world, lowner.data());
+    if (P.k_self > 0) {  // local-neighbour searches go to the ranks the pairs left light
+      std::vector<double> pload((size_t)world, 0.0);
+      for (int q = 0; q < n_pairs; ++q) pload[owner[q]] += cost[q];
+      partition_units(lcost.data(), n_samples, world, pload.data(), lowner.data());
     }
     std::vector<RankPlan> plan((size_t)world);
     std::vector<std::vector<char>> need((size_t)world, std::vector<char>((size_t)n_samples, 0));

@@ -68,7 +68,7 @@ __device__ __forceinline__ float max16(const uint32_t (&v)[16]) {
 template <int D_PAD, bool FOLD>
 __global__ void __launch_bounds__(T2_THREADS, 1)
 knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict__ auxs,
-               const KnnItem* __restrict__ items, int n_items, int k, int cap) {
+               const KnnItem* __restrict__ items, int n_items, int k, int cap, int stagger) {
   using C = T2Cfg<D_PAD>;
   extern __shared__ __align__(1024) unsigned char smem[];
   __half* smA = reinterpret_cast<__half*>(smem + C::OFF_A);
@@ -202,6 +202,18 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
       const int qrow = wi.qblock * QBLOCK + row_local;
       const bool valid_row = qrow < pb.nq;
       const int n_tiles = (pb.nr + TILE_N - 1) / TILE_N;
+      // The 16 epilogue warps wait on the same barriers and would move in lock step: all of them drain tensor memory
+      // (ALU idle), then all of them do arithmetic (TMEM port idle).  The warps of the second column half start each
+      // phase `stagger` cycles late and stay behind (the accumulators are ready long before they are consumed), so
+      // one half drains while the other computes.
+      auto hold_back = [&]() {
+        if (stagger > 0 && half == 1) {
+          const long long t0 = clock64();
+          while (clock64() - t0 < stagger) {
+          }
+        }
+      };
+      hold_back();
       // ------------------------------------------------ phase A: group maxima of the approximate scores
       {
         float run = -INFINITY;
@@ -289,6 +301,7 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
       }
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(thr_ready);
+      hold_back();
       // ------------------------------------------------ phase B: filter, survivors to the candidate lists
       {
         const uint32_t row_mask = valid_row ? 0xffffffffu : 0u;
@@ -495,13 +508,14 @@ knn_tc2_finish_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __r
 template <int D_PAD, bool FOLD>
 void launch_main(Context& ctx, const KnnProblem* d_probs, const KnnTc2Aux* d_aux, const KnnItem* d_items,
                  int n_items, int k, int cap) {
+  const int stagger = ctx.knn_stagger;
   using C = T2Cfg<D_PAD>;
   static_assert(C::SMEM_BYTES <= 227 * 1024, "shared memory budget");
   CG_CUDA(cudaFuncSetAttribute(knn_tc2_kernel<D_PAD, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                C::SMEM_BYTES));
   const int grid = n_items < ctx.sm_count ? n_items : ctx.sm_count;
   knn_tc2_kernel<D_PAD, FOLD><<<grid, T2_THREADS, C::SMEM_BYTES, ctx.stream>>>(d_probs, d_aux, d_items, n_items, k,
-                                                                              cap);
+                                                                              cap, stagger);
   ctx.stats.kernels++;
   CG_CUDA(cudaGetLastError());
 }

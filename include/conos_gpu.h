@@ -169,6 +169,10 @@ int cg_pair_reduction(cg_context* ctx, int which, int32_t* n_rows, int32_t* n_co
  * dropped, :336); sigma = res$d.  Query the sizes with NULL outputs. */
 int cg_pair_cca(cg_context* ctx, int which, int32_t* n_u, int32_t* n_v, int32_t* d, double* u, double* v,
                 int32_t* rows_u, int32_t* rows_v, double* sigma);
+/* The rotations of ALL pairs of the most recent cg_pairs_edges call at once: n_rows / n_cols [n_pairs], offsets
+ * [n_pairs + 1] (doubles) into `rot`; call with rot == NULL to size the buffer (offsets[n_pairs]), then again. */
+int cg_pair_reductions_all(cg_context* ctx, int32_t* n_rows, int32_t* n_cols, int64_t* offsets, double* rot,
+                           int64_t rot_capacity);
 /* CPCA: the other fields of cpcaF's result for pair `which` (src/cpca.cpp:93-100; self$pairs$CPCA keeps them,
  * R/conos.R:242): D = q'C_i q at convergence, column-major n_cols x 2 like the reference's t(D) (column 0 = sample a);
  * niter [n_cols]. */
@@ -216,6 +220,10 @@ int cg_comm_rank(const cg_context* ctx, int* rank, int* world);
  * matrix and its upload), so a rank touches about S / sqrt(world) samples.  owner[q] = rank.  sample_cost may be NULL. */
 int cg_partition_pairs(const int32_t* a, const int32_t* b, const double* cost, int n_pairs, const double* sample_cost,
                        int n_samples, int world, int32_t* owner);
+/* Independent units (the samples' local-neighbour searches, cost ~ 0.4 cells^2 in the unit of the pair costs) onto
+ * ranks that already carry initial_load[r] (the sum of their pair costs; may be NULL): longest processing time first,
+ * so the ranks the pair quantisation left light take the local work. */
+int cg_partition_units(const double* cost, int n, int world, const double* initial_load, int32_t* owner);
 /* Gram matrices X'X of the samples, computed once per job: owner[s] = rank that computes the matrix of sample s (it
  * must hold the sample's counts; -1: nobody needs it), n_genes[s] = its gene count (known to every rank).  Every
  * rank calls this with the same tables before cg_pairs_edges; the matrices travel by ncclBroadcast over NVLink.
