@@ -56,6 +56,75 @@ static int run_case(Context& ctx, int K, int M, int N, bool check, int reps) {
   return (check && worst > 6e-5) ? 1 : 0;  // 3 * 2^-16: bf16 hi+lo keeps 16 bits, lo*lo is dropped
 }
 
+// The Gram product X'X as ensure_grams (reduce.cu) runs it: symmetric tiles only, fp16 hi+lo operands, FP32 chunks of
+// `chunk_slabs` x 64 cells summed in FP64; accuracy against an FP64 host product on 4000 sampled entries.
+static int run_gram(Context& ctx, int K, int G, int chunk_slabs, bool fp16) {
+  std::mt19937 rng(K + G);
+  std::uniform_real_distribution<double> u(0.0, 3.0);
+  std::vector<int> p(G + 1, 0), idx;
+  std::vector<double> x;
+  for (int g = 0; g < G; ++g) {      // CSC by gene, ~7.5 % dense, values like log-scale expression
+    for (int c = 0; c < K; ++c)
+      if (rng() % 1000 < 75) { idx.push_back(c); x.push_back(0.3 + u(rng)); }
+    p[g + 1] = (int)idx.size();
+  }
+  // CSR by cell for the tile-wise operand builder
+  std::vector<int> rp(K + 1, 0), ci(idx.size());
+  std::vector<double> rx(idx.size());
+  for (int c : idx) rp[c + 1]++;
+  for (int c = 0; c < K; ++c) rp[c + 1] += rp[c];
+  {
+    std::vector<int> cur(rp.begin(), rp.end() - 1);
+    for (int g = 0; g < G; ++g)
+      for (int t = p[g]; t < p[g + 1]; ++t) { ci[cur[idx[t]]] = g; rx[cur[idx[t]]++] = x[t]; }
+  }
+  DevBuf<int> drp(rp.size()), dci(ci.size());
+  DevBuf<double> drx(rx.size()), dC((size_t)G * G);
+  drp.upload(rp.data(), rp.size(), ctx.stream);
+  dci.upload(ci.data(), ci.size(), ctx.stream);
+  drx.upload(rx.data(), rx.size(), ctx.stream);
+  DevBuf<__nv_bfloat16> hi(TiledOperand::elems(G, K)), lo(TiledOperand::elems(G, K));
+  TiledOperand op;
+  op.hi = hi.p; op.lo = lo.p;
+  tiled_from_csr(ctx, drp.p, dci.p, drx.p, K, G, op, fp16);
+  GemmProblem gp{op.hi, op.lo, op.hi, op.lo, op.rows_pad, op.rows_pad, op.k_pad, G, G, dC.p, (long long)G, 1, 1};
+  gp.chunk_slabs = chunk_slabs;
+  gp.fp16 = fp16 ? 1 : 0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float ms = 0;
+  GemmPlan plan;
+  gemm_plan(ctx, &gp, 1, plan);
+  for (int r = 0; r < 4; ++r) {
+    cudaEventRecord(e0, ctx.stream);
+    gemm_run(ctx, plan);
+    cudaEventRecord(e1, ctx.stream);
+    CG_CUDA(cudaStreamSynchronize(ctx.stream));
+    cudaEventElapsedTime(&ms, e0, e1);
+  }
+  std::vector<double> C((size_t)G * G);
+  dC.download(C.data(), C.size(), ctx.stream);
+  CG_CUDA(cudaStreamSynchronize(ctx.stream));
+  double worst = 0;
+  for (int t = 0; t < 4000; ++t) {
+    int m = (int)(rng() % G), n = (int)(rng() % G);
+    if (m > n) std::swap(m, n);   // upper triangle is what the kernel computes
+    double s = 0;
+    int a = p[m], b = p[n];
+    while (a < p[m + 1] && b < p[n + 1]) {
+      if (idx[a] == idx[b]) { s += x[a] * x[b]; ++a; ++b; }
+      else if (idx[a] < idx[b]) ++a; else ++b;
+    }
+    const double err = fabs(C[(size_t)n * G + m] - s) / (s > 0 ? s : 1.0);
+    if (err > worst) worst = err;
+  }
+  const double useful = 2.0 * K * (double)G * G / 2.0 * 1.125;  // 72 of 128 tiles touch the upper triangle
+  printf("gram K=%d G=%d %s chunk=%d slabs: %.3f ms, %.0f TFLOP/s issued (x3, upper tiles), max relative error %.3e\n", K, G,
+         fp16 ? "fp16x3" : "bf16x3", chunk_slabs, ms, 3.0 * useful / (ms * 1e-3) / 1e12, worst);
+  // one FP32 accumulation over 50 000 cells: ~1e-4; 4096-cell chunks: ~1e-5; 1024-cell chunks: ~2e-6
+  return worst > (chunk_slabs == 0 ? 3e-4 : (chunk_slabs > 16 ? 3e-5 : 6e-6)) ? 1 : 0;
+}
+
 int main(int argc, char** argv) {
   Context ctx;
   try {
@@ -74,6 +143,10 @@ int main(int argc, char** argv) {
     rc |= run_case(ctx, 1000, 300, 513, true, 1);
     rc |= run_case(ctx, 2000, 2000, 224, false, 3);
     rc |= run_case(ctx, 50000, 2000, 2000, false, 3);
+    rc |= run_gram(ctx, 50000, 2000, 0, false);   // round 1: bf16 pairs, one FP32 accumulation over all cells
+    rc |= run_gram(ctx, 50000, 2000, 0, true);
+    rc |= run_gram(ctx, 50000, 2000, 64, true);
+    rc |= run_gram(ctx, 50000, 2000, 16, true);   // the default of the library
     printf(rc ? "GEMM_PROBE FAIL\n" : "GEMM_PROBE OK\n");
     return rc;
   } catch (const std::exception& e) {

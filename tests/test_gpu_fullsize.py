@@ -107,11 +107,11 @@ def test_fullsize_pair_default_mode_vs_oracle(ctx, oracle, pair_panel, oracle_pa
         mine, theirs = rot[:, side::2], red["CPC"][:, side::2]
         cosines = np.linalg.svd(mine.T @ theirs, compute_uv=False)
         print(f"side {side}: smallest principal cosine {cosines.min():.9f}")
-        assert cosines.min() > 1 - 1e-4
+        assert cosines.min() > 1 - 1e-6   # measured 1 - 8e-8
     op1, op2 = oracle.project_pair([osamples[names[0]], osamples[names[1]]], red["genes"], red["CPC"][:, :30])
     i2, j2, x2 = oracle.neighbor_matrix(op1, op2, 30)
     a = set(zip(f.tolist(), (t - N_CELLS).tolist()))
     b = set(zip(i2.tolist(), j2.tolist()))
     jac = len(a & b) / len(a | b)
     print(f"fullsize pair, default mode: {len(a)} edges vs {len(b)} (oracle), Jaccard {jac:.6f}")
-    assert jac > 0.97
+    assert jac > 0.998   # measured 0.99947 (round 1, single FP32 accumulation of the Gram matrix: 0.981)

@@ -331,7 +331,7 @@ def test_device_pca_rotation(ctx, oracle, small_panel, ncomps, score, exact):
         g = con.buildGraph(k=10, k_self=5, space="PCA", ncomps=ncomps, n_odgenes=300, score_component_variance=score)
     finally:
         ctx.lib.cg_set_option(ctx.h, b"exact_reduction", 0.0)
-    cos_tol, dot_tol, nv_tol, jac_tol = (1e-10, 1e-8, 1e-8, 0.999) if exact else (1e-6, None, 1e-4, 0.98)
+    cos_tol, dot_tol, nv_tol, jac_tol = (1e-10, 1e-8, 1e-8, 0.999) if exact else (1e-6, None, 1e-4, 0.995)
     r = ncomps // 2
     for key, red in ref["pairs"].items():
         mine = con.pairs["PCA"][key]
@@ -354,6 +354,7 @@ def test_device_pca_rotation(ctx, oracle, small_panel, ncomps, score, exact):
     mine_e = {(min(a, b), max(a, b)) for a, b in mine_e}
     ref_e = {(min(a, b), max(a, b)) for a, b in ref_e}
     jacc = len(mine_e & ref_e) / len(mine_e | ref_e)
+    print(f"JACCARD pca exact={exact} ncomps={ncomps}: {jacc:.6f}")
     assert jacc > jac_tol, jacc
 
 
@@ -429,7 +430,9 @@ def test_device_cpca_rotation(ctx, oracle, small_panel, exact):
     mine_e = {(min(a, b), max(a, b)) for a, b in zip(g.vertices[g.edge_from].tolist(), g.vertices[g.edge_to].tolist())}
     ref_e = {(min(a, b), max(a, b))
              for a, b in zip(og["vertices"][og["from"]].tolist(), og["vertices"][og["to"]].tolist())}
-    assert len(mine_e & ref_e) / len(mine_e | ref_e) > (0.995 if exact else 0.97)
+    jacc = len(mine_e & ref_e) / len(mine_e | ref_e)
+    print(f"JACCARD cpca exact={exact}: {jacc:.6f}")
+    assert jacc > 0.995   # measured 1.000000 in both modes (round 1's default mode: > 0.97)
 
 
 def test_cca_with_oracle_variates(ctx, oracle, small_panel):
@@ -459,7 +462,7 @@ def test_device_cca_reduction(ctx, oracle, small_panel, exact):
         g = con.buildGraph(k=10, k_self=5, space="CCA", ncomps=10, n_odgenes=300)
     finally:
         ctx.lib.cg_set_option(ctx.h, b"exact_reduction", 0.0)
-    rt, at, jt = (1e-8, 1e-7, 0.995) if exact else (1e-3, 5e-3, 0.9)
+    rt, at, jt = (1e-8, 1e-7, 0.995) if exact else (1e-3, 5e-3, 0.995)   # measured 1.000000 in both modes
     for key, red in ref["pairs"].items():
         mine = con.pairs["CCA"][key]
         assert np.array_equal(mine["rows_u"], np.nonzero(red["keep"][0])[0])
@@ -492,7 +495,9 @@ def test_device_cca_reduction(ctx, oracle, small_panel, exact):
     mine_e = {(min(a, b), max(a, b)) for a, b in zip(g.vertices[g.edge_from].tolist(), g.vertices[g.edge_to].tolist())}
     ref_e = {(min(a, b), max(a, b))
              for a, b in zip(og["vertices"][og["from"]].tolist(), og["vertices"][og["to"]].tolist())}
-    assert len(mine_e & ref_e) / len(mine_e | ref_e) > jt
+    jacc = len(mine_e & ref_e) / len(mine_e | ref_e)
+    print(f"JACCARD cca exact={exact}: {jacc:.6f}")
+    assert jacc > jt
 
 
 @pytest.mark.parametrize("n_types,ncomps", [(2, 30), (6, 20)])
@@ -550,7 +555,8 @@ def test_reference_fixture_on_gpu(ctx, golden, exact):
         assert set(mine) == set(ref)
         np.testing.assert_allclose([mine[e] for e in sorted(common)], [ref[e] for e in sorted(common)], rtol=1e-6)
     else:
-        assert jac > 0.9, jac
+        print(f"JACCARD reference fixture exact={exact}: {jac:.6f}")
+        assert jac > 0.995, jac   # measured 1.000000 (round 1: > 0.9)
 
 
 def test_unconverged_tensor_core_pairs_go_to_fp64(ctx, small_panel):
