@@ -194,6 +194,7 @@ struct Context {
   // kNN engine: 0 = auto (two-phase tensor-core kernel, streaming kernel for small problems and redo blocks),
   // 1 = streaming tensor-core kernel only, 2 = exact SIMT kernel only
   int knn_engine = 0;
+  int knn_ld32 = 0;               // two-phase kernel: read the accumulators with two x32 loads instead of four x16
   int knn_stagger = 0;            // two-phase kernel: cycles the second column half of the epilogue starts late
   int knn_cand_cap = 64;          // candidate slots per (row, half) the two-phase kernel may use (tests shrink it)
   cudaMemPool_t panel_pool = nullptr;  // resident panel buffers (see PoolBinding)

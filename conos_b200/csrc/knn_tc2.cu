@@ -65,7 +65,32 @@ __device__ __forceinline__ float max16(const uint32_t (&v)[16]) {
   return m;
 }
 
-template <int D_PAD, bool FOLD>
+// 64 accumulator columns of this thread's lane: four x16 loads or (LD32) two x32 loads
+template <bool LD32>
+__device__ __forceinline__ void load_scores(uint32_t taddr, uint32_t (&v0)[16], uint32_t (&v1)[16],
+                                            uint32_t (&v2)[16], uint32_t (&v3)[16]) {
+  if constexpr (LD32) {
+    uint32_t a[32], b[32];
+    ptx::tmem_ld_32x32b_x32(taddr, a);
+    ptx::tmem_ld_32x32b_x32(taddr + 32, b);
+    ptx::tmem_wait_ld();
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      v0[c] = a[c];
+      v1[c] = a[16 + c];
+      v2[c] = b[c];
+      v3[c] = b[16 + c];
+    }
+  } else {
+    ptx::tmem_ld_32x32b_x16(taddr, v0);
+    ptx::tmem_ld_32x32b_x16(taddr + 16, v1);
+    ptx::tmem_ld_32x32b_x16(taddr + 32, v2);
+    ptx::tmem_ld_32x32b_x16(taddr + 48, v3);
+    ptx::tmem_wait_ld();
+  }
+}
+
+template <int D_PAD, bool FOLD, bool LD32>
 __global__ void __launch_bounds__(T2_THREADS, 1)
 knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict__ auxs,
                const KnnItem* __restrict__ items, int n_items, int k, int cap, int stagger) {
@@ -230,11 +255,7 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
 #endif
           const uint32_t taddr = tm_lane + (stage * 2 + mb) * TILE_N + half * 64;
           uint32_t v0[16], v1[16], v2[16], v3[16];
-          ptx::tmem_ld_32x32b_x16(taddr, v0);
-          ptx::tmem_ld_32x32b_x16(taddr + 16, v1);
-          ptx::tmem_ld_32x32b_x16(taddr + 32, v2);
-          ptx::tmem_ld_32x32b_x16(taddr + 48, v3);
-          ptx::tmem_wait_ld();
+          load_scores<LD32>(taddr, v0, v1, v2, v3);
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive_a(acc_empty_a + stage * 8);
@@ -319,11 +340,7 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
 #endif
           const uint32_t taddr = tm_lane + (stage * 2 + mb) * TILE_N + half * 64;
           uint32_t v0[16], v1[16], v2[16], v3[16];
-          ptx::tmem_ld_32x32b_x16(taddr, v0);
-          ptx::tmem_ld_32x32b_x16(taddr + 16, v1);
-          ptx::tmem_ld_32x32b_x16(taddr + 32, v2);
-          ptx::tmem_ld_32x32b_x16(taddr + 48, v3);
-          ptx::tmem_wait_ld();
+          load_scores<LD32>(taddr, v0, v1, v2, v3);
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive_a(acc_empty_a + stage * 8);
@@ -505,16 +522,27 @@ knn_tc2_finish_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __r
   if (!ok && lane == 0) blk_fail[item] = 1;
 }
 
+template <int D_PAD, bool FOLD, bool LD32>
+void launch_main_impl(Context& ctx, const KnnProblem* d_probs, const KnnTc2Aux* d_aux, const KnnItem* d_items,
+                      int n_items, int k, int cap);
+
 template <int D_PAD, bool FOLD>
 void launch_main(Context& ctx, const KnnProblem* d_probs, const KnnTc2Aux* d_aux, const KnnItem* d_items,
+                 int n_items, int k, int cap) {
+  if (ctx.knn_ld32) launch_main_impl<D_PAD, FOLD, true>(ctx, d_probs, d_aux, d_items, n_items, k, cap);
+  else launch_main_impl<D_PAD, FOLD, false>(ctx, d_probs, d_aux, d_items, n_items, k, cap);
+}
+
+template <int D_PAD, bool FOLD, bool LD32>
+void launch_main_impl(Context& ctx, const KnnProblem* d_probs, const KnnTc2Aux* d_aux, const KnnItem* d_items,
                  int n_items, int k, int cap) {
   const int stagger = ctx.knn_stagger;
   using C = T2Cfg<D_PAD>;
   static_assert(C::SMEM_BYTES <= 227 * 1024, "shared memory budget");
-  CG_CUDA(cudaFuncSetAttribute(knn_tc2_kernel<D_PAD, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CG_CUDA(cudaFuncSetAttribute(knn_tc2_kernel<D_PAD, FOLD, LD32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                C::SMEM_BYTES));
   const int grid = n_items < ctx.sm_count ? n_items : ctx.sm_count;
-  knn_tc2_kernel<D_PAD, FOLD><<<grid, T2_THREADS, C::SMEM_BYTES, ctx.stream>>>(d_probs, d_aux, d_items, n_items, k,
+  knn_tc2_kernel<D_PAD, FOLD, LD32><<<grid, T2_THREADS, C::SMEM_BYTES, ctx.stream>>>(d_probs, d_aux, d_items, n_items, k,
                                                                               cap, stagger);
   ctx.stats.kernels++;
   CG_CUDA(cudaGetLastError());

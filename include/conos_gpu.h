@@ -73,7 +73,9 @@ int cg_timer_stop(cg_context* ctx, double* ms);
  * tensor-core GEMM per sample (fp32 accumulation); 0 keeps the FP64 sparse product, which the exact mode, cached
  * rotations and cg_keep_projections always use.
  * "max_batch_bytes" (default 48 GB): scratch budget of one batch of pairs inside cg_pairs_edges; the result never
- * depends on how the pair list is cut into batches (tests set 1 to get one pair per batch). */
+ * depends on how the pair list is cut into batches (tests set 1 to get one pair per batch).
+ * "knn_stagger" (cycles, default 0) and "knn_ld32" (default 0): scheduling experiments of the two-phase kernel's
+ * epilogue (measured without effect, results identical); kept for re-measurement only. */
 int cg_set_option(cg_context* ctx, const char* name, double value);
 /* counters: "knn_redo_blocks" (256-row blocks recomputed by the streaming kernel), "eig_redo_pairs" (pairs the
  * tensor-core eigen solver handed to the FP64 driver), "kernel_launches" */
