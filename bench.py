@@ -82,6 +82,7 @@ class ClockSampler:
         self.proc = None
         self.nvml = None
         self.stop_flag = False
+        self.period = float(os.environ.get("CONOS_BENCH_CLOCK_PERIOD_S", "0.05"))
         self.sm, self.reasons, self.sm_max = [], set(), None
 
     def start(self):
@@ -124,7 +125,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(self.period)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -401,9 +402,9 @@ def main():
     gc.collect()
     gc.freeze()
     barrier()
-    lib.cg_knn_timing(ctx.h, 1)
+    lib.cg_knn_timing(ctx.h, 0 if os.environ.get("CONOS_BENCH_NO_KNN_TIMING") else 1)
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("CONOS_BENCH_NO_SAMPLER"):
         sampler.start()
     n_launch0 = ctx.kernel_launches()
     lib.cg_timer_start(ctx.h)
@@ -415,13 +416,12 @@ def main():
         g = device_step()
         step_ms.append(round(1e3 * (time.perf_counter() - t1), 1))
     gc.enable()
-    if os.environ.get("CONOS_BENCH_STAGES"):
-        sys.stderr.write(f"[steps rank {rank}] {step_ms}\n")
+    sys.stderr.write(f"[steps rank {rank}] {step_ms}\n")
     ms = C.c_double(0)
     lib.cg_timer_stop(ctx.h, C.byref(ms))
     barrier()
     wall = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if rank == 0 and not os.environ.get("CONOS_BENCH_NO_SAMPLER") else None
     launches = ctx.kernel_launches() - n_launch0
     knn_scores = ctx.stat("knn_scores")
     kms, kl, kc, kb = C.c_double(0), C.c_uint64(0), C.c_double(0), C.c_double(0)
@@ -582,6 +582,7 @@ def main():
                        "ncomps": cfg["ncomps"], "pairs": n_pairs,
                        "l2": "inputs larger than L2 (panel and per-pair operands exceed 126 MB per step)",
                        "panel_generation_s": t_gen},
+            "steps_ms": step_ms,
             "mnn_edges_per_s": n_inter * K / (dev_ms * 1e-3), "mnn_edges": n_inter,
             "graph": {"vertices": graph_sizes[0], "edges": graph_sizes[1]},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline}

@@ -1,4 +1,5 @@
-"""Device time of the exact cross-kNN (both directions) of one n x n problem for several option values."""
+"""Device time of the exact cross-kNN (both directions) of one n x n problem for several option values.
+Fixed options for all runs: OPTS=name=value,name=value."""
 import ctypes as C, json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -13,6 +14,9 @@ cent = rng.normal(0, 3.0, (20, d))
 A = cent[rng.integers(0, 20, n)] + rng.normal(0, 1, (n, d))
 B = cent[rng.integers(0, 20, n)] + rng.normal(0, 1, (n, d))
 ctx = conos_b200.Context(0)
+for kv in os.environ.get("OPTS", "").split(","):
+    if kv:
+        ctx.check(ctx.lib.cg_set_option(ctx.h, kv.split("=")[0].encode(), float(kv.split("=")[1])))
 ref = None
 for v in values:
     ctx.check(ctx.lib.cg_set_option(ctx.h, opt.encode(), v))
