@@ -202,8 +202,9 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
         const cg_pair& pr = pairs[q];
         const Sample& sa = panel.samples[pr.a];
         const Sample& sb = panel.samples[pr.b];
-        const bool ok = pr.n_genes >= 32 && sa.n_genes >= 32 && sb.n_genes >= 32 && sa.n_genes <= 4096 &&
-                        sb.n_genes <= 4096;
+        // 8192 genes: 537 MB of FP64 Gram matrix per sample (the union of 100 real top-2000 od lists is 5-8 thousand)
+        const bool ok = pr.n_genes >= 32 && sa.n_genes >= 32 && sb.n_genes >= 32 && sa.n_genes <= 8192 &&
+                        sb.n_genes <= 8192;
         (ok ? tc_pairs : fp64_pairs).push_back(q);
       }
       todo = tc_pairs;

@@ -527,6 +527,39 @@ def test_device_pca_wide_spectrum_default_mode(ctx, n_types, ncomps):
             np.testing.assert_allclose(b["nv"][side], a["nv"][side], rtol=1e-3)
 
 
+def test_device_pca_large_gene_universe_default_mode(ctx):
+    """A gene universe above 4096 (the union of many samples' od lists on real data): the tensor-core Gram matrix and
+    eigen solver still serve it (no FP64 fallback), and the subspaces agree with the FP64 path."""
+    import ctypes as C
+    import conos_b200
+    from conos_b200.panel import make_panel
+    panel = make_panel(17, 2, [1500, 1300], n_genes=6000, n_types=5, n_pcs=20, use_torch=False)
+    res = {}
+    try:
+        for exact in (1, 0):
+            ctx.lib.cg_set_option(ctx.h, b"exact_reduction", float(exact))
+            con = conos_b200.Conos(panel, ctx=ctx)
+            ctx.lib.cg_profile(ctx.h, 1)
+            con.buildGraph(k=10, k_self=5, space="PCA", ncomps=20, n_odgenes=6000)
+            buf = C.create_string_buffer(8192)
+            ctx.lib.cg_profile_dump(ctx.h, buf, 8192)
+            ctx.lib.cg_profile(ctx.h, 0)
+            prof = dict(kv.split("=") for kv in buf.value.decode().split(";") if kv)
+            res[exact] = (con.pairs["PCA"], prof)
+    finally:
+        ctx.lib.cg_set_option(ctx.h, b"exact_reduction", 0.0)
+        ctx.lib.cg_profile(ctx.h, 0)
+    # the default mode went through the tensor-core solver: two problems (one per side), none handed to FP64
+    assert float(res[0][1].get("reduction.eig.problems", 0)) == 2.0, res[0][1]
+    assert float(res[0][1].get("reduction.eig.fp64_redo_pairs", 0)) == 0.0
+    for key in res[1][0]:
+        a, b = res[1][0][key], res[0][0][key]
+        assert a["CPC"].shape[0] > 4096
+        for side in (0, 1):
+            cs = _principal_cosines(a["CPC"][:, side::2], b["CPC"][:, side::2])
+            assert cs.min() > 1 - 1e-5, (key, side, cs.min())
+
+
 @pytest.mark.parametrize("exact", [True, False])
 def test_reference_fixture_on_gpu(ctx, golden, exact):
     """buildGraph(ncomps=25) on the reference's own fixture, as tests/testthat/test_functions.R:24 calls it, against

@@ -1,4 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python tools/knn_time.py knn_acc16 0 1 0 1 2>&1 | tail -4
-CONOS_K2_DEBUG=1 python tools/knn_time.py knn_acc16 0 1 2>&1 | grep -E "k2" | awk '!seen[$0]++' | head -4
+CONOS_BENCH_STAGES=1 python bench.py --no-e2e --no-atlas --no-check --steps 5 2> gpurun_out/w.err > gpurun_out/w.json
+grep -E "stages rank|steps rank" gpurun_out/w.err
+python tools/profile_stages.py --config 2 --reps 2 2>/dev/null | tail -40
