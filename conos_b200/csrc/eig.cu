@@ -1346,16 +1346,17 @@ void top_eigenvectors_shared_gram(Context& ctx, const TcEigSample* samples, int 
       launch_clustered(eig_rr_kernel<B>, n_probs, csize, smem, s, (const EigWork*)dw.p, r, tol, 0, csize);
       ctx.stats.kernels++;
     }
+    // Chebyshev filter of the next sweep: per-problem degree (<= degree) from the current residuals, see
+    // tc_coeff_kernel.  Launched before the host looks at the convergence flags so that one round trip per sweep
+    // brings both the flags and the degrees.
+    tc_coeff_kernel<<<(n_probs + 127) / 128, 128, 0, s>>>(dP.p, n_probs, degree, r, colres.p, al.p, be.p, cc.p, deg.p);
+    ctx.stats.kernels++;
     conv.download(hc.data(), (size_t)n_probs, s);
+    deg.download(hdeg.data(), (size_t)n_probs, s);
     CG_CUDA(cudaStreamSynchronize(s));
     bool all = true;
     for (int p = 0; p < n_probs; ++p) all = all && hc[p] != 0;
     if (all || outer == max_outer) break;
-    // Chebyshev filter: per-problem degree (<= degree) from the current residuals, see tc_coeff_kernel
-    tc_coeff_kernel<<<(n_probs + 127) / 128, 128, 0, s>>>(dP.p, n_probs, degree, r, colres.p, al.p, be.p, cc.p, deg.p);
-    ctx.stats.kernels++;
-    deg.download(hdeg.data(), (size_t)n_probs, s);
-    CG_CUDA(cudaStreamSynchronize(s));
     int sweep = 1;
     for (int p = 0; p < n_probs; ++p)
       if (!hc[p] && hdeg[p] > sweep) sweep = hdeg[p];

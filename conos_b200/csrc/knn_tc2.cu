@@ -21,10 +21,18 @@
 // block and of the reference tiles, streamed twice), warp 1 MMA issuer (tcgen05.mma kind::tf32, two
 // M=128 x N=128 accumulators per tile, double buffered = 512 TMEM columns), warps 2-17 epilogue: thread =
 // (query row, 64-column half), tcgen05.ld 32x32b.x16.
+#include <algorithm>
 #include <cuda_fp16.h>
 
 #include "knn.cuh"
 #include "ptx.cuh"
+
+// Measurement builds (never shipped): -DTC2_MMA_ONLY drops the accumulators, -DTC2_LOAD_ONLY drains them without
+// arithmetic; with TC2_MMA_ONLY, -DTC2_EXP=1 lets ONE epilogue warp do the hand-shake, 3 removes the reference-tile
+// ring, 4 removes the ring and the consumer hand-shake (pure MMA issue).  Results: DESIGN.md K2.
+#ifndef TC2_EXP
+#define TC2_EXP 0
+#endif
 
 namespace cg {
 namespace {
@@ -120,7 +128,7 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(acc_full + s, 1);
-      ptx::mbar_init(acc_empty + s, 16);
+      ptx::mbar_init(acc_empty + s, TC2_EXP == 1 ? 1 : 16);
     }
     ptx::mbar_init(thr_ready, 16);
     ptx::fence_mbar_init();
@@ -149,6 +157,7 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
         ptx::bulk_g2s(smA, q_mma + (size_t)wi.qblock * QBLOCK * D_PAD, C::A_BYTES, a_full);
         const int n_tiles = (pb.nr + TILE_N - 1) / TILE_N;
         for (int ph2 = 0; ph2 < 2; ++ph2) {
+          if (TC2_EXP >= 3) break;
           for (int t = 0; t < n_tiles; ++t) {
             ptx::mbar_wait(b_empty + slot, ph ^ 1);
             ptx::mbar_arrive_expect_tx(b_full + slot, C::B_BYTES);
@@ -184,8 +193,8 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
         for (int ph2 = 0; ph2 < 2; ++ph2) {
           if (ph2 == 1) ptx::mbar_wait(thr_ready, it & 1);  // the rows' thresholds are in the A tile (FOLD)
           for (int t = 0; t < n_tiles; ++t) {
-            ptx::mbar_wait_a(b_full_a + slot * 8, ph);
-            ptx::mbar_wait_a(acc_empty_a + stage * 8, aph ^ 1);
+            if (TC2_EXP < 3) ptx::mbar_wait_a(b_full_a + slot * 8, ph);
+            if (TC2_EXP != 4) ptx::mbar_wait_a(acc_empty_a + stage * 8, aph ^ 1);
             ptx::tc_fence_after();
             const uint64_t bd = bdesc0 + (uint64_t)((slot * (uint32_t)C::B_BYTES) >> 4);
 #pragma unroll
@@ -196,7 +205,7 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
                 ptx::mma_f16_ss(d_tmem, adesc[mb][ks], bd + (uint64_t)(ks * 2), idesc, ks > 0 ? 1u : 0u);
               }
             }
-            ptx::mma_commit_a(b_empty_a + slot * 8);
+            if (TC2_EXP < 3) ptx::mma_commit_a(b_empty_a + slot * 8);
             ptx::mma_commit_a(acc_full_a + stage * 8);
             if (++slot == C::NSTAGE) { slot = 0; ph ^= 1; }
             aph ^= stage;
@@ -244,6 +253,7 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
         float run = -INFINITY;
         int tcount = 0;
         for (int t = 0; t < n_tiles; ++t, ++g) {
+          if (TC2_EXP == 4 || (TC2_EXP == 1 && e != 0)) break;
           const uint32_t stage = g & 1, aph = (g >> 1) & 1;
           ptx::mbar_wait_a(acc_full_a + stage * 8, aph);
           ptx::tc_fence_after();
@@ -259,6 +269,10 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive_a(acc_empty_a + stage * 8);
+#ifdef TC2_LOAD_ONLY  // measurement build: tensor pipe + hand-shake + tensor-memory drain, no arithmetic
+          if (v0[0] == 0x7fc12345u) run = __uint_as_float(v0[1] ^ v1[2] ^ v2[3] ^ v3[4]);  // keeps the loads alive
+          continue;
+#endif
           const int nv = pb.nr - t * TILE_N - half * 64;  // valid columns of this thread's 64
           if (nv < 64) {  // zero padding rows of the last reference tile never count
 #pragma unroll
@@ -329,6 +343,7 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
         int* cbase = ax.cand + ((size_t)(ax.row0 + qrow) * 2 + half) * KNN_TC2_CAND_STRIDE;
         int cnt = 0;
         for (int t = 0; t < n_tiles; ++t, ++g) {
+          if (TC2_EXP == 4 || (TC2_EXP == 1 && e != 0)) break;
           const uint32_t stage = g & 1, aph = (g >> 1) & 1;
           ptx::mbar_wait_a(acc_full_a + stage * 8, aph);
           ptx::tc_fence_after();
@@ -344,6 +359,10 @@ knn_tc2_kernel(const KnnProblem* __restrict__ probs, const KnnTc2Aux* __restrict
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive_a(acc_empty_a + stage * 8);
+#ifdef TC2_LOAD_ONLY
+          if (v0[0] == 0x7fc12345u) cnt += (int)(v0[1] ^ v1[2] ^ v2[3] ^ v3[4]);
+          continue;
+#endif
           uint32_t ma = 0, mb2 = 0;
           if (FOLD) {
             // accumulator = dot - thr: collect the sign bits (highest column first), survivors = NOT sign
@@ -629,6 +648,9 @@ void knn_tc2_run(Context& ctx, const KnnProblem* d_probs, const KnnProblem* h_pr
     std::vector<int> h_fail(items.size());
     fail.download(h_fail.data(), items.size(), ctx.stream);
     CG_CUDA(cudaStreamSynchronize(ctx.stream));
+#if defined(TC2_MMA_ONLY) || defined(TC2_LOAD_ONLY)  // measurement builds produce no results: nothing to redo
+    std::fill(h_fail.begin(), h_fail.end(), 0);
+#endif
     for (size_t q = 0; q < items.size(); ++q)
       if (h_fail[q]) {
         redo.push_back(items[q]);

@@ -1,5 +1,6 @@
 #!/bin/bash
+# K2 hand-shake dissection (measurement builds of knn_tc2.cu, see the TC2_EXP switch)
 mkdir -p gpurun_out
-CONOS_BENCH_STAGES=1 python bench.py --no-e2e --no-atlas --no-check --steps 5 2> gpurun_out/w.err > gpurun_out/w.json
-grep -E "stages rank|steps rank" gpurun_out/w.err
-python tools/profile_stages.py --config 2 --reps 2 2>/dev/null | tail -40
+cp conos_b200/libconosgpu.so /tmp/full.so
+for v in MMA_ONLY E1 E2 E3 E4; do cp build/libconosgpu_$v.so conos_b200/libconosgpu.so; echo $v; timeout 90 python tools/knn_time.py knn_stagger 0 0 2>&1 | tail -1; done
+cp /tmp/full.so conos_b200/libconosgpu.so
