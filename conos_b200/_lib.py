@@ -124,6 +124,12 @@ SIGNATURES = {
     "cg_adjust_weights": (C.c_int, [_VP, c_dbl_p, c_int_p, c_int_p, C.c_int64, c_int_p, C.c_int, C.c_int, c_dbl_p]),
     "cg_reference_wij": (C.c_int, [_VP, c_int_p, c_int_p, c_dbl_p, C.c_int64, C.c_double, c_int_p, c_int_p, c_dbl_p,
                                    c_i64_p]),
+    "cg_smooth_matrix": (C.c_int, [_VP, _VP, c_int_p, c_int_p, c_dbl_p, C.c_int64, C.c_int32, c_dbl_p, C.c_int32,
+                                   C.POINTER(C.c_uint8), C.c_int32, C.c_double, C.c_double, C.c_double, C.c_int32,
+                                   c_int_p, c_dbl_p]),
+    "cg_propagate_labels": (C.c_int, [_VP, _VP, c_int_p, c_int_p, c_dbl_p, C.c_int64, C.c_int32, c_int_p, C.c_int32,
+                                      C.c_int32, C.c_double, C.c_double, C.c_double, C.c_int32, c_dbl_p, c_int_p,
+                                      c_dbl_p]),
 }
 
 _lib: Optional[C.CDLL] = None

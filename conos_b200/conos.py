@@ -716,6 +716,109 @@ class Conos:
                 rr = nc.value // 2 if space == "PCA" else nc.value
                 cache[key]["nv"] = [nv[0, :rr], nv[1, :rr]]
 
+    # ------------------------------------------------------------------ diffusion over the graph
+    def propagateLabels(self, labels: Dict[str, object], method: str = "diffusion", max_iters: int = 100,
+                        diffusion_fading: float = 10.0, diffusion_fading_const: float = 0.1, tol: float = 0.025,
+                        fixed_initial_labels: bool = True) -> dict:
+        """Conos$propagateLabels(labels, method='diffusion') (R/conclass.R:910-925) -> propagateLabelsDiffusion
+        (R/conos.R:1071-1083) -> propagate_labels (src/propagate_labels.cpp:67-118) on the device.
+        `labels`: cell name -> label.  Returns labels (per vertex, first maximum like which.max), uncertainty
+        (1 - max probability), label_distribution (n_vertices x n_labels, rows = V(graph)$name order) and label_names
+        (numbered by first appearance among the labelled cells that are in the graph, like order_strings)."""
+        if method == "solver":
+            raise NotImplementedError("method='solver' (a sparse Laplacian solve on the CPU) is outside the device path")
+        if method != "diffusion":
+            raise ValueError(f"Unknown method: {method}. Only 'solver' and 'diffusion' are supported.")
+        if self.graph is None:
+            raise ValueError("run buildGraph() first")
+        from . import ops
+        g = self.graph
+        names = np.asarray(g.names, dtype=object)
+        pos = {n: t for t, n in enumerate(names)}
+        label_ids: Dict[object, int] = {}
+        lab = np.full(len(names), -1, np.int32)
+        for cell, l in labels.items():          # labels[intersect(names(labels), V(graph)$name)]: the caller's order
+            t = pos.get(cell)
+            if t is None:
+                continue
+            lab[t] = label_ids.setdefault(l, len(label_ids))
+        dist = ops.propagate_labels(g.edge_from, g.edge_to, g.weight, len(names), lab, len(label_ids),
+                                    max_n_iters=max_iters, diffusion_fading=diffusion_fading,
+                                    diffusion_fading_const=diffusion_fading_const, tol=tol,
+                                    fixed_initial_labels=fixed_initial_labels, ctx=self.ctx)
+        label_names = list(label_ids)
+        # which.max / max skip nothing in R: a row of NaN (no label reaches the vertex) gives integer(0) / NaN there;
+        # here such vertices get label None and uncertainty NaN
+        best = np.zeros(len(names), np.int64)
+        conf = np.full(len(names), np.nan)
+        if dist.shape[1] > 0:
+            ok = ~np.isnan(dist).any(axis=1)
+            best[ok] = np.argmax(dist[ok], axis=1)
+            conf[ok] = dist[ok].max(axis=1)
+        out_labels = np.array([label_names[b] if o else None for b, o in zip(best, ~np.isnan(conf))], dtype=object)
+        return {"labels": out_labels, "uncertainty": 1.0 - conf, "label_distribution": dist,
+                "label_names": label_names, "cells": names}
+
+    def _od_genes_uniformly(self, n_genes: int) -> List[str]:
+        """getOdGenesUniformly (R/conos.R:505-513): genes by their best rank in any sample's od list; ties in gene-name
+        order (group_by sorts the groups, arrange is stable)."""
+        rank: Dict[str, int] = {}
+        for s in self.samples.values():
+            for r, gname in enumerate(s.od_genes):
+                if gname not in rank or r < rank[gname]:
+                    rank[gname] = r
+        genes = sorted(rank, key=lambda gname: (rank[gname], gname))
+        return genes[:min(n_genes, len(genes))]
+
+    def correctGenes(self, genes: Optional[Sequence[str]] = None, n_od_genes: int = 500, fading: float = 10.0,
+                     fading_const: float = 0.5, max_iters: int = 15, tol: float = 5e-3, name: str = "diffusion",
+                     count_matrix: Optional[np.ndarray] = None, count_matrix_cells: Optional[Sequence[str]] = None,
+                     normalize: bool = True) -> np.ndarray:
+        """Conos$correctGenes (R/conclass.R:862-893): expression smoothed over the joint graph by smooth_count_matrix
+        (src/propagate_labels.cpp:177-222).  Default matrix: cells x genes of the samples' count matrices over the
+        genes common to all samples and in `genes` (default: getOdGenesUniformly(n.od.genes)), rows reordered to
+        V(graph)$name.  `count_matrix` (genes x cells like the reference's argument) needs `count_matrix_cells`.
+        Note: like the reference this passes tol only through the default of smooth_count_matrix (1e-3) -- `tol` is an
+        argument of correctGenes that the reference never forwards (R/conclass.R:890-891)."""
+        if self.graph is None:
+            raise ValueError("run buildGraph() first")
+        from . import ops
+        g = self.graph
+        vn = np.asarray(g.names, dtype=object)
+        if count_matrix is None:
+            if genes is None:
+                genes = self._od_genes_uniformly(n_od_genes)
+            common = None
+            for s in self.samples.values():
+                gs = set(s.genes)
+                common = gs if common is None else common & gs
+            first = next(iter(self.samples.values()))
+            keep = [gname for gname in first.genes if gname in common and gname in set(genes)]   # Reduce(intersect) order
+            blocks, cells = [], []
+            for s in self.samples.values():
+                col = {gname: t for t, gname in enumerate(s.genes)}
+                idx = np.array([col[gname] for gname in keep], dtype=np.int64)
+                blocks.append(np.asarray(sp.csc_matrix(s.counts)[:, idx].todense(), dtype=np.float64))
+                cells.extend(s.cells)
+            cm = np.vstack(blocks)
+            self._corrected_genes = keep
+        else:
+            if count_matrix_cells is None:
+                raise ValueError("count_matrix needs count_matrix_cells (its column names)")
+            cm = np.asarray(count_matrix, dtype=np.float64).T
+            cells = list(count_matrix_cells)
+        row = {c: t for t, c in enumerate(cells)}
+        if not all(c in row for c in vn):
+            raise ValueError("count.matrix does not provide values for all the vertices in the alignment graph!")
+        cm = cm[np.array([row[c] for c in vn], dtype=np.int64)]
+        res = ops.smooth_count_matrix(g.edge_from, g.edge_to, g.weight, cm, max_n_iters=max_iters,
+                                      diffusion_fading=fading, diffusion_fading_const=fading_const, normalize=normalize,
+                                      ctx=self.ctx)
+        if not hasattr(self, "expression_adj"):
+            self.expression_adj = {}
+        self.expression_adj[name] = res
+        return res
+
     def close(self):
         """Release the device-resident panel (R: the object going out of scope / rm(con); gc())."""
         try:

@@ -180,3 +180,54 @@ def buildWijMatrix(x: sp.spmatrix, perplexity: float = 50, ctx=None) -> sp.csc_m
     a.sort_indices()
     is_ = np.repeat(np.arange(a.shape[1], dtype=np.int32), np.diff(a.indptr))
     return referenceWij(is_, a.indices, a.data ** 2, perplexity, a.shape[0], ctx=ctx)
+
+
+def smooth_count_matrix(edge_from, edge_to, edge_weights, count_matrix, is_label_fixed=None, max_n_iters: int = 10,
+                        diffusion_fading: float = 1.0, diffusion_fading_const: float = 0.1, tol: float = 1e-3,
+                        normalize: bool = False, ctx=None, graph=None, return_info: bool = False):
+    """smooth_count_matrix (src/propagate_labels.cpp:177-222): vertices are 0-based row indices of `count_matrix`
+    (n_vertices x n_cols).  `graph`: a device graph handle instead of the host edge list."""
+    c = _ctx(ctx)
+    m = np.array(count_matrix, dtype=np.float64, order="F", copy=True)
+    if m.ndim != 2:
+        raise ValueError("count_matrix must be a matrix")
+    ef = np.ascontiguousarray(edge_from, np.int32) if edge_from is not None else np.zeros(0, np.int32)
+    et = np.ascontiguousarray(edge_to, np.int32) if edge_to is not None else np.zeros(0, np.int32)
+    w = np.ascontiguousarray(edge_weights, np.float64) if edge_weights is not None else np.zeros(0)
+    if len(ef) != len(w) or len(et) != len(w):
+        raise ValueError("Size of edge_verts must match size of edge_weights")
+    fx = None
+    if is_label_fixed is not None and len(is_label_fixed):
+        fx = np.ascontiguousarray(is_label_fixed, np.uint8)
+        if len(fx) != m.shape[0]:
+            raise ValueError("is_label_fixed must have one entry per vertex")
+    it, nrm = C.c_int32(0), C.c_double(0)
+    c.check(c.lib.cg_smooth_matrix(c.h, graph, ptr(ef, C.c_int32), ptr(et, C.c_int32), ptr(w, C.c_double), len(w),
+                                   m.shape[0], ptr(m, C.c_double), m.shape[1],
+                                   None if fx is None else ptr(fx, C.c_uint8), int(max_n_iters), float(diffusion_fading),
+                                   float(diffusion_fading_const), float(tol), int(bool(normalize)), C.byref(it),
+                                   C.byref(nrm)))
+    return (m, it.value, nrm.value) if return_info else m
+
+
+def propagate_labels(edge_from, edge_to, edge_weights, n_vertices: int, label_of_vertex, n_labels: int,
+                     max_n_iters: int = 10, diffusion_fading: float = 10.0, diffusion_fading_const: float = 0.5,
+                     tol: float = 5e-3, fixed_initial_labels: bool = False, ctx=None, graph=None,
+                     return_info: bool = False):
+    """propagate_labels (src/propagate_labels.cpp:67-118) on integer ids: label_of_vertex[v] in [0, n_labels) or -1."""
+    c = _ctx(ctx)
+    ef = np.ascontiguousarray(edge_from, np.int32) if edge_from is not None else np.zeros(0, np.int32)
+    et = np.ascontiguousarray(edge_to, np.int32) if edge_to is not None else np.zeros(0, np.int32)
+    w = np.ascontiguousarray(edge_weights, np.float64) if edge_weights is not None else np.zeros(0)
+    if len(ef) != len(w) or len(et) != len(w):
+        raise ValueError("Incorrect dimension of input vectors")
+    lab = np.ascontiguousarray(label_of_vertex, np.int32)
+    if len(lab) != n_vertices:
+        raise ValueError("one label id per vertex expected")
+    out = np.zeros((n_vertices, n_labels), dtype=np.float64, order="F")
+    it, nrm = C.c_int32(0), C.c_double(0)
+    c.check(c.lib.cg_propagate_labels(c.h, graph, ptr(ef, C.c_int32), ptr(et, C.c_int32), ptr(w, C.c_double), len(w),
+                                      int(n_vertices), ptr(lab, C.c_int32), int(n_labels), int(max_n_iters),
+                                      float(diffusion_fading), float(diffusion_fading_const), float(tol),
+                                      int(bool(fixed_initial_labels)), ptr(out, C.c_double), C.byref(it), C.byref(nrm)))
+    return (out, it.value, nrm.value) if return_info else out

@@ -23,6 +23,8 @@
  *   _conos_getSumWeightMatrix    src/edge_rebalancing.cpp:14-36                       -> cg_sum_weight_matrix
  *   _conos_adjustWeightsByCellBalancingC  src/edge_rebalancing.cpp:39-48              -> cg_adjust_weights
  *   _conos_referenceWij          src/edgeweights.cpp:160-184                          -> cg_reference_wij
+ *   _conos_smooth_count_matrix   src/propagate_labels.cpp:177-222 -> cg_smooth_matrix
+ *   _conos_propagate_labels      src/propagate_labels.cpp:67-118                       -> cg_propagate_labels
  *   edge table -> graph_from_edgelist -> simplify                 R/conclass.R:321-343 -> cg_assemble_graph
  *   papply / plapply fork pools over pairs and samples            R/conclass.R:224,1074; R/conos.R:399,589
  *                                                        -> cg_comm_init, cg_partition_pairs, cg_edges_allgatherv
@@ -301,6 +303,29 @@ int cg_adjust_weights(cg_context* ctx, double* weights, const int32_t* row_inds,
  * 2 * n_edges; *n_out receives the triplet count */
 int cg_reference_wij(cg_context* ctx, const int32_t* from, const int32_t* to, const double* d, int64_t n_edges,
                      double perplexity, int32_t* out_from, int32_t* out_to, double* out_w, int64_t* n_out);
+
+/* ---- diffusion over the graph (the consumers of the joint graph next to the path: SURVEY.md 8(f) rank 3) -------- */
+/* smooth_count_matrix(edge_verts, edge_weights, count_matrix, is_label_fixed, max_n_iters, diffusion_fading,
+ * diffusion_fading_const, tol, verbose, normalize)  src/propagate_labels.cpp:177-222 -> :120-175; called by
+ * Conos$correctGenes (R/conclass.R:862-893).  Vertices are 0-based integers = rows of `matrix` (the reference maps the
+ * vertex names to the row names, :199-202); `matrix` is an R matrix (column-major n_vertices x n_cols), updated in
+ * place.  Edges: either a graph handle (its simplified edge list is already on the device; from / to / weight are
+ * ignored) or host arrays.  is_fixed: NULL or one byte per vertex.  *n_iters receives the iteration index at which the
+ * loop stopped (the reference prints it), *inf_norm the last max |new - old|.  As in the reference the matrix of the
+ * iteration BEFORE the one that met `tol` is returned.  Error "Negative edge length" like Edge::Edge (:24-26). */
+int cg_smooth_matrix(cg_context* ctx, const cg_graph* graph, const int32_t* from, const int32_t* to,
+                     const double* weight, int64_t n_edges, int32_t n_vertices, double* matrix, int32_t n_cols,
+                     const uint8_t* is_fixed, int32_t max_n_iters, double fading, double fading_const, double tol,
+                     int32_t normalize, int32_t* n_iters, double* inf_norm);
+/* propagate_labels(edge_verts, edge_weights, vert_labels, max_n_iters, verbose, diffusion_fading,
+ * diffusion_fading_const, tol, fixed_initial_labels)  src/propagate_labels.cpp:67-118; called by
+ * propagateLabelsDiffusion (R/conos.R:1071-1083).  label_of_vertex: label id per vertex, -1 = unlabelled (the caller
+ * numbers labels by first appearance like order_strings, :33-38); label_dist: n_vertices x n_labels column-major,
+ * rows divided by their sums (:100-106; a vertex no label reaches gets 0 / 0 = NaN as in R). */
+int cg_propagate_labels(cg_context* ctx, const cg_graph* graph, const int32_t* from, const int32_t* to,
+                        const double* weight, int64_t n_edges, int32_t n_vertices, const int32_t* label_of_vertex,
+                        int32_t n_labels, int32_t max_n_iters, double fading, double fading_const, double tol,
+                        int32_t fixed_initial_labels, double* label_dist, int32_t* n_iters, double* inf_norm);
 
 #ifdef __cplusplus
 }

@@ -395,3 +395,59 @@ int oracle_reference_wij(const int* from, const int* to, const double* d, int n_
   free(head); free(next); free(reverse);
   return ne;
 }
+
+/* ------------------------------------------------------------------ graph diffusion
+ * src/propagate_labels.cpp:120-175 (smooth_count_matrix_c) with the edge weights of parse_edges (:40-62):
+ * w' = (w - min_w) / max_w, min_w = max(min w, 0), max_w = max w - min_w; length = 1 - w' (negative: error -1);
+ * per iteration every edge adds exp(-fading * (length + fading_const)) times the OLD row of one end to the new row
+ * of the other (unless that vertex is fixed), rows are divided by 1 + sum of the weights when normalize, and the
+ * loop stops BEFORE taking the new matrix when max |new - old| < tol (:166-170).  cm is n_vertices x n_cols
+ * column-major (R matrix), updated in place; is_fixed NULL or n_vertices bytes.  Returns the iteration index at
+ * which the loop stopped (max_n_iters if it ran out), inf_norm = the last norm.                                   */
+int oracle_smooth_matrix(const int* from, const int* to, const double* weights, long long n_edges, int n_vertices,
+                         double* cm, int n_cols, const unsigned char* is_fixed, int max_n_iters, double fading,
+                         double fading_const, double tol, int normalize, double* inf_norm_out) {
+  if (n_vertices == 0 || n_cols == 0) return 0;
+  double mn = 1e300, mx = -1e300;
+  for (long long e = 0; e < n_edges; ++e) { if (weights[e] < mn) mn = weights[e]; if (weights[e] > mx) mx = weights[e]; }
+  double min_w = mn > 0.0 ? mn : 0.0, max_w = mx - min_w;
+  double* ew = (double*)malloc(sizeof(double) * (size_t)(n_edges > 0 ? n_edges : 1));
+  for (long long e = 0; e < n_edges; ++e) {
+    double len = 1.0 - (weights[e] - min_w) / max_w;
+    if (len < 0) { free(ew); return -1; }
+    ew[e] = exp(-fading * (len + fading_const));
+  }
+  size_t N = (size_t)n_vertices * n_cols;
+  double* nw = (double*)malloc(sizeof(double) * N);
+  double* sw = (double*)malloc(sizeof(double) * (size_t)n_vertices);
+  for (int v = 0; v < n_vertices; ++v) sw[v] = 1.0;
+  double inf_norm = 1e10;
+  int iter = 0;
+  for (iter = 0; iter < max_n_iters; ++iter) {
+    memcpy(nw, cm, sizeof(double) * N);
+    for (long long e = 0; e < n_edges; ++e) {
+      int a = from[e], b = to[e];
+      double w = ew[e];
+      if (!is_fixed || !is_fixed[a]) {
+        for (int c = 0; c < n_cols; ++c) nw[(size_t)c * n_vertices + a] += cm[(size_t)c * n_vertices + b] * w;
+        if (normalize) sw[a] += w;
+      }
+      if (!is_fixed || !is_fixed[b]) {
+        for (int c = 0; c < n_cols; ++c) nw[(size_t)c * n_vertices + b] += cm[(size_t)c * n_vertices + a] * w;
+        if (normalize) sw[b] += w;
+      }
+    }
+    if (normalize)
+      for (int v = 0; v < n_vertices; ++v) {
+        for (int c = 0; c < n_cols; ++c) nw[(size_t)c * n_vertices + v] /= sw[v];
+        sw[v] = 1.0;
+      }
+    inf_norm = 0.0;
+    for (size_t t = 0; t < N; ++t) { double d = fabs(nw[t] - cm[t]); if (d > inf_norm) inf_norm = d; }
+    if (inf_norm < tol) break;
+    memcpy(cm, nw, sizeof(double) * N);
+  }
+  if (inf_norm_out) *inf_norm_out = inf_norm;
+  free(ew); free(nw); free(sw);
+  return iter;
+}

@@ -668,3 +668,61 @@ def build_graph(samples: Dict[str, Sample], k: int = 15, k_self: int = 10, k_sel
         out["balanced"] = adjust_weights_by_cell_balancing(adj, fac[g["vertices"]].astype(str), balance_edge_weights,
                                                            same_factor_downweight)
     return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# graph diffusion -- src/propagate_labels.cpp:65-222
+# ----------------------------------------------------------------------------------------------------
+def smooth_count_matrix(edge_from, edge_to, edge_weights, count_matrix, is_label_fixed=None, max_n_iters=10,
+                        diffusion_fading=1.0, diffusion_fading_const=0.1, tol=1e-3, normalize=False, return_info=False):
+    """smooth_count_matrix (:177-222) on 0-based vertex ids = rows of count_matrix."""
+    m = np.array(count_matrix, dtype=np.float64, order="F", copy=True)
+    ef = np.ascontiguousarray(edge_from, dtype=np.int32)
+    et = np.ascontiguousarray(edge_to, dtype=np.int32)
+    w = np.ascontiguousarray(edge_weights, dtype=np.float64)
+    if m.shape[0] == 0 or m.shape[1] == 0 or len(w) == 0:
+        return (m, 0, 1e10) if return_info else m
+    fx = None if is_label_fixed is None or len(is_label_fixed) == 0 else np.ascontiguousarray(is_label_fixed, np.uint8)
+    nrm = ctypes.c_double(0)
+    f = lib().oracle_smooth_matrix
+    f.restype = ctypes.c_int
+    it = f(_p(ef, ctypes.c_int), _p(et, ctypes.c_int), _p(w, ctypes.c_double), ctypes.c_longlong(len(w)), m.shape[0],
+           _p(m, ctypes.c_double), m.shape[1], None if fx is None else _p(fx, ctypes.c_ubyte), int(max_n_iters),
+           ctypes.c_double(diffusion_fading), ctypes.c_double(diffusion_fading_const), ctypes.c_double(tol),
+           int(bool(normalize)), ctypes.byref(nrm))
+    if it < 0:
+        raise ValueError("Negative edge length")
+    return (m, it, nrm.value) if return_info else m
+
+
+def propagate_labels(edge_from, edge_to, edge_weights, n_vertices, label_of_vertex, n_labels, max_n_iters=10,
+                     diffusion_fading=10.0, diffusion_fading_const=0.5, tol=5e-3, fixed_initial_labels=False,
+                     return_info=False):
+    """propagate_labels (:67-118) on integer ids: one-hot rows, smooth_count_matrix_c with normalize = true, rows
+    divided by their sums."""
+    lab = np.asarray(label_of_vertex)
+    probs = np.zeros((n_vertices, n_labels), dtype=np.float64, order="F")
+    has = lab >= 0
+    probs[np.flatnonzero(has), lab[has]] = 1.0
+    fixed = (has & bool(fixed_initial_labels)).astype(np.uint8)
+    ef = np.ascontiguousarray(edge_from, dtype=np.int32)
+    et = np.ascontiguousarray(edge_to, dtype=np.int32)
+    w = np.ascontiguousarray(edge_weights, dtype=np.float64)
+    it, nv = 0, 1e10
+    if n_vertices and n_labels:
+        nrm = ctypes.c_double(0)
+        f = lib().oracle_smooth_matrix
+        f.restype = ctypes.c_int
+        it = f(_p(ef, ctypes.c_int), _p(et, ctypes.c_int), _p(w, ctypes.c_double), ctypes.c_longlong(len(w)),
+               n_vertices, _p(probs, ctypes.c_double), n_labels, _p(fixed, ctypes.c_ubyte), int(max_n_iters),
+               ctypes.c_double(diffusion_fading), ctypes.c_double(diffusion_fading_const), ctypes.c_double(tol), 1,
+               ctypes.byref(nrm))
+        if it < 0:
+            raise ValueError("Negative edge length")
+        nv = nrm.value
+    with np.errstate(invalid="ignore", divide="ignore"):
+        s = np.zeros(n_vertices)
+        for c in range(n_labels):          # Rcpp::sum of the row, left to right
+            s = s + probs[:, c]
+        probs = np.asfortranarray(probs / s[:, None])
+    return (probs, it, nv) if return_info else probs

@@ -3,6 +3,8 @@ golden vectors for this path (parity unpinned); these tests pin th
 slow, obviously-correct NumPy / pure-Python versions and against the committed regression fixtures."""
 import os
 
+import math
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -226,3 +228,55 @@ def test_reference_fixture_and_golden_vectors(oracle, golden):
     idx, dist = oracle.cross_knn(A, B, 15, "angular")
     assert np.array_equal(idx, vec["knn_idx"])
     assert np.array_equal(dist.view(np.uint32), vec["knn_dist"].view(np.uint32))
+
+
+def test_smooth_count_matrix_against_slow_restatement(oracle):
+    """src/propagate_labels.cpp:120-175 restated edge by edge in NumPy (rows as vectors, the reference's own loop order)
+    against the C oracle: bit-identical, including the stop-before-update rule and fixed vertices."""
+    rng = np.random.default_rng(11)
+    n, n_edges, n_cols = 60, 400, 5
+    ef = rng.integers(0, n, n_edges)
+    et = rng.integers(0, n, n_edges)
+    w = rng.uniform(0.1, 1.0, n_edges)
+    m0 = rng.random((n, n_cols))
+    fixed = rng.random(n) < 0.25
+
+    def slow(max_iters, fading, const, tol, normalize, is_fixed):
+        cm = m0.copy()
+        min_w = max(w.min(), 0.0)
+        max_w = w.max() - min_w
+        length = 1.0 - (w - min_w) / max_w
+        ew = np.array([math.exp(-fading * (l + const)) for l in length])   # libm, like the C oracle (np.exp is SIMD)
+        sw = np.ones(n)
+        it, nrm = 0, 1e10
+        for it in range(max_iters):
+            new = cm.copy()
+            for e in range(n_edges):
+                a, b = ef[e], et[e]
+                if is_fixed is None or not is_fixed[a]:
+                    new[a] = new[a] + cm[b] * ew[e]
+                    if normalize:
+                        sw[a] += ew[e]
+                if is_fixed is None or not is_fixed[b]:
+                    new[b] = new[b] + cm[a] * ew[e]
+                    if normalize:
+                        sw[b] += ew[e]
+            if normalize:
+                new = new / sw[:, None]
+                sw[:] = 1.0
+            nrm = np.abs(new - cm).max()
+            if nrm < tol:
+                break
+            cm = new
+        else:
+            it = max_iters
+        return cm, it, nrm
+
+    for args in ((4, 1.0, 0.1, 1e-3, False, None), (6, 10.0, 0.5, 5e-3, True, fixed), (40, 2.0, 0.1, 0.02, True, None)):
+        sm, sit, snrm = slow(*args)
+        om, oit, onrm = oracle.smooth_count_matrix(ef, et, w, m0, args[5], max_n_iters=args[0], diffusion_fading=args[1],
+                                                   diffusion_fading_const=args[2], tol=args[3], normalize=args[4],
+                                                   return_info=True)
+        assert oit == sit
+        assert np.array_equal(om, sm)
+        assert onrm == snrm
