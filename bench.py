@@ -599,6 +599,42 @@ def main():
         line["e2e_breakdown_ms"] = {k: round(v, 2) for k, v in con.timings.items()}
         line["e2e_steps_ms"] = e2e_each
     line["knn_recall_at_k"] = knn_recall(ctx, min(cfg["k"], 30), cfg["ncomps"])
+    # ---- diffusion sub-record: propagate_labels over the graph this run built, HBM-bound
+    if g_host is not None and world == 1 and not args.no_check and g_host.ecount() > 0:
+        from conos_b200 import ops
+        nv_, ne_, n_lab = g_host.vcount(), g_host.ecount(), 20
+        rng_ = np.random.default_rng(1)
+        lab_ = np.where(rng_.random(nv_) < 0.1, rng_.integers(0, n_lab, nv_), -1).astype(np.int32)
+
+        def run_diffusion(iters):
+            torch.cuda.synchronize()
+            t_ = time.perf_counter()
+            ops.propagate_labels(g_host.edge_from, g_host.edge_to, g_host.weight, nv_, lab_, n_lab, max_n_iters=iters,
+                                 tol=0.0, fixed_initial_labels=True, ctx=ctx)
+            return time.perf_counter() - t_
+        run_diffusion(1)
+        t_2 = min(run_diffusion(2) for _ in range(3))
+        t_22 = min(run_diffusion(22) for _ in range(3))
+        per_iter = (t_22 - t_2) / 20.0
+        # algorithmic HBM bytes of one iteration: the incidence lists (int32 neighbour + f64 weight per entry, two
+        # entries per edge) + the matrix read once and written once (the gathers of neighbour rows hit L2: 64 MB)
+        by = 2.0 * ne_ * 12 + 2.0 * nv_ * n_lab * 8
+        line["diffusion"] = {"workload": f"propagate_labels on this graph ({nv_} vertices, {ne_} edges), {n_lab} labels, "
+                                         f"10 % of the vertices labelled and fixed",
+                             "ms_per_iteration": 1e3 * per_iter, "algorithmic_bytes_per_iteration": by,
+                             "achieved_gbs": by / per_iter / 1e9, "peak_gbs": peaks["hbm_gbs"],
+                             "frac": by / per_iter / 1e9 / peaks["hbm_gbs"],
+                             "gathered_bytes_per_iteration": 2.0 * ne_ * n_lab * 8,
+                             "ms_call_22_iterations_host_edge_list": 1e3 * t_22,
+                             "note": "per iteration = (22-iteration call - 2-iteration call) / 20, wall clock around "
+                                     "the C-ABI call with the edge list in host memory"}
+        if not args.no_cpu_baseline:
+            import conos_oracle as oracle_d
+            oracle_d.build()
+            t_ = time.perf_counter()
+            oracle_d.propagate_labels(g_host.edge_from, g_host.edge_to, g_host.weight, nv_, lab_, n_lab, max_n_iters=2,
+                                      tol=0.0, fixed_initial_labels=True)
+            line["diffusion"]["cpu_oracle_ms_per_iteration"] = 1e3 * (time.perf_counter() - t_) / 2.0
     # ---- graph checks (outside every timed region)
     if not args.no_check and g_host is not None and world > 1:
         # the N-rank graph against the graph one rank builds alone: every array, bit for bit

@@ -146,7 +146,22 @@ diffuse_step_kernel(const long long* __restrict__ row_p, const int* __restrict__
     for (int c = lane; c < n_cols; c += 32) {
       const double o = orow[c];
       double acc = o, sw = 1.0;
-      for (long long t = p0; t < p1; ++t) {
+      long long t = p0;
+      // eight neighbour rows in flight per lane (the gathers are L2 latency bound); the sums keep the edge order
+      for (; t + 8 <= p1; t += 8) {
+        double w[8], x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          w[u] = wv[t + u];
+          x[u] = old_m[(size_t)other[t + u] * n_cols + c];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          acc = __dadd_rn(acc, __dmul_rn(x[u], w[u]));
+          sw = __dadd_rn(sw, w[u]);
+        }
+      }
+      for (; t < p1; ++t) {
         const double w = wv[t];
         acc = __dadd_rn(acc, __dmul_rn(old_m[(size_t)other[t] * n_cols + c], w));
         sw = __dadd_rn(sw, w);
@@ -237,7 +252,9 @@ int diffuse(Context& c, const Incidence& inc, const unsigned char* d_fixed, DevB
   cudaStream_t st = c.stream;
   DevBuf<double> nxt((size_t)n_vertices * n_cols);
   DevBuf<unsigned long long> norm(1);
-  const int grid = std::min(nblocks((size_t)n_vertices, 8), (unsigned)(c.sm_count * 8));
+  // one resident wave (8 CTAs of 8 warps per SM) with a grid-stride loop; 4x .. 32x and one warp per vertex without
+  // a loop were measured equal or slower (0.37-0.50 ms per iteration on the configs[1] graph)
+  const int grid = (int)std::min(nblocks((size_t)n_vertices, 8), (unsigned)(c.sm_count * 8));
   double inf_norm = 1e10;
   int iter = 0;
   for (iter = 0; iter < max_n_iters; ++iter) {

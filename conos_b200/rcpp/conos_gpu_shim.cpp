@@ -9,6 +9,7 @@
 #include <Rcpp.h>
 
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "conos_gpu.h"
@@ -175,6 +176,78 @@ S4 referenceWij(IntegerVector i, IntegerVector j, NumericVector d, int threads, 
   return sparseMatrix(_["i"] = ri + 1, _["j"] = rj + 1, _["x"] = rx, _["dims"] = IntegerVector::create(nv, nv));
 }
 
+// ---- diffusion over the graph.  The reference's entry points take vertex NAMES
+// (StringMatrix edge_verts) and number them in C++ (parse_edges / order_strings, src/propagate_labels.cpp:33-62); the
+// numbering is done here the same way, the arithmetic runs on the device.
+static std::vector<int32_t> vertex_ids(const StringMatrix& edge_verts, std::vector<std::string> names,
+                                       std::unordered_map<std::string, int32_t>& ids) {
+  if (names.empty())
+    for (int e = 0; e < edge_verts.nrow(); ++e) {
+      names.push_back(as<std::string>(edge_verts(e, 0)));
+      names.push_back(as<std::string>(edge_verts(e, 1)));
+    }
+  for (const auto& s : names) ids.emplace(s, (int32_t)ids.size());
+  std::vector<int32_t> ft(2 * (size_t)edge_verts.nrow());
+  for (int e = 0; e < edge_verts.nrow(); ++e) {
+    ft[e] = ids.at(as<std::string>(edge_verts(e, 0)));
+    ft[(size_t)edge_verts.nrow() + e] = ids.at(as<std::string>(edge_verts(e, 1)));
+  }
+  return ft;
+}
+
+// [[Rcpp::export]]   same name and arguments as src/propagate_labels.cpp:177
+SEXP smooth_count_matrix(StringMatrix edge_verts, std::vector<double> edge_weights, NumericMatrix count_matrix,
+                         std::vector<bool> is_label_fixed, int max_n_iters = 10, double diffusion_fading = 1.0,
+                         double diffusion_fading_const = 0.1, double tol = 1e-3, bool verbose = true,
+                         bool normalize = false) {
+  if (count_matrix.nrow() == 0 || count_matrix.ncol() == 0) { warning("Empty matrix passed"); return count_matrix; }
+  if ((size_t)edge_verts.nrow() != edge_weights.size()) stop("Size of edge_verts must match size of edge_weights");
+  if (edge_verts.nrow() == 0) { warning("Empty graph passed"); return count_matrix; }
+  if (edge_verts.ncol() != 2) stop("Matrix edge_verts must have exactly 2 columns");
+  std::unordered_map<std::string, int32_t> ids;
+  const std::vector<int32_t> ft = vertex_ids(edge_verts, as<std::vector<std::string>>(rownames(count_matrix)), ids);
+  NumericMatrix res = clone(count_matrix);
+  std::vector<uint8_t> fx(is_label_fixed.begin(), is_label_fixed.end());
+  int32_t it = 0;
+  double nrm = 0;
+  const int64_t E = edge_verts.nrow();
+  check(cg_smooth_matrix(ctx_get(), nullptr, ft.data(), ft.data() + E, edge_weights.data(), E, res.nrow(), res.begin(),
+                         res.ncol(), fx.empty() ? nullptr : fx.data(), max_n_iters, diffusion_fading,
+                         diffusion_fading_const, tol, normalize, &it, &nrm));
+  if (verbose) Rcout << "Stop after " << it << " iterations. Norm: " << nrm << std::endl;
+  return res;
+}
+
+// [[Rcpp::export]]   same name and arguments as src/propagate_labels.cpp:67
+NumericMatrix propagate_labels(StringMatrix edge_verts, std::vector<double> edge_weights, StringVector vert_labels,
+                               int max_n_iters = 10, bool verbose = true, double diffusion_fading = 10,
+                               double diffusion_fading_const = 0.5, double tol = 5e-3,
+                               bool fixed_initial_labels = false) {
+  if ((size_t)edge_verts.nrow() != edge_weights.size() || edge_verts.ncol() != 2)
+    stop("Incorrect dimension of input vectors");
+  std::unordered_map<std::string, int32_t> ids, label_ids;
+  const std::vector<int32_t> ft = vertex_ids(edge_verts, {}, ids);
+  for (int t = 0; t < vert_labels.size(); ++t) label_ids.emplace(as<std::string>(vert_labels[t]), (int32_t)label_ids.size());
+  std::vector<int32_t> lab(ids.size(), -1);
+  StringVector vn = vert_labels.names();
+  for (int t = 0; t < vert_labels.size(); ++t)
+    lab[ids.at(as<std::string>(vn[t]))] = label_ids.at(as<std::string>(vert_labels[t]));
+  NumericMatrix res((int)ids.size(), (int)label_ids.size());
+  int32_t it = 0;
+  double nrm = 0;
+  const int64_t E = edge_verts.nrow();
+  check(cg_propagate_labels(ctx_get(), nullptr, ft.data(), ft.data() + E, edge_weights.data(), E, (int32_t)ids.size(),
+                            lab.data(), (int32_t)label_ids.size(), max_n_iters, diffusion_fading, diffusion_fading_const,
+                            tol, fixed_initial_labels, res.begin(), &it, &nrm));
+  if (verbose) Rcout << "Stop after " << it << " iterations. Norm: " << nrm << std::endl;
+  CharacterVector rn(ids.size()), cn(label_ids.size());
+  for (const auto& kv : ids) rn[kv.second] = kv.first;
+  for (const auto& kv : label_ids) cn[kv.second] = kv.first;
+  rownames(res) = rn;
+  colnames(res) = cn;
+  return res;
+}
+
 // [[Rcpp::export]]   the one native call Conos$buildGraph makes instead of updatePairs + its two papply loops + rbind +
 // graph_from_edgelist + simplify + adjustWeightsByCellBalancing (R/conclass.R:199-368).
 // samples: list of list(p, i, x, Dim, v, qv, pca); pairs: list of list(a, b, genes_a, genes_b [, k] [, rot] [, u, v,
@@ -316,6 +389,8 @@ List buildGraphGPU(List samples, List pairs, List params, int n_devices = 1) {
 //       {"_conos_getSumWeightMatrix", (DL_FUNC) &_conos_getSumWeightMatrix, 5},
 //       {"_conos_adjustWeightsByCellBalancingC", (DL_FUNC) &_conos_adjustWeightsByCellBalancingC, 5},
 //       {"_conos_referenceWij", (DL_FUNC) &_conos_referenceWij, 5},
+//       {"_conos_propagate_labels", (DL_FUNC) &_conos_propagate_labels, 9},
+//       {"_conos_smooth_count_matrix", (DL_FUNC) &_conos_smooth_count_matrix, 10},
 //       {"_conos_crossKnnExact", (DL_FUNC) &_conos_crossKnnExact, 4},          // new
 //       {"_conos_knnExact", (DL_FUNC) &_conos_knnExact, 3},                    // new
 //       {"_conos_getNeighborMatrixGPU", (DL_FUNC) &_conos_getNeighborMatrixGPU, 9},  // new

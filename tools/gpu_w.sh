@@ -1,6 +1,4 @@
 #!/bin/bash
-# K2 hand-shake dissection (measurement builds of knn_tc2.cu, see the TC2_EXP switch)
 mkdir -p gpurun_out
-cp conos_b200/libconosgpu.so /tmp/full.so
-for v in MMA_ONLY E1 E2 E3 E4; do cp build/libconosgpu_$v.so conos_b200/libconosgpu.so; echo $v; timeout 90 python tools/knn_time.py knn_stagger 0 0 2>&1 | tail -1; done
-cp /tmp/full.so conos_b200/libconosgpu.so
+python tools/diffusion_probe.py > gpurun_out/w_diff.log 2>&1 && cat gpurun_out/w_diff.log | tail -1 && \
+ncu --set full --clock-control none --import-source on -k regex:diffuse_step -c 3 -o gpurun_out/n_diffuse -f python tools/diffusion_probe.py > gpurun_out/w_ncu.log 2>&1; tail -2 gpurun_out/w_ncu.log
