@@ -155,6 +155,31 @@ int main() {
     CHECK(fetch(ctx, g, g_seq), ctx);
     std::printf("sequence: %zu vertices, %zu edges, %lld inter-sample rows\n", g_seq.vertices.size(), g_seq.from.size(),
                 (long long)n_inter);
+    {
+      // the consumer next to the path (propagate_labels, src/propagate_labels.cpp:67): every 7th vertex labelled with
+      // one of three labels, once on the device graph handle and once on the fetched edge list -- identical bits
+      const int32_t nv = (int32_t)g_seq.vertices.size(), n_lab = 3;
+      std::vector<int32_t> lab(nv, -1);
+      for (int32_t v = 0; v < nv; v += 7) lab[v] = (v / 7) % n_lab;
+      std::vector<double> da((size_t)nv * n_lab), db((size_t)nv * n_lab);
+      int32_t ita = 0, itb = 0;
+      double na = 0, nb = 0;
+      CHECK(cg_propagate_labels(ctx, g, nullptr, nullptr, nullptr, 0, nv, lab.data(), n_lab, 20, 10.0, 0.1, 1e-3, 1,
+                                da.data(), &ita, &na), ctx);
+      CHECK(cg_propagate_labels(ctx, nullptr, g_seq.from.data(), g_seq.to.data(), g_seq.weight.data(),
+                                (int64_t)g_seq.from.size(), nv, lab.data(), n_lab, 20, 10.0, 0.1, 1e-3, 1, db.data(), &itb,
+                                &nb), ctx);
+      if (ita != itb || std::memcmp(da.data(), db.data(), da.size() * sizeof(double)) != 0) {
+        std::fprintf(stderr, "propagate_labels: graph handle and edge list disagree (%d vs %d iterations)\n", ita, itb);
+        return 1;
+      }
+      for (int32_t v = 0; v < nv; v += 7)
+        if (da[(size_t)lab[v] * nv + v] != 1.0) {
+          std::fprintf(stderr, "a fixed label moved\n");
+          return 1;
+        }
+      std::printf("propagate_labels: %d iterations, norm %.3g\n", ita, na);
+    }
     cg_graph_free(g);
     cg_edges_free(edges);
     cg_panel_free(panel);
