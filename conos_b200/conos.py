@@ -123,6 +123,7 @@ class Conos:
         self._panel_col: Dict[str, Optional[np.ndarray]] = {}
         self._vocab = None
         self._od_membership = {}
+        self._od_pair_memo = {}
         self._cell_names = None
         self._pinned = {}
         self.timings: Dict[str, float] = {}
@@ -148,6 +149,7 @@ class Conos:
             self.samples[n] = s
         self._vocab = None
         self._od_membership = {}
+        self._od_pair_memo = {}
         self._cell_names = None
         self._drop_panel()
 
@@ -194,6 +196,7 @@ class Conos:
         arr = (CgSample * len(names))()
         keep = []
         self._panel_col = {}
+        self._od_pair_memo = {}        # the memo holds columns of the uploaded matrices
         self._h2d_bytes = 0
         for t, n in enumerate(names):
             s = self.samples[n]
@@ -278,6 +281,9 @@ class Conos:
         restricted to genes present in both samples, first n.odgenes.
         Gene ids are ranks in sort() order, so "count 2 first, then count 1, names ascending inside a count" is two
         flatnonzero calls on the per-sample membership vectors of the top-n lists (cached per n.odgenes)."""
+        hit = self._od_pair_memo.get((na, nb, n_odgenes))     # pure function of the samples and the uploaded columns
+        if hit is not None:
+            return hit
         self._ensure_vocab()
         allnames, per = self._vocab
         col_a, od_a = per[na]
@@ -298,7 +304,9 @@ class Conos:
             ga = pca_[ga]
         if pcb_ is not None:
             gb = pcb_[gb]
-        return ids, np.ascontiguousarray(ga, np.int32), np.ascontiguousarray(gb, np.int32)
+        out = (ids, np.ascontiguousarray(ga, np.int32), np.ascontiguousarray(gb, np.int32))
+        self._od_pair_memo[(na, nb, n_odgenes)] = out
+        return out
 
     def _gene_names(self, ids) -> List[str]:
         allnames = self._vocab[0]
@@ -454,6 +462,7 @@ class Conos:
             self._job = job
         t_0 = time.perf_counter()
         self._panel_col = {}
+        self._od_pair_memo = {}        # the memo holds columns of the uploaded matrices
         arr, keep = self._sample_array(names, n_odgenes)
         cache = self.pairs.setdefault(space, {})
         if balancing_factor_per_sample is not None:

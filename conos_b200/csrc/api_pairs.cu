@@ -2,6 +2,8 @@
 #include <cmath>
 #include <map>
 
+#include <thread>
+
 #include "api_core.cuh"
 #include "hub.cuh"
 #include "reduce.cuh"
@@ -193,6 +195,31 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
 
     // ---- reductions (rotation per pair, column-major G x d_eff doubles on the device)
     std::vector<PairReduction> red(nb_pairs);
+    if (P.space != CG_SPACE_CCA) {
+      // scaledMatricesP2 factors of every pair of the batch, once, on several host threads (the reduction and the
+      // projection operands both need them; at the atlas one thread spends 0.3 s per use on exp / sqrt)
+      if (P.var_scale)
+        for (int q = 0; q < nb_pairs; ++q) {
+          const Sample& sa = panel->samples[pairs[p0 + q].a];
+          const Sample& sb = panel->samples[pairs[p0 + q].b];
+          CG_CHECK(!sa.h_v.empty() && !sa.h_qv.empty() && !sb.h_v.empty() && !sb.h_qv.empty(),
+                   "var.scale = TRUE needs misc$varinfo$v and $qv for every sample");
+        }
+      auto factors = [&](int q0, int q1) {
+        for (int q = q0; q < q1; ++q) {
+          const cg_pair& pr = pairs[p0 + q];
+          pair_scale_factors(panel->samples[pr.a], panel->samples[pr.b], pr, P.var_scale != 0, red[q].h_fa, red[q].h_fb);
+        }
+      };
+      const int nt = nb_pairs >= 64 ? 8 : 1;
+      if (nt == 1) {
+        factors(0, nb_pairs);
+      } else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; ++t) th.emplace_back(factors, nb_pairs * t / nt, nb_pairs * (t + 1) / nt);
+        for (auto& t : th) t.join();
+      }
+    }
     {
       StageScope sc(c, "reduction");
       compute_pair_reductions(c, *panel, pairs + p0, nb_pairs, P, red);
@@ -289,8 +316,8 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
         }
       } else {
         const int G = pr.n_genes;
-        std::vector<double> fa, fb;
-        pair_scale_factors(sa, sb, pr, P.var_scale != 0, fa, fb);
+        const std::vector<double>& fa = R.h_fa;   // computed for the whole batch above
+        const std::vector<double>& fb = R.h_fb;
         // centering (R/conos.R:784-789): per-gene scaled means, and the quirk of the default path:
         // `centering` is an atomic vector, so centering[[n]] is ONE number per sample (m[1], m[2])
         std::vector<double> ca(G), cb(G);
@@ -452,19 +479,39 @@ int cg_pair_reductions_all(cg_context* ctx, int32_t* n_rows, int32_t* n_cols, in
   CG_CHECK(ctx, "NULL context");
   CG_CUDA(cudaStreamSynchronize(ctx->c.stream));  // the asynchronous copies into the pinned arena have landed
   int64_t off = 0;
+  std::vector<int64_t> offs(ctx->kept.size() + 1, 0);
   for (size_t q = 0; q < ctx->kept.size(); ++q) {
     const auto& k = ctx->kept[q];
     const int64_t n = (int64_t)k.n_rows * k.n_cols;
     if (n_rows) n_rows[q] = k.n_rows;
     if (n_cols) n_cols[q] = k.n_cols;
     if (offsets) offsets[q] = off;
-    if (rot && k.rot_host && n > 0) {
-      CG_CHECK(off + n <= rot_capacity, "rotation buffer too small");
-      memcpy(rot + off, k.rot_host, (size_t)n * sizeof(double));
-    }
+    offs[q] = off;
+    if (rot && k.rot_host && n > 0) CG_CHECK(off + n <= rot_capacity, "rotation buffer too small");
     off += n;
   }
+  offs[ctx->kept.size()] = off;
   if (offsets) offsets[ctx->kept.size()] = off;
+  if (rot && off > 0) {
+    // the atlas fetches 4950 rotations = 2.4 GB into freshly allocated (not yet touched) host memory: the copy is
+    // bound by page faults of one thread (0.5 s); eight threads take contiguous ranges of the pair list
+    const size_t nq = ctx->kept.size();
+    const int nt = off * (int64_t)sizeof(double) > ((int64_t)64 << 20) ? 8 : 1;
+    auto copy_range = [&](size_t q0, size_t q1) {
+      for (size_t q = q0; q < q1; ++q) {
+        const auto& k = ctx->kept[q];
+        const int64_t n = (int64_t)k.n_rows * k.n_cols;
+        if (k.rot_host && n > 0) memcpy(rot + offs[q], k.rot_host, (size_t)n * sizeof(double));
+      }
+    };
+    if (nt == 1) {
+      copy_range(0, nq);
+    } else {
+      std::vector<std::thread> th;
+      for (int t = 0; t < nt; ++t) th.emplace_back(copy_range, nq * t / nt, nq * (t + 1) / nt);
+      for (auto& t : th) t.join();
+    }
+  }
   CG_API_END(ctx)
 }
 

@@ -249,20 +249,15 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
         const int G = pr.n_genes;
         Sample* sm[2] = {&panel.samples[pr.a], &panel.samples[pr.b]};
         std::vector<double> f[2];
-        f[0].assign(G, 1.0);
-        f[1].assign(G, 1.0);
-        if (P.var_scale) {
-          CG_CHECK(!sm[0]->h_qv.empty() && !sm[1]->h_qv.empty() && !sm[0]->h_v.empty() && !sm[1]->h_v.empty(),
-                   "var.scale = TRUE needs misc$varinfo$v and $qv for every sample");
-          for (int g = 0; g < G; ++g) {
-            const int ca = pr.genes_a[g], cb = pr.genes_b[g];  // the gene's column in either sample
-            CG_CHECK(ca >= 0 && ca < sm[0]->n_genes && cb >= 0 && cb < sm[1]->n_genes, "pair gene column out of range");
-            const double cqv = std::exp((sm[0]->h_logqv[ca] + sm[1]->h_logqv[cb]) / 2.0);
-            const double fa = std::sqrt(cqv / sm[0]->h_expv[ca]);
-            const double fb = std::sqrt(cqv / sm[1]->h_expv[cb]);
-            f[0][g] = std::isfinite(fa) ? fa : 0.0;
-            f[1][g] = std::isfinite(fb) ? fb : 0.0;
-          }
+        if ((int)out[todo[t]].h_fa.size() == G && (int)out[todo[t]].h_fb.size() == G) {
+          f[0] = out[todo[t]].h_fa;   // computed up front by the caller (same function)
+          f[1] = out[todo[t]].h_fb;
+        } else {
+          for (int g = 0; g < G; ++g)
+            CG_CHECK(pr.genes_a[g] >= 0 && pr.genes_a[g] < sm[0]->n_genes && pr.genes_b[g] >= 0 &&
+                         pr.genes_b[g] < sm[1]->n_genes,
+                     "pair gene column out of range");
+          pair_factors(*sm[0], *sm[1], pr, P.var_scale != 0, f[0], f[1]);
         }
         for (int side = 0; side < 2; ++side) {
           const int Gs = sm[side]->n_genes;
@@ -379,20 +374,7 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
         const int* gcols[2] = {pr.genes_a, pr.genes_b};
         // scale factors (same arithmetic as api_pairs.cu: scaledMatricesP2)
         std::vector<double> f[2];
-        f[0].assign(b.G, 1.0);
-        f[1].assign(b.G, 1.0);
-        if (P.var_scale) {
-          CG_CHECK(!sm[0]->h_qv.empty() && !sm[1]->h_qv.empty() && !sm[0]->h_v.empty() && !sm[1]->h_v.empty(),
-                   "var.scale = TRUE needs misc$varinfo$v and $qv for every sample");
-          for (int g = 0; g < b.G; ++g) {
-            const int ca = pr.genes_a[g], cb = pr.genes_b[g];
-            const double cqv = std::exp((sm[0]->h_logqv[ca] + sm[1]->h_logqv[cb]) / 2.0);
-            const double fa = std::sqrt(cqv / sm[0]->h_expv[ca]);
-            const double fb = std::sqrt(cqv / sm[1]->h_expv[cb]);
-            f[0][g] = std::isfinite(fa) ? fa : 0.0;
-            f[1][g] = std::isfinite(fb) ? fb : 0.0;
-          }
-        }
+        pair_factors(*sm[0], *sm[1], pr, P.var_scale != 0, f[0], f[1]);
         b.tr.alloc(2);
         for (int side = 0; side < 2; ++side) {
           b.C[side].alloc((size_t)b.Gp * b.Gp);

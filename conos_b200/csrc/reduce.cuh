@@ -21,6 +21,9 @@ struct PairReduction {
   std::vector<int> h_rows_u, h_rows_v;
   std::vector<double> h_sigma;  // singular values (res$d)
   std::vector<double> h_ul, h_vl;  // gene loadings t(sm) %*% u with unit columns, column-major G x d (R/conos.R:349-353)
+  // scaledMatricesP2 factors of the pair's genes, when the caller computed them up front (cg_pairs_edges does, for
+  // all pairs of a batch on several host threads: one exp and two sqrt per gene and pair is 0.3 s at the atlas)
+  std::vector<double> h_fa, h_fb;
 };
 
 void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs, int n_pairs, const cg_params& P,
