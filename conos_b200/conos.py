@@ -281,9 +281,11 @@ class Conos:
         restricted to genes present in both samples, first n.odgenes.
         Gene ids are ranks in sort() order, so "count 2 first, then count 1, names ascending inside a count" is two
         flatnonzero calls on the per-sample membership vectors of the top-n lists (cached per n.odgenes)."""
-        hit = self._od_pair_memo.get((na, nb, n_odgenes))     # pure function of the samples and the uploaded columns
-        if hit is not None:
-            return hit
+        # pure function of the samples and of the uploaded columns: memoised (the atlas asks 4950 times per call)
+        memo = self.__dict__.setdefault("_od_pair_memo", {})
+        hit = memo.get((na, nb, n_odgenes))
+        if hit is not None and hit[3] is self._panel_col.get(na) and hit[4] is self._panel_col.get(nb):
+            return hit[:3]
         self._ensure_vocab()
         allnames, per = self._vocab
         col_a, od_a = per[na]
@@ -305,7 +307,7 @@ class Conos:
         if pcb_ is not None:
             gb = pcb_[gb]
         out = (ids, np.ascontiguousarray(ga, np.int32), np.ascontiguousarray(gb, np.int32))
-        self._od_pair_memo[(na, nb, n_odgenes)] = out
+        memo[(na, nb, n_odgenes)] = out + (pca_, pcb_)
         return out
 
     def _gene_names(self, ids) -> List[str]:
@@ -838,9 +840,12 @@ class Conos:
         self._panel = None
 
     def __del__(self):
-        import sys
-        if not sys.is_finalizing():
-            self.close()
+        try:
+            import sys
+            if not sys.is_finalizing():
+                self.close()
+        except Exception:      # interpreter teardown: the import machinery may already be gone
+            pass
 
     def _out(self, key: str, n: int, dtype):
         """Result buffer in pinned host memory when torch is importable (grow-only, reused across calls; the
