@@ -411,10 +411,24 @@ def main():
     t0 = time.perf_counter()
     step_ms = []
     gc.disable()    # no collector pauses inside the timed steps (a 35 ms stall on one rank stalls all of them)
+    trace = bool(os.environ.get("CONOS_BENCH_TRACE"))   # host-clock stage times of every step (no synchronisation added)
+    traces = []
     for _ in range(K):
+        if trace:
+            lib.cg_profile(ctx.h, 2)
         t1 = time.perf_counter()
         g = device_step()
         step_ms.append(round(1e3 * (time.perf_counter() - t1), 1))
+        if trace:
+            buf = C.create_string_buffer(8192)
+            lib.cg_profile_dump(ctx.h, buf, 8192)
+            traces.append((step_ms[-1], buf.value.decode(), {k: round(v, 1) for k, v in con.timings.items()}))
+    if trace:
+        lib.cg_profile(ctx.h, 0)
+        med = sorted(step_ms)[len(step_ms) // 2]
+        for ms_, st_, py_ in traces:
+            if ms_ > med + 4 or ms_ == med:
+                sys.stderr.write(f"[trace rank {rank}] {ms_} ms (median {med}) {st_} py {json.dumps(py_)}\n")
     gc.enable()
     sys.stderr.write(f"[steps rank {rank}] {step_ms}\n")
     ms = C.c_double(0)

@@ -66,6 +66,7 @@ int cg_init(int device, cg_context** out) {
     CG_CUDA(cudaMemPoolCreate(&ctx->c.panel_pool, &props));
     CG_CUDA(cudaMemPoolSetAttribute(ctx->c.panel_pool, cudaMemPoolAttrReleaseThreshold, &thr));
   }
+  ctx->c.refresh_free_bytes();
   *out = ctx;
   CG_API_END(ctx)
 }
@@ -215,7 +216,8 @@ int cg_get_stat(cg_context* ctx, const char* name, double* value) {
 
 int cg_profile(cg_context* ctx, int enable) {
   if (!ctx) return 1;
-  ctx->c.profile = enable != 0;
+  ctx->c.profile = enable == 1;
+  ctx->c.profile_host = enable == 2;
   ctx->c.stage_ms.clear();
   return 0;
 }

@@ -35,6 +35,7 @@ struct cg_panel {
   cudaStream_t stream = nullptr;   // its stream, checked against the registry of live streams
   std::vector<cg::Sample> samples;
   std::vector<int> offsets;
+  size_t device_bytes = 0;         // what the resident samples hold (keeps the context's free-memory estimate honest)
 };
 
 struct cg_edges {

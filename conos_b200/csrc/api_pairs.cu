@@ -31,14 +31,6 @@ void pair_scale_factors(const Sample& sa, const Sample& sb, const cg_pair& pr, b
   }
 }
 
-size_t free_device_bytes() {
-  size_t f = 0, t = 0;
-  if (cudaMemGetInfo(&f, &t) != cudaSuccess) {
-    cudaGetLastError();
-    return (size_t)8 << 30;
-  }
-  return f;
-}
 
 }  // namespace
 
@@ -89,6 +81,11 @@ int cg_panel_create(cg_context* ctx, const cg_sample* samples, int n_samples, cg
       for (int s = 0; s < n_samples; ++s) sample_finish(ctx->c, pn->samples[s], lane.ev[s]);
     }
     CG_CUDA(cudaStreamSynchronize(lane.st));
+    for (const auto& s : pn->samples) {
+      if (s.has_counts) pn->device_bytes += (size_t)s.nnz * 24 + ((size_t)s.n_cells + s.n_genes) * 24;
+      pn->device_bytes += (size_t)s.n_cells * s.n_pcs * 12;
+    }
+    ctx->c.free_bytes_seen -= std::min(ctx->c.free_bytes_seen, pn->device_bytes);
     *out = pn;
     return 0;
   } catch (const std::exception& e) {
@@ -97,7 +94,12 @@ int cg_panel_create(cg_context* ctx, const cg_sample* samples, int n_samples, cg
   }
 }
 
-void cg_panel_free(cg_panel* panel) { delete panel; }
+void cg_panel_free(cg_panel* panel) {
+  if (!panel) return;
+  // the blocks go back to the panel pool, which keeps them: they are free again as far as this context is concerned
+  if (::cg::stream_alive(panel->stream) && panel->ctx) panel->ctx->c.free_bytes_seen += panel->device_bytes;
+  delete panel;
+}
 
 int cg_panel_offsets(const cg_panel* panel, int32_t* offsets) {
   if (!panel || !offsets) return 1;
@@ -151,10 +153,26 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
   SimParams sp{P.metric, P.matching, P.cor_base, P.l2_sigma, P.min_similarity};
 
   // ---- batches of pairs bounded by device memory
+  // per-pair footprint (bytes); pairs with a bad sample index are rejected below
+  auto need_of = [&](const cg_pair& pr) -> size_t {
+    if (pr.a < 0 || pr.a >= S || pr.b < 0 || pr.b >= S) return 0;
+    const Sample& sa = panel->samples[pr.a];
+    const Sample& sb = panel->samples[pr.b];
+    const size_t na = sa.n_cells, nb = sb.n_cells;
+    size_t need = (round_up(na, KNN_ROW_PAD) + round_up(nb, KNN_ROW_PAD)) * 64 * 4  // panels
+                  + (na + nb) * (size_t)P.k1 * 8 * 2                                   // kNN out + matching temps
+                  + ((size_t)sa.n_genes + sb.n_genes) * 64 * 8                         // W
+                  + (size_t)(pr.n_genes > 0 ? pr.n_genes : 0) * 64 * 8 * 2;
+    if (ctx->keep_projections) need += (na + nb) * 64 * 8;
+    return need;
+  };
+  size_t need_all = 0;
+  for (int q = 0; q < n_pairs; ++q) need_all += need_of(pairs[q]);
   int p0 = 0;
   while (p0 < n_pairs) {
-    // per-pair footprint (bytes)
-    const size_t budget = std::min<size_t>(free_device_bytes() / 3, c.max_batch_bytes);
+    // free memory: the context's estimate when the whole call fits comfortably, a fresh look otherwise (the query is
+    // the one runtime call of this path that stalls for 1-100 ms on some hosts)
+    const size_t budget = std::min<size_t>(c.free_bytes_for(need_all) / 3, c.max_batch_bytes);
     size_t used = 0;
     int p1 = p0;
     // a batch shares k.cur (R/conclass.R:230-233) and the width of the common space: it ends where either changes
@@ -181,12 +199,7 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
                        pr.genes_b[g] < sb.n_genes,
                    "pair gene column out of range");
       }
-      const size_t na = sa.n_cells, nb = sb.n_cells;
-      size_t need = (round_up(na, KNN_ROW_PAD) + round_up(nb, KNN_ROW_PAD)) * 64 * 4  // panels
-                    + (na + nb) * (size_t)P.k1 * 8 * 2                                   // kNN out + matching temps
-                    + ((size_t)sa.n_genes + sb.n_genes) * 64 * 8                         // W
-                    + (size_t)pr.n_genes * 64 * 8 * 2;
-      if (ctx->keep_projections) need += (na + nb) * 64 * 8;
+      const size_t need = need_of(pr);
       if (p1 > p0 && used + need > budget) break;
       used += need;
       ++p1;
@@ -597,13 +610,16 @@ int cg_local_edges(cg_context* ctx, cg_panel* panel, const int32_t* samples, int
     }
   }
   StageScope sc_le(c, "local_edges");
+  std::vector<LocalProblem> lp(n);
   for (int t = 0; t < n; ++t) {
-    Sample& s = panel->samples[samples[t]];
-    const size_t before = (*edges)->t.n;
-    local_append_edges(c, idx[t].p, dist[t].p, s.n_cells, kp1, s.offset, P.metric, P.l2_sigma, P.k_self_weight,
-                       (*edges)->t);
-    if (sample_edge_counts) sample_edge_counts[t] = (int64_t)((*edges)->t.n - before);
+    const Sample& s = panel->samples[samples[t]];
+    lp[t] = LocalProblem{idx[t].p, dist[t].p, s.n_cells, s.offset};
   }
+  std::vector<long long> lcounts(n, 0);
+  local_append_edges_batch(c, lp.data(), n, kp1, P.metric, P.l2_sigma, P.k_self_weight, (*edges)->t, lcounts.data());
+  if (sample_edge_counts)
+    for (int t = 0; t < n; ++t) sample_edge_counts[t] = (int64_t)lcounts[t];
+  // idx / dist go out of scope here and are released in stream order
   CG_API_END(ctx)
 }
 

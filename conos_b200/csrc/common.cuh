@@ -210,7 +210,29 @@ struct Context {
   int tc_eig_max_sweeps = 40;  // tensor-core eigen solver: sweeps before a problem is handed to the FP64 driver
   size_t max_batch_bytes = (size_t)48 << 30;  // scratch budget of one batch of pairs in cg_pairs_edges (tests shrink it)
   // optional per-stage wall-clock profile (stream synchronised at both ends of a stage)
+  // Free device memory as of the last look.  cudaMemGetInfo is erratic on some hosts (tests/cuda/api_stall_probe.cu:
+  // mean 0.13 ms, 1 % of the calls 1-100 ms, while launches / syncs / stream-ordered allocations never exceed 2 ms),
+  // and the pools keep what they once reserved, so the hot calls use this estimate and only look again when a job
+  // does not obviously fit (see cg_pairs_edges).
+  size_t free_bytes_seen = 0;
+  size_t refresh_free_bytes() {
+    size_t f = 0, t = 0;
+    if (cudaMemGetInfo(&f, &t) != cudaSuccess) {
+      cudaGetLastError();
+      f = (size_t)8 << 30;
+    }
+    free_bytes_seen = f;
+    return f;
+  }
+  // budget for scratch of `want` bytes: the estimate when the job fits a third of it with room to spare, a fresh look
+  // otherwise
+  size_t free_bytes_for(size_t want) {
+    if (free_bytes_seen == 0 || want > free_bytes_seen / 4) return refresh_free_bytes();
+    return free_bytes_seen;
+  }
   bool profile = false;
+  bool profile_host = false;  // cg_profile(ctx, 2): host wall clock per stage WITHOUT synchronising (where does the host
+                              // thread sit when a step is slow?); adds nothing to the step
   std::map<std::string, double> stage_ms;
 };
 
@@ -221,19 +243,44 @@ struct StageScope {
   const char* name;
   std::chrono::steady_clock::time_point t0;
   StageScope(Context& ctx, const char* n) : c(ctx), name(n) {
-    if (c.profile) {
-      cudaStreamSynchronize(c.stream);
-      t0 = std::chrono::steady_clock::now();
-    }
+    if (c.profile) cudaStreamSynchronize(c.stream);
+    if (c.profile || c.profile_host) t0 = std::chrono::steady_clock::now();
   }
   ~StageScope() {
-    if (c.profile) {
-      cudaStreamSynchronize(c.stream);
+    if (c.profile) cudaStreamSynchronize(c.stream);
+    if (c.profile || c.profile_host)
       c.stage_ms[name] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    }
   }
 };
 
 __host__ __device__ inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
+
+#ifdef CG_COUNT_SYNCS  // measurement build: which call sites make the host wait for the stream, and how often
+struct SyncCounter {
+  std::mutex mu;
+  std::map<std::string, long long> sites;
+  ~SyncCounter() {
+    if (!getenv("CG_COUNT_SYNCS_DUMP")) return;
+    long long total = 0;
+    for (auto& kv : sites) total += kv.second;
+    fprintf(stderr, "[syncs] total %lld\n", total);
+    for (auto& kv : sites) fprintf(stderr, "[syncs] %6lld  %s\n", kv.second, kv.first.c_str());
+  }
+};
+inline SyncCounter& sync_counter() {
+  static SyncCounter c;
+  return c;
+}
+inline cudaError_t counted_stream_sync(cudaStream_t s, const char* file, int line) {
+  {
+    SyncCounter& c = sync_counter();
+    std::lock_guard<std::mutex> lk(c.mu);
+    const char* base = strrchr(file, '/');
+    c.sites[std::string(base ? base + 1 : file) + ":" + std::to_string(line)]++;
+  }
+  return cudaStreamSynchronize(s);
+}
+#define cudaStreamSynchronize(s) ::cg::counted_stream_sync((s), __FILE__, __LINE__)
+#endif
 
 }  // namespace cg

@@ -15,7 +15,7 @@ void EdgeTable::reserve(size_t cap, cudaStream_t s) {
     CG_CUDA(cudaMemcpyAsync(t.p, to.p, n * sizeof(int), cudaMemcpyDeviceToDevice, s));
     CG_CUDA(cudaMemcpyAsync(ty.p, type.p, n * sizeof(int), cudaMemcpyDeviceToDevice, s));
     CG_CUDA(cudaMemcpyAsync(ww.p, w.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    CG_CUDA(cudaStreamSynchronize(s));
+    // the old blocks are released in stream order, after these copies
   }
   from = std::move(f);
   to = std::move(t);
@@ -200,8 +200,7 @@ void mnn_append_edges(Context& ctx, const MnnProblem* h_probs, int n_probs, int 
     ctx.stats.kernels++;
     CG_CUDA(cudaGetLastError());
   }
-  out.n += (size_t)total;
-  CG_CUDA(cudaStreamSynchronize(ctx.stream));
+  out.n += (size_t)total;   // temporaries are released in stream order: no host wait
 }
 
 void local_append_edges(Context& ctx, const int* d_idx, const float* d_dist, int n, int kp1, int off, int metric,
@@ -229,6 +228,50 @@ void local_append_edges(Context& ctx, const int* d_idx, const float* d_dist, int
   }
   out.n += (size_t)total;
   CG_CUDA(cudaStreamSynchronize(ctx.stream));
+}
+
+// The same for several samples with ONE host round trip: the columns of all samples are counted into one array, one
+// scan gives every row its place in the table, the total and the per-sample counts come back together.  Rows are
+// appended sample by sample, row by row -- the order of consecutive local_append_edges calls.
+void local_append_edges_batch(Context& ctx, const LocalProblem* probs, int n_probs, int kp1, int metric,
+                              double l2_sigma, double k_self_weight, EdgeTable& out, long long* counts) {
+  std::vector<long long> base(n_probs + 1, 0);
+  for (int p = 0; p < n_probs; ++p) base[p + 1] = base[p] + probs[p].n;
+  const long long N = base[n_probs];
+  if (counts)
+    for (int p = 0; p < n_probs; ++p) counts[p] = 0;
+  if (N == 0 || kp1 <= 0) return;
+  DevBuf<int> tmp_i((size_t)N * kp1), cnt((size_t)N);
+  DevBuf<double> tmp_w((size_t)N * kp1);
+  DevBuf<long long> offs((size_t)N + 1);
+  for (int p = 0; p < n_probs; ++p) {
+    if (probs[p].n == 0) continue;
+    local_columns_kernel<<<(probs[p].n + 7) / 8, 256, 0, ctx.stream>>>(
+        probs[p].idx, probs[p].dist, probs[p].n, kp1, probs[p].off, metric, l2_sigma, k_self_weight,
+        tmp_i.p + base[p] * kp1, tmp_w.p + base[p] * kp1, cnt.p + base[p]);
+    ctx.stats.kernels++;
+  }
+  CG_CUDA(cudaGetLastError());
+  exclusive_scan_i32_to_i64(ctx, cnt.p, offs.p, (size_t)N, offs.p + N);
+  std::vector<long long> h_off(n_probs + 1, 0);
+  for (int p = 0; p <= n_probs; ++p)
+    CG_CUDA(cudaMemcpyAsync(&h_off[p], offs.p + base[p], sizeof(long long), cudaMemcpyDeviceToHost, ctx.stream));
+  CG_CUDA(cudaStreamSynchronize(ctx.stream));
+  const long long total = h_off[n_probs];
+  if (counts)
+    for (int p = 0; p < n_probs; ++p) counts[p] = h_off[p + 1] - h_off[p];
+  out.reserve(out.n + (size_t)total, ctx.stream);
+  if (total > 0)
+    for (int p = 0; p < n_probs; ++p) {
+      if (probs[p].n == 0) continue;
+      const long long nt = (long long)probs[p].n * kp1;
+      local_compact_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, ctx.stream>>>(
+          probs[p].n, kp1, probs[p].off, tmp_i.p + base[p] * kp1, tmp_w.p + base[p] * kp1, cnt.p + base[p],
+          offs.p + base[p], out.from.p + out.n, out.to.p + out.n, out.w.p + out.n, out.type.p + out.n);
+      ctx.stats.kernels++;
+    }
+  CG_CUDA(cudaGetLastError());
+  out.n += (size_t)total;
 }
 
 // ==================================================================== graph assembly

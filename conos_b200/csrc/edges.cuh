@@ -43,6 +43,14 @@ void mnn_append_edges(Context& ctx, const MnnProblem* h_probs, int n_probs, int 
 
 // Appends the within-sample edges of one sample (neighbour, query), by query then neighbour ascending, type 0.
 // idx/dist: [n][kp1] self-kNN including the point itself; self and exact-zero distances are dropped.
+struct LocalProblem {
+  const int* idx;      // [n][kp1] self-kNN indices of the sample's cells
+  const float* dist;   // [n][kp1]
+  int n;               // cells
+  int off;             // global id of the sample's first cell
+};
+void local_append_edges_batch(Context& ctx, const LocalProblem* probs, int n_probs, int kp1, int metric,
+                              double l2_sigma, double k_self_weight, EdgeTable& out, long long* counts);
 void local_append_edges(Context& ctx, const int* d_idx, const float* d_dist, int n, int kp1, int off, int metric,
                         double l2_sigma, double k_self_weight, EdgeTable& out);
 

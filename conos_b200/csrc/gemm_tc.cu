@@ -294,8 +294,7 @@ void gemm_run(Context& ctx, const GemmPlan& plan) {
 void gemm_tn_bf16x3(Context& ctx, const GemmProblem* h_probs, int n_probs) {
   GemmPlan plan;
   gemm_plan(ctx, h_probs, n_probs, plan);
-  gemm_run(ctx, plan);
-  CG_CUDA(cudaStreamSynchronize(ctx.stream));
+  gemm_run(ctx, plan);   // the plan's device tables are released in stream order
 }
 
 void tiled_from_csc(Context& ctx, const int* csc_p, const int* csc_i, const double* csc_x, int n_cells, int n_genes,

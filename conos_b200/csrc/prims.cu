@@ -92,7 +92,7 @@ void scan_impl(Context& ctx, const Tin* d_in, Tout* d_out, size_t n, Tout* d_tot
   scan_down_kernel<Tin, Tout><<<(unsigned)nb, SCAN_THREADS, 0, ctx.stream>>>(d_in, n, partial_excl.p, d_out, d_total);
   ctx.stats.kernels++;
   CG_CUDA(cudaGetLastError());
-  CG_CUDA(cudaStreamSynchronize(ctx.stream));  // partial buffers are freed on return
+  // no host wait: the partial buffers are released in stream order (cudaFreeAsync on the stream they were used on)
 }
 
 // ------------------------------------------------------------------ segmented bitonic sort
@@ -215,8 +215,7 @@ void segmented_sort_u64(Context& ctx, unsigned long long* d_keys, const long lon
     CG_CUDA(cudaFuncSetAttribute(segsort_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     segsort_cta_kernel<<<h_count, 512, smem, ctx.stream>>>(d_keys, d_seg_off, list.p);
     ctx.stats.kernels++;
-    CG_CUDA(cudaGetLastError());
-    CG_CUDA(cudaStreamSynchronize(ctx.stream));
+    CG_CUDA(cudaGetLastError());   // `list` is released in stream order
   }
 }
 

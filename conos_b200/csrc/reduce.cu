@@ -344,8 +344,12 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
     // chunks of pairs bounded by memory (2 covariance matrices per pair)
     size_t i0 = 0;
     while (i0 < todo.size()) {
-      size_t freeb = 0, totb = 0;
-      cudaMemGetInfo(&freeb, &totb);
+      size_t need_fp64 = 0;
+      for (size_t t = i0; t < todo.size(); ++t) {
+        const size_t Gp = (size_t)std::max(pairs[todo[t]].n_genes, B);
+        need_fp64 += 2 * (Gp * Gp * 8 + Gp * (2 * B + r) * 8);
+      }
+      const size_t freeb = ctx.free_bytes_for(need_fp64);
       size_t per = 0;
       size_t i1 = i0;
       size_t used = 0;
@@ -525,8 +529,10 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
     StageScope sc(ctx, "reduction.cpca_init");
     size_t c0 = 0;
     while (c0 < expl.size()) {
-      size_t freeb = 0, totb = 0;
-      cudaMemGetInfo(&freeb, &totb);
+      size_t need_init = 0;
+      for (size_t t = c0; t < expl.size(); ++t)
+        need_init += (size_t)bufs[expl[t]].Gp * bufs[expl[t]].Gp * 8 + (size_t)bufs[expl[t]].Gp * 64 * 8 * 4;
+      const size_t freeb = ctx.free_bytes_for(need_init);
       size_t c1 = c0, used = 0;
       while (c1 < expl.size()) {
         if (bufs[expl[c1]].ncomp != bufs[expl[c0]].ncomp) break;
@@ -661,8 +667,7 @@ void ensure_grams(Context& ctx, Sample* const* samples, int n) {
       mirror_upper_kernel<<<nblk(G * G), 256, 0, ctx.stream>>>(todo[t]->gram.p, todo[t]->n_genes);
       ctx.stats.kernels++;
     }
-    CG_CUDA(cudaGetLastError());
-    CG_CUDA(cudaStreamSynchronize(ctx.stream));
+    CG_CUDA(cudaGetLastError());   // the operand panels are released in stream order
     i0 = i1;
   }
 }

@@ -262,7 +262,6 @@ void build_projection_operands(Context& ctx, const WBuildProblem* h_probs, int n
   wbuild_kernel<<<grid, 256, 0, ctx.stream>>>(dp.p, d, d_pad);
   ctx.stats.kernels++;
   CG_CUDA(cudaGetLastError());
-  CG_CUDA(cudaStreamSynchronize(ctx.stream));
 }
 
 void project_and_prep(Context& ctx, const ProjProblem* h_probs, int n_probs, int d, int d_pad, Metric metric) {

@@ -82,7 +82,9 @@ int cg_set_option(cg_context* ctx, const char* name, double value);
 /* counters: "knn_redo_blocks" (256-row blocks recomputed by the streaming kernel), "eig_redo_pairs" (pairs the
  * tensor-core eigen solver handed to the FP64 driver), "kernel_launches" */
 int cg_get_stat(cg_context* ctx, const char* name, double* value);
-/* optional per-stage wall-clock profile: enable (resets), then dump "name=ms;name=ms;..." into buf */
+/* optional per-stage wall-clock profile: enable (resets), then dump "name=ms;name=ms;..." into buf.  enable = 1
+ * synchronises the stream at both ends of every stage (device time per stage, slows the step); enable = 2 only reads
+ * the host clock (where the host thread spends a step; free) */
 int cg_profile(cg_context* ctx, int enable);
 int cg_profile_dump(cg_context* ctx, char* buf, int buf_len);
 /* optional CUDA-event timing of the dominant kernel (cross-kNN): enable, then read and reset.  `candidates` follows

@@ -1,7 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_knn.py tests/test_gpu_fullsize.py -q -m gpu -x 2>&1 | tail -2
-python tools/knn_time.py knn_stagger 0 0 2>&1 | tail -2
-python bench.py --no-e2e --no-atlas --no-check --steps 8 2> gpurun_out/w.err | python -c "
+python -m pytest tests -q -m gpu -x 2>&1 | tail -2
+python bench.py --no-atlas --no-check --steps 150 2> gpurun_out/w.err | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); print(round(d['ms_per_step'],1), d['steps_ms'], 'knn avg launch', round(d['roofline']['avg_launch_ms'],2), 'frac', round(d['roofline']['frac'],4))"
+d=json.loads(sys.stdin.read()); s=d['steps_ms']; m=sorted(s)[len(s)//2]; print('mean', round(d['ms_per_step'],1), 'median', m, 'n>median+4:', sum(1 for x in s if x>m+4), 'max', max(s), 'e2e', d['e2e'])"
