@@ -387,6 +387,7 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
                                   P.space == CG_SPACE_CCA ? B.rows_v.p : nullptr, B.na, B.nb, sa.offset, sb.offset});
     }
     if (!h_stage_d.empty()) {
+      StageScope sc_up(c, "pair_setup.upload");
       CG_CUDA(cudaMemcpyAsync(d_stage_d.p, h_stage_d.data(), h_stage_d.size() * sizeof(double), cudaMemcpyHostToDevice,
                               c.stream));
       CG_CUDA(cudaMemcpyAsync(d_stage_i.p, h_stage_i.data(), h_stage_i.size() * sizeof(int), cudaMemcpyHostToDevice,
