@@ -172,6 +172,10 @@ int cg_set_option(cg_context* ctx, const char* name, double value) {
     ctx->c.knn_ld32 = value != 0.0;
     return 0;
   }
+  if (strcmp(name, "eig_cluster") == 0) {
+    ctx->c.eig_cluster = (int)value;
+    return 0;
+  }
   if (strcmp(name, "knn_stagger") == 0) {
     ctx->c.knn_stagger = value < 0 ? 0 : (int)value;
     return 0;

@@ -195,6 +195,7 @@ struct Context {
   // 1 = streaming tensor-core kernel only, 2 = exact SIMT kernel only
   int knn_engine = 0;
   int knn_ld32 = 0;               // two-phase kernel: read the accumulators with two x32 loads instead of four x16
+  int eig_cluster = 0;            // 0 = automatic, 1 / 4 = force the single-CTA / clustered eigen kernels (tests)
   int knn_stagger = 0;            // two-phase kernel: cycles the second column half of the epilogue starts late
   int knn_cand_cap = 64;          // candidate slots per (row, half) the two-phase kernel may use (tests shrink it)
   cudaMemPool_t panel_pool = nullptr;  // resident panel buffers (see PoolBinding)

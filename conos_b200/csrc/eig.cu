@@ -289,21 +289,36 @@ struct EigSmem {
 // products, row updates, residuals -- are split by rows, the B x B factorisations are repeated by every CTA on the
 // same (cluster-summed) matrix.  One CTA per problem leaves most of the 148 SMs idle and makes the orthonormalisation
 // and Rayleigh-Ritz steps the latency floor of the eigen stage whatever the number of problems.
+//
+// Every sum over rows is taken over the SAME EIG_CLUSTER base slices in the same order whether one CTA or a cluster
+// works on the problem (a lone CTA walks the base slices one after the other): the result of a problem does not
+// depend on the cluster width, i.e. on how many other problems share its launch -- which is what keeps the graph
+// bit-identical across batch cuts and GPU counts.
 constexpr int EIG_CLUSTER = 4;
 struct RowSlice {
   int r0, r1;       // rows of this CTA
+  int per;          // rows of a base slice (a multiple of 8: the warp-strided loops of the helpers start at r0 + warp)
+  int G;
   unsigned rank, size;
 };
 __device__ __forceinline__ RowSlice row_slice(int G, int csize) {
   RowSlice sl;
   sl.size = (unsigned)csize;
   sl.rank = csize > 1 ? cooperative_groups::this_cluster().block_rank() : 0u;
-  // slices are multiples of 8 rows (the warp-strided loops of the helpers start at r0 + warp)
-  const int per = ((G + csize - 1) / csize + 7) & ~7;
-  sl.r0 = min(G, (int)sl.rank * per);
-  sl.r1 = min(G, sl.r0 + per);
+  sl.per = ((G + EIG_CLUSTER - 1) / EIG_CLUSTER + 7) & ~7;
+  sl.G = G;
+  if (csize > 1) {
+    sl.r0 = min(G, (int)sl.rank * sl.per);
+    sl.r1 = min(G, sl.r0 + sl.per);
+  } else {
+    sl.r0 = 0;
+    sl.r1 = G;
+  }
   return sl;
 }
+// rows of base slice b
+__device__ __forceinline__ int base_r0(const RowSlice& sl, int b) { return min(sl.G, b * sl.per); }
+__device__ __forceinline__ int base_r1(const RowSlice& sl, int b) { return min(sl.G, (b + 1) * sl.per); }
 // problem of this CTA: clusters are consecutive CTAs
 __device__ __forceinline__ int cluster_problem(int csize) { return (int)blockIdx.x / csize; }
 
@@ -314,7 +329,13 @@ template <int B>
 __device__ void block_gram(const double* __restrict__ X, const double* __restrict__ Y, const RowSlice& sl,
                            double (*S)[B + 1], double (*part)[B + 1]) {
   if (sl.size == 1) {
-    block_gram_rows<B>(X, Y, sl.r0, sl.r1, S);
+    // the base slices one after the other, added like the cluster adds its partials: 0 + p0 + p1 + p2 + p3
+    for (int b = 0; b < EIG_CLUSTER; ++b) {
+      block_gram_rows<B>(X, Y, base_r0(sl, b), base_r1(sl, b), part);
+      for (int t = threadIdx.x; t < B * B; t += EIG_THREADS)
+        S[t / B][t % B] = (b == 0 ? 0.0 : S[t / B][t % B]) + part[t / B][t % B];
+      __syncthreads();
+    }
     return;
   }
   namespace cgr = cooperative_groups;
@@ -513,23 +534,29 @@ __global__ void __launch_bounds__(EIG_THREADS) eig_rr_kernel(const EigWork* __re
   {
     constexpr int NP = EIG_THREADS / B;
     const int j = tid % B, part = tid / B;
-    double acc = 0.0;
-    if (j < r) {
-      const double th = sm.ev[j];
-      for (int row = sl.r0 + part; row < sl.r1; row += NP) {
-        const double d = w.Z[(size_t)row * B + j] - th * w.Q[(size_t)row * B + j];
-        acc = fma(d, d, acc);
+    // one pass per base slice: a cluster has one slice per CTA, a lone CTA walks all of them (same sums, same order)
+    const int nb = sl.size == 1 ? EIG_CLUSTER : 1;
+    for (int b = 0; b < nb; ++b) {
+      const int q0 = sl.size == 1 ? base_r0(sl, b) : sl.r0, q1 = sl.size == 1 ? base_r1(sl, b) : sl.r1;
+      double acc = 0.0;
+      if (j < r) {
+        const double th = sm.ev[j];
+        for (int row = q0 + part; row < q1; row += NP) {
+          const double d = w.Z[(size_t)row * B + j] - th * w.Q[(size_t)row * B + j];
+          acc = fma(d, d, acc);
+        }
       }
-    }
-    sm.S[part][j] = acc;
-    __syncthreads();
-    if (tid < B) {
-      double tot = 0.0;
+      sm.S[part][j] = acc;
+      __syncthreads();
+      if (tid < B) {
+        double tot = 0.0;
 #pragma unroll
-      for (int q = 0; q < NP; ++q) tot += sm.S[q][tid];
-      sm.cs[tid] = tot;  // cs holds 3 * B / 2 >= B doubles
+        for (int q = 0; q < NP; ++q) tot += sm.S[q][tid];
+        // cs holds 3 * B / 2 >= B doubles; the cluster form adds 0 + v0 + v1 + v2 + v3 in cluster_sum_vector
+        sm.cs[tid] = sl.size == 1 ? ((b == 0 ? 0.0 : sm.cs[tid]) + tot) : tot;
+      }
+      __syncthreads();
     }
-    __syncthreads();
     cluster_sum_vector(sm.cs, B, &sm.rowbuf[0][0], sl);
   }
   if (tid == 0 && sl.rank == 0) {
@@ -694,9 +721,10 @@ void launch_clustered(void (*kernel)(KArgs...), int n_probs, int csize, size_t s
 // cluster width for problems of G rows: slices below ~250 rows are not worth the cluster barriers
 // and with hundreds of problems the single-CTA form already fills the machine (the repeated B x B factorisations of a
 // cluster would only add work: 496 CPCA problems ran 1.5x slower clustered)
-inline int eig_cluster_size(int maxG, int n_probs) {
+inline int eig_cluster_size(const Context& ctx, int maxG, int n_probs) {
+  if (ctx.eig_cluster == 1 || ctx.eig_cluster == EIG_CLUSTER) return ctx.eig_cluster;  // tests force either form
   if (maxG < 1024) return 1;
-  return n_probs <= 96 ? EIG_CLUSTER : (n_probs <= 192 ? 2 : 1);
+  return n_probs <= 96 ? EIG_CLUSTER : 1;   // 1 or EIG_CLUSTER only: the base slices are EIG_CLUSTER wide
 }
 
 // Generic FP64 driver: `matmul(works)` must fill Z = Op(Q) for every problem (Q, Z row-major [G][B] on the device).
@@ -743,7 +771,7 @@ void run_eig_generic(Context& ctx, const int* rows, double* const* Vout, double*
   CG_CUDA(cudaFuncSetAttribute(eig_rr_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CG_CUDA(cudaFuncSetAttribute(eig_project_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 gi((unsigned)(((size_t)maxG * B + 255) / 256), n_probs);
-  const int csize = eig_cluster_size(maxG, n_probs);
+  const int csize = eig_cluster_size(ctx, maxG, n_probs);
   eig_init_kernel<B><<<gi, 256, 0, s>>>(dw.p);
   launch_clustered(eig_orth_kernel<B>, n_probs, csize, smem, s, (const EigWork*)dw.p, csize);
   ctx.stats.kernels += 2;
@@ -1310,7 +1338,7 @@ void top_eigenvectors_shared_gram(Context& ctx, const TcEigSample* samples, int 
   CG_CUDA(cudaFuncSetAttribute(eig_orth_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CG_CUDA(cudaFuncSetAttribute(eig_rr_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned colblocks = (unsigned)n_cols_total;  // one CTA per column
-  const int csize = eig_cluster_size(maxG, n_probs);
+  const int csize = eig_cluster_size(ctx, maxG, n_probs);
   DevBuf<int> deg((size_t)n_probs);
   auto column = [&](int mode, const float* a, const float* b, const float* c, int step) {
     tc_column_kernel<<<colblocks, 256, 0, s>>>(dS.p, dP.p, dcs.p, dcl.p, (int)n_cols_total, mode, a, b, c, deg.p,

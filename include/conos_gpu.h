@@ -76,6 +76,8 @@ int cg_timer_stop(cg_context* ctx, double* ms);
  * rotations and cg_keep_projections always use.
  * "max_batch_bytes" (default 48 GB): scratch budget of one batch of pairs inside cg_pairs_edges; the result never
  * depends on how the pair list is cut into batches (tests set 1 to get one pair per batch).
+ * "eig_cluster" (default 0 = automatic): 1 / 4 force the single-CTA / four-CTA-cluster form of the eigen
+ * factorisation kernels; results are bit-identical (every row sum runs over the same four slices in the same order).
  * "knn_stagger" (cycles, default 0) and "knn_ld32" (default 0): scheduling experiments of the two-phase kernel's
  * epilogue (measured without effect, results identical); kept for re-measurement only. */
 int cg_set_option(cg_context* ctx, const char* name, double value);

@@ -72,6 +72,30 @@ def test_graph_independent_of_batches(ctx):
     con.close()
 
 
+@pytest.mark.parametrize("space,ncomps", [("PCA", 20), ("CPCA", 12), ("CCA", 10)])
+def test_graph_independent_of_eigen_cluster_width(ctx, space, ncomps):
+    """The eigen factorisation kernels run one CTA per problem when a launch holds many problems and a four-CTA cluster
+    per problem when it holds few (a rank of an 8-GPU run): every sum over rows is taken over the same four slices in
+    the same order in both forms, so rotations and graph are bit-identical.  Forced here through the option."""
+    import conos_b200
+    panel = _panel(4)
+    out = {}
+    try:
+        for width in (1, 4):
+            ctx.check(ctx.lib.cg_set_option(ctx.h, b"eig_cluster", float(width)))
+            con = conos_b200.Conos(panel, ctx=ctx)
+            g = con.buildGraph(k=10, k_self=5, space=space, ncomps=ncomps, n_odgenes=400)
+            key = "u" if space == "CCA" else "CPC"
+            out[width] = (g, {k: np.array(v[key]) for k, v in con.pairs[space].items()})
+            con.close()
+    finally:
+        ctx.lib.cg_set_option(ctx.h, b"eig_cluster", 0.0)
+    for k in out[1][1]:
+        assert np.array_equal(out[1][1][k], out[4][1][k]), k
+    for a in ("vertices", "edge_from", "edge_to", "weight", "type"):
+        assert np.array_equal(getattr(out[1][0], a), getattr(out[4][0], a)), a
+
+
 def test_clean_exit_after_neighbor_matrix():
     """The interpreter must exit with status 0 with live contexts, panels and the edge table of the last
     cg_neighbor_matrix call still around (round 1: segmentation fault at teardown)."""
