@@ -422,10 +422,15 @@ def main():
         if trace:
             buf = C.create_string_buffer(8192)
             lib.cg_profile_dump(ctx.h, buf, 8192)
-            traces.append((step_ms[-1], buf.value.decode(), {k: round(v, 1) for k, v in con.timings.items()}))
+            py_ = {k: round(v, 1) for k, v in con.timings.items()}
+            py_["scratch_pool_mb"] = round(ctx.stat("scratch_pool_reserved_bytes") / 2**20)
+            py_["panel_pool_mb"] = round(ctx.stat("panel_pool_reserved_bytes") / 2**20)
+            traces.append((step_ms[-1], buf.value.decode(), py_))
     if trace:
         lib.cg_profile(ctx.h, 0)
         med = sorted(step_ms)[len(step_ms) // 2]
+        pools = [(t_[2]["scratch_pool_mb"], t_[2]["panel_pool_mb"]) for t_ in traces]
+        sys.stderr.write(f"[trace rank {rank}] pool MB per step (scratch, panel): {pools}\n")
         for ms_, st_, py_ in traces:
             if ms_ > med + 4 or ms_ == med:
                 sys.stderr.write(f"[trace rank {rank}] {ms_} ms (median {med}) {st_} py {json.dumps(py_)}\n")

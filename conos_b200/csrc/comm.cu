@@ -325,7 +325,10 @@ void share_grams(Context& c, cg_panel& panel, const int* owner, const int* n_gen
       mine.push_back(&panel.samples[s]);
     }
   }
-  ensure_grams(c, mine.data(), (int)mine.size());
+  {
+    StageScope sc(c, "share_grams.compute");
+    ensure_grams(c, mine.data(), (int)mine.size());
+  }
   if (world == 1) return;
   Comm& cm = *c.comm;
   size_t scratch_elems = 0;
@@ -341,6 +344,7 @@ void share_grams(Context& c, cg_panel& panel, const int* owner, const int* n_gen
     }
   }
   DevBuf<double> scratch(scratch_elems);
+  StageScope* sc_q = new StageScope(c, "share_grams.enqueue");
   CG_NCCL(cm, cm.GroupStart());
   for (int s = 0; s < S; ++s) {
     if (owner[s] < 0) continue;
@@ -349,6 +353,8 @@ void share_grams(Context& c, cg_panel& panel, const int* owner, const int* n_gen
     CG_NCCL(cm, cm.Broadcast(buf, buf, (size_t)n_genes[s] * n_genes[s], ncclFloat64, owner[s], cm.comm, st));
   }
   CG_NCCL(cm, cm.GroupEnd());
+  delete sc_q;
+  StageScope sc_w(c, "share_grams.wait");
   CG_CUDA(cudaStreamSynchronize(st));  // `scratch` is released on return
 }
 

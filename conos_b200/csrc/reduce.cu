@@ -616,9 +616,12 @@ void ensure_grams(Context& ctx, Sample* const* samples, int n) {
     if (!dup) todo.push_back(s);
   }
   if (todo.empty()) return;
-  for (Sample* s : todo) {
-    CG_CHECK(s->n_genes <= 16384, "subset the counts matrix to the od-gene universe before upload (Gram matrix too big)");
-    s->gram.alloc((size_t)s->n_genes * s->n_genes);
+  {
+    StageScope sc_a(ctx, "gram.alloc");
+    for (Sample* s : todo) {
+      CG_CHECK(s->n_genes <= 16384, "subset the counts matrix to the od-gene universe before upload (Gram matrix too big)");
+      s->gram.alloc((size_t)s->n_genes * s->n_genes);
+    }
   }
   if (ctx.exact_reduction) {
     for (Sample* s : todo) {
@@ -644,6 +647,7 @@ void ensure_grams(Context& ctx, Sample* const* samples, int n) {
     }
     std::vector<DevBuf<__nv_bfloat16>> hi(i1 - i0), lo(i1 - i0);
     std::vector<GemmProblem> gps;
+    StageScope* sc_o = new StageScope(ctx, "gram.operands");
     for (size_t t = i0; t < i1; ++t) {
       Sample* s = todo[t];
       hi[t - i0].alloc(TiledOperand::elems(s->n_genes, s->n_cells));
@@ -661,7 +665,12 @@ void ensure_grams(Context& ctx, Sample* const* samples, int n) {
       gp.fp16 = fp16 ? 1 : 0;
       gps.push_back(gp);
     }
-    gemm_tn_bf16x3(ctx, gps.data(), (int)gps.size());
+    delete sc_o;
+    {
+      StageScope sc_g(ctx, "gram.gemm");
+      gemm_tn_bf16x3(ctx, gps.data(), (int)gps.size());
+    }
+    StageScope sc_m(ctx, "gram.mirror_and_release");
     for (size_t t = i0; t < i1; ++t) {
       const size_t G = (size_t)todo[t]->n_genes;
       mirror_upper_kernel<<<nblk(G * G), 256, 0, ctx.stream>>>(todo[t]->gram.p, todo[t]->n_genes);
