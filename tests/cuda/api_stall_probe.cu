@@ -31,8 +31,15 @@ void run(const char* name, double seconds, F f) {
   printf("\n");
 }
 
+__global__ void big_smem(int* p) {
+  extern __shared__ int sm[];
+  sm[threadIdx.x] = 1;
+  if (p && threadIdx.x == 0) *p = sm[0];
+}
+
 int main(int argc, char** argv) {
   const double secs = argc > 1 ? atof(argv[1]) : 8.0;
+  if (argc > 2) cudaSetDevice(atoi(argv[2]));   // several instances, one per GPU: do the calls of one process stall another's?
   cudaStream_t st;
   cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
   cudaMemPool_t pool;
@@ -42,6 +49,9 @@ int main(int argc, char** argv) {
   int* d = nullptr;
   cudaMalloc(&d, 4);
   run("cudaMemGetInfo", secs, [&] { size_t f, t; cudaMemGetInfo(&f, &t); });
+  run("cudaFuncSetAttribute", secs, [&] { cudaFuncSetAttribute(big_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 << 10); });
+  run("cudaMallocAsync+FreeAsync 200MB", secs, [&] { void* p; cudaMallocAsync(&p, 200 << 20, st); cudaFreeAsync(p, st); });
+  run("cudaEventCreate+Destroy", secs, [&] { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); cudaEventDestroy(e); });
   run("cudaMallocAsync+FreeAsync 1MB", secs, [&] { void* p; cudaMallocAsync(&p, 1 << 20, st); cudaFreeAsync(p, st); });
   run("launch + stream sync", secs, [&] { tiny<<<1, 32, 0, st>>>(d); cudaStreamSynchronize(st); });
   run("launch (async), sync per 64", secs, [&] { for (int i = 0; i < 64; ++i) tiny<<<1, 32, 0, st>>>(d); cudaStreamSynchronize(st); });
