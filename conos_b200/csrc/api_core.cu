@@ -172,6 +172,11 @@ int cg_set_option(cg_context* ctx, const char* name, double value) {
     ctx->c.knn_ld32 = value != 0.0;
     return 0;
   }
+  if (strcmp(name, "refresh_free_memory") == 0) {
+    if (cudaSetDevice(ctx->c.device) != cudaSuccess) cudaGetLastError();
+    ctx->c.refresh_free_bytes();
+    return 0;
+  }
   if (strcmp(name, "eig_cluster") == 0) {
     ctx->c.eig_cluster = (int)value;
     return 0;

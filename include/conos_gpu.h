@@ -76,6 +76,10 @@ int cg_timer_stop(cg_context* ctx, double* ms);
  * rotations and cg_keep_projections always use.
  * "max_batch_bytes" (default 48 GB): scratch budget of one batch of pairs inside cg_pairs_edges; the result never
  * depends on how the pair list is cut into batches (tests set 1 to get one pair per batch).
+ * "refresh_free_memory" (any value): look up the free device memory again.  The batch sizes of cg_pairs_edges come
+ * from an estimate taken at cg_init and adjusted by the panels this context holds (the driver query stalls for up to
+ * 100 ms on some hosts, so it stays out of the hot calls unless a job does not obviously fit); a caller that has since
+ * given most of the device to something else should say so here.
  * "eig_cluster" (default 0 = automatic): 1 / 4 force the single-CTA / four-CTA-cluster form of the eigen
  * factorisation kernels; results are bit-identical (every row sum runs over the same four slices in the same order).
  * "knn_stagger" (cycles, default 0) and "knn_ld32" (default 0): scheduling experiments of the two-phase kernel's
