@@ -11,6 +11,14 @@
 using namespace cg;
 
 namespace {
+// a slice of the batch slab of cg_pairs_edges (same `.p` as a DevBuf, no ownership)
+template <class T>
+struct SlicePtr {
+  T* p = nullptr;
+};
+}  // namespace
+
+namespace {
 
 // scaledMatricesP2 (R/conos.R:18-46): cqv = exp(rowMeans(log qv)), cgsf = sqrt(cqv / exp(v)), non-finite -> 0
 void pair_scale_factors(const Sample& sa, const Sample& sb, const cg_pair& pr, bool var_scale, std::vector<double>& fa,
@@ -240,15 +248,47 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
     StageScope* sc_setup = new StageScope(c, "pair_setup");
 
     // ---- projection operands
+    // The per-pair device arrays of a batch (projected panels, projection operands, kNN output) are carved out of
+    // ONE allocation: at the atlas nine stream-ordered allocations and nine frees per pair (4950 pairs) cost more host
+    // time than everything else in this stage.  256-byte aligned slices; W slices are contiguous (one memset).
     struct PairBuf {
-      DevBuf<double> Wa, Wb, shift, fa, fb, ca, cb, p64a, p64b;
-      DevBuf<int> cols_a, cols_b, rows_u, rows_v;
-      DevBuf<float> ta, tb;
-      DevBuf<int> i_ab, i_ba;
-      DevBuf<float> d_ab, d_ba;
+      SlicePtr<double> Wa, Wb, shift;
+      DevBuf<double> p64a, p64b;        // only with cg_keep_projections
+      DevBuf<int> rows_u, rows_v;       // only CCA
+      SlicePtr<float> ta, tb;
+      SlicePtr<int> i_ab, i_ba;
+      SlicePtr<float> d_ab, d_ba;
       int na = 0, nb = 0, d = 0, d_pad = 32;
     };
     std::vector<PairBuf> pb(nb_pairs);
+    auto al = [](size_t bytes) { return (bytes + 255) & ~(size_t)255; };
+    size_t slab_w = 0, slab_rest = 0;
+    for (int q = 0; q < nb_pairs; ++q) {
+      const cg_pair& pr = pairs[p0 + q];
+      const PairReduction& R = red[q];
+      const size_t na = P.space == CG_SPACE_CCA ? (size_t)R.n_u : (size_t)panel->samples[pr.a].n_cells;
+      const size_t nb = P.space == CG_SPACE_CCA ? (size_t)R.n_v : (size_t)panel->samples[pr.b].n_cells;
+      const int dp = knn_d_pad(R.d);
+      slab_rest += al(KnnPanel::elems((int)na, R.d) * sizeof(float)) + al(KnnPanel::elems((int)nb, R.d) * sizeof(float));
+      slab_rest += 2 * al(na * P.k1 * sizeof(int)) + 2 * al(nb * P.k1 * sizeof(int));   // idx + dist (4 bytes each)
+      if (P.space != CG_SPACE_CCA) {
+        slab_w += al((size_t)panel->samples[pr.a].n_genes * dp * sizeof(double)) +
+                  al((size_t)panel->samples[pr.b].n_genes * dp * sizeof(double));
+        slab_rest += al((size_t)2 * dp * sizeof(double));
+      }
+    }
+    DevBuf<unsigned char> slab(slab_w + slab_rest);
+    size_t off_w = 0, off_rest = slab_w;
+    auto take_w = [&](size_t bytes) {
+      unsigned char* r = slab.p + off_w;
+      off_w += al(bytes);
+      return r;
+    };
+    auto take = [&](size_t bytes) {
+      unsigned char* r = slab.p + off_rest;
+      off_rest += al(bytes);
+      return r;
+    };
     // the small per-pair vectors (scale factors, centering, gene columns) of the whole batch travel in two uploads
     size_t stage_d = 0, stage_i = 0;
     if (P.space != CG_SPACE_CCA)
@@ -290,8 +330,8 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
       CG_CHECK(d_all < 0 || d_all == B.d, "all pairs of one call must share the number of components");
       d_all = B.d;
       d_pad_all = B.d_pad;
-      B.ta.alloc(KnnPanel::elems(B.na, B.d));
-      B.tb.alloc(KnnPanel::elems(B.nb, B.d));
+      B.ta.p = reinterpret_cast<float*>(take(KnnPanel::elems(B.na, B.d) * sizeof(float)));
+      B.tb.p = reinterpret_cast<float*>(take(KnnPanel::elems(B.nb, B.d) * sizeof(float)));
       keep.n_rows = R.n_rows;
       keep.n_cols = R.n_cols;
       keep.rot = std::move(R.h_rot);
@@ -358,9 +398,9 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
         h_stage_i.insert(h_stage_i.end(), pr.genes_a, pr.genes_a + G);
         const int* dgb = d_stage_i.p + h_stage_i.size();
         h_stage_i.insert(h_stage_i.end(), pr.genes_b, pr.genes_b + G);
-        B.Wa.alloc((size_t)sa.n_genes * B.d_pad);
-        B.Wb.alloc((size_t)sb.n_genes * B.d_pad);
-        B.shift.alloc((size_t)2 * B.d_pad);
+        B.Wa.p = reinterpret_cast<double*>(take_w((size_t)sa.n_genes * B.d_pad * sizeof(double)));
+        B.Wb.p = reinterpret_cast<double*>(take_w((size_t)sb.n_genes * B.d_pad * sizeof(double)));
+        B.shift.p = reinterpret_cast<double*>(take((size_t)2 * B.d_pad * sizeof(double)));
         wprobs.push_back(WBuildProblem{R.rot.p, dfa, dca, dga, B.Wa.p, B.shift.p, G, sa.n_genes});
         wprobs.push_back(WBuildProblem{R.rot.p, dfb, dcb, dgb, B.Wb.p, B.shift.p + B.d_pad, G, sb.n_genes});
         if (ctx->keep_projections) {
@@ -376,10 +416,10 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
         pgenes.push_back(sa.n_genes);
         pgenes.push_back(sb.n_genes);
       }
-      B.i_ab.alloc((size_t)B.na * P.k1);
-      B.d_ab.alloc((size_t)B.na * P.k1);
-      B.i_ba.alloc((size_t)B.nb * P.k1);
-      B.d_ba.alloc((size_t)B.nb * P.k1);
+      B.i_ab.p = reinterpret_cast<int*>(take((size_t)B.na * P.k1 * sizeof(int)));
+      B.d_ab.p = reinterpret_cast<float*>(take((size_t)B.na * P.k1 * sizeof(float)));
+      B.i_ba.p = reinterpret_cast<int*>(take((size_t)B.nb * P.k1 * sizeof(int)));
+      B.d_ba.p = reinterpret_cast<float*>(take((size_t)B.nb * P.k1 * sizeof(float)));
       kprobs.push_back(KnnProblem{B.ta.p, B.tb.p, B.na, B.nb, B.i_ab.p, B.d_ab.p});
       kprobs.push_back(KnnProblem{B.tb.p, B.ta.p, B.nb, B.na, B.i_ba.p, B.d_ba.p});
       mprobs.push_back(MnnProblem{B.i_ab.p, B.d_ab.p, B.i_ba.p, B.d_ba.p,
@@ -396,7 +436,9 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
     delete sc_setup;
     if (!wprobs.empty()) {
       StageScope sc(c, "projection");
-      build_projection_operands(c, wprobs.data(), (int)wprobs.size(), d_all, d_pad_all);
+      CG_CHECK(off_w <= slab_w && off_rest <= slab_w + slab_rest, "internal: batch slab overrun");
+      if (off_w) CG_CUDA(cudaMemsetAsync(slab.p, 0, off_w, c.stream));   // all W operands at once
+      build_projection_operands(c, wprobs.data(), (int)wprobs.size(), d_all, d_pad_all, /*zeroed=*/true);
       // default mode: one tensor-core GEMM per sample for all of its pair sides (fp32 accumulation, the accuracy class
       // of the tensor-core rotations it multiplies).  The FP64 SpMM serves the exact mode, rotations the caller
       // supplied (exact inputs: the projection stays exact too), d > 32, gene universes beyond the dense operand and

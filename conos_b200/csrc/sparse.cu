@@ -252,12 +252,14 @@ void sample_finish(Context& ctx, Sample& s, cudaEvent_t ready) {
   s.h_colsum.resize(s.n_genes);
 }
 
-void build_projection_operands(Context& ctx, const WBuildProblem* h_probs, int n_probs, int d, int d_pad) {
+void build_projection_operands(Context& ctx, const WBuildProblem* h_probs, int n_probs, int d, int d_pad,
+                               bool zeroed) {
   if (n_probs == 0) return;
   DevBuf<WBuildProblem> dp;
   dp.upload(h_probs, n_probs, ctx.stream);
-  for (int p = 0; p < n_probs; ++p)
-    CG_CUDA(cudaMemsetAsync(h_probs[p].W, 0, (size_t)h_probs[p].n_genes_sample * d_pad * sizeof(double), ctx.stream));
+  if (!zeroed)   // the caller may have cleared all operands with one memset (they are slices of one allocation)
+    for (int p = 0; p < n_probs; ++p)
+      CG_CUDA(cudaMemsetAsync(h_probs[p].W, 0, (size_t)h_probs[p].n_genes_sample * d_pad * sizeof(double), ctx.stream));
   dim3 grid(32, n_probs);
   wbuild_kernel<<<grid, 256, 0, ctx.stream>>>(dp.p, d, d_pad);
   ctx.stats.kernels++;

@@ -71,7 +71,8 @@ struct WBuildProblem {
   int G;
   int n_genes_sample;
 };
-void build_projection_operands(Context& ctx, const WBuildProblem* h_probs, int n_probs, int d, int d_pad);
+void build_projection_operands(Context& ctx, const WBuildProblem* h_probs, int n_probs, int d, int d_pad,
+                               bool zeroed = false);
 void project_and_prep(Context& ctx, const ProjProblem* h_probs, int n_probs, int d, int d_pad, Metric metric);
 
 }  // namespace cg
