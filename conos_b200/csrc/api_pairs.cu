@@ -296,10 +296,12 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
         stage_d += 4 * (size_t)pairs[p0 + q].n_genes;
         stage_i += 2 * (size_t)pairs[p0 + q].n_genes;
       }
-    std::vector<double> h_stage_d;
-    std::vector<int> h_stage_i;
-    h_stage_d.reserve(stage_d);
-    h_stage_i.reserve(stage_i);
+    // staged in page-locked memory (the context's arena: valid until the next cg_pairs_edges call) and filled by
+    // several host threads after the loop below has handed out the slices
+    double* h_stage_d = stage_d ? static_cast<double*>(c.rot_arena.take(stage_d * sizeof(double))) : nullptr;
+    int* h_stage_i = stage_i ? static_cast<int*>(c.rot_arena.take(stage_i * sizeof(int))) : nullptr;
+    size_t used_d = 0, used_i = 0;
+    std::vector<size_t> off_d(nb_pairs, 0), off_i(nb_pairs, 0);
     DevBuf<double> d_stage_d(stage_d);
     DevBuf<int> d_stage_i(stage_i);
     std::vector<WBuildProblem> wprobs;
@@ -369,35 +371,18 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
         }
       } else {
         const int G = pr.n_genes;
-        const std::vector<double>& fa = R.h_fa;   // computed for the whole batch above
-        const std::vector<double>& fb = R.h_fb;
-        // centering (R/conos.R:784-789): per-gene scaled means, and the quirk of the default path:
-        // `centering` is an atomic vector, so centering[[n]] is ONE number per sample (m[1], m[2])
-        std::vector<double> ca(G), cb(G);
-        for (int g = 0; g < G; ++g) {
-          ca[g] = fa[g] * sa.h_colsum[pr.genes_a[g]] / (double)sa.n_cells;
-          cb[g] = fb[g] * sb.h_colsum[pr.genes_b[g]] / (double)sb.n_cells;
-        }
-        if (P.common_centering) {
-          CG_CHECK(G >= 2, "common centering needs at least two od genes");
-          const double na = sa.n_cells, nb = sb.n_cells;
-          const double m0 = (ca[0] * na + cb[0] * nb) / (na + nb);
-          const double m1 = (ca[1] * na + cb[1] * nb) / (na + nb);
-          std::fill(ca.begin(), ca.end(), m0);
-          std::fill(cb.begin(), cb.end(), m1);
-        }
-        const double* dfa = d_stage_d.p + h_stage_d.size();
-        h_stage_d.insert(h_stage_d.end(), fa.begin(), fa.end());
-        const double* dfb = d_stage_d.p + h_stage_d.size();
-        h_stage_d.insert(h_stage_d.end(), fb.begin(), fb.end());
-        const double* dca = d_stage_d.p + h_stage_d.size();
-        h_stage_d.insert(h_stage_d.end(), ca.begin(), ca.end());
-        const double* dcb = d_stage_d.p + h_stage_d.size();
-        h_stage_d.insert(h_stage_d.end(), cb.begin(), cb.end());
-        const int* dga = d_stage_i.p + h_stage_i.size();
-        h_stage_i.insert(h_stage_i.end(), pr.genes_a, pr.genes_a + G);
-        const int* dgb = d_stage_i.p + h_stage_i.size();
-        h_stage_i.insert(h_stage_i.end(), pr.genes_b, pr.genes_b + G);
+        if (P.common_centering) CG_CHECK(G >= 2, "common centering needs at least two od genes");
+        // slices of the staging arrays: [fa | fb | ca | cb] and [genes_a | genes_b]; filled after the loop
+        off_d[q] = used_d;
+        off_i[q] = used_i;
+        const double* dfa = d_stage_d.p + used_d;
+        const double* dfb = dfa + G;
+        const double* dca = dfb + G;
+        const double* dcb = dca + G;
+        const int* dga = d_stage_i.p + used_i;
+        const int* dgb = dga + G;
+        used_d += 4 * (size_t)G;
+        used_i += 2 * (size_t)G;
         B.Wa.p = reinterpret_cast<double*>(take_w((size_t)sa.n_genes * B.d_pad * sizeof(double)));
         B.Wb.p = reinterpret_cast<double*>(take_w((size_t)sb.n_genes * B.d_pad * sizeof(double)));
         B.shift.p = reinterpret_cast<double*>(take((size_t)2 * B.d_pad * sizeof(double)));
@@ -426,12 +411,48 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
                                   P.space == CG_SPACE_CCA ? B.rows_u.p : nullptr,
                                   P.space == CG_SPACE_CCA ? B.rows_v.p : nullptr, B.na, B.nb, sa.offset, sb.offset});
     }
-    if (!h_stage_d.empty()) {
+    if (used_d) {
       StageScope sc_up(c, "pair_setup.upload");
-      CG_CUDA(cudaMemcpyAsync(d_stage_d.p, h_stage_d.data(), h_stage_d.size() * sizeof(double), cudaMemcpyHostToDevice,
-                              c.stream));
-      CG_CUDA(cudaMemcpyAsync(d_stage_i.p, h_stage_i.data(), h_stage_i.size() * sizeof(int), cudaMemcpyHostToDevice,
-                              c.stream));
+      // scale factors, centering and gene columns of every pair into its slices
+      auto fill = [&](int q0, int q1) {
+        for (int q = q0; q < q1; ++q) {
+          const cg_pair& pr = pairs[p0 + q];
+          const Sample& sa = panel->samples[pr.a];
+          const Sample& sb = panel->samples[pr.b];
+          const int G = pr.n_genes;
+          const std::vector<double>& fa = red[q].h_fa;   // computed for the whole batch above
+          const std::vector<double>& fb = red[q].h_fb;
+          double* o = h_stage_d + off_d[q];
+          double *ofa = o, *ofb = o + G, *oca = o + 2 * (size_t)G, *ocb = o + 3 * (size_t)G;
+          // centering (R/conos.R:784-789): per-gene scaled means, and the quirk of the default path:
+          // `centering` is an atomic vector, so centering[[n]] is ONE number per sample (m[1], m[2])
+          for (int g = 0; g < G; ++g) {
+            ofa[g] = fa[g];
+            ofb[g] = fb[g];
+            oca[g] = fa[g] * sa.h_colsum[pr.genes_a[g]] / (double)sa.n_cells;
+            ocb[g] = fb[g] * sb.h_colsum[pr.genes_b[g]] / (double)sb.n_cells;
+          }
+          if (P.common_centering) {
+            const double na = sa.n_cells, nb = sb.n_cells;
+            const double m0 = (oca[0] * na + ocb[0] * nb) / (na + nb);
+            const double m1 = (oca[1] * na + ocb[1] * nb) / (na + nb);
+            std::fill(oca, oca + G, m0);
+            std::fill(ocb, ocb + G, m1);
+          }
+          memcpy(h_stage_i + off_i[q], pr.genes_a, (size_t)G * sizeof(int));
+          memcpy(h_stage_i + off_i[q] + G, pr.genes_b, (size_t)G * sizeof(int));
+        }
+      };
+      const int nt = nb_pairs >= 64 ? 8 : 1;
+      if (nt == 1) {
+        fill(0, nb_pairs);
+      } else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; ++t) th.emplace_back(fill, nb_pairs * t / nt, nb_pairs * (t + 1) / nt);
+        for (auto& t : th) t.join();
+      }
+      CG_CUDA(cudaMemcpyAsync(d_stage_d.p, h_stage_d, used_d * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+      CG_CUDA(cudaMemcpyAsync(d_stage_i.p, h_stage_i, used_i * sizeof(int), cudaMemcpyHostToDevice, c.stream));
     }
     delete sc_setup;
     if (!wprobs.empty()) {
