@@ -4,6 +4,8 @@
 
 #include "eig.cuh"
 #include "gemm_tc.cuh"
+#include <thread>
+
 #include "reduce.cuh"
 #include "stage.cuh"
 
@@ -237,41 +239,34 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
         n_c += 2 * (size_t)pr.n_genes;
         n_v += ((size_t)panel.samples[pr.a].n_genes + panel.samples[pr.b].n_genes) * r;
       }
-      std::vector<double> h_f;
-      std::vector<int> h_c;
-      h_f.reserve(n_f);
-      h_c.reserve(n_c);
+      // staged in the context's page-locked arena (valid until the next cg_pairs_edges call): the loop hands out the
+      // slices, several host threads fill them (the atlas has 9900 of them per call)
+      double* h_f = static_cast<double*>(ctx.rot_arena.take(std::max<size_t>(n_f, 1) * sizeof(double)));
+      int* h_c = static_cast<int*>(ctx.rot_arena.take(std::max<size_t>(n_c, 1) * sizeof(int)));
       DevBuf<double> d_f(n_f), d_V(n_v), d_theta(2 * (size_t)r * todo.size());
       DevBuf<int> d_c(n_c);
-      size_t o_v = 0;
+      size_t o_v = 0, o_f = 0, o_c = 0;
+      std::vector<size_t> off_f(2 * todo.size()), off_c(2 * todo.size());
       for (size_t t = 0; t < todo.size(); ++t) {
         const cg_pair& pr = pairs[todo[t]];
         const int G = pr.n_genes;
         Sample* sm[2] = {&panel.samples[pr.a], &panel.samples[pr.b]};
-        std::vector<double> f[2];
-        if ((int)out[todo[t]].h_fa.size() == G && (int)out[todo[t]].h_fb.size() == G) {
-          f[0] = out[todo[t]].h_fa;   // computed up front by the caller (same function)
-          f[1] = out[todo[t]].h_fb;
-        } else {
-          for (int g = 0; g < G; ++g)
-            CG_CHECK(pr.genes_a[g] >= 0 && pr.genes_a[g] < sm[0]->n_genes && pr.genes_b[g] >= 0 &&
-                         pr.genes_b[g] < sm[1]->n_genes,
-                     "pair gene column out of range");
-          pair_factors(*sm[0], *sm[1], pr, P.var_scale != 0, f[0], f[1]);
-        }
+        PairReduction& R = out[todo[t]];
+        for (int g = 0; g < G; ++g)
+          CG_CHECK(pr.genes_a[g] >= 0 && pr.genes_a[g] < sm[0]->n_genes && pr.genes_b[g] >= 0 &&
+                       pr.genes_b[g] < sm[1]->n_genes,
+                   "pair gene column out of range");
+        if ((int)R.h_fa.size() != G || (int)R.h_fb.size() != G)   // not computed up front by the caller
+          pair_factors(*sm[0], *sm[1], pr, P.var_scale != 0, R.h_fa, R.h_fb);
         for (int side = 0; side < 2; ++side) {
           const int Gs = sm[side]->n_genes;
-          const int* cols = side == 0 ? pr.genes_a : pr.genes_b;
-          std::vector<double> fu((size_t)Gs, 0.0);
-          for (int g = 0; g < G; ++g) {
-            CG_CHECK(cols[g] >= 0 && cols[g] < Gs, "pair gene column out of range");
-            fu[cols[g]] = f[side][g];
-          }
-          pbs[t].hf[side] = f[side];
-          pbs[t].f[side] = d_f.p + h_f.size();
-          h_f.insert(h_f.end(), fu.begin(), fu.end());
-          pbs[t].cols[side] = d_c.p + h_c.size();
-          h_c.insert(h_c.end(), cols, cols + G);
+          if (P.score_component_variance) pbs[t].hf[side] = side == 0 ? R.h_fa : R.h_fb;
+          off_f[2 * t + side] = o_f;
+          off_c[2 * t + side] = o_c;
+          pbs[t].f[side] = d_f.p + o_f;
+          pbs[t].cols[side] = d_c.p + o_c;
+          o_f += (size_t)Gs;
+          o_c += (size_t)G;
           pbs[t].V[side] = d_V.p + o_v;
           o_v += (size_t)Gs * r;
           pbs[t].theta[side] = d_theta.p + (2 * t + side) * (size_t)r;
@@ -280,8 +275,35 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
           tp.push_back(TcEigProblem{side == 0 ? pr.a : pr.b, seed, pbs[t].f[side], pbs[t].V[side], pbs[t].theta[side]});
         }
       }
-      CG_CUDA(cudaMemcpyAsync(d_f.p, h_f.data(), h_f.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-      CG_CUDA(cudaMemcpyAsync(d_c.p, h_c.data(), h_c.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+      {
+        // scale factor per gene of the sample's universe (zero outside the pair's gene set) and the gene columns
+        auto fill = [&](size_t t0, size_t t1) {
+          for (size_t t = t0; t < t1; ++t) {
+            const cg_pair& pr = pairs[todo[t]];
+            const int G = pr.n_genes;
+            const PairReduction& R = out[todo[t]];
+            for (int side = 0; side < 2; ++side) {
+              const int Gs = panel.samples[side == 0 ? pr.a : pr.b].n_genes;
+              const int* cols = side == 0 ? pr.genes_a : pr.genes_b;
+              const std::vector<double>& f = side == 0 ? R.h_fa : R.h_fb;
+              double* fu = h_f + off_f[2 * t + side];
+              std::fill(fu, fu + Gs, 0.0);
+              for (int g = 0; g < G; ++g) fu[cols[g]] = f[g];
+              memcpy(h_c + off_c[2 * t + side], cols, (size_t)G * sizeof(int));
+            }
+          }
+        };
+        const int nt = todo.size() >= 64 ? 8 : 1;
+        if (nt == 1) {
+          fill(0, todo.size());
+        } else {
+          std::vector<std::thread> th;
+          for (int k = 0; k < nt; ++k) th.emplace_back(fill, todo.size() * k / nt, todo.size() * (k + 1) / nt);
+          for (auto& x : th) x.join();
+        }
+      }
+      if (o_f) CG_CUDA(cudaMemcpyAsync(d_f.p, h_f, o_f * sizeof(double), cudaMemcpyHostToDevice, st));
+      if (o_c) CG_CUDA(cudaMemcpyAsync(d_c.p, h_c, o_c * sizeof(int), cudaMemcpyHostToDevice, st));
       {
         StageScope sc(ctx, "reduction.eig");
         top_eigenvectors_shared_gram(ctx, ts.data(), S, tp.data(), (int)tp.size(), r, ctx.tc_eig_tol, ctx.tc_eig_max_sweeps, ctx.tc_eig_degree,
