@@ -232,7 +232,7 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
           pair_scale_factors(panel->samples[pr.a], panel->samples[pr.b], pr, P.var_scale != 0, red[q].h_fa, red[q].h_fb);
         }
       };
-      const int nt = nb_pairs >= 64 ? 8 : 1;
+      const int nt = host_fill_threads(c, (size_t)nb_pairs, 64);
       if (nt == 1) {
         factors(0, nb_pairs);
       } else {
@@ -443,7 +443,7 @@ int cg_pairs_edges(cg_context* ctx, cg_panel* panel, const cg_pair* pairs, int n
           memcpy(h_stage_i + off_i[q] + G, pr.genes_b, (size_t)G * sizeof(int));
         }
       };
-      const int nt = nb_pairs >= 64 ? 8 : 1;
+      const int nt = host_fill_threads(c, (size_t)nb_pairs, 64);
       if (nt == 1) {
         fill(0, nb_pairs);
       } else {
@@ -573,7 +573,7 @@ int cg_pair_reductions_all(cg_context* ctx, int32_t* n_rows, int32_t* n_cols, in
     // the atlas fetches 4950 rotations = 2.4 GB into freshly allocated (not yet touched) host memory: the copy is
     // bound by page faults of one thread (0.5 s); eight threads take contiguous ranges of the pair list
     const size_t nq = ctx->kept.size();
-    const int nt = off * (int64_t)sizeof(double) > ((int64_t)64 << 20) ? 8 : 1;
+    const int nt = host_fill_threads(ctx->c, (size_t)off * sizeof(double), (size_t)64 << 20);
     auto copy_range = [&](size_t q0, size_t q1) {
       for (size_t q = q0; q < q1; ++q) {
         const auto& k = ctx->kept[q];

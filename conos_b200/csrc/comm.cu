@@ -109,6 +109,7 @@ void comm_destroy(Context& c) {
   if (c.comm->comm && c.comm->CommDestroy) c.comm->CommDestroy(c.comm->comm);
   delete c.comm;  // the library handle stays mapped: other contexts (or the host process) may use it
   c.comm = nullptr;
+  c.comm_world = 1;
 }
 
 // Partition of the pair list with sample locality.  The samples are cut into g contiguous groups of about equal
@@ -394,6 +395,7 @@ int cg_comm_init(cg_context* ctx, int rank, int world, const void* id) {
   comm_destroy(ctx->c);
   Comm* cm = new Comm();
   ctx->c.comm = cm;
+  ctx->c.comm_world = world;
   cm->rank = rank;
   cm->world = world;
   if (world > 1) {

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <chrono>
 #include <map>
 #include <mutex>
@@ -179,6 +180,7 @@ struct Comm;  // NCCL communicator of a multi-GPU run (comm.cu); nullptr for a s
 struct Context {
   int device = 0;
   Comm* comm = nullptr;
+  int comm_world = 1;             // ranks of the job this context belongs to (they share the host's cores)
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   std::string last_error;
@@ -255,6 +257,15 @@ struct StageScope {
 };
 
 __host__ __device__ inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
+
+// host threads for the table-filling loops of a call: up to 8, fewer when several ranks of a job share the host
+inline int host_fill_threads(const Context& c, size_t items, size_t min_items) {
+  if (items < min_items) return 1;
+  unsigned hw = std::thread::hardware_concurrency();
+  if (hw == 0) hw = 8;
+  const int per = (int)(hw / (unsigned)(c.comm_world > 1 ? c.comm_world : 1));
+  return per < 1 ? 1 : (per > 8 ? 8 : per);
+}
 
 #ifdef CG_COUNT_SYNCS  // measurement build: which call sites make the host wait for the stream, and how often
 struct SyncCounter {

@@ -293,7 +293,7 @@ void compute_pair_reductions(Context& ctx, cg_panel& panel, const cg_pair* pairs
             }
           }
         };
-        const int nt = todo.size() >= 64 ? 8 : 1;
+        const int nt = host_fill_threads(ctx, todo.size(), 64);
         if (nt == 1) {
           fill(0, todo.size());
         } else {
