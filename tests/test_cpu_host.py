@@ -183,3 +183,35 @@ def test_gene_universe_mapping_host_side():
     ids2, ga2, gb2 = con._common_od_genes("A", "B", 3)
     assert ids2.tolist() == ids.tolist()
     assert ga2.tolist() == [3, 1, 2] and gb2.tolist() == [0, 2, 1]
+
+
+def test_od_genes_uniformly_host_side():
+    """getOdGenesUniformly (R/conos.R:505-513): genes by their best rank in any sample's od list, ties in gene-name
+    order (group_by sorts the groups, arrange(rank) is stable), first n.genes."""
+    import numpy as np
+    import scipy.sparse as sp
+    from conos_b200.conos import Conos, Pagoda2
+    mk = lambda od: Pagoda2(counts=sp.csc_matrix((2, 6)), genes=list("abcdef"), cells=["x", "y"],
+                            varinfo_v=np.zeros(6), varinfo_qv=np.ones(6), pca=None, od_genes=od)
+    con = object.__new__(Conos)
+    con.samples = {"A": mk(["d", "a", "f"]), "B": mk(["b", "a", "c"]), "C": mk(["c", "e"])}
+    # best ranks: d 0, b 0, c 0 (from C), a 1, e 1, f 2 -> ties by name
+    assert con._od_genes_uniformly(10) == ["b", "c", "d", "a", "e", "f"]
+    assert con._od_genes_uniformly(4) == ["b", "c", "d", "a"]
+
+
+def test_propagate_labels_argument_checks_without_device():
+    """Conos$propagateLabels: unknown method is an error with the reference's message (R/conclass.R:915-917); no graph
+    is an error before any device call."""
+    import pytest
+    from conos_b200.conos import Conos
+    con = object.__new__(Conos)
+    con.graph = None
+    with pytest.raises(ValueError, match="Only 'solver' and 'diffusion' are supported"):
+        con.propagateLabels({}, method="magic")
+    with pytest.raises(NotImplementedError):
+        con.propagateLabels({}, method="solver")
+    with pytest.raises(ValueError, match="buildGraph"):
+        con.propagateLabels({})
+    with pytest.raises(ValueError, match="buildGraph"):
+        con.correctGenes()
