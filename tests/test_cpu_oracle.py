@@ -280,3 +280,33 @@ def test_smooth_count_matrix_against_slow_restatement(oracle):
         assert oit == sit
         assert np.array_equal(om, sm)
         assert onrm == snrm
+
+
+def _diffusion_golden():
+    import importlib.util
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_diffusion_vectors", os.path.join(here, "make_diffusion_vectors.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.inputs(), np.load(os.path.join(here, "diffusion_vectors.npz"))
+
+
+def test_diffusion_golden_vectors(oracle):
+    """The committed diffusion vectors (tests/golden/make_diffusion_vectors.py: the fixture's joint graph) are what the
+    oracle gives today: iteration counts equal, values to 1e-13 (exp() of another libm may differ in the last bit)."""
+    (ef, et, w, n, lab, m), vec = _diffusion_golden()
+    for fixed in (0, 1):
+        for name, tol in (("default", 0.025), ("tight", 1e-6)):
+            d, it, _ = oracle.propagate_labels(ef, et, w, n, lab, 3, max_n_iters=100, diffusion_fading=10.0,
+                                               diffusion_fading_const=0.1, tol=tol, fixed_initial_labels=bool(fixed),
+                                               return_info=True)
+            assert it == int(vec[f"labels_fixed{fixed}_{name}_iters"][0])
+            np.testing.assert_allclose(d, vec[f"labels_fixed{fixed}_{name}"], rtol=1e-13, atol=1e-300, equal_nan=True)
+            if fixed:
+                assert np.array_equal(d[lab >= 0], np.eye(3)[lab[lab >= 0]])   # fixed labels stay one-hot
+    for norm in (0, 1):
+        r, it, _ = oracle.smooth_count_matrix(ef, et, w, m, max_n_iters=15, diffusion_fading=10.0,
+                                              diffusion_fading_const=0.5, tol=1e-3, normalize=bool(norm), return_info=True)
+        assert it == int(vec[f"smooth_norm{norm}_iters"][0])
+        np.testing.assert_allclose(r, vec[f"smooth_norm{norm}"], rtol=1e-13, atol=1e-300)

@@ -170,3 +170,29 @@ def test_correct_genes_on_the_joint_graph(ctx, oracle, small_panel):
     np.testing.assert_allclose(res, om, rtol=1e-12, atol=1e-300)
     assert np.abs(res - cm).max() > 1e-3          # it did smooth
     con.close()
+
+
+def test_diffusion_matches_committed_golden_vectors(ctx):
+    """The device against tests/golden/diffusion_vectors.npz (the oracle's output on the joint graph of the reference's
+    own fixture, committed): no oracle run involved."""
+    import importlib.util
+    import os
+    from conos_b200 import ops
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_diffusion_vectors", os.path.join(here, "make_diffusion_vectors.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    ef, et, w, n, lab, m = mod.inputs()
+    vec = np.load(os.path.join(here, "diffusion_vectors.npz"))
+    for fixed in (0, 1):
+        for name, tol in (("default", 0.025), ("tight", 1e-6)):
+            d, it, _ = ops.propagate_labels(ef, et, w, n, lab, 3, max_n_iters=100, diffusion_fading=10.0,
+                                            diffusion_fading_const=0.1, tol=tol, fixed_initial_labels=bool(fixed), ctx=ctx,
+                                            return_info=True)
+            assert it == int(vec[f"labels_fixed{fixed}_{name}_iters"][0])
+            np.testing.assert_allclose(d, vec[f"labels_fixed{fixed}_{name}"], rtol=1e-11, atol=1e-300, equal_nan=True)
+    for norm in (0, 1):
+        r, it, _ = ops.smooth_count_matrix(ef, et, w, m, max_n_iters=15, diffusion_fading=10.0, diffusion_fading_const=0.5,
+                                           tol=1e-3, normalize=bool(norm), ctx=ctx, return_info=True)
+        assert it == int(vec[f"smooth_norm{norm}_iters"][0])
+        np.testing.assert_allclose(r, vec[f"smooth_norm{norm}"], rtol=1e-11, atol=1e-300)
