@@ -98,6 +98,43 @@ class ConosGraph:
         n = len(self.vertices)
         return sp.csr_matrix((self.adj_x, self.adj_i, self.adj_p), shape=(n, n))
 
+    def scanpy_matrices(self, cell_ids=None) -> dict:
+        """The graph matrices saveConosForScanPy writes (R/integrations.R:170-180, 219-232):
+        graph.conn = as_adjacency_matrix(graph, attr='weight')[cell.ids, cell.ids] as a dgCMatrix (slots x, i, p, Dim)
+        and graph.dist with x <- 1 - x.  `cell_ids`: the row names of the joint count matrix (cells in sample order);
+        default = the vertex order.  Every cell id must be a vertex of the graph (R fails on a missing name too)."""
+        a = self.as_adj().tocsc()
+        if cell_ids is not None:
+            pos = {n: t for t, n in enumerate(np.asarray(self.names, dtype=object))}
+            try:
+                perm = np.fromiter((pos[c] for c in cell_ids), np.int64, len(cell_ids))
+            except KeyError as e:
+                raise KeyError(f"cell {e.args[0]!r} is not a vertex of the graph") from None
+            a = a[perm][:, perm].tocsc()
+        a.sort_indices()
+        shape = np.array(a.shape, np.int32)
+        conn = {"data": a.data.astype(np.float64), "indices": a.indices.astype(np.int32),
+                "indptr": a.indptr.astype(np.int32), "shape": shape}
+        dist = {"data": 1.0 - conn["data"], "indices": conn["indices"], "indptr": conn["indptr"], "shape": shape}
+        return {"graph_connectivities": conn, "graph_distances": dist}
+
+    def save_for_scanpy(self, path: str, cell_ids=None) -> None:
+        """Write graph_connectivities/{data,shape,indices,indptr} and graph_distances/... into an HDF5 file like
+        saveConosForScanPy (alignment.graph part, R/integrations.R:219-232).  Needs h5py, as the reference needs
+        rhdf5 (R/integrations.R:112-114)."""
+        if not path.endswith(".h5"):
+            raise ValueError(f"File {path} must have the file extension *.h5")
+        try:
+            import h5py
+        except ImportError:
+            raise ImportError('The package "h5py" is required for save_for_scanpy(). Please install.') from None
+        mats = self.scanpy_matrices(cell_ids)
+        with h5py.File(path, "w") as f:
+            for group, m in mats.items():
+                g = f.create_group(group)
+                for key in ("data", "shape", "indices", "indptr"):
+                    g.create_dataset(key, data=m[key])
+
     def vcount(self) -> int:
         return len(self.vertices)
 

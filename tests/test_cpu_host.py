@@ -215,3 +215,42 @@ def test_propagate_labels_argument_checks_without_device():
         con.propagateLabels({})
     with pytest.raises(ValueError, match="buildGraph"):
         con.correctGenes()
+
+
+def test_scanpy_graph_matrices_host_side():
+    """ConosGraph.scanpy_matrices: as_adjacency_matrix(graph, attr='weight')[cell.ids, cell.ids] as dgCMatrix slots and
+    distances 1 - x (R/integrations.R:170-180); the HDF5 writer asks for h5py like the reference asks for rhdf5."""
+    import numpy as np
+    import pytest
+    from conos_b200.conos import ConosGraph
+    names = np.array(["c2", "c0", "c3", "c1"], dtype=object)            # vertex order = first appearance
+    ef, et = np.array([0, 0, 1], np.int32), np.array([1, 3, 2], np.int32)
+    w = np.array([0.5, 0.25, 0.75])
+    dense = np.zeros((4, 4))
+    dense[ef, et] = w
+    dense += dense.T
+    import scipy.sparse as sp
+    csr = sp.csr_matrix(dense)
+    g = ConosGraph(names=names, vertices=np.arange(4, dtype=np.int32), edge_from=ef, edge_to=et, weight=w,
+                   type=np.ones(3, np.int32), adj_p=csr.indptr.astype(np.int64), adj_i=csr.indices.astype(np.int32),
+                   adj_x=csr.data)
+    cell_ids = ["c0", "c1", "c2", "c3"]
+    m = g.scanpy_matrices(cell_ids)
+    perm = [1, 3, 0, 2]
+    want = dense[np.ix_(perm, perm)]
+    c = m["graph_connectivities"]
+    got = sp.csc_matrix((c["data"], c["indices"], c["indptr"]), shape=tuple(c["shape"])).toarray()
+    assert np.array_equal(got, want) and list(c["shape"]) == [4, 4]
+    assert all(np.all(np.diff(c["indices"][c["indptr"][j]:c["indptr"][j + 1]]) > 0) for j in range(4))   # dgCMatrix order
+    d = m["graph_distances"]
+    assert np.array_equal(d["data"], 1.0 - c["data"]) and np.array_equal(d["indices"], c["indices"])
+    assert np.array_equal(g.scanpy_matrices()["graph_connectivities"]["data"], sp.csc_matrix(dense).data)
+    with pytest.raises(KeyError, match="not a vertex"):
+        g.scanpy_matrices(["c0", "nope"])
+    with pytest.raises(ValueError, match="extension"):
+        g.save_for_scanpy("/tmp/x.hdf5")
+    try:
+        import h5py  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError, match="h5py"):
+            g.save_for_scanpy("/tmp/x.h5")
