@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -142,30 +143,38 @@ struct DevBuf {
 // blocks are kept between calls (grow-only), reset() rewinds the cursor.  A pointer stays valid until the next reset.
 struct PinnedArena {
   std::vector<char*> blocks;
-  std::vector<size_t> caps;
-  size_t cur = 0, off = 0;
-  void reset() { cur = 0; off = 0; }
+  std::vector<size_t> caps, used;
+  size_t first_open = 0;  // blocks before this one are full for requests of the smallest size seen (search start)
+  void reset() {
+    std::fill(used.begin(), used.end(), (size_t)0);
+    first_open = 0;
+  }
+  // first fit over ALL blocks: a call that asks for the same sizes as the one before it finds them again whatever
+  // order the blocks were created in (a forward-only cursor made the second atlas call pin 2.4 GB once more)
   void* take(size_t bytes) {
     bytes = (bytes + 255) & ~(size_t)255;
-    while (cur < blocks.size() && off + bytes > caps[cur]) { ++cur; off = 0; }
-    if (cur == blocks.size()) {
-      const size_t cap = bytes > ((size_t)32 << 20) ? bytes : ((size_t)32 << 20);
-      char* b = nullptr;
-      CG_CUDA(cudaHostAlloc(&b, cap, cudaHostAllocDefault));
-      blocks.push_back(b);
-      caps.push_back(cap);
-      off = 0;
-    }
-    void* r = blocks[cur] + off;
-    off += bytes;
-    return r;
+    while (first_open < blocks.size() && caps[first_open] - used[first_open] < 256) ++first_open;
+    for (size_t b = first_open; b < blocks.size(); ++b)
+      if (used[b] + bytes <= caps[b]) {
+        void* r = blocks[b] + used[b];
+        used[b] += bytes;
+        return r;
+      }
+    const size_t cap = bytes > ((size_t)32 << 20) ? bytes : ((size_t)32 << 20);
+    char* nb = nullptr;
+    CG_CUDA(cudaHostAlloc(&nb, cap, cudaHostAllocDefault));
+    blocks.push_back(nb);
+    caps.push_back(cap);
+    used.push_back(bytes);
+    return nb;
   }
   void release() {
     for (char* b : blocks)
       if (cudaFreeHost(b) != cudaSuccess) cudaGetLastError();
     blocks.clear();
     caps.clear();
-    cur = off = 0;
+    used.clear();
+    first_open = 0;
   }
   ~PinnedArena() { release(); }
 };
